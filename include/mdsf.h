@@ -1,0 +1,131 @@
+/*
+ * mdsf.h -- C ABI of libmdsf.so, the B200 (sm_100a) engine behind dens.compute_sf().
+ *
+ * The reference (joeyelk/MD-Structure-Factor) is pure Python and has no FFI; its whole hot
+ * path is the frame loop of dens.compute_sf (reference dens.py:277-321).  This header is the
+ * boundary a maintainer binds with ctypes (see INTEGRATION.md for the stub) to replace exactly
+ * that loop.  Every entry point cites the reference lines whose work it takes over.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a
+ * negative MDSF_E* code on failure; mdsf_last_error() gives the message for the calling
+ * thread's last failure.  Host arrays stay owned by the caller.  One handle = one GPU + its
+ * streams; calls on one handle are not thread-safe, different handles are independent.
+ * There is no CPU fallback: without a CUDA device mdsf_create() fails with MDSF_ECUDA.
+ */
+#ifndef MDSF_H
+#define MDSF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDSF_ABI_VERSION 1
+
+enum {
+    MDSF_OK = 0,
+    MDSF_EINVAL = -1,   /* bad argument / unsupported configuration            */
+    MDSF_ECUDA = -2,    /* CUDA runtime / cuFFT failure (no device, OOM, ...)  */
+    MDSF_ERANGE = -3,   /* an atom's stamp leaves the padded grid (the reference
+                           raises a numpy shape error or corrupts memory here)  */
+    MDSF_ESTATE = -4    /* call order violated (e.g. push before set_atoms)     */
+};
+
+enum { MDSF_F32 = 0, MDSF_F64 = 1 };
+enum { MDSF_FOLD_REFERENCE = 0,   /* reproduce the corner rule of dens.py:107 (default) */
+       MDSF_FOLD_PERIODIC = 1 };  /* mathematically periodic fold                       */
+enum { MDSF_FFT_AUTO = 0, MDSF_FFT_NATIVE = 1, MDSF_FFT_CUFFT = 2 };
+
+typedef struct mdsf_handle mdsf_handle;
+
+/* Everything that is frame-invariant.  The host computes N, dr, box, half widths and B with
+ * the same numpy expressions as dens.py:179-231 and passes them in, so they are identical to
+ * the reference's by construction. */
+typedef struct mdsf_config {
+    int32_t abi_version;     /* MDSF_ABI_VERSION                                              */
+    int32_t device;          /* CUDA device ordinal                                           */
+    int32_t n[3];            /* Nspatialgrid, even (dens.py:181-189)                          */
+    int32_t nborder;         /* Nborder B (dens.py:231)                                       */
+    double  dr[3];           /* L / Nspatialgrid, float64 (dens.py:202)                       */
+    double  box[3];          /* mean box L, exact value of the dims dtype (dens.py:52)        */
+    double  ucell[9];        /* row-major 3x3, rows = unit lattice vectors (dens.py:301)      */
+    int32_t ntypes;          /* number of distinct labels in typ                              */
+    const double*  amp;      /* [ntypes]  Nel / sigma^3            (dens.py:308)              */
+    const double*  two_sig2; /* [ntypes]  2 * sigma^2              (dens.py:308)              */
+    const int32_t* halfw;    /* [ntypes][3] trunc(get_borders)     (dens.py:38-43,287)        */
+    int32_t coord_dtype;     /* MDSF_F32 / MDSF_F64: dtype of the coordinate array            */
+    int32_t arith_dtype;     /* dtype numpy promotes (coords, dims) to for rescale and wrap   */
+    int32_t fold_mode;       /* MDSF_FOLD_*                                                   */
+    int32_t fft_mode;        /* MDSF_FFT_*                                                    */
+    int32_t batch_frames;    /* frames per device batch (even, >= 2); 0 = pick automatically  */
+    int32_t tile_x, tile_y;  /* splat tile in columns; 0 = pick automatically                 */
+    int32_t keep_density;    /* keep per-frame densities of the last batch for the debug tap  */
+    int32_t reserved[7];
+} mdsf_config;
+
+/* Create / destroy an engine.  Replaces the allocations of dens.py:237-263. */
+int mdsf_create(const mdsf_config* cfg, mdsf_handle** out);
+int mdsf_destroy(mdsf_handle* h);
+
+/* Atom types are frame-invariant (dens.py:287,305-306 look typ[im] up per atom per frame). */
+int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* type_id);
+
+/* Pinned host memory for trajectory staging (new; the reference holds the trajectory in
+ * pageable numpy memory, main_gromacs.py:200-202). */
+int mdsf_host_alloc(size_t bytes, void** out);
+int mdsf_host_free(void* p);
+int mdsf_host_register(void* p, size_t bytes);
+int mdsf_host_unregister(void* p);
+
+/* Queue `nframes` consecutive frames (coords[nframes][natoms][3], coord_dtype) for the whole
+ * per-frame path: rescale (dens.py:56-58), PBC wrap (dens.py:209-221), cell index
+ * (dens.py:285), Gaussian stamp (dens.py:287-308), fold (dens.py:311), FFT (dens.py:313),
+ * |F|^2 accumulation (dens.py:315-318).  `scale` is a[it][0..2] = avgdims/dims per frame as
+ * doubles holding the exact dims-dtype values.  Atoms with index in [wrap_lo, wrap_hi) are
+ * wrapped (the reference's >=1e6-atom branch only wraps the first nframes atoms).
+ * If `write_back` is non-zero the rescaled+wrapped coordinates are copied back into `coords`
+ * (the reference mutates its argument in place); they are valid after mdsf_sync().
+ * Asynchronous: returns once the work is queued; `coords` must stay valid and unmodified
+ * until mdsf_sync() (pinned memory) -- pageable memory is staged before return. */
+int mdsf_push_frames(mdsf_handle* h, void* coords, int64_t nframes, const double* scale,
+                     int64_t wrap_lo, int64_t wrap_hi, int32_t write_back);
+
+/* RANDOM_NOISE mode of the reference (dens.py:279-280): feed ready-made real densities
+ * d1[nframes][Nx][Ny][Nz] (float64, host) straight into FFT + accumulation. */
+int mdsf_push_density(mdsf_handle* h, const double* d1, int64_t nframes);
+
+/* Wait for all queued frames; reports deferred device-side errors (MDSF_ERANGE). */
+int mdsf_sync(mdsf_handle* h);
+
+/* sf[Nx][Ny][Nz/2+1] (float64), the sum over all pushed frames of |rfftn(d1)|^2, i.e. the
+ * array dens.py:318 accumulates.  Host or device destination. */
+int mdsf_read_sf(mdsf_handle* h, double* sf_host);
+int mdsf_export_sf_device(mdsf_handle* h, void* sf_device);
+/* Add a partial sf (device pointer, same shape) -- used after a cross-GPU reduce. */
+int mdsf_reset(mdsf_handle* h);
+
+/* Parity taps (tests only; each synchronises). `frame` indexes the frames of the LAST push. */
+int mdsf_debug_cell_indices(mdsf_handle* h, int64_t frame, int32_t* ir_out /* [natoms][3] */);
+int mdsf_debug_coords(mdsf_handle* h, int64_t frame, double* r_out /* [natoms][3] */);
+int mdsf_debug_density(mdsf_handle* h, int64_t frame, double* d1_out /* [Nx][Ny][Nz] */);
+
+/* Introspection for bench.py / DESIGN.md: kernel launches issued so far, frames processed,
+ * name of the FFT path in use ("native" / "cufft"), device time of the last batch. */
+int64_t mdsf_kernel_launches(const mdsf_handle* h);
+int64_t mdsf_frames_done(const mdsf_handle* h);
+const char* mdsf_fft_path(const mdsf_handle* h);
+int mdsf_batch_frames(const mdsf_handle* h);
+/* Record CUDA events around every stage of subsequent batches; query the accumulated
+ * per-stage device milliseconds: out[0..5] = h2d, prep+bin, splat(+zfft), fft, accumulate, total */
+int mdsf_enable_timing(mdsf_handle* h, int32_t on);
+int mdsf_stage_ms(mdsf_handle* h, double* out6, int64_t* batches);
+
+const char* mdsf_last_error(void);
+int mdsf_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDSF_H */

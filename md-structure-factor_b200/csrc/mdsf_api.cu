@@ -1,0 +1,705 @@
+// libmdsf.so -- host side of the C ABI declared in include/mdsf.h.
+// One handle = one GPU, three streams (H2D copy, compute, D2H write-back) and a double-buffered
+// coordinate staging area, so the copy of batch b+1 overlaps the kernels of batch b.
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <cufft.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mdsf.h"
+#include "mdsf_common.cuh"
+#include "mdsf_fft.cuh"
+#include "mdsf_prep.cuh"
+#include "mdsf_splat.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(MDSF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CF(call)                                                                              \
+    do {                                                                                      \
+        cufftResult r_ = (call);                                                              \
+        if (r_ != CUFFT_SUCCESS) return fail(MDSF_ECUDA, "%s failed: cufft error %d (%s:%d)", #call, (int)r_, __FILE__, __LINE__); \
+    } while (0)
+
+static const int kSlots = 2;
+static const int kMaxSmem = 227 * 1024;
+
+struct AxisPlan {
+    FftPlan plan{};
+    bool native = false;
+    double2* d_tw = nullptr;
+    int* d_rev = nullptr;     // frequency index -> position
+};
+
+struct mdsf_handle {
+    mdsf_config cfg{};
+    GridParams gp{};
+    TypeTable tt{};
+    int device = 0;
+    int nsm = 148;
+    size_t csize = 4;                 // sizeof coordinate dtype
+    bool native_fft = false;
+    int F = 2;                        // frames per batch
+    long long ncell = 0;
+    // streams / events
+    cudaStream_t s_copy = nullptr, s_comp = nullptr, s_back = nullptr;
+    cudaEvent_t ev_h2d[kSlots]{}, ev_free[kSlots]{}, ev_prep[kSlots]{}, ev_back[kSlots]{};
+    bool slot_used[kSlots]{};
+    int next_slot = 0;
+    // device buffers
+    double *d_amp = nullptr, *d_two = nullptr;
+    int* d_halfw = nullptr;
+    int* d_type = nullptr;
+    void* d_stage[kSlots]{};
+    AtomRec* d_recs = nullptr;
+    unsigned *d_cnt = nullptr, *d_off = nullptr;
+    unsigned *d_keys[2]{}, *d_vals[2]{};
+    unsigned* d_tile_start = nullptr;
+    void* d_cub = nullptr;
+    size_t cub_bytes = 0;
+    double2* d_vol = nullptr;
+    double2* d_dump = nullptr;
+    double* d_P = nullptr;
+    double* d_sf = nullptr;
+    int* d_err = nullptr;
+    int* h_err = nullptr;
+    AxisPlan ax[3];
+    cufftHandle cufft_plan = 0;
+    int cufft_batch = 0;
+    // splat launch geometry
+    long long natoms = 0;
+    long long maxpairs_frame = 0;
+    int chunk = 128, xycap = 1, zcap = 2;
+    size_t splat_smem = 0;
+    int sort_bits = 1;
+    // y/x pass geometry
+    int Wy = 16, Wx = 16, thr_y = 256, thr_x = 256;
+    // bookkeeping
+    long long launches = 0, frames_done = 0;
+    int last_batch_frames = 0;
+    bool timing = false;
+    cudaEvent_t tev[8]{};
+    double stage_ms[6]{};
+    long long timed_batches = 0;
+    std::vector<int> halfw_host;
+};
+
+// ------------------------------------------------------------------------------------------
+static bool factorize(int n, FftPlan& plan) {
+    plan.n = n;
+    plan.nstages = 0;
+    int e = 0;
+    while (n % 2 == 0) { n /= 2; ++e; }
+    if (e > 0) {
+        const int count = (e + 3) / 4, base = e / count, rem = e % count;
+        for (int i = 0; i < count; ++i) plan.radix[plan.nstages++] = 1 << (base + (i < rem ? 1 : 0));
+    }
+    const int odd[] = {3, 5, 7, 11, 13};
+    for (int p : odd)
+        while (n % p == 0) {
+            if (plan.nstages >= MDSF_MAX_RADIX_STAGES) return false;
+            plan.radix[plan.nstages++] = p;
+            n /= p;
+        }
+    return n == 1 && plan.nstages > 0;
+}
+
+static int digit_position(int k, int n, const FftPlan& plan, int stage) {
+    if (stage >= plan.nstages) return 0;
+    const int r = plan.radix[stage], m = n / r;
+    return (k % r) * m + digit_position(k / r, m, plan, stage + 1);
+}
+
+static int build_axis(AxisPlan& ax, int n, bool want_native) {
+    std::vector<int> rev(n);
+    ax.native = want_native && factorize(n, ax.plan);
+    if (ax.native) {
+        std::vector<double2> tw(n);
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int j = 0; j < n; ++j) {
+            const long double a = two_pi * (long double)j / (long double)n;
+            tw[j].x = (double)cosl(a);
+            tw[j].y = (double)(-sinl(a));
+        }
+        for (int k = 0; k < n; ++k) rev[k] = digit_position(k, n, ax.plan, 0);
+        CU(cudaMalloc(&ax.d_tw, sizeof(double2) * n));
+        CU(cudaMemcpy(ax.d_tw, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
+    } else {
+        ax.plan.n = n;
+        ax.plan.nstages = 0;
+        for (int k = 0; k < n; ++k) rev[k] = k;
+    }
+    CU(cudaMalloc(&ax.d_rev, sizeof(int) * n));
+    CU(cudaMemcpy(ax.d_rev, rev.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    return MDSF_OK;
+}
+
+static int grid_for(long long n, int threads, int nsm) {
+    long long b = (n + threads - 1) / threads;
+    long long cap = (long long)nsm * 16;
+    return (int)std::max(1LL, std::min(b, cap));
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int mdsf_abi_version(void) { return MDSF_ABI_VERSION; }
+extern "C" const char* mdsf_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
+    if (!cfg || !out) return fail(MDSF_EINVAL, "null argument");
+    if (cfg->abi_version != MDSF_ABI_VERSION) return fail(MDSF_EINVAL, "ABI version mismatch (%d != %d)", cfg->abi_version, MDSF_ABI_VERSION);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(MDSF_ECUDA, "no CUDA device available (%s); libmdsf has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(MDSF_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+    for (int d = 0; d < 3; ++d) {
+        if (cfg->n[d] < 2 || cfg->n[d] % 2) return fail(MDSF_EINVAL, "grid size n[%d]=%d must be even and >= 2", d, cfg->n[d]);
+        if (cfg->nborder > cfg->n[d]) return fail(MDSF_EINVAL, "Nborder %d exceeds grid size %d: the reference's fold slices are ill-formed here", cfg->nborder, cfg->n[d]);
+        if (!(cfg->dr[d] > 0)) return fail(MDSF_EINVAL, "dr[%d] must be positive", d);
+    }
+    if (cfg->ntypes < 1 || !cfg->amp || !cfg->two_sig2 || !cfg->halfw) return fail(MDSF_EINVAL, "type tables missing");
+    if (cfg->nborder < 0) return fail(MDSF_EINVAL, "negative Nborder");
+    for (int t = 0; t < cfg->ntypes * 3; ++t)
+        if (cfg->halfw[t] < 0 || cfg->halfw[t] > cfg->nborder) return fail(MDSF_EINVAL, "half width %d outside [0, Nborder=%d]", cfg->halfw[t], cfg->nborder);
+    if (cfg->coord_dtype != MDSF_F32 && cfg->coord_dtype != MDSF_F64) return fail(MDSF_EINVAL, "bad coord_dtype");
+    if (cfg->arith_dtype != MDSF_F32 && cfg->arith_dtype != MDSF_F64) return fail(MDSF_EINVAL, "bad arith_dtype");
+    if (cfg->coord_dtype == MDSF_F64 && cfg->arith_dtype == MDSF_F32) return fail(MDSF_EINVAL, "float64 coordinates never promote to float32");
+
+    CU(cudaSetDevice(cfg->device));
+    mdsf_handle* h = new mdsf_handle();
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    h->nsm = prop.multiProcessorCount;
+    h->csize = cfg->coord_dtype == MDSF_F32 ? 4 : 8;
+    GridParams& gp = h->gp;
+    for (int d = 0; d < 3; ++d) { gp.n[d] = cfg->n[d]; gp.dr[d] = cfg->dr[d]; gp.box[d] = cfg->box[d]; }
+    for (int i = 0; i < 9; ++i) gp.u[i] = cfg->ucell[i];
+    gp.nb = cfg->nborder;
+    gp.fold_mode = cfg->fold_mode;
+    // z decouples when ucell[2][0]=ucell[2][1]=0 (b_z feeds only c_2) and ucell[0][2]=ucell[1][2]=0
+    gp.separable = (gp.u[6] == 0.0 && gp.u[7] == 0.0 && gp.u[2] == 0.0 && gp.u[5] == 0.0) ? 1 : 0;
+    h->ncell = (long long)gp.n[0] * gp.n[1] * gp.n[2];
+
+    // ---- FFT plans
+    const bool want_native = cfg->fft_mode != MDSF_FFT_CUFFT;
+    for (int d = 0; d < 3; ++d) {
+        int rc = build_axis(h->ax[d], gp.n[d], want_native);
+        if (rc) return rc;
+    }
+    h->native_fft = h->ax[0].native && h->ax[1].native && h->ax[2].native;
+    if (gp.n[2] > 4096 || gp.n[1] > 2048 || gp.n[0] > 2048) h->native_fft = false;
+    if (!h->native_fft) {
+        if (cfg->fft_mode == MDSF_FFT_NATIVE)
+            return fail(MDSF_EINVAL, "grid %dx%dx%d has a prime factor > 13 (or an axis too long); native FFT unavailable", gp.n[0], gp.n[1], gp.n[2]);
+        for (int d = 0; d < 3; ++d) {   // library path works in natural order on every axis
+            std::vector<int> ident(gp.n[d]);
+            for (int k = 0; k < gp.n[d]; ++k) ident[k] = k;
+            CU(cudaMemcpy(h->ax[d].d_rev, ident.data(), sizeof(int) * gp.n[d], cudaMemcpyHostToDevice));
+            h->ax[d].native = false;
+        }
+    }
+    // z-column padding in shared memory: keep the last stage's stride odd
+    gp.pad_shift = 31;
+    if (h->native_fft) {
+        const int last = h->ax[2].plan.radix[h->ax[2].plan.nstages - 1];
+        if (last == 16) gp.pad_shift = 4; else if (last == 8) gp.pad_shift = 3; else if (last == 4) gp.pad_shift = 2;
+    }
+    gp.nzp = gp.n[2] + (gp.pad_shift < 31 ? (gp.n[2] >> gp.pad_shift) : 0);
+
+    // ---- splat tile
+    int ncol;
+    if (cfg->tile_x > 0 && cfg->tile_y > 0) {
+        gp.tx = cfg->tile_x; gp.ty = cfg->tile_y;
+        if (gp.tx * gp.ty > MDSF_MAX_TILE_COLS) return fail(MDSF_EINVAL, "tile %dx%d exceeds %d columns", gp.tx, gp.ty, MDSF_MAX_TILE_COLS);
+    } else {
+        ncol = 32;
+        while (ncol > 4 && (size_t)2 * ncol * gp.nzp * 8 > 64 * 1024) ncol >>= 1;
+        while (ncol > 1 && (size_t)2 * ncol * gp.nzp * 8 > 160 * 1024) ncol >>= 1;
+        const int txs[6] = {1, 1, 2, 2, 4, 4}, tys[6] = {1, 2, 2, 4, 4, 8};
+        int l = 0;
+        while ((1 << l) < ncol) ++l;
+        gp.tx = txs[l]; gp.ty = tys[l];
+    }
+    gp.ntx = (gp.n[0] + gp.tx - 1) / gp.tx;
+    gp.nty = (gp.n[1] + gp.ty - 1) / gp.ty;
+
+    // ---- batch size
+    int F = cfg->batch_frames;
+    if (F <= 0) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const double per_pair = (double)h->ncell * 16.0 * (cfg->keep_density ? 2 : 1);
+        const double budget = std::min(8.0e9, (double)free_b * 0.25);
+        int pairs = (int)std::max(1.0, std::floor(budget / per_pair));
+        F = 2 * std::min(pairs, MDSF_MAX_BATCH / 2);
+    }
+    if (F < 2) F = 2;
+    if (F % 2) ++F;
+    if (F > MDSF_MAX_BATCH) F = MDSF_MAX_BATCH;
+    h->F = F;
+
+    // ---- type tables
+    const int nt = cfg->ntypes;
+    CU(cudaMalloc(&h->d_amp, sizeof(double) * nt));
+    CU(cudaMalloc(&h->d_two, sizeof(double) * nt));
+    CU(cudaMalloc(&h->d_halfw, sizeof(int) * nt * 3));
+    CU(cudaMemcpy(h->d_amp, cfg->amp, sizeof(double) * nt, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_two, cfg->two_sig2, sizeof(double) * nt, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_halfw, cfg->halfw, sizeof(int) * nt * 3, cudaMemcpyHostToDevice));
+    h->halfw_host.assign(cfg->halfw, cfg->halfw + nt * 3);
+    h->tt.amp = h->d_amp; h->tt.two_sig2 = h->d_two; h->tt.halfw = h->d_halfw;
+    h->cfg.amp = nullptr; h->cfg.two_sig2 = nullptr; h->cfg.halfw = nullptr;   // caller-owned, not kept
+
+    // ---- volumes
+    const int npairs = F / 2;
+    CU(cudaMalloc(&h->d_vol, sizeof(double2) * h->ncell * npairs));
+    if (cfg->keep_density) CU(cudaMalloc(&h->d_dump, sizeof(double2) * h->ncell * npairs));
+    CU(cudaMalloc(&h->d_P, sizeof(double) * h->ncell));
+    CU(cudaMemset(h->d_P, 0, sizeof(double) * h->ncell));
+    CU(cudaMalloc(&h->d_sf, sizeof(double) * (long long)gp.n[0] * gp.n[1] * (gp.n[2] / 2 + 1)));
+    CU(cudaMalloc(&h->d_err, sizeof(int)));
+    CU(cudaMemset(h->d_err, 0, sizeof(int)));
+    CU(cudaMallocHost(&h->h_err, sizeof(int)));
+    *h->h_err = 0;
+
+    CU(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_back, cudaStreamNonBlocking));
+    for (int s = 0; s < kSlots; ++s) {
+        CU(cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_free[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_prep[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_back[s], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&h->tev[i]));
+
+    if (!h->native_fft) {
+        int dims[3] = {gp.n[0], gp.n[1], gp.n[2]};
+        CF(cufftPlanMany(&h->cufft_plan, 3, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2Z, npairs));
+        CF(cufftSetStream(h->cufft_plan, h->s_comp));
+        h->cufft_batch = npairs;
+    } else {
+        // y / x pass tiles: [n][W] complex in shared memory
+        auto pick = [&](int n, int& W, int& thr) {
+            W = 16;
+            while (W > 1 && (size_t)n * W * 24 + (size_t)n * 16 > 200 * 1024) W >>= 1;
+            thr = 256;
+        };
+        pick(gp.n[1], h->Wy, h->thr_y);
+        pick(gp.n[0], h->Wx, h->thr_x);
+        CU(cudaFuncSetAttribute(fft_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_x_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    }
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    *out = h;
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_destroy(mdsf_handle* h) {
+    if (!h) return MDSF_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->cufft_plan) cufftDestroy(h->cufft_plan);
+    void* bufs[] = {h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1], h->d_recs, h->d_cnt,
+                    h->d_off, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_tile_start, h->d_cub,
+                    h->d_vol, h->d_dump, h->d_P, h->d_sf, h->d_err};
+    for (void* b : bufs) if (b) cudaFree(b);
+    for (int d = 0; d < 3; ++d) { if (h->ax[d].d_tw) cudaFree(h->ax[d].d_tw); if (h->ax[d].d_rev) cudaFree(h->ax[d].d_rev); }
+    if (h->h_err) cudaFreeHost(h->h_err);
+    for (int s = 0; s < kSlots; ++s) {
+        if (h->ev_h2d[s]) cudaEventDestroy(h->ev_h2d[s]);
+        if (h->ev_free[s]) cudaEventDestroy(h->ev_free[s]);
+        if (h->ev_prep[s]) cudaEventDestroy(h->ev_prep[s]);
+        if (h->ev_back[s]) cudaEventDestroy(h->ev_back[s]);
+    }
+    for (int i = 0; i < 8; ++i) if (h->tev[i]) cudaEventDestroy(h->tev[i]);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_back) cudaStreamDestroy(h->s_back);
+    delete h;
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* type_id) {
+    if (!h || !type_id) return fail(MDSF_EINVAL, "null argument");
+    if (natoms < 1 || natoms >= MDSF_MAX_ATOMS) return fail(MDSF_EINVAL, "natoms=%lld outside [1, %d)", (long long)natoms, MDSF_MAX_ATOMS);
+    if (h->d_type) return fail(MDSF_ESTATE, "atoms already set on this handle");
+    CU(cudaSetDevice(h->device));
+    const GridParams& g0 = h->gp;
+    const int nt = h->cfg.ntypes;
+    // worst-case (image, tile) pairs per atom of each type: exact maximum over every admissible cell index
+    std::vector<long long> bound(nt);
+    int xymax = 1, zmax = 2;
+    for (int t = 0; t < nt; ++t) {
+        long long m[2] = {1, 1};
+        for (int d = 0; d < 2; ++d) {
+            const int A = h->halfw_host[t * 3 + d], N = g0.n[d], tl = d == 0 ? g0.tx : g0.ty;
+            for (int ir = A - g0.nb; ir <= N + g0.nb - A; ++ir) m[d] = std::max<long long>(m[d], stamp_tiles_1d(ir, A, N, tl));
+        }
+        bound[t] = m[0] * m[1];
+        xymax = std::max(xymax, std::min(g0.tx, 2 * h->halfw_host[t * 3]) * std::min(g0.ty, 2 * h->halfw_host[t * 3 + 1]));
+        zmax = std::max(zmax, 2 * h->halfw_host[t * 3 + 2]);
+    }
+    long long maxpairs = 0;
+    for (int64_t a = 0; a < natoms; ++a) {
+        if (type_id[a] < 0 || type_id[a] >= nt) return fail(MDSF_EINVAL, "type_id[%lld]=%d out of range", (long long)a, type_id[a]);
+        maxpairs += bound[type_id[a]];
+    }
+    h->natoms = natoms;
+    h->gp.natoms = (int)natoms;
+    h->maxpairs_frame = maxpairs;
+    const long long cap = maxpairs * h->F;
+    if (cap >= (1LL << 32) - 2) return fail(MDSF_EINVAL, "pair capacity %lld overflows 32-bit offsets; lower batch_frames", cap);
+    const long long nkeys = (long long)h->F * g0.ntx * g0.nty;
+    if (nkeys >= (1LL << 31)) return fail(MDSF_EINVAL, "too many tiles per batch");
+    h->sort_bits = 1;
+    while ((1LL << h->sort_bits) <= nkeys) ++h->sort_bits;
+
+    // splat shared-memory budget -> pairs per chunk
+    h->xycap = xymax; h->zcap = zmax;
+    const size_t tile_b = (size_t)2 * g0.tx * g0.ty * g0.nzp * 8 + (h->native_fft ? (size_t)2 * g0.n[2] * 8 : 0);
+    int chunk = 128;
+    auto smem_for = [&](int c) { return tile_b + (size_t)2 * c * (xymax + zmax) * 8 + (size_t)2 * c * sizeof(PairSlot) + 2 * 4 * 32 * 4 + 2 * 16 * 4; };
+    const size_t soft = tile_b <= 70 * 1024 ? 110 * 1024 : kMaxSmem;    // two CTAs per SM when the tile allows
+    while (chunk > 32 && smem_for(chunk) > soft) chunk -= 32;
+    if (smem_for(chunk) > (size_t)kMaxSmem) {
+        chunk = 128;
+        while (chunk > 32 && smem_for(chunk) > (size_t)kMaxSmem) chunk -= 32;
+    }
+    if (smem_for(chunk) > (size_t)kMaxSmem) return fail(MDSF_EINVAL, "splat tile does not fit shared memory (%zu bytes)", smem_for(chunk));
+    h->chunk = chunk;
+    h->splat_smem = smem_for(chunk);
+
+    CU(cudaMalloc(&h->d_type, sizeof(int) * natoms));
+    CU(cudaMemcpy(h->d_type, type_id, sizeof(int) * natoms, cudaMemcpyHostToDevice));
+    for (int s = 0; s < kSlots; ++s) CU(cudaMalloc(&h->d_stage[s], h->csize * 3 * natoms * h->F));
+    CU(cudaMalloc(&h->d_recs, sizeof(AtomRec) * natoms * h->F));
+    CU(cudaMalloc(&h->d_cnt, sizeof(unsigned) * natoms * h->F));
+    CU(cudaMalloc(&h->d_off, sizeof(unsigned) * natoms * h->F));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&h->d_keys[i], sizeof(unsigned) * std::max(1LL, cap)));
+        CU(cudaMalloc(&h->d_vals[i], sizeof(unsigned) * std::max(1LL, cap)));
+    }
+    CU(cudaMalloc(&h->d_tile_start, sizeof(unsigned) * (nkeys + 2)));
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b1, h->d_cnt, h->d_off, (long long)natoms * h->F, h->s_comp);
+    cub::DeviceRadixSort::SortPairs(nullptr, b2, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], cap, 0, h->sort_bits, h->s_comp);
+    h->cub_bytes = std::max(b1, b2) + 256;
+    CU(cudaMalloc(&h->d_cub, h->cub_bytes));
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(MDSF_EINVAL, "null argument");
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return MDSF_OK;
+}
+extern "C" int mdsf_host_free(void* p) { if (p) CU(cudaFreeHost(p)); return MDSF_OK; }
+extern "C" int mdsf_host_register(void* p, size_t bytes) { CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return MDSF_OK; }
+extern "C" int mdsf_host_unregister(void* p) { CU(cudaHostUnregister(p)); return MDSF_OK; }
+
+// ------------------------------------------------------------------------------------------
+// FFT + accumulation of the pair volumes currently in d_vol (nf frames -> (nf+1)/2 pairs).
+// `z_done`: the z pass already ran inside the fused splat kernel.
+static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done) {
+    const GridParams& gp = h->gp;
+    const int npairs = (nf + 1) / 2;
+    if (h->native_fft) {
+        if (!z_done) {
+            const long long ncolumns = (long long)gp.n[0] * gp.n[1];
+            int ncol = 16;
+            while (ncol > 1 && (size_t)2 * ncol * gp.nzp * 8 > 96 * 1024) ncol >>= 1;
+            const size_t sm = (size_t)2 * ncol * gp.nzp * 8 + (size_t)2 * gp.n[2] * 8;
+            dim3 grid((unsigned)((ncolumns + ncol - 1) / ncol), npairs);
+            fft_z_kernel<<<grid, 256, sm, h->s_comp>>>(h->d_vol, h->ax[2].plan, h->ax[2].d_tw, ncolumns, ncol, gp.nzp, gp.pad_shift);
+            ++h->launches;
+        }
+        if (h->timing) CU(cudaEventRecord(h->tev[3], h->s_comp));
+        {
+            const size_t sm = (size_t)2 * gp.n[1] * h->Wy * 8 + (size_t)2 * gp.n[1] * 8;
+            dim3 grid((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0], npairs);
+            fft_y_kernel<<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy);
+            ++h->launches;
+        }
+        if (h->timing) CU(cudaEventRecord(h->tev[4], h->s_comp));
+        {
+            const size_t sm = (size_t)(npairs > 1 ? 3 : 2) * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
+            dim3 grid((gp.n[2] + h->Wx - 1) / h->Wx, gp.n[1]);
+            fft_x_accum_kernel<<<grid, h->thr_x, sm, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].plan, h->ax[0].d_tw,
+                                                                      gp.n[0], gp.n[1], gp.n[2], h->Wx, npairs);
+            ++h->launches;
+        }
+    } else {
+        if (h->timing) CU(cudaEventRecord(h->tev[3], h->s_comp));
+        if (npairs == h->cufft_batch) {
+            CF(cufftExecZ2Z(h->cufft_plan, (cufftDoubleComplex*)h->d_vol, (cufftDoubleComplex*)h->d_vol, CUFFT_FORWARD));
+        } else {   // partial last batch: zero the unused pair volumes and transform the whole batch
+            CU(cudaMemsetAsync(h->d_vol + (long long)npairs * h->ncell, 0, sizeof(double2) * h->ncell * (h->cufft_batch - npairs), h->s_comp));
+            CF(cufftExecZ2Z(h->cufft_plan, (cufftDoubleComplex*)h->d_vol, (cufftDoubleComplex*)h->d_vol, CUFFT_FORWARD));
+        }
+        if (h->timing) CU(cudaEventRecord(h->tev[4], h->s_comp));
+        accumulate_power_kernel<<<grid_for(h->ncell, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_vol, h->d_P, h->ncell, npairs);
+        ++h->launches;
+    }
+    CU(cudaGetLastError());
+    return MDSF_OK;
+}
+
+template <typename C, typename P>
+static void launch_prep(mdsf_handle* h, void* stage, const BatchScales& sc, int nf, long long wlo, long long whi) {
+    const long long total = (long long)nf * h->natoms;
+    prep_atoms_kernel<C, P><<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(
+        (C*)stage, h->d_type, h->d_recs, h->d_cnt, h->gp, h->tt, sc, nf, wlo, whi, h->d_err);
+}
+
+static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, long long wlo, long long whi, int write_back) {
+    const GridParams& gp = h->gp;
+    const int slot = h->next_slot;
+    h->next_slot = (h->next_slot + 1) % kSlots;
+    const size_t bytes = h->csize * 3 * h->natoms * nf;
+    // H2D on the copy stream once the slot's previous consumers are done
+    if (h->slot_used[slot]) {
+        CU(cudaStreamWaitEvent(h->s_copy, h->ev_free[slot], 0));
+        CU(cudaStreamWaitEvent(h->s_copy, h->ev_back[slot], 0));
+    }
+    if (h->timing) { CU(cudaStreamWaitEvent(h->s_copy, h->tev[7], 0)); CU(cudaEventRecord(h->tev[0], h->s_copy)); }
+    CU(cudaMemcpyAsync(h->d_stage[slot], src, bytes, cudaMemcpyHostToDevice, h->s_copy));
+    CU(cudaEventRecord(h->ev_h2d[slot], h->s_copy));
+    CU(cudaStreamWaitEvent(h->s_comp, h->ev_h2d[slot], 0));
+    if (h->timing) CU(cudaEventRecord(h->tev[1], h->s_comp));
+
+    BatchScales sc;
+    for (int f = 0; f < nf; ++f) for (int d = 0; d < 3; ++d) sc.a[f][d] = scale[f * 3 + d];
+    const bool c32 = h->cfg.coord_dtype == MDSF_F32, p32 = h->cfg.arith_dtype == MDSF_F32;
+    if (c32 && p32) launch_prep<float, float>(h, h->d_stage[slot], sc, nf, wlo, whi);
+    else if (c32) launch_prep<float, double>(h, h->d_stage[slot], sc, nf, wlo, whi);
+    else launch_prep<double, double>(h, h->d_stage[slot], sc, nf, wlo, whi);
+    ++h->launches;
+    CU(cudaEventRecord(h->ev_prep[slot], h->s_comp));
+    if (write_back) {
+        CU(cudaStreamWaitEvent(h->s_back, h->ev_prep[slot], 0));
+        CU(cudaMemcpyAsync(src, h->d_stage[slot], bytes, cudaMemcpyDeviceToHost, h->s_back));
+    }
+    CU(cudaEventRecord(h->ev_back[slot], h->s_back));
+
+    // deterministic binning: scan -> emit -> stable radix sort by (frame, tile) -> list starts
+    const long long total = (long long)nf * h->natoms;
+    const long long cap = h->maxpairs_frame * nf;
+    // an odd batch gets a phantom last frame with empty lists (imaginary part of the last pair)
+    const unsigned nkeys = (unsigned)((nf + (nf & 1)) * gp.ntx * gp.nty);
+    size_t cb = h->cub_bytes;
+    cub::DeviceScan::ExclusiveSum(h->d_cub, cb, h->d_cnt, h->d_off, total, h->s_comp);
+    fill_u32_kernel<<<grid_for(cap, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_keys[0], nkeys, cap);
+    emit_pairs_kernel<<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_off, h->d_keys[0], h->d_vals[0], gp, h->tt, nf);
+    int bits = 1;
+    while ((1LL << bits) <= (long long)nkeys) ++bits;
+    cb = h->cub_bytes;
+    cub::DeviceRadixSort::SortPairs(h->d_cub, cb, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], cap, 0, bits, h->s_comp);
+    tile_starts_kernel<<<grid_for(cap + 1, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_keys[1], cap, nkeys, h->d_tile_start);
+    h->launches += 3;
+    if (h->timing) CU(cudaEventRecord(h->tev[2], h->s_comp));
+
+    // splat (+ fused z FFT on the native path)
+    const int npairs = (nf + 1) / 2;
+    dim3 grid(gp.ntx * gp.nty, npairs);
+    if (h->native_fft)
+        splat_zfft_kernel<true><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
+                                                                        gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->chunk, h->xycap, h->zcap);
+    else
+        splat_zfft_kernel<false><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
+                                                                         gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->chunk, h->xycap, h->zcap);
+    ++h->launches;
+    CU(cudaGetLastError());
+    int rc = transform_and_accumulate(h, nf, h->native_fft);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev_free[slot], h->s_comp));
+    if (h->timing) {
+        CU(cudaEventRecord(h->tev[7], h->s_comp));
+        CU(cudaEventSynchronize(h->tev[7]));
+        float ms;
+        const int a[6] = {0, 1, 2, 3, 4, 0}, b[6] = {1, 2, 3, 4, 7, 7};
+        for (int i = 0; i < 6; ++i) {
+            CU(cudaEventElapsedTime(&ms, h->tev[a[i]], h->tev[b[i]]));
+            h->stage_ms[i] += ms;
+        }
+        ++h->timed_batches;
+    }
+    h->slot_used[slot] = true;
+    h->frames_done += nf;
+    h->last_batch_frames = nf;
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_push_frames(mdsf_handle* h, void* coords, int64_t nframes, const double* scale,
+                                int64_t wrap_lo, int64_t wrap_hi, int32_t write_back) {
+    if (!h || !coords || !scale) return fail(MDSF_EINVAL, "null argument");
+    if (!h->d_type) return fail(MDSF_ESTATE, "mdsf_set_atoms must be called before mdsf_push_frames");
+    if (nframes < 0) return fail(MDSF_EINVAL, "negative frame count");
+    CU(cudaSetDevice(h->device));
+    const size_t frame_bytes = h->csize * 3 * h->natoms;
+    int64_t done = 0;
+    while (done < nframes) {
+        const int nf = (int)std::min<int64_t>(h->F, nframes - done);
+        int rc = run_batch(h, (char*)coords + frame_bytes * done, nf, scale + 3 * done, wrap_lo, wrap_hi, write_back);
+        if (rc) return rc;
+        done += nf;
+    }
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_push_density(mdsf_handle* h, const double* d1, int64_t nframes) {
+    if (!h || !d1) return fail(MDSF_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    int64_t done = 0;
+    double* d_tmp = nullptr;
+    CU(cudaMalloc(&d_tmp, sizeof(double) * h->ncell * h->F));
+    while (done < nframes) {
+        const int nf = (int)std::min<int64_t>(h->F, nframes - done);
+        CU(cudaMemcpyAsync(d_tmp, d1 + done * h->ncell, sizeof(double) * h->ncell * nf, cudaMemcpyHostToDevice, h->s_comp));
+        const int npairs = (nf + 1) / 2;
+        pack_density_kernel<<<grid_for(h->ncell * npairs, 256, h->nsm), 256, 0, h->s_comp>>>(d_tmp, h->d_vol, h->ncell, nf);
+        ++h->launches;
+        if (h->d_dump) CU(cudaMemcpyAsync(h->d_dump, h->d_vol, sizeof(double2) * h->ncell * npairs, cudaMemcpyDeviceToDevice, h->s_comp));
+        int rc = transform_and_accumulate(h, nf, false);
+        if (rc) { cudaFree(d_tmp); return rc; }
+        h->frames_done += nf;
+        h->last_batch_frames = nf;
+        done += nf;
+    }
+    CU(cudaStreamSynchronize(h->s_comp));
+    CU(cudaFree(d_tmp));
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_sync(mdsf_handle* h) {
+    if (!h) return fail(MDSF_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->s_comp));
+    CU(cudaStreamSynchronize(h->s_copy));
+    CU(cudaStreamSynchronize(h->s_comp));
+    CU(cudaStreamSynchronize(h->s_back));
+    if (*h->h_err) {
+        *h->h_err = 0;
+        cudaMemset(h->d_err, 0, sizeof(int));
+        return fail(MDSF_ERANGE, "an atom's Gaussian stamp leaves the padded grid (coordinate more than one box outside the cell, NaN, or half width > Nborder); the reference fails with a numpy shape error here");
+    }
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_export_sf_device(mdsf_handle* h, void* sf_device) {
+    if (!h || !sf_device) return fail(MDSF_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    const GridParams& gp = h->gp;
+    const long long total = (long long)gp.n[0] * gp.n[1] * (gp.n[2] / 2 + 1);
+    export_sf_kernel<<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_P, (double*)sf_device, h->ax[0].d_rev, h->ax[1].d_rev,
+                                                                         h->ax[2].d_rev, gp.n[0], gp.n[1], gp.n[2]);
+    ++h->launches;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->s_comp));
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_read_sf(mdsf_handle* h, double* sf_host) {
+    if (!h || !sf_host) return fail(MDSF_EINVAL, "null argument");
+    int rc = mdsf_sync(h);
+    if (rc) return rc;
+    rc = mdsf_export_sf_device(h, h->d_sf);
+    if (rc) return rc;
+    const GridParams& gp = h->gp;
+    const long long total = (long long)gp.n[0] * gp.n[1] * (gp.n[2] / 2 + 1);
+    CU(cudaMemcpy(sf_host, h->d_sf, sizeof(double) * total, cudaMemcpyDeviceToHost));
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_reset(mdsf_handle* h) {
+    if (!h) return fail(MDSF_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(h->d_P, 0, sizeof(double) * h->ncell));
+    h->frames_done = 0;
+    return MDSF_OK;
+}
+
+// ------------------------------------------------------------------------------------------ taps
+extern "C" int mdsf_debug_cell_indices(mdsf_handle* h, int64_t frame, int32_t* ir_out) {
+    if (!h || !ir_out) return fail(MDSF_EINVAL, "null argument");
+    if (frame < 0 || frame >= h->last_batch_frames) return fail(MDSF_EINVAL, "frame %lld not in the last batch (%d frames)", (long long)frame, h->last_batch_frames);
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<AtomRec> recs(h->natoms);
+    CU(cudaMemcpy(recs.data(), h->d_recs + frame * h->natoms, sizeof(AtomRec) * h->natoms, cudaMemcpyDeviceToHost));
+    for (long long a = 0; a < h->natoms; ++a) for (int d = 0; d < 3; ++d) ir_out[a * 3 + d] = recs[a].ir[d];
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_debug_coords(mdsf_handle* h, int64_t frame, double* r_out) {
+    if (!h || !r_out) return fail(MDSF_EINVAL, "null argument");
+    if (frame < 0 || frame >= h->last_batch_frames) return fail(MDSF_EINVAL, "frame %lld not in the last batch (%d frames)", (long long)frame, h->last_batch_frames);
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<AtomRec> recs(h->natoms);
+    CU(cudaMemcpy(recs.data(), h->d_recs + frame * h->natoms, sizeof(AtomRec) * h->natoms, cudaMemcpyDeviceToHost));
+    for (long long a = 0; a < h->natoms; ++a) for (int d = 0; d < 3; ++d) r_out[a * 3 + d] = recs[a].r[d];
+    return MDSF_OK;
+}
+
+extern "C" int mdsf_debug_density(mdsf_handle* h, int64_t frame, double* d1_out) {
+    if (!h || !d1_out) return fail(MDSF_EINVAL, "null argument");
+    if (!h->d_dump) return fail(MDSF_ESTATE, "create the handle with keep_density=1 to use the density tap");
+    if (frame < 0 || frame >= h->last_batch_frames) return fail(MDSF_EINVAL, "frame %lld not in the last batch (%d frames)", (long long)frame, h->last_batch_frames);
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    double* d_tmp = nullptr;
+    CU(cudaMalloc(&d_tmp, sizeof(double) * h->ncell));
+    unpack_density_kernel<<<grid_for(h->ncell, 256, h->nsm), 256>>>(h->d_dump + (frame / 2) * h->ncell, d_tmp, h->ncell, (int)(frame % 2));
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(d1_out, d_tmp, sizeof(double) * h->ncell, cudaMemcpyDeviceToHost));
+    CU(cudaFree(d_tmp));
+    return MDSF_OK;
+}
+
+extern "C" int64_t mdsf_kernel_launches(const mdsf_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t mdsf_frames_done(const mdsf_handle* h) { return h ? h->frames_done : 0; }
+extern "C" const char* mdsf_fft_path(const mdsf_handle* h) { return (h && h->native_fft) ? "native" : "cufft"; }
+extern "C" int mdsf_batch_frames(const mdsf_handle* h) { return h ? h->F : 0; }
+extern "C" int mdsf_enable_timing(mdsf_handle* h, int32_t on) {
+    if (!h) return fail(MDSF_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    h->timing = on != 0;
+    for (double& v : h->stage_ms) v = 0;
+    h->timed_batches = 0;
+    if (on) CU(cudaEventRecord(h->tev[7], h->s_comp));
+    return MDSF_OK;
+}
+extern "C" int mdsf_stage_ms(mdsf_handle* h, double* out6, int64_t* batches) {
+    if (!h || !out6) return fail(MDSF_EINVAL, "null argument");
+    for (int i = 0; i < 6; ++i) out6[i] = h->stage_ms[i];
+    if (batches) *batches = h->timed_batches;
+    return MDSF_OK;
+}

@@ -1,0 +1,76 @@
+// Shared definitions of the mdsf engine (sm_100a).  See include/mdsf.h for the C ABI and
+// DESIGN.md for the data layout.  Reference line numbers refer to joeyelk/MD-Structure-Factor.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MDSF_MAX_BATCH 64          // frames per device batch (scale factors travel as kernel params)
+#define MDSF_MAX_TILE_COLS 32      // columns per splat tile (one bit each in a 32-bit hit mask)
+#define MDSF_ATOM_BITS 26          // atom index bits inside a pair payload
+#define MDSF_MAX_ATOMS (1 << MDSF_ATOM_BITS)
+#define MDSF_MAX_RADIX_STAGES 12
+
+// Frame-invariant geometry, passed to kernels by value.
+struct GridParams {
+    int n[3];           // Nspatialgrid (dens.py:181-189)
+    int nb;             // Nborder (dens.py:231)
+    int fold_mode;      // 0 = reference corner rule (dens.py:107), 1 = periodic
+    int separable;      // ucell couples z to nothing else -> exp splits into xy and z factors
+    int tx, ty;         // splat tile, in (x,y) columns; a tile spans all z
+    int ntx, nty;       // tiles per dimension
+    int natoms;
+    int nzp;            // padded z length of one column in shared memory
+    int pad_shift;      // column position p is stored at p + (p >> pad_shift)
+    double dr[3];       // dens.py:202
+    double box[3];      // mean box (dens.py:52)
+    double u[9];        // ucell row-major (dens.py:301)
+};
+
+struct TypeTable {
+    const double* amp;       // Nel / sigma^3
+    const double* two_sig2;  // 2 sigma^2
+    const int*    halfw;     // [ntypes][3]
+};
+
+// One rescaled+wrapped atom of one frame: what dens.py:285-287 derives per atom.
+struct AtomRec {
+    double r[3];   // coordinate as float64 (value of the coords-dtype number)
+    int ir[3];     // trunc(r/dr)  (dens.py:285)
+    int type;
+};
+
+struct BatchScales {
+    double a[MDSF_MAX_BATCH][3];   // avgdims/dims per frame (dens.py:53)
+};
+
+// The stamp of an atom covers padded-grid indices p in [ir-A, ir+A) (dens.py:292-297, with the
+// +Nborder offset removed).  Split by side s in {-1,0,+1} (low padding / cell / high padding);
+// remap_grid_tcl (dens.py:86-108) moves side s to c = p - s*N.
+__host__ __device__ inline void stamp_segment(int ir, int A, int N, int s, int& plo, int& phi) {
+    int p0 = ir - A, p1 = ir + A;
+    if (s < 0)       { plo = p0;               phi = p1 < 0 ? p1 : 0; }
+    else if (s == 0) { plo = p0 > 0 ? p0 : 0;  phi = p1 < N ? p1 : N; }
+    else             { plo = p0 > N ? p0 : N;  phi = p1; }
+}
+
+// number of tiles (width t) a stamp touches along one dimension, summed over its segments
+__host__ __device__ inline int stamp_tiles_1d(int ir, int A, int N, int t) {
+    int cnt = 0;
+    for (int s = -1; s <= 1; ++s) {
+        int plo, phi;
+        stamp_segment(ir, A, N, s, plo, phi);
+        if (phi > plo) {
+            int clo = plo - s * N, chi = phi - s * N;
+            cnt += (chi - 1) / t - clo / t + 1;
+        }
+    }
+    return cnt;
+}
+
+// destination z of padded index pz for an image with x side sx and y side sy (dens.py:95-107)
+__device__ __forceinline__ int fold_z(int pz, int nz, int nb, bool corner_xy, int sy, int fold_mode) {
+    int sz = pz < 0 ? -1 : (pz >= nz ? 1 : 0);
+    if (sz == 0) return pz;
+    if (fold_mode == 0 && corner_xy && sz != sy) return pz + (sz < 0 ? nb : -nb);
+    return pz - sz * nz;
+}

@@ -1,0 +1,381 @@
+// Hand-written fp64 FFT passes for sm_100a (replaces np.fft.rfftn, dens.py:313).
+//
+// Two real frames travel as one complex volume (re = frame 2q, im = frame 2q+1), so every pass
+// is a plain complex transform; |A|^2+|B|^2 of the two real transforms is recovered from
+// (|C(k)|^2 + |C(-k)|^2)/2 when S(q) is read out.  Each pass is an in-place decimation-in-
+// frequency FFT over one axis of a shared-memory tile: a stage loads R points into registers,
+// applies an R-point DFT and the inter-stage twiddles, and writes the R results back to the
+// SAME addresses, so stages only need a barrier between them.  The output of a DIF transform
+// is digit-reversed; nothing is reordered per frame -- the volume and the |C|^2 accumulator
+// stay in "position space" on all three axes and mdsf_read_sf() applies the three digit
+// reversal tables once.  There is no tensor-core work here: nothing on this path is a dense
+// contraction, the passes are bound by shared-memory/HBM traffic and the fp64 pipe.
+#pragma once
+#include "mdsf_common.cuh"
+
+struct FftPlan {
+    int n;
+    int nstages;
+    int radix[MDSF_MAX_RADIX_STAGES];
+};
+
+#define MDSF_SQRT1_2 0.70710678118654752440
+#define MDSF_SQRT3_2 0.86602540378443864676
+
+// ------------------------------------------------------------------ in-register DFTs (forward)
+template <int R> struct Dft;
+
+template <> struct Dft<2> {
+    __device__ __forceinline__ static void run(double (&xr)[2], double (&xi)[2], const double*, const double*, int) {
+        double ar = xr[0], ai = xi[0];
+        xr[0] = ar + xr[1]; xi[0] = ai + xi[1];
+        xr[1] = ar - xr[1]; xi[1] = ai - xi[1];
+    }
+};
+
+__device__ __forceinline__ void dft4(double& r0, double& i0, double& r1, double& i1,
+                                     double& r2, double& i2, double& r3, double& i3) {
+    double ar = r0 + r2, ai = i0 + i2, br = r0 - r2, bi = i0 - i2;
+    double cr = r1 + r3, ci = i1 + i3, dr_ = r1 - r3, di = i1 - i3;
+    r0 = ar + cr; i0 = ai + ci;
+    r2 = ar - cr; i2 = ai - ci;
+    r1 = br + di; i1 = bi - dr_;     // b - i d
+    r3 = br - di; i3 = bi + dr_;     // b + i d
+}
+
+template <> struct Dft<4> {
+    __device__ __forceinline__ static void run(double (&xr)[4], double (&xi)[4], const double*, const double*, int) {
+        dft4(xr[0], xi[0], xr[1], xi[1], xr[2], xi[2], xr[3], xi[3]);
+    }
+};
+
+__device__ __forceinline__ void dft8(double* xr, double* xi) {   // xr[0..7] natural in, natural out
+    // even / odd 4-point transforms
+    dft4(xr[0], xi[0], xr[2], xi[2], xr[4], xi[4], xr[6], xi[6]);   // E0..E3 in slots 0,2,4,6
+    dft4(xr[1], xi[1], xr[3], xi[3], xr[5], xi[5], xr[7], xi[7]);   // O0..O3 in slots 1,3,5,7
+    double er[4] = {xr[0], xr[2], xr[4], xr[6]}, ei[4] = {xi[0], xi[2], xi[4], xi[6]};
+    double or_[4], oi[4];
+    or_[0] = xr[1]; oi[0] = xi[1];
+    or_[1] = (xr[3] + xi[3]) * MDSF_SQRT1_2; oi[1] = (xi[3] - xr[3]) * MDSF_SQRT1_2;   // * (1-i)/sqrt2
+    or_[2] = xi[5]; oi[2] = -xr[5];                                                    // * (-i)
+    or_[3] = (xi[7] - xr[7]) * MDSF_SQRT1_2; oi[3] = -(xr[7] + xi[7]) * MDSF_SQRT1_2;  // * (-1-i)/sqrt2
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        xr[k] = er[k] + or_[k]; xi[k] = ei[k] + oi[k];
+        xr[k + 4] = er[k] - or_[k]; xi[k + 4] = ei[k] - oi[k];
+    }
+}
+
+template <> struct Dft<8> {
+    __device__ __forceinline__ static void run(double (&xr)[8], double (&xi)[8], const double*, const double*, int) {
+        dft8(xr, xi);
+    }
+};
+
+template <> struct Dft<16> {
+    __device__ __forceinline__ static void run(double (&xr)[16], double (&xi)[16], const double*, const double*, int) {
+        double er[8], ei[8], or_[8], oi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { er[k] = xr[2 * k]; ei[k] = xi[2 * k]; or_[k] = xr[2 * k + 1]; oi[k] = xi[2 * k + 1]; }
+        dft8(er, ei);
+        dft8(or_, oi);
+        // w16^k = cos(pi k/8) - i sin(pi k/8)
+        const double c[8] = {1.0, 0.92387953251128675613, MDSF_SQRT1_2, 0.38268343236508977173,
+                             0.0, -0.38268343236508977173, -MDSF_SQRT1_2, -0.92387953251128675613};
+        const double s[8] = {0.0, 0.38268343236508977173, MDSF_SQRT1_2, 0.92387953251128675613,
+                             1.0, 0.92387953251128675613, MDSF_SQRT1_2, 0.38268343236508977173};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double tr, ti;
+            if (k == 0) { tr = or_[0]; ti = oi[0]; }
+            else if (k == 4) { tr = oi[4]; ti = -or_[4]; }
+            else { tr = or_[k] * c[k] + oi[k] * s[k]; ti = oi[k] * c[k] - or_[k] * s[k]; }
+            xr[k] = er[k] + tr; xi[k] = ei[k] + ti;
+            xr[k + 8] = er[k] - tr; xi[k + 8] = ei[k] - ti;
+        }
+    }
+};
+
+template <> struct Dft<3> {
+    __device__ __forceinline__ static void run(double (&xr)[3], double (&xi)[3], const double*, const double*, int) {
+        double tr = xr[1] + xr[2], ti = xi[1] + xi[2];
+        double sr = (xr[1] - xr[2]) * MDSF_SQRT3_2, si = (xi[1] - xi[2]) * MDSF_SQRT3_2;
+        double mr = xr[0] - 0.5 * tr, mi = xi[0] - 0.5 * ti;
+        xr[0] += tr; xi[0] += ti;
+        xr[1] = mr + si; xi[1] = mi - sr;    // m - i s
+        xr[2] = mr - si; xi[2] = mi + sr;    // m + i s
+    }
+};
+
+// Odd prime radices (5, 7, 11, 13): direct symmetric DFT; roots come from the axis twiddle
+// table (tw[m * n/R] = exp(-2 pi i m / R)).
+template <int R> struct Dft {
+    __device__ __forceinline__ static void run(double (&xr)[R], double (&xi)[R], const double* twr, const double* twi, int n) {
+        constexpr int H = (R - 1) / 2;
+        const int step = n / R;
+        double sr[H], si[H], dr_[H], di[H];
+        double y0r = xr[0], y0i = xi[0];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            sr[j] = xr[j + 1] + xr[R - 1 - j]; si[j] = xi[j + 1] + xi[R - 1 - j];
+            dr_[j] = xr[j + 1] - xr[R - 1 - j]; di[j] = xi[j + 1] - xi[R - 1 - j];
+            y0r += sr[j]; y0i += si[j];
+        }
+        double outr[R], outi[R];
+        outr[0] = y0r; outi[0] = y0i;
+#pragma unroll
+        for (int k = 1; k <= H; ++k) {
+            double ar = xr[0], ai = xi[0], br = 0.0, bi = 0.0;
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
+                const int m = (j * k) % R;
+                const double c = twr[m * step], s = -twi[m * step];   // cos, sin of 2 pi m / R
+                ar += sr[j - 1] * c; ai += si[j - 1] * c;
+                br += dr_[j - 1] * s; bi += di[j - 1] * s;
+            }
+            outr[k] = ar + bi; outi[k] = ai - br;          // A - i B
+            outr[R - k] = ar - bi; outi[R - k] = ai + br;  // A + i B
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) { xr[k] = outr[k]; xi[k] = outi[k]; }
+    }
+};
+
+// ------------------------------------------------------------------ one DIF stage over a tile
+// Tile addressing: point p of transform f lives at f*fs + pos(p)*es with pos(p) = p + (p >> pad).
+// ZPASS: transforms are contiguous rows (es = 1), consecutive lanes take consecutive
+// butterflies of one row.  Otherwise transforms are columns of a [n][W] tile (fs = 1) and
+// consecutive lanes take consecutive columns.
+template <int R, bool ZPASS>
+__device__ __forceinline__ void fft_stage(double* __restrict__ sre, double* __restrict__ sim,
+                                          const double* __restrict__ twr, const double* __restrict__ twi,
+                                          int n, int L, int nfft, int fs, int es, int pad)
+{
+    const int M = L / R;
+    const int nbf = n / R;
+    const int tws = n / L;
+    const int items = nfft * nbf;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        int f, bf;
+        if (ZPASS) { f = it / nbf; bf = it - f * nbf; }
+        else       { bf = it / nfft; f = it - bf * nfft; }
+        const int b = bf / M, n2 = bf - b * M;
+        const int base = b * L + n2;
+        double xr[R], xi[R];
+        int addr[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int p = base + j * M;
+            addr[j] = f * fs + (p + (p >> pad)) * es;
+            xr[j] = sre[addr[j]]; xi[j] = sim[addr[j]];
+        }
+        Dft<R>::run(xr, xi, twr, twi, n);
+        if (M > 1) {
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                const int ti = n2 * k * tws;
+                const double wr = twr[ti], wi = twi[ti];
+                const double yr = xr[k] * wr - xi[k] * wi;
+                xi[k] = xr[k] * wi + xi[k] * wr;
+                xr[k] = yr;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) { sre[addr[k]] = xr[k]; sim[addr[k]] = xi[k]; }
+    }
+}
+
+// all stages of one axis, over a tile resident in shared memory (caller syncs before/after)
+template <bool ZPASS>
+__device__ void fft_tile(double* sre, double* sim, const double* twr, const double* twi,
+                         const FftPlan& plan, int nfft, int fs, int es, int pad)
+{
+    int L = plan.n;
+    for (int s = 0; s < plan.nstages; ++s) {
+        const int R = plan.radix[s];
+        switch (R) {
+            case 16: fft_stage<16, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            case 8:  fft_stage<8, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            case 4:  fft_stage<4, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            case 2:  fft_stage<2, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            case 3:  fft_stage<3, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            case 5:  fft_stage<5, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            case 7:  fft_stage<7, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            case 11: fft_stage<11, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            case 13: fft_stage<13, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
+            default: break;
+        }
+        L /= R;
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void load_twiddles(double* twr, double* twi, const double2* __restrict__ tw, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 w = tw[i];
+        twr[i] = w.x; twi[i] = w.y;
+    }
+}
+
+// ------------------------------------------------------------------ z pass (stand-alone)
+// grid = (column groups, pairs).  A group is `ncol` consecutive (x,y) columns, contiguous in
+// memory.  Used by mdsf_push_density and by the un-fused debug path; the production path runs
+// the same stages inside splat_zfft_kernel without the load.
+__global__ void __launch_bounds__(256)
+fft_z_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw,
+                             long long ncolumns, int ncol, int nzp, int pad)
+{
+    extern __shared__ double smem[];
+    const int nz = plan.n;
+    double* sre = smem;
+    double* sim = sre + (size_t)ncol * nzp;
+    double* twr = sim + (size_t)ncol * nzp;
+    double* twi = twr + nz;
+    load_twiddles(twr, twi, tw, nz);
+    const long long col0 = (long long)blockIdx.x * ncol;
+    const int nc = (int)min((long long)ncol, ncolumns - col0);
+    double2* base = vol + ((long long)blockIdx.y * ncolumns + col0) * nz;
+    for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
+        const int c = i / nz, z = i - c * nz;
+        const double2 v = base[i];
+        const int a = c * nzp + z + (z >> pad);
+        sre[a] = v.x; sim[a] = v.y;
+    }
+    __syncthreads();
+    fft_tile<true>(sre, sim, twr, twi, plan, nc, nzp, 1, pad);
+    for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
+        const int c = i / nz, z = i - c * nz;
+        const int a = c * nzp + z + (z >> pad);
+        base[i] = make_double2(sre[a], sim[a]);
+    }
+}
+
+// ------------------------------------------------------------------ y pass, in place
+// grid = (z chunks, Nx, pairs); tile = [Ny][W] at fixed x.
+__global__ void __launch_bounds__(256)
+fft_y_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw,
+                             int nx, int ny, int nz, int W)
+{
+    extern __shared__ double smem[];
+    double* sre = smem;
+    double* sim = sre + (size_t)ny * W;
+    double* twr = sim + (size_t)ny * W;
+    double* twi = twr + ny;
+    load_twiddles(twr, twi, tw, ny);
+    const int z0 = blockIdx.x * W;
+    const int w = min(W, nz - z0);
+    double2* base = vol + (((long long)blockIdx.z * nx + blockIdx.y) * ny) * (long long)nz + z0;
+    for (int i = threadIdx.x; i < ny * W; i += blockDim.x) {
+        const int y = i / W, z = i - y * W;
+        double2 v = make_double2(0.0, 0.0);
+        if (z < w) v = base[(long long)y * nz + z];
+        sre[i] = v.x; sim[i] = v.y;
+    }
+    __syncthreads();
+    fft_tile<false>(sre, sim, twr, twi, plan, W, 1, W, 31);
+    for (int i = threadIdx.x; i < ny * W; i += blockDim.x) {
+        const int y = i / W, z = i - y * W;
+        if (z < w) base[(long long)y * nz + z] = make_double2(sre[i], sim[i]);
+    }
+}
+
+// ------------------------------------------------------------------ x pass + |C|^2 accumulation
+// grid = (z chunks, Ny); tile = [Nx][W] at fixed y; loops over the pairs of the batch and adds
+// sum_q |C_q|^2 to the resident fp64 accumulator P in one read-modify-write (dens.py:315-318).
+__global__ void __launch_bounds__(256)
+fft_x_accum_kernel(const double2* __restrict__ vol, double* __restrict__ P, FftPlan plan,
+                   const double2* __restrict__ tw, int nx, int ny, int nz, int W, int npairs)
+{
+    extern __shared__ double smem[];
+    double* sre = smem;
+    double* sim = sre + (size_t)nx * W;
+    double* twr = sim + (size_t)nx * W;
+    double* twi = twr + nx;
+    double* acc = twi + nx;                 // [nx*W], only touched when the batch holds > 1 pair
+    load_twiddles(twr, twi, tw, nx);
+    const int z0 = blockIdx.x * W;
+    const int w = min(W, nz - z0);
+    const int y = blockIdx.y;
+    const long long xstride = (long long)ny * nz;
+    const long long off = (long long)y * nz + z0;
+    for (int q = 0; q < npairs; ++q) {
+        const double2* base = vol + (long long)q * nx * xstride + off;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nx * W; i += blockDim.x) {
+            const int x = i / W, z = i - x * W;
+            double2 v = make_double2(0.0, 0.0);
+            if (z < w) v = base[(long long)x * xstride + z];
+            sre[i] = v.x; sim[i] = v.y;
+        }
+        __syncthreads();
+        fft_tile<false>(sre, sim, twr, twi, plan, W, 1, W, 31);
+        if (npairs > 1) {
+            for (int i = threadIdx.x; i < nx * W; i += blockDim.x) {
+                const double v = sre[i] * sre[i] + sim[i] * sim[i];
+                acc[i] = q == 0 ? v : acc[i] + v;
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < nx * W; i += blockDim.x) {
+        const int x = i / W, z = i - x * W;
+        if (z < w) P[(long long)x * xstride + off + z] += (npairs > 1) ? acc[i] : sre[i] * sre[i] + sim[i] * sim[i];
+    }
+}
+
+// ------------------------------------------------------------------ library-FFT path helper
+// P += sum_q |vol_q|^2 after a cuFFT Z2Z (grids whose sizes have prime factors > 13)
+__global__ void accumulate_power_kernel(const double2* __restrict__ vol, double* __restrict__ P,
+                                        long long ncell, int npairs)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncell;
+         i += (long long)gridDim.x * blockDim.x) {
+        double a = 0.0;
+        for (int q = 0; q < npairs; ++q) {
+            const double2 v = vol[(long long)q * ncell + i];
+            a += v.x * v.x + v.y * v.y;
+        }
+        P[i] += a;
+    }
+}
+
+// ------------------------------------------------------------------ S(q) read-out
+// sf[kx][ky][kz] = (P[pos(k)] + P[pos(-k)]) / 2 for kz in [0, Nz/2]: the half spectrum that
+// dens.py:318 accumulates.  rev* map a frequency index to its position (identity for cuFFT).
+__global__ void export_sf_kernel(const double* __restrict__ P, double* __restrict__ sf,
+                                 const int* __restrict__ revx, const int* __restrict__ revy,
+                                 const int* __restrict__ revz, int nx, int ny, int nz)
+{
+    const int m = nz / 2 + 1;
+    const long long total = (long long)nx * ny * m;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int kz = (int)(i % m);
+        const long long t = i / m;
+        const int ky = (int)(t % ny), kx = (int)(t / ny);
+        const long long a = ((long long)revx[kx] * ny + revy[ky]) * nz + revz[kz];
+        const long long b = ((long long)revx[(nx - kx) % nx] * ny + revy[(ny - ky) % ny]) * nz + revz[(nz - kz) % nz];
+        sf[i] = 0.5 * (P[a] + P[b]);
+    }
+}
+
+// pack real densities d1[frame][cell] into complex pair volumes (RANDOM_NOISE mode, dens.py:280)
+__global__ void pack_density_kernel(const double* __restrict__ d1, double2* __restrict__ vol,
+                                    long long ncell, int nframes)
+{
+    const int npairs = (nframes + 1) / 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncell * npairs;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i / ncell, c = i - q * ncell;
+        const double re = d1[(2 * q) * ncell + c];
+        const double im = (2 * q + 1 < nframes) ? d1[(2 * q + 1) * ncell + c] : 0.0;
+        vol[i] = make_double2(re, im);
+    }
+}
+
+// un-pack a pair volume (before any FFT) into the real density of one frame (debug tap)
+__global__ void unpack_density_kernel(const double2* __restrict__ vol, double* __restrict__ d1,
+                                      long long ncell, int part)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncell;
+         i += (long long)gridDim.x * blockDim.x) d1[i] = part ? vol[i].y : vol[i].x;
+}

@@ -1,0 +1,120 @@
+// K1/K2: per-atom preparation and deterministic binning of (atom image, tile) pairs.
+#pragma once
+#include "mdsf_common.cuh"
+
+// ---- K1: rescale (dens.py:56-58) o wrap (dens.py:209-221) o cell index (dens.py:285) ----------
+// C = dtype of the coordinate array, P = dtype numpy promotes (coords, dims) to.  Every
+// arithmetic step is done in P and rounded back to C exactly where numpy stores into the
+// coords array, so the wrapped coordinates and the cell indices are bit-identical.
+template <typename P> __device__ __forceinline__ P mul_rn(P a, P b);
+template <> __device__ __forceinline__ float  mul_rn<float>(float a, float b)   { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <typename P> __device__ __forceinline__ P add_rn(P a, P b);
+template <> __device__ __forceinline__ float  add_rn<float>(float a, float b)   { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename C, typename P>
+__global__ void __launch_bounds__(256)
+prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], rewritten in place
+                  const int* __restrict__ type_id,   // [natoms]
+                  AtomRec* __restrict__ recs,        // [nframes][natoms]
+                  unsigned* __restrict__ pair_count, // [nframes*natoms]
+                  GridParams gp, TypeTable tt, BatchScales sc, int nframes,
+                  long long wrap_lo, long long wrap_hi, int* __restrict__ err_flag)
+{
+    const long long total = (long long)nframes * gp.natoms;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(idx / gp.natoms);
+        const int a = (int)(idx - (long long)f * gp.natoms);
+        C* src = coords + idx * 3;
+        const int t = type_id[a];
+        AtomRec rec;
+        rec.type = t;
+        unsigned tiles[2] = {0u, 0u};
+        bool bad = false;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            // rc[it,:,i] *= a[it,i]   (dens.py:58)
+            C r = (C)mul_rn<P>((P)src[d], (P)sc.a[f][d]);
+            if (a >= wrap_lo && a < wrap_hi) {
+                const P L = (P)gp.box[d];
+                // np.where(r < L, r, r - L) then np.where(r > 0, r, r + L)   (dens.py:211-212)
+                if (!((P)r < L)) r = (C)add_rn<P>((P)r, -L);
+                if (!((P)r > (P)0)) r = (C)add_rn<P>((P)r, L);
+            }
+            src[d] = r;
+            const double rd = (double)r;
+            const double q = rd / gp.dr[d];            // IEEE fp64 divide, as numpy (dens.py:285)
+            const int A = tt.halfw[t * 3 + d];
+            int ir = 0;
+            if (!(q > -2147483000.0 && q < 2147483000.0)) bad = true;   // also catches NaN
+            else ir = (int)q;                          // astype(int): truncation toward zero
+            // the stamp [ir-A, ir+A) must stay inside the padded grid [-B, N+B)  (dens.py:292-297)
+            if (ir - A < -gp.nb || ir + A > gp.n[d] + gp.nb) bad = true;
+            rec.r[d] = rd;
+            rec.ir[d] = ir;
+            if (d < 2 && !bad) tiles[d] = stamp_tiles_1d(ir, A, gp.n[d], d == 0 ? gp.tx : gp.ty);
+        }
+        recs[idx] = rec;
+        if (bad) { atomicExch(err_flag, 1); pair_count[idx] = 0; }
+        else pair_count[idx] = tiles[0] * tiles[1];
+    }
+}
+
+// ---- K2a: emit (key = frame*ntiles + tile, payload = atom | sx | sy) at scanned offsets ------
+__global__ void __launch_bounds__(256)
+emit_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ pair_count,
+                  const unsigned* __restrict__ pair_off, unsigned* __restrict__ keys,
+                  unsigned* __restrict__ vals, GridParams gp, TypeTable tt, int nframes)
+{
+    const long long total = (long long)nframes * gp.natoms;
+    const int ntiles = gp.ntx * gp.nty;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (pair_count[idx] == 0) continue;
+        const int f = (int)(idx / gp.natoms);
+        const int a = (int)(idx - (long long)f * gp.natoms);
+        const AtomRec rec = recs[idx];
+        const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1];
+        unsigned o = pair_off[idx];
+        for (int sx = -1; sx <= 1; ++sx) {
+            int xlo, xhi;
+            stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
+            if (xhi <= xlo) continue;
+            const int tx0 = (xlo - sx * gp.n[0]) / gp.tx, tx1 = (xhi - 1 - sx * gp.n[0]) / gp.tx;
+            for (int sy = -1; sy <= 1; ++sy) {
+                int ylo, yhi;
+                stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
+                if (yhi <= ylo) continue;
+                const int ty0 = (ylo - sy * gp.n[1]) / gp.ty, ty1 = (yhi - 1 - sy * gp.n[1]) / gp.ty;
+                const unsigned payload = (unsigned)a | ((unsigned)(sx + 1) << MDSF_ATOM_BITS) |
+                                         ((unsigned)(sy + 1) << (MDSF_ATOM_BITS + 2));
+                for (int tX = tx0; tX <= tx1; ++tX)
+                    for (int tY = ty0; tY <= ty1; ++tY) {
+                        keys[o] = (unsigned)(f * ntiles + tX * gp.nty + tY);
+                        vals[o] = payload;
+                        ++o;
+                    }
+            }
+        }
+    }
+}
+
+__global__ void fill_u32_kernel(unsigned* __restrict__ p, unsigned v, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- K2c: list boundaries in the sorted key array: start[k] = first index with key >= k -----
+__global__ void __launch_bounds__(256)
+tile_starts_kernel(const unsigned* __restrict__ keys, long long n, unsigned nkeys,
+                   unsigned* __restrict__ start /* [nkeys+1] */)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i <= n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long kprev = (i == 0) ? -1 : (long long)min(keys[i - 1], nkeys);
+        const long long kcur = (i == n) ? (long long)nkeys : (long long)min(keys[i], nkeys);
+        for (long long k = kprev + 1; k <= kcur; ++k) start[k] = (unsigned)i;
+    }
+}

@@ -1,0 +1,194 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the golden vectors of the
+unmodified reference and against the CPU oracle.  Tolerances (north_star): cell indices and
+wrapped coordinates bit-exact; density 1e-13 of its peak; S(q) 1e-5 per-bin relative and 1e-12
+normalised by max(S)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dens_oracle as orc
+from tests.helpers import CASES, load_case, sf_errors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mdsf():
+    import mdsf_b200
+    mdsf_b200.native.load()
+    mdsf_b200.dens.PRINT_DETAILS = False
+    return mdsf_b200
+
+
+def run_engine(mdsf, c, fft_mode, batch=0, tile=(0, 0), fold=None, keep=True):
+    """Push a golden case through the engine; returns dict(sf, ir, d1, coords_after, N)."""
+    dens = mdsf.dens
+    r = c["coords"].copy()
+    dims = c["dims"]
+    arith = np.float32 if (r.dtype == np.float32 and dims.dtype == np.float32) else np.float64
+    L = np.average(dims, axis=0)
+    scale = (L / dims).astype(np.float64)
+    eng, n, dr, nb = dens.make_engine(L, c["typ"], c["rad"], c["ucell"], c["sres"], r.dtype, arith, keep_density=keep,
+                                      batch_frames=batch, fft_mode=fft_mode, tile=tile, fold_mode=fold)
+    out = dict(N=n, dr=dr, ir=[], d1=[], fft=eng.fft_path)
+    try:
+        T = r.shape[0]
+        F = eng.batch_frames
+        for s in range(0, T, F):        # one batch at a time so the taps see every frame
+            e = min(T, s + F)
+            eng.push_frames(r[s:e], scale[s:e], dens._wrapped_atoms(T, r.shape[1]), write_back=True)
+            eng.sync()
+            for f in range(e - s):
+                out["ir"].append(eng.debug_cell_indices(f))
+                if keep:
+                    out["d1"].append(eng.debug_density(f))
+        out["sf"] = eng.read_sf()
+        out["launches"] = eng.kernel_launches
+    finally:
+        eng.close()
+    out["coords_after"] = r
+    return out
+
+
+@pytest.mark.parametrize("fft_mode", ["native", "cufft"])
+@pytest.mark.parametrize("name", CASES)
+def test_engine_matches_reference_golden(mdsf, name, fft_mode):
+    c = load_case(name)
+    got = run_engine(mdsf, c, fft_mode)
+    assert got["fft"] == fft_mode
+    assert got["launches"] > 0
+    assert np.array_equal(got["N"], c["ref_N"])
+    # rescale + wrap: bit-exact in the coords dtype
+    assert np.array_equal(got["coords_after"], c["coords_after"])
+    # cell indices: bit-exact (reference dens.py:285 on the mutated coordinates)
+    for t in range(c["coords"].shape[0]):
+        ref_ir = orc.cell_indices(c["coords_after"][t], got["dr"])
+        assert np.array_equal(got["ir"][t].astype(np.int64), ref_ir)
+    # periodic density incl. the reference's corner rule
+    d1 = np.stack(got["d1"])
+    assert np.abs(d1 - c["d1"]).max() <= 1e-13 * np.abs(c["d1"]).max()
+    rel, norm = sf_errors(got["sf"], c["ref_sf"])
+    assert rel <= 1e-5, rel
+    assert norm <= 1e-12, norm
+
+
+@pytest.mark.parametrize("name", ["mono_f32", "corner_na_f64"])
+def test_compute_sf_dropin_writes_reference_npz(mdsf, name, tmp_path):
+    c = load_case(name)
+    r = c["coords"].copy()
+    out = str(tmp_path / "out_sf")
+    mdsf.dens.compute_sf(r, c["dims"].copy(), c["typ"], out, c["rad"], c["ucell"], c["sres"])
+    z = np.load(out + ".npz")
+    assert sorted(z.files) == sorted(["sf", "sfplt", "L", "N", "kgrid", "kgridplt"])
+    assert np.array_equal(r, c["coords_after"])                 # in-place side effect kept
+    assert z["L"].dtype == c["ref_L"].dtype and np.array_equal(z["L"], c["ref_L"])
+    assert np.array_equal(z["N"], c["ref_N"])
+    assert np.array_equal(z["kgrid"], c["ref_kgrid"])
+    assert np.array_equal(z["kgridplt"][..., :3], c["ref_kgridplt"][..., :3])
+    for key in ("sf", "sfplt"):
+        rel, norm = sf_errors(z[key], c["ref_" + key])
+        assert rel <= 1e-5 and norm <= 1e-12
+    rel, norm = sf_errors(z["kgridplt"][..., 3], c["ref_kgridplt"][..., 3])
+    assert rel <= 1e-5 and norm <= 1e-12
+
+
+def test_unknown_label_raises_keyerror_like_reference(mdsf, tmp_path):
+    c = load_case("gas_f64_ortho")
+    typ = c["typ"].copy()
+    typ[0] = "XX"
+    with pytest.raises(KeyError):
+        mdsf.dens.compute_sf(c["coords"].copy(), c["dims"], typ, str(tmp_path / "x"), c["rad"], c["ucell"], c["sres"])
+
+
+def test_atom_far_outside_box_is_reported(mdsf, tmp_path):
+    c = load_case("gas_f64_ortho")
+    r = c["coords"].copy()
+    r[0, 0, 0] = 5.0 * c["dims"][0, 0]      # > one box outside: the reference breaks with a shape error
+    with pytest.raises(mdsf.native.MdsfError) as ei:
+        mdsf.dens.compute_sf(r, c["dims"], c["typ"], str(tmp_path / "x"), c["rad"], c["ucell"], c["sres"])
+    assert ei.value.code == -3
+
+
+def test_bitwise_reproducible_and_batch_invariant(mdsf):
+    c = load_case("mono_f32")
+    a = run_engine(mdsf, c, "native", batch=2)
+    b = run_engine(mdsf, c, "native", batch=2)
+    assert np.array_equal(a["sf"], b["sf"])                     # deterministic: no float atomics anywhere
+    assert all(np.array_equal(x, y) for x, y in zip(a["d1"], b["d1"]))
+    d = run_engine(mdsf, c, "native", batch=4, tile=(2, 2))
+    assert all(np.array_equal(x, y) for x, y in zip(a["d1"], d["d1"]))   # tile shape does not change the sums
+    rel, norm = sf_errors(d["sf"], a["sf"])
+    assert norm <= 1e-14
+
+
+def test_periodic_fold_switch_differs_only_in_corners(mdsf):
+    c = load_case("corner_na_f64")
+    ref = run_engine(mdsf, c, "native", fold="reference")
+    per = run_engine(mdsf, c, "native", fold="periodic")
+    taps = {}
+    r = c["coords"].copy()
+    orc.structure_factor(r, c["dims"].copy(), c["typ"], c["rad"], c["ucell"], c["sres"], fold_mode="periodic", taps=taps)
+    assert np.abs(per["d1"][0] - taps["d1"][0]).max() <= 1e-13 * taps["d1"][0].max()
+    assert np.abs(per["d1"][0] - ref["d1"][0]).max() > 1e-6
+    assert abs(per["d1"][0].sum() - ref["d1"][0].sum()) <= 1e-10 * ref["d1"][0].sum()
+
+
+def test_general_ucell_uses_full_expression(mdsf):
+    c = load_case("gas_f64_ortho")
+    c = dict(c)
+    c["ucell"] = np.array([[1.0, 0.0, 0.0], [0.3, 0.9, 0.1], [0.05, 0.2, 0.95]])
+    taps = {}
+    r = c["coords"].copy()
+    ref = orc.structure_factor(r, c["dims"].copy(), c["typ"], c["rad"], c["ucell"], c["sres"], taps=taps)
+    got = run_engine(mdsf, c, "native")
+    d1 = np.stack(got["d1"])
+    assert np.abs(d1 - np.stack(taps["d1"])).max() <= 1e-13 * np.stack(taps["d1"]).max()
+    rel, norm = sf_errors(got["sf"], ref["sf"])
+    assert rel <= 1e-5 and norm <= 1e-12
+
+
+def test_random_noise_mode_goes_through_gpu_fft(mdsf, tmp_path):
+    c = load_case("gas_f64_ortho")
+    dens = mdsf.dens
+    dens.RANDOM_NOISE = 1
+    try:
+        np.random.seed(7)
+        out = str(tmp_path / "noise")
+        dens.compute_sf(c["coords"].copy(), c["dims"], c["typ"], out, c["rad"], c["ucell"], c["sres"])
+        z = np.load(out + ".npz")
+        np.random.seed(7)
+        n = c["ref_N"]
+        ref = sum(orc.power_spectrum(np.random.rand(int(n[0]), int(n[1]), int(n[2]))) for _ in range(c["coords"].shape[0]))
+        rel, norm = sf_errors(z["sf"], ref)
+        assert rel <= 1e-8 and norm <= 1e-13
+    finally:
+        dens.RANDOM_NOISE = 0
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 64), (12, 20, 28), (22, 26, 30), (256, 8, 128), (34, 38, 46)])
+def test_native_and_library_fft_agree_with_numpy(mdsf, shape):
+    """Power spectrum of arbitrary real volumes: hand-written passes (radix 2..16, 3, 5, 7, 11, 13)
+    and the cuFFT path (prime factors > 13) both against np.fft.rfftn."""
+    rng = np.random.default_rng(sum(shape))
+    vols = rng.standard_normal((3,) + shape)
+    ref = sum(orc.power_spectrum(v) for v in vols)
+    native_ok = all(_smooth(s) for s in shape)
+    for mode in (["native", "cufft"] if native_ok else ["auto"]):
+        eng = mdsf.native.Engine(shape, 1, (1, 1, 1), shape, np.eye(3), [1.0], [1.0], [[1, 1, 1]], np.float64, np.float64,
+                                 fft_mode={"auto": 0, "native": 1, "cufft": 2}[mode], batch_frames=2)
+        try:
+            assert eng.fft_path == ("cufft" if not native_ok else mode)
+            eng.push_density(vols)
+            sf = eng.read_sf()
+        finally:
+            eng.close()
+        rel, norm = sf_errors(sf, ref)
+        assert rel <= 1e-9 and norm <= 1e-13, (mode, rel, norm)
+
+
+def _smooth(n):
+    for p in (2, 3, 5, 7, 11, 13):
+        while n % p == 0:
+            n //= p
+    return n == 1
