@@ -88,7 +88,8 @@ int mdsf_host_unregister(void* p);
  * If `write_back` is non-zero the rescaled+wrapped coordinates are copied back into `coords`
  * (the reference mutates its argument in place); they are valid after mdsf_sync().
  * Asynchronous: returns once the work is queued; `coords` must stay valid and unmodified
- * until mdsf_sync() (pinned memory) -- pageable memory is staged before return. */
+ * until mdsf_sync() (pinned memory) -- pageable memory is staged before return.  `coords` may
+ * also be a DEVICE pointer (frames already resident in HBM): the copy is then device-to-device. */
 int mdsf_push_frames(mdsf_handle* h, void* coords, int64_t nframes, const double* scale,
                      int64_t wrap_lo, int64_t wrap_hi, int32_t write_back);
 
@@ -103,7 +104,7 @@ int mdsf_sync(mdsf_handle* h);
  * array dens.py:318 accumulates.  Host or device destination. */
 int mdsf_read_sf(mdsf_handle* h, double* sf_host);
 int mdsf_export_sf_device(mdsf_handle* h, void* sf_device);
-/* Add a partial sf (device pointer, same shape) -- used after a cross-GPU reduce. */
+/* Zero the accumulator (start a new trajectory on the same handle). */
 int mdsf_reset(mdsf_handle* h);
 
 /* Parity taps (tests only; each synchronises). `frame` indexes the frames of the LAST push. */
@@ -118,9 +119,14 @@ int64_t mdsf_frames_done(const mdsf_handle* h);
 const char* mdsf_fft_path(const mdsf_handle* h);
 int mdsf_batch_frames(const mdsf_handle* h);
 /* Record CUDA events around every stage of subsequent batches; query the accumulated
- * per-stage device milliseconds: out[0..5] = h2d, prep+bin, splat(+zfft), fft, accumulate, total */
+ * per-stage device milliseconds: out[0..5] = copy, prep+bin, splat+zfft, y pass, x pass+accumulate
+ * (library path: FFT, accumulate), compute-stream total */
 int mdsf_enable_timing(mdsf_handle* h, int32_t on);
 int mdsf_stage_ms(mdsf_handle* h, double* out6, int64_t* batches);
+/* CUDA-event stopwatch around everything queued between the two calls (start: copy stream,
+ * stop: compute stream; stop waits for completion). */
+int mdsf_timer_start(mdsf_handle* h);
+int mdsf_timer_stop(mdsf_handle* h, double* ms_out);
 
 const char* mdsf_last_error(void);
 int mdsf_abi_version(void);

@@ -99,9 +99,9 @@ struct mdsf_handle {
     long long launches = 0, frames_done = 0;
     int last_batch_frames = 0;
     bool timing = false;
-    cudaEvent_t tev[8]{};
-    double stage_ms[6]{};
+    std::vector<cudaEvent_t> tev;     // 6 events per timed batch: h2d start, compute start, binned, splat done, y done, end
     long long timed_batches = 0;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     std::vector<int> halfw_host;
 };
 
@@ -294,7 +294,8 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaEventCreateWithFlags(&h->ev_prep[s], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_back[s], cudaEventDisableTiming));
     }
-    for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&h->tev[i]));
+    CU(cudaEventCreate(&h->timer0));
+    CU(cudaEventCreate(&h->timer1));
 
     if (!h->native_fft) {
         int dims[3] = {gp.n[0], gp.n[1], gp.n[2]};
@@ -337,7 +338,9 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
         if (h->ev_prep[s]) cudaEventDestroy(h->ev_prep[s]);
         if (h->ev_back[s]) cudaEventDestroy(h->ev_back[s]);
     }
-    for (int i = 0; i < 8; ++i) if (h->tev[i]) cudaEventDestroy(h->tev[i]);
+    for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+    if (h->timer0) cudaEventDestroy(h->timer0);
+    if (h->timer1) cudaEventDestroy(h->timer1);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_back) cudaStreamDestroy(h->s_back);
@@ -426,7 +429,7 @@ extern "C" int mdsf_host_unregister(void* p) { CU(cudaHostUnregister(p)); return
 // ------------------------------------------------------------------------------------------
 // FFT + accumulation of the pair volumes currently in d_vol (nf frames -> (nf+1)/2 pairs).
 // `z_done`: the z pass already ran inside the fused splat kernel.
-static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done) {
+static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEvent_t* tv = nullptr) {
     const GridParams& gp = h->gp;
     const int npairs = (nf + 1) / 2;
     if (h->native_fft) {
@@ -439,14 +442,14 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done) {
             fft_z_kernel<<<grid, 256, sm, h->s_comp>>>(h->d_vol, h->ax[2].plan, h->ax[2].d_tw, ncolumns, ncol, gp.nzp, gp.pad_shift);
             ++h->launches;
         }
-        if (h->timing) CU(cudaEventRecord(h->tev[3], h->s_comp));
+        if (tv) CU(cudaEventRecord(tv[3], h->s_comp));
         {
             const size_t sm = (size_t)2 * gp.n[1] * h->Wy * 8 + (size_t)2 * gp.n[1] * 8;
             dim3 grid((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0], npairs);
             fft_y_kernel<<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy);
             ++h->launches;
         }
-        if (h->timing) CU(cudaEventRecord(h->tev[4], h->s_comp));
+        if (tv) CU(cudaEventRecord(tv[4], h->s_comp));
         {
             const size_t sm = (size_t)(npairs > 1 ? 3 : 2) * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
             dim3 grid((gp.n[2] + h->Wx - 1) / h->Wx, gp.n[1]);
@@ -455,14 +458,14 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done) {
             ++h->launches;
         }
     } else {
-        if (h->timing) CU(cudaEventRecord(h->tev[3], h->s_comp));
+        if (tv) CU(cudaEventRecord(tv[3], h->s_comp));
         if (npairs == h->cufft_batch) {
             CF(cufftExecZ2Z(h->cufft_plan, (cufftDoubleComplex*)h->d_vol, (cufftDoubleComplex*)h->d_vol, CUFFT_FORWARD));
         } else {   // partial last batch: zero the unused pair volumes and transform the whole batch
             CU(cudaMemsetAsync(h->d_vol + (long long)npairs * h->ncell, 0, sizeof(double2) * h->ncell * (h->cufft_batch - npairs), h->s_comp));
             CF(cufftExecZ2Z(h->cufft_plan, (cufftDoubleComplex*)h->d_vol, (cufftDoubleComplex*)h->d_vol, CUFFT_FORWARD));
         }
-        if (h->timing) CU(cudaEventRecord(h->tev[4], h->s_comp));
+        if (tv) CU(cudaEventRecord(tv[4], h->s_comp));
         accumulate_power_kernel<<<grid_for(h->ncell, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_vol, h->d_P, h->ncell, npairs);
         ++h->launches;
     }
@@ -487,11 +490,16 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
         CU(cudaStreamWaitEvent(h->s_copy, h->ev_free[slot], 0));
         CU(cudaStreamWaitEvent(h->s_copy, h->ev_back[slot], 0));
     }
-    if (h->timing) { CU(cudaStreamWaitEvent(h->s_copy, h->tev[7], 0)); CU(cudaEventRecord(h->tev[0], h->s_copy)); }
-    CU(cudaMemcpyAsync(h->d_stage[slot], src, bytes, cudaMemcpyHostToDevice, h->s_copy));
+    cudaEvent_t* tv = nullptr;
+    if (h->timing) {
+        for (int i = 0; i < 6; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tev.push_back(e); }
+        tv = &h->tev[h->tev.size() - 6];
+        CU(cudaEventRecord(tv[0], h->s_copy));
+    }
+    CU(cudaMemcpyAsync(h->d_stage[slot], src, bytes, cudaMemcpyDefault, h->s_copy));
     CU(cudaEventRecord(h->ev_h2d[slot], h->s_copy));
     CU(cudaStreamWaitEvent(h->s_comp, h->ev_h2d[slot], 0));
-    if (h->timing) CU(cudaEventRecord(h->tev[1], h->s_comp));
+    if (tv) CU(cudaEventRecord(tv[1], h->s_comp));
 
     BatchScales sc;
     for (int f = 0; f < nf; ++f) for (int d = 0; d < 3; ++d) sc.a[f][d] = scale[f * 3 + d];
@@ -503,7 +511,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     CU(cudaEventRecord(h->ev_prep[slot], h->s_comp));
     if (write_back) {
         CU(cudaStreamWaitEvent(h->s_back, h->ev_prep[slot], 0));
-        CU(cudaMemcpyAsync(src, h->d_stage[slot], bytes, cudaMemcpyDeviceToHost, h->s_back));
+        CU(cudaMemcpyAsync(src, h->d_stage[slot], bytes, cudaMemcpyDefault, h->s_back));
     }
     CU(cudaEventRecord(h->ev_back[slot], h->s_back));
 
@@ -522,7 +530,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     cub::DeviceRadixSort::SortPairs(h->d_cub, cb, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], cap, 0, bits, h->s_comp);
     tile_starts_kernel<<<grid_for(cap + 1, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_keys[1], cap, nkeys, h->d_tile_start);
     h->launches += 3;
-    if (h->timing) CU(cudaEventRecord(h->tev[2], h->s_comp));
+    if (tv) CU(cudaEventRecord(tv[2], h->s_comp));
 
     // splat (+ fused z FFT on the native path)
     const int npairs = (nf + 1) / 2;
@@ -535,20 +543,10 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
                                                                          gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->chunk, h->xycap, h->zcap);
     ++h->launches;
     CU(cudaGetLastError());
-    int rc = transform_and_accumulate(h, nf, h->native_fft);
+    int rc = transform_and_accumulate(h, nf, h->native_fft, tv);
     if (rc) return rc;
     CU(cudaEventRecord(h->ev_free[slot], h->s_comp));
-    if (h->timing) {
-        CU(cudaEventRecord(h->tev[7], h->s_comp));
-        CU(cudaEventSynchronize(h->tev[7]));
-        float ms;
-        const int a[6] = {0, 1, 2, 3, 4, 0}, b[6] = {1, 2, 3, 4, 7, 7};
-        for (int i = 0; i < 6; ++i) {
-            CU(cudaEventElapsedTime(&ms, h->tev[a[i]], h->tev[b[i]]));
-            h->stage_ms[i] += ms;
-        }
-        ++h->timed_batches;
-    }
+    if (tv) { CU(cudaEventRecord(tv[5], h->s_comp)); ++h->timed_batches; }
     h->slot_used[slot] = true;
     h->frames_done += nf;
     h->last_batch_frames = nf;
@@ -692,14 +690,44 @@ extern "C" int mdsf_enable_timing(mdsf_handle* h, int32_t on) {
     CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
     h->timing = on != 0;
-    for (double& v : h->stage_ms) v = 0;
+    for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+    h->tev.clear();
     h->timed_batches = 0;
-    if (on) CU(cudaEventRecord(h->tev[7], h->s_comp));
     return MDSF_OK;
 }
 extern "C" int mdsf_stage_ms(mdsf_handle* h, double* out6, int64_t* batches) {
     if (!h || !out6) return fail(MDSF_EINVAL, "null argument");
-    for (int i = 0; i < 6; ++i) out6[i] = h->stage_ms[i];
-    if (batches) *batches = h->timed_batches;
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    for (int i = 0; i < 6; ++i) out6[i] = 0;
+    const size_t nb = h->tev.size() / 6;
+    for (size_t b = 0; b < nb; ++b) {
+        cudaEvent_t* tv = &h->tev[b * 6];
+        float ms;
+        CU(cudaEventElapsedTime(&ms, tv[0], tv[1])); out6[0] += ms;     // copy (overlaps the previous batch's kernels)
+        for (int i = 1; i < 5; ++i) { CU(cudaEventElapsedTime(&ms, tv[i], tv[i + 1])); out6[i] += ms; }
+        CU(cudaEventElapsedTime(&ms, tv[1], tv[5])); out6[5] += ms;     // compute-stream time of the batch
+    }
+    if (batches) *batches = (int64_t)nb;
+    return MDSF_OK;
+}
+
+// Device-side stopwatch over everything queued between the two calls: the start event goes on
+// the copy stream (every batch begins there), the stop event on the compute stream.
+extern "C" int mdsf_timer_start(mdsf_handle* h) {
+    if (!h) return fail(MDSF_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaEventRecord(h->timer0, h->s_copy));
+    return MDSF_OK;
+}
+extern "C" int mdsf_timer_stop(mdsf_handle* h, double* ms_out) {
+    if (!h || !ms_out) return fail(MDSF_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->timer1, h->s_comp));
+    CU(cudaEventSynchronize(h->timer1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->timer0, h->timer1));
+    *ms_out = ms;
     return MDSF_OK;
 }

@@ -22,7 +22,8 @@ EXPORTS = [
     "mdsf_host_register", "mdsf_host_unregister", "mdsf_push_frames", "mdsf_push_density", "mdsf_sync",
     "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
     "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_batch_frames",
-    "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_last_error", "mdsf_abi_version",
+    "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_timer_start", "mdsf_timer_stop", "mdsf_last_error",
+    "mdsf_abi_version",
 ]
 
 
@@ -79,6 +80,8 @@ def load():
         "mdsf_batch_frames": (C.c_int, [vp]),
         "mdsf_enable_timing": (C.c_int, [vp, i32]),
         "mdsf_stage_ms": (C.c_int, [vp, dp, C.POINTER(i64)]),
+        "mdsf_timer_start": (C.c_int, [vp]),
+        "mdsf_timer_stop": (C.c_int, [vp, dp]),
         "mdsf_last_error": (C.c_char_p, []),
         "mdsf_abi_version": (C.c_int, []),
     }
@@ -182,6 +185,13 @@ class Engine:
         _check(self._lib.mdsf_push_frames(self._h, C.c_void_p(coords.ctypes.data), coords.shape[0], _dptr(scale),
                                           int(lo), int(hi), 1 if write_back else 0))
 
+    def push_frames_ptr(self, ptr, nframes, scale, wrap_range=None, write_back=False):
+        """Same as push_frames for a raw host or DEVICE pointer to (nframes, Na, 3) coordinates."""
+        scale = np.ascontiguousarray(scale, dtype=np.float64).reshape(nframes, 3)
+        lo, hi = (0, self.natoms) if wrap_range is None else wrap_range
+        _check(self._lib.mdsf_push_frames(self._h, C.c_void_p(int(ptr)), int(nframes), _dptr(scale), int(lo), int(hi),
+                                          1 if write_back else 0))
+
     def push_density(self, d1):
         d1 = np.ascontiguousarray(d1, dtype=np.float64)
         if d1.ndim == 3:
@@ -240,9 +250,17 @@ class Engine:
     def enable_timing(self, on=True):
         _check(self._lib.mdsf_enable_timing(self._h, 1 if on else 0))
 
+    def timer_start(self):
+        _check(self._lib.mdsf_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        _check(self._lib.mdsf_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def stage_ms(self):
         out = np.zeros(6)
         nb = C.c_int64()
         _check(self._lib.mdsf_stage_ms(self._h, _dptr(out), C.byref(nb)))
-        names = ["h2d", "prep_bin", "splat_zfft", "fft_y", "fft_x_accum", "total"]
+        names = ["copy", "prep_bin", "splat_zfft", "fft_y", "fft_x_accum", "total"]
         return dict(zip(names, out.tolist())), int(nb.value)
