@@ -106,13 +106,13 @@ struct mdsf_handle {
 };
 
 // ------------------------------------------------------------------------------------------
-static bool factorize(int n, FftPlan& plan) {
+static bool factorize(int n, FftPlan& plan, int max_log2 = 4) {
     plan.n = n;
     plan.nstages = 0;
     int e = 0;
     while (n % 2 == 0) { n /= 2; ++e; }
     if (e > 0) {
-        const int count = (e + 3) / 4, base = e / count, rem = e % count;
+        const int count = (e + max_log2 - 1) / max_log2, base = e / count, rem = e % count;
         for (int i = 0; i < count; ++i) plan.radix[plan.nstages++] = 1 << (base + (i < rem ? 1 : 0));
     }
     const int odd[] = {3, 5, 7, 11, 13};
@@ -131,9 +131,9 @@ static int digit_position(int k, int n, const FftPlan& plan, int stage) {
     return (k % r) * m + digit_position(k / r, m, plan, stage + 1);
 }
 
-static int build_axis(AxisPlan& ax, int n, bool want_native) {
+static int build_axis(AxisPlan& ax, int n, bool want_native, int max_log2) {
     std::vector<int> rev(n);
-    ax.native = want_native && factorize(n, ax.plan);
+    ax.native = want_native && factorize(n, ax.plan, max_log2);
     if (ax.native) {
         std::vector<double2> tw(n);
         const long double two_pi = 6.283185307179586476925286766559005768L;
@@ -206,7 +206,10 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     // ---- FFT plans
     const bool want_native = cfg->fft_mode != MDSF_FFT_CUFFT;
     for (int d = 0; d < 3; ++d) {
-        int rc = build_axis(h->ax[d], gp.n[d], want_native);
+        const char* env = getenv(d == 2 ? "MDSF_RADIX_LOG2_Z" : "MDSF_RADIX_LOG2_XY");
+        int max_log2 = env ? atoi(env) : (d == 2 ? 3 : 4);
+        if (max_log2 < 1 || max_log2 > 4) max_log2 = 4;
+        int rc = build_axis(h->ax[d], gp.n[d], want_native, max_log2);
         if (rc) return rc;
     }
     h->native_fft = h->ax[0].native && h->ax[1].native && h->ax[2].native;
@@ -227,17 +230,18 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         const int last = h->ax[2].plan.radix[h->ax[2].plan.nstages - 1];
         if (last == 16) gp.pad_shift = 4; else if (last == 8) gp.pad_shift = 3; else if (last == 4) gp.pad_shift = 2;
     }
-    gp.nzp = gp.n[2] + (gp.pad_shift < 31 ? (gp.n[2] >> gp.pad_shift) : 0);
+    gp.nzp = (gp.n[2] + (gp.pad_shift < 31 ? (gp.n[2] >> gp.pad_shift) : 0)) | 1;   // odd: columns start in different banks
 
     // ---- splat tile
     int ncol;
     if (cfg->tile_x > 0 && cfg->tile_y > 0) {
         gp.tx = cfg->tile_x; gp.ty = cfg->tile_y;
-        if (gp.tx * gp.ty > MDSF_MAX_TILE_COLS) return fail(MDSF_EINVAL, "tile %dx%d exceeds %d columns", gp.tx, gp.ty, MDSF_MAX_TILE_COLS);
+        const int nc = gp.tx * gp.ty;
+        if (nc < 4 || nc > MDSF_MAX_TILE_COLS || (nc & (nc - 1))) return fail(MDSF_EINVAL, "tile %dx%d: the column count must be 4, 8, 16 or 32", gp.tx, gp.ty);
     } else {
         ncol = 32;
-        while (ncol > 4 && (size_t)2 * ncol * gp.nzp * 8 > 64 * 1024) ncol >>= 1;
-        while (ncol > 1 && (size_t)2 * ncol * gp.nzp * 8 > 160 * 1024) ncol >>= 1;
+        while (ncol > 4 && (size_t)2 * ncol * gp.nzp * 8 > 72 * 1024) ncol >>= 1;
+        if ((size_t)2 * ncol * gp.nzp * 8 > 200 * 1024) return fail(MDSF_EINVAL, "grid too long in z (%d) for the column-tile splat", gp.n[2]);
         const int txs[6] = {1, 1, 2, 2, 4, 4}, tys[6] = {1, 2, 2, 4, 4, 8};
         int l = 0;
         while ((1 << l) < ncol) ++l;
@@ -305,9 +309,9 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     } else {
         // y / x pass tiles: [n][W] complex in shared memory
         auto pick = [&](int n, int& W, int& thr) {
-            W = 16;
-            while (W > 1 && (size_t)n * W * 24 + (size_t)n * 16 > 200 * 1024) W >>= 1;
-            thr = 256;
+            W = 8;
+            while (W > 1 && (size_t)n * W * 24 + (size_t)n * 16 > 100 * 1024) W >>= 1;
+            thr = MDSF_PASS_THREADS;
         };
         pick(gp.n[1], h->Wy, h->thr_y);
         pick(gp.n[0], h->Wx, h->thr_x);
@@ -387,7 +391,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     h->xycap = xymax; h->zcap = zmax;
     const size_t tile_b = (size_t)2 * g0.tx * g0.ty * g0.nzp * 8 + (h->native_fft ? (size_t)2 * g0.n[2] * 8 : 0);
     int chunk = 128;
-    auto smem_for = [&](int c) { return tile_b + (size_t)2 * c * (xymax + zmax) * 8 + (size_t)2 * c * sizeof(PairSlot) + 2 * 4 * 32 * 4 + 2 * 16 * 4; };
+    auto smem_for = [&](int c) { return tile_b + (size_t)2 * c * (xymax + zmax) * 8 + (size_t)2 * c * sizeof(PairSlot) + 2 * 4 * MDSF_OWNERS * 4 + 2 * 16 * 4; };
     const size_t soft = tile_b <= 70 * 1024 ? 110 * 1024 : kMaxSmem;    // two CTAs per SM when the tile allows
     while (chunk > 32 && smem_for(chunk) > soft) chunk -= 32;
     if (smem_for(chunk) > (size_t)kMaxSmem) {
@@ -446,15 +450,17 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
         {
             const size_t sm = (size_t)2 * gp.n[1] * h->Wy * 8 + (size_t)2 * gp.n[1] * 8;
             dim3 grid((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0], npairs);
-            fft_y_kernel<<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy);
+            int logw = 0; while ((1 << logw) < h->Wy) ++logw;
+            fft_y_kernel<<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy, logw);
             ++h->launches;
         }
         if (tv) CU(cudaEventRecord(tv[4], h->s_comp));
         {
-            const size_t sm = (size_t)(npairs > 1 ? 3 : 2) * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
+            const size_t sm = (size_t)3 * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
+            int logw = 0; while ((1 << logw) < h->Wx) ++logw;
             dim3 grid((gp.n[2] + h->Wx - 1) / h->Wx, gp.n[1]);
             fft_x_accum_kernel<<<grid, h->thr_x, sm, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].plan, h->ax[0].d_tw,
-                                                                      gp.n[0], gp.n[1], gp.n[2], h->Wx, npairs);
+                                                                      gp.n[0], gp.n[1], gp.n[2], h->Wx, logw, npairs);
             ++h->launches;
         }
     } else {

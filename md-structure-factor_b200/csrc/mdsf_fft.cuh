@@ -142,14 +142,25 @@ template <int R> struct Dft {
 };
 
 // ------------------------------------------------------------------ one DIF stage over a tile
-// Tile addressing: point p of transform f lives at f*fs + pos(p)*es with pos(p) = p + (p >> pad).
-// ZPASS: transforms are contiguous rows (es = 1), consecutive lanes take consecutive
-// butterflies of one row.  Otherwise transforms are columns of a [n][W] tile (fs = 1) and
-// consecutive lanes take consecutive columns.
-template <int R, bool ZPASS>
+// Tile addressing in shared memory: point p of transform f lives at f*fs + pos(p)*es with
+// pos(p) = p + (p >> pad).  ZPASS: transforms are contiguous rows (es = 1) and consecutive lanes
+// take consecutive butterflies of one row.  Otherwise the tile is [n][W] (fs = 1, es = W, W a
+// power of two) and consecutive lanes take consecutive columns, i.e. contiguous global memory.
+// A stage may take its input straight from global memory (first stage of a y/x pass) and may
+// send its output straight back (last stage), so a 2-stage transform crosses shared memory once.
+enum { IO_SMEM = 0, IO_GLOBAL = 1, IO_POWER = 2 };
+
+struct GlobalTile {
+    double2* base;        // element (p, f) at base[p * row_stride + f]
+    long long row_stride;
+    int w;                // valid columns (f < w)
+};
+
+template <int R, bool ZPASS, int IN, int OUT>
 __device__ __forceinline__ void fft_stage(double* __restrict__ sre, double* __restrict__ sim,
                                           const double* __restrict__ twr, const double* __restrict__ twi,
-                                          int n, int L, int nfft, int fs, int es, int pad)
+                                          int n, int L, int nfft, int fs, int es, int pad, int logw,
+                                          const GlobalTile& g, double* __restrict__ power, bool first_power)
 {
     const int M = L / R;
     const int nbf = n / R;
@@ -158,16 +169,25 @@ __device__ __forceinline__ void fft_stage(double* __restrict__ sre, double* __re
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         int f, bf;
         if (ZPASS) { f = it / nbf; bf = it - f * nbf; }
-        else       { bf = it / nfft; f = it - bf * nfft; }
+        else       { bf = it >> logw; f = it & (nfft - 1); }
         const int b = bf / M, n2 = bf - b * M;
         const int base = b * L + n2;
         double xr[R], xi[R];
-        int addr[R];
+        if (IN == IO_GLOBAL) {
+            const bool ok = f < g.w;
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            const int p = base + j * M;
-            addr[j] = f * fs + (p + (p >> pad)) * es;
-            xr[j] = sre[addr[j]]; xi[j] = sim[addr[j]];
+            for (int j = 0; j < R; ++j) {
+                double2 v = make_double2(0.0, 0.0);
+                if (ok) v = g.base[(long long)(base + j * M) * g.row_stride + f];
+                xr[j] = v.x; xi[j] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int p = base + j * M;
+                const int a = f * fs + (p + (p >> pad)) * es;
+                xr[j] = sre[a]; xi[j] = sim[a];
+            }
         }
         Dft<R>::run(xr, xi, twr, twi, n);
         if (M > 1) {
@@ -180,34 +200,84 @@ __device__ __forceinline__ void fft_stage(double* __restrict__ sre, double* __re
                 xr[k] = yr;
             }
         }
+        if (OUT == IO_GLOBAL) {
+            if (f < g.w) {
 #pragma unroll
-        for (int k = 0; k < R; ++k) { sre[addr[k]] = xr[k]; sim[addr[k]] = xi[k]; }
+                for (int k = 0; k < R; ++k) g.base[(long long)(base + k * M) * g.row_stride + f] = make_double2(xr[k], xi[k]);
+            }
+        } else if (OUT == IO_POWER) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int a = (base + k * M) * es + f;
+                const double v = xr[k] * xr[k] + xi[k] * xi[k];
+                power[a] = first_power ? v : power[a] + v;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int p = base + k * M;
+                const int a = f * fs + (p + (p >> pad)) * es;
+                sre[a] = xr[k]; sim[a] = xi[k];
+            }
+        }
     }
 }
 
-// all stages of one axis, over a tile resident in shared memory (caller syncs before/after)
-template <bool ZPASS>
-__device__ void fft_tile(double* sre, double* sim, const double* twr, const double* twi,
-                         const FftPlan& plan, int nfft, int fs, int es, int pad)
+template <bool ZPASS, int IN, int OUT>
+__device__ __forceinline__ void fft_stage_dispatch(int R, double* sre, double* sim, const double* twr, const double* twi,
+                                                   int n, int L, int nfft, int fs, int es, int pad, int logw,
+                                                   const GlobalTile& g, double* power, bool first_power)
 {
+    switch (R) {
+        case 16: fft_stage<16, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        case 8:  fft_stage<8, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        case 4:  fft_stage<4, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        case 2:  fft_stage<2, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        case 3:  fft_stage<3, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        case 5:  fft_stage<5, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        case 7:  fft_stage<7, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        case 11: fft_stage<11, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        case 13: fft_stage<13, ZPASS, IN, OUT>(sre, sim, twr, twi, n, L, nfft, fs, es, pad, logw, g, power, first_power); break;
+        default: break;
+    }
+}
+
+// all stages of one axis over a tile resident in shared memory (z pass; caller syncs before)
+__device__ __forceinline__ void fft_tile_z(double* sre, double* sim, const double* twr, const double* twi,
+                                           const FftPlan& plan, int nfft, int fs, int pad)
+{
+    GlobalTile none{nullptr, 0, 0};
     int L = plan.n;
     for (int s = 0; s < plan.nstages; ++s) {
-        const int R = plan.radix[s];
-        switch (R) {
-            case 16: fft_stage<16, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            case 8:  fft_stage<8, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            case 4:  fft_stage<4, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            case 2:  fft_stage<2, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            case 3:  fft_stage<3, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            case 5:  fft_stage<5, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            case 7:  fft_stage<7, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            case 11: fft_stage<11, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            case 13: fft_stage<13, ZPASS>(sre, sim, twr, twi, plan.n, L, nfft, fs, es, pad); break;
-            default: break;
-        }
-        L /= R;
+        fft_stage_dispatch<true, IO_SMEM, IO_SMEM>(plan.radix[s], sre, sim, twr, twi, plan.n, L, nfft, fs, 1, pad, 0, none, nullptr, false);
+        L /= plan.radix[s];
         __syncthreads();
     }
+}
+
+// y/x pass over a [n][W] tile: first stage from global, last stage to global (POWER = false) or
+// into the |C|^2 tile `power` (POWER = true).
+template <bool POWER>
+__device__ __forceinline__ void fft_tile_strided(double* sre, double* sim, const double* twr, const double* twi,
+                                                 const FftPlan& plan, int W, int logw, const GlobalTile& g,
+                                                 double* power, bool first_power)
+{
+    constexpr int LAST = POWER ? IO_POWER : IO_GLOBAL;
+    const int n = plan.n;
+    if (plan.nstages == 1) {
+        fft_stage_dispatch<false, IO_GLOBAL, LAST>(plan.radix[0], sre, sim, twr, twi, n, n, W, 1, W, 31, logw, g, power, first_power);
+        return;
+    }
+    int L = n;
+    fft_stage_dispatch<false, IO_GLOBAL, IO_SMEM>(plan.radix[0], sre, sim, twr, twi, n, L, W, 1, W, 31, logw, g, power, first_power);
+    L /= plan.radix[0];
+    __syncthreads();
+    for (int s = 1; s + 1 < plan.nstages; ++s) {
+        fft_stage_dispatch<false, IO_SMEM, IO_SMEM>(plan.radix[s], sre, sim, twr, twi, n, L, W, 1, W, 31, logw, g, power, first_power);
+        L /= plan.radix[s];
+        __syncthreads();
+    }
+    fft_stage_dispatch<false, IO_SMEM, LAST>(plan.radix[plan.nstages - 1], sre, sim, twr, twi, n, L, W, 1, W, 31, logw, g, power, first_power);
 }
 
 __device__ __forceinline__ void load_twiddles(double* twr, double* twi, const double2* __restrict__ tw, int n) {
@@ -217,13 +287,18 @@ __device__ __forceinline__ void load_twiddles(double* twr, double* twi, const do
     }
 }
 
+#define MDSF_PASS_THREADS 128
+#ifndef MDSF_PASS_MINBLOCKS
+#define MDSF_PASS_MINBLOCKS 4
+#endif
+
 // ------------------------------------------------------------------ z pass (stand-alone)
 // grid = (column groups, pairs).  A group is `ncol` consecutive (x,y) columns, contiguous in
 // memory.  Used by mdsf_push_density and by the un-fused debug path; the production path runs
 // the same stages inside splat_zfft_kernel without the load.
 __global__ void __launch_bounds__(256)
 fft_z_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw,
-                             long long ncolumns, int ncol, int nzp, int pad)
+             long long ncolumns, int ncol, int nzp, int pad)
 {
     extern __shared__ double smem[];
     const int nz = plan.n;
@@ -242,7 +317,7 @@ fft_z_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict_
         sre[a] = v.x; sim[a] = v.y;
     }
     __syncthreads();
-    fft_tile<true>(sre, sim, twr, twi, plan, nc, nzp, 1, pad);
+    fft_tile_z(sre, sim, twr, twi, plan, nc, nzp, pad);
     for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
         const int c = i / nz, z = i - c * nz;
         const int a = c * nzp + z + (z >> pad);
@@ -251,10 +326,10 @@ fft_z_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict_
 }
 
 // ------------------------------------------------------------------ y pass, in place
-// grid = (z chunks, Nx, pairs); tile = [Ny][W] at fixed x.
-__global__ void __launch_bounds__(256)
+// grid = (z chunks, Nx, pairs); tile = [Ny][W] at fixed x; rows are W*16 contiguous bytes.
+__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_PASS_MINBLOCKS)
 fft_y_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw,
-                             int nx, int ny, int nz, int W)
+             int nx, int ny, int nz, int W, int logw)
 {
     extern __shared__ double smem[];
     double* sre = smem;
@@ -262,63 +337,46 @@ fft_y_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict_
     double* twr = sim + (size_t)ny * W;
     double* twi = twr + ny;
     load_twiddles(twr, twi, tw, ny);
-    const int z0 = blockIdx.x * W;
-    const int w = min(W, nz - z0);
-    double2* base = vol + (((long long)blockIdx.z * nx + blockIdx.y) * ny) * (long long)nz + z0;
-    for (int i = threadIdx.x; i < ny * W; i += blockDim.x) {
-        const int y = i / W, z = i - y * W;
-        double2 v = make_double2(0.0, 0.0);
-        if (z < w) v = base[(long long)y * nz + z];
-        sre[i] = v.x; sim[i] = v.y;
-    }
     __syncthreads();
-    fft_tile<false>(sre, sim, twr, twi, plan, W, 1, W, 31);
-    for (int i = threadIdx.x; i < ny * W; i += blockDim.x) {
-        const int y = i / W, z = i - y * W;
-        if (z < w) base[(long long)y * nz + z] = make_double2(sre[i], sim[i]);
-    }
+    const int z0 = blockIdx.x * W;
+    GlobalTile g;
+    g.base = vol + (((long long)blockIdx.z * nx + blockIdx.y) * ny) * (long long)nz + z0;
+    g.row_stride = nz;
+    g.w = min(W, nz - z0);
+    fft_tile_strided<false>(sre, sim, twr, twi, plan, W, logw, g, nullptr, false);
 }
 
 // ------------------------------------------------------------------ x pass + |C|^2 accumulation
-// grid = (z chunks, Ny); tile = [Nx][W] at fixed y; loops over the pairs of the batch and adds
-// sum_q |C_q|^2 to the resident fp64 accumulator P in one read-modify-write (dens.py:315-318).
-__global__ void __launch_bounds__(256)
-fft_x_accum_kernel(const double2* __restrict__ vol, double* __restrict__ P, FftPlan plan,
-                   const double2* __restrict__ tw, int nx, int ny, int nz, int W, int npairs)
+// grid = (z chunks, Ny); tile = [Nx][W] at fixed y; loops over the pairs of the batch, keeps
+// sum_q |C_q|^2 in shared memory and adds it to the resident fp64 accumulator P with one
+// read-modify-write per batch (dens.py:315-318).
+__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_PASS_MINBLOCKS)
+fft_x_accum_kernel(double2* __restrict__ vol, double* __restrict__ P, FftPlan plan,
+                   const double2* __restrict__ tw, int nx, int ny, int nz, int W, int logw, int npairs)
 {
     extern __shared__ double smem[];
     double* sre = smem;
     double* sim = sre + (size_t)nx * W;
-    double* twr = sim + (size_t)nx * W;
+    double* acc = sim + (size_t)nx * W;
+    double* twr = acc + (size_t)nx * W;
     double* twi = twr + nx;
-    double* acc = twi + nx;                 // [nx*W], only touched when the batch holds > 1 pair
     load_twiddles(twr, twi, tw, nx);
     const int z0 = blockIdx.x * W;
-    const int w = min(W, nz - z0);
     const int y = blockIdx.y;
     const long long xstride = (long long)ny * nz;
     const long long off = (long long)y * nz + z0;
+    GlobalTile g;
+    g.row_stride = xstride;
+    g.w = min(W, nz - z0);
     for (int q = 0; q < npairs; ++q) {
-        const double2* base = vol + (long long)q * nx * xstride + off;
         __syncthreads();
-        for (int i = threadIdx.x; i < nx * W; i += blockDim.x) {
-            const int x = i / W, z = i - x * W;
-            double2 v = make_double2(0.0, 0.0);
-            if (z < w) v = base[(long long)x * xstride + z];
-            sre[i] = v.x; sim[i] = v.y;
-        }
-        __syncthreads();
-        fft_tile<false>(sre, sim, twr, twi, plan, W, 1, W, 31);
-        if (npairs > 1) {
-            for (int i = threadIdx.x; i < nx * W; i += blockDim.x) {
-                const double v = sre[i] * sre[i] + sim[i] * sim[i];
-                acc[i] = q == 0 ? v : acc[i] + v;
-            }
-        }
+        g.base = vol + (long long)q * nx * xstride + off;
+        fft_tile_strided<true>(sre, sim, twr, twi, plan, W, logw, g, acc, q == 0);
     }
+    __syncthreads();
     for (int i = threadIdx.x; i < nx * W; i += blockDim.x) {
-        const int x = i / W, z = i - x * W;
-        if (z < w) P[(long long)x * xstride + off + z] += (npairs > 1) ? acc[i] : sre[i] * sre[i] + sim[i] * sim[i];
+        const int x = i >> logw, z = i & (W - 1);
+        if (z < g.w) P[(long long)x * xstride + off + z] += acc[i];
     }
 }
 
