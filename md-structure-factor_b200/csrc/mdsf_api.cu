@@ -68,8 +68,11 @@ struct mdsf_handle {
     bool slot_used[kSlots]{};
     int next_slot = 0;
     // device buffers
-    double *d_amp = nullptr, *d_two = nullptr;
-    int* d_halfw = nullptr;
+    double *d_amp = nullptr, *d_two = nullptr, *d_ctab = nullptr, *d_tables = nullptr;
+    int *d_halfw = nullptr, *d_ctab_off = nullptr;
+    unsigned* d_toff = nullptr;
+    std::vector<double> two_host;
+    int logS = 4;
     int* d_type = nullptr;
     void* d_stage[kSlots]{};
     AtomRec* d_recs = nullptr;
@@ -90,7 +93,7 @@ struct mdsf_handle {
     // splat launch geometry
     long long natoms = 0;
     long long maxpairs_frame = 0;
-    int chunk = 128, xycap = 1, zcap = 2;
+    int chunk = 128;
     size_t splat_smem = 0;
     int sort_bits = 1;
     // y/x pass geometry
@@ -113,7 +116,7 @@ static bool factorize(int n, FftPlan& plan, int max_log2 = 4) {
     while (n % 2 == 0) { n /= 2; ++e; }
     if (e > 0) {
         const int count = (e + max_log2 - 1) / max_log2, base = e / count, rem = e % count;
-        for (int i = 0; i < count; ++i) plan.radix[plan.nstages++] = 1 << (base + (i < rem ? 1 : 0));
+        for (int i = 0; i < count; ++i) plan.radix[plan.nstages++] = 1 << (base + (i >= count - rem ? 1 : 0));
     }
     const int odd[] = {3, 5, 7, 11, 13};
     for (int p : odd)
@@ -198,9 +201,14 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     for (int d = 0; d < 3; ++d) { gp.n[d] = cfg->n[d]; gp.dr[d] = cfg->dr[d]; gp.box[d] = cfg->box[d]; }
     for (int i = 0; i < 9; ++i) gp.u[i] = cfg->ucell[i];
     gp.nb = cfg->nborder;
+    gp.debug_skip = getenv("MDSF_SPLAT_SKIP") ? atoi(getenv("MDSF_SPLAT_SKIP")) : 0;
     gp.fold_mode = cfg->fold_mode;
     // z decouples when ucell[2][0]=ucell[2][1]=0 (b_z feeds only c_2) and ucell[0][2]=ucell[1][2]=0
     gp.separable = (gp.u[6] == 0.0 && gp.u[7] == 0.0 && gp.u[2] == 0.0 && gp.u[5] == 0.0) ? 1 : 0;
+    gp.cxx = gp.u[0] * gp.u[0] + gp.u[1] * gp.u[1];
+    gp.cyy = gp.u[3] * gp.u[3] + gp.u[4] * gp.u[4];
+    gp.gxy = gp.u[0] * gp.u[3] + gp.u[1] * gp.u[4];
+    gp.czz = gp.u[8] * gp.u[8];
     h->ncell = (long long)gp.n[0] * gp.n[1] * gp.n[2];
 
     // ---- FFT plans
@@ -240,13 +248,16 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         if (nc < 4 || nc > MDSF_MAX_TILE_COLS || (nc & (nc - 1))) return fail(MDSF_EINVAL, "tile %dx%d: the column count must be 4, 8, 16 or 32", gp.tx, gp.ty);
     } else {
         ncol = 32;
-        while (ncol > 4 && (size_t)2 * ncol * gp.nzp * 8 > 72 * 1024) ncol >>= 1;
+        while (ncol > 4 && (size_t)2 * ncol * gp.nzp * 8 > 80 * 1024) ncol >>= 1;
         if ((size_t)2 * ncol * gp.nzp * 8 > 200 * 1024) return fail(MDSF_EINVAL, "grid too long in z (%d) for the column-tile splat", gp.n[2]);
         const int txs[6] = {1, 1, 2, 2, 4, 4}, tys[6] = {1, 2, 2, 4, 4, 8};
         int l = 0;
         while ((1 << l) < ncol) ++l;
         gp.tx = txs[l]; gp.ty = tys[l];
     }
+    if ((gp.tx & (gp.tx - 1)) || (gp.ty & (gp.ty - 1))) return fail(MDSF_EINVAL, "tile sizes must be powers of two");
+    gp.nslab = 128 / (gp.tx * gp.ty);
+    gp.zs = (gp.n[2] + gp.nslab - 1) / gp.nslab;
     gp.ntx = (gp.n[0] + gp.tx - 1) / gp.tx;
     gp.nty = (gp.n[1] + gp.ty - 1) / gp.ty;
 
@@ -274,7 +285,27 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     CU(cudaMemcpy(h->d_two, cfg->two_sig2, sizeof(double) * nt, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_halfw, cfg->halfw, sizeof(int) * nt * 3, cudaMemcpyHostToDevice));
     h->halfw_host.assign(cfg->halfw, cfg->halfw + nt * 3);
+    h->two_host.assign(cfg->two_sig2, cfg->two_sig2 + nt);
     h->tt.amp = h->d_amp; h->tt.two_sig2 = h->d_two; h->tt.halfw = h->d_halfw;
+    h->tt.ctab = nullptr; h->tt.ctab_off = nullptr; h->tt.toff = nullptr;
+    if (gp.separable && gp.gxy != 0.0) {
+        // cross-term table of every type: C[i][j] = exp(-2 gxy dx dy i j / (2 sigma^2))
+        std::vector<int> off(nt);
+        std::vector<double> ctab;
+        for (int t = 0; t < nt; ++t) {
+            off[t] = (int)ctab.size();
+            const int ax2 = 2 * cfg->halfw[t * 3], ay2 = 2 * cfg->halfw[t * 3 + 1];
+            for (int i = 0; i < ax2; ++i)
+                for (int j = 0; j < ay2; ++j)
+                    ctab.push_back(std::exp(-(2.0 * gp.gxy * gp.dr[0] * gp.dr[1] * (double)i * (double)j) / cfg->two_sig2[t]));
+        }
+        if (ctab.empty()) ctab.push_back(1.0);
+        CU(cudaMalloc(&h->d_ctab, sizeof(double) * ctab.size()));
+        CU(cudaMalloc(&h->d_ctab_off, sizeof(int) * nt));
+        CU(cudaMemcpy(h->d_ctab, ctab.data(), sizeof(double) * ctab.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->d_ctab_off, off.data(), sizeof(int) * nt, cudaMemcpyHostToDevice));
+        h->tt.ctab = h->d_ctab; h->tt.ctab_off = h->d_ctab_off;
+    }
     h->cfg.amp = nullptr; h->cfg.two_sig2 = nullptr; h->cfg.halfw = nullptr;   // caller-owned, not kept
 
     // ---- volumes
@@ -330,7 +361,7 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->cufft_plan) cufftDestroy(h->cufft_plan);
-    void* bufs[] = {h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1], h->d_recs, h->d_cnt,
+    void* bufs[] = {h->d_ctab, h->d_ctab_off, h->d_toff, h->d_tables, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1], h->d_recs, h->d_cnt,
                     h->d_off, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_tile_start, h->d_cub,
                     h->d_vol, h->d_dump, h->d_P, h->d_sf, h->d_err};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -361,43 +392,57 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     const int nt = h->cfg.ntypes;
     // worst-case (image, tile) pairs per atom of each type: exact maximum over every admissible cell index
     std::vector<long long> bound(nt);
-    int xymax = 1, zmax = 2;
+    int zmax = 2;
     for (int t = 0; t < nt; ++t) {
         long long m[2] = {1, 1};
         for (int d = 0; d < 2; ++d) {
             const int A = h->halfw_host[t * 3 + d], N = g0.n[d], tl = d == 0 ? g0.tx : g0.ty;
             for (int ir = A - g0.nb; ir <= N + g0.nb - A; ++ir) m[d] = std::max<long long>(m[d], stamp_tiles_1d(ir, A, N, tl));
         }
-        bound[t] = m[0] * m[1];
-        xymax = std::max(xymax, std::min(g0.tx, 2 * h->halfw_host[t * 3]) * std::min(g0.ty, 2 * h->halfw_host[t * 3 + 1]));
+        long long mz = 1;
+        {
+            const int A = h->halfw_host[t * 3 + 2], N = g0.n[2];
+            for (int ir = A - g0.nb; ir <= N + g0.nb - A; ++ir)
+                for (int sx = 0; sx <= 1; ++sx)
+                    for (int sy = -1; sy <= 1; ++sy) {
+                        int a1, a2, a3, a4;
+                        const unsigned sm = image_slabmask(ir, A, sx, sy, N, g0.nb, g0.fold_mode, g0.zs, a1, a2, a3, a4);
+                        mz = std::max<long long>(mz, __builtin_popcount(sm));
+                    }
+        }
+        bound[t] = m[0] * m[1] * mz;
         zmax = std::max(zmax, 2 * h->halfw_host[t * 3 + 2]);
     }
     long long maxpairs = 0;
+    std::vector<unsigned> toff(natoms);
+    long long tstride = 0;
     for (int64_t a = 0; a < natoms; ++a) {
         if (type_id[a] < 0 || type_id[a] >= nt) return fail(MDSF_EINVAL, "type_id[%lld]=%d out of range", (long long)a, type_id[a]);
         maxpairs += bound[type_id[a]];
+        toff[a] = (unsigned)tstride;
+        const int* hw = &h->halfw_host[type_id[a] * 3];
+        tstride += 2 * (hw[0] + hw[1] + hw[2]);
     }
+    if (tstride * h->F >= (1LL << 32)) return fail(MDSF_EINVAL, "factor tables overflow 32-bit offsets; lower batch_frames");
+    h->gp.tstride = tstride;
     h->natoms = natoms;
     h->gp.natoms = (int)natoms;
     h->maxpairs_frame = maxpairs;
     const long long cap = maxpairs * h->F;
     if (cap >= (1LL << 32) - 2) return fail(MDSF_EINVAL, "pair capacity %lld overflows 32-bit offsets; lower batch_frames", cap);
-    const long long nkeys = (long long)h->F * g0.ntx * g0.nty;
+    const long long nkeys = (long long)h->F * g0.ntx * g0.nty * g0.nslab;
     if (nkeys >= (1LL << 31)) return fail(MDSF_EINVAL, "too many tiles per batch");
     h->sort_bits = 1;
     while ((1LL << h->sort_bits) <= nkeys) ++h->sort_bits;
 
-    // splat shared-memory budget -> pairs per chunk
-    h->xycap = xymax; h->zcap = zmax;
+    // splat shared-memory budget -> pairs per chunk; per-pair table stride 2^logS >= tx + ty + max 2Az
+    h->logS = 0;
+    while ((1 << h->logS) < g0.tx + g0.ty + zmax) ++h->logS;
     const size_t tile_b = (size_t)2 * g0.tx * g0.ty * g0.nzp * 8 + (h->native_fft ? (size_t)2 * g0.n[2] * 8 : 0);
     int chunk = 128;
-    auto smem_for = [&](int c) { return tile_b + (size_t)2 * c * (xymax + zmax) * 8 + (size_t)2 * c * sizeof(PairSlot) + 2 * 4 * MDSF_OWNERS * 4 + 2 * 16 * 4; };
-    const size_t soft = tile_b <= 70 * 1024 ? 110 * 1024 : kMaxSmem;    // two CTAs per SM when the tile allows
+    auto smem_for = [&](int c) { return tile_b + ((size_t)2 * c * 8 << h->logS) + (size_t)2 * c * sizeof(PairSlot) + 2 * 4 * 32 * 4 + 64; };
+    const size_t soft = tile_b <= 80 * 1024 ? 112 * 1024 : kMaxSmem;    // two CTAs per SM when the tile allows
     while (chunk > 32 && smem_for(chunk) > soft) chunk -= 32;
-    if (smem_for(chunk) > (size_t)kMaxSmem) {
-        chunk = 128;
-        while (chunk > 32 && smem_for(chunk) > (size_t)kMaxSmem) chunk -= 32;
-    }
     if (smem_for(chunk) > (size_t)kMaxSmem) return fail(MDSF_EINVAL, "splat tile does not fit shared memory (%zu bytes)", smem_for(chunk));
     h->chunk = chunk;
     h->splat_smem = smem_for(chunk);
@@ -406,6 +451,10 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     CU(cudaMemcpy(h->d_type, type_id, sizeof(int) * natoms, cudaMemcpyHostToDevice));
     for (int s = 0; s < kSlots; ++s) CU(cudaMalloc(&h->d_stage[s], h->csize * 3 * natoms * h->F));
     CU(cudaMalloc(&h->d_recs, sizeof(AtomRec) * natoms * h->F));
+    CU(cudaMalloc(&h->d_toff, sizeof(unsigned) * natoms));
+    CU(cudaMemcpy(h->d_toff, toff.data(), sizeof(unsigned) * natoms, cudaMemcpyHostToDevice));
+    h->tt.toff = h->d_toff;
+    CU(cudaMalloc(&h->d_tables, sizeof(double) * std::max(1LL, tstride * h->F)));
     CU(cudaMalloc(&h->d_cnt, sizeof(unsigned) * natoms * h->F));
     CU(cudaMalloc(&h->d_off, sizeof(unsigned) * natoms * h->F));
     for (int i = 0; i < 2; ++i) {
@@ -483,7 +532,7 @@ template <typename C, typename P>
 static void launch_prep(mdsf_handle* h, void* stage, const BatchScales& sc, int nf, long long wlo, long long whi) {
     const long long total = (long long)nf * h->natoms;
     prep_atoms_kernel<C, P><<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(
-        (C*)stage, h->d_type, h->d_recs, h->d_cnt, h->gp, h->tt, sc, nf, wlo, whi, h->d_err);
+        (C*)stage, h->d_type, h->d_recs, h->d_cnt, h->d_tables, h->gp, h->tt, sc, nf, wlo, whi, h->d_err);
 }
 
 static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, long long wlo, long long whi, int write_back) {
@@ -525,7 +574,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     const long long total = (long long)nf * h->natoms;
     const long long cap = h->maxpairs_frame * nf;
     // an odd batch gets a phantom last frame with empty lists (imaginary part of the last pair)
-    const unsigned nkeys = (unsigned)((nf + (nf & 1)) * gp.ntx * gp.nty);
+    const unsigned nkeys = (unsigned)((nf + (nf & 1)) * gp.ntx * gp.nty * gp.nslab);
     size_t cb = h->cub_bytes;
     cub::DeviceScan::ExclusiveSum(h->d_cub, cb, h->d_cnt, h->d_off, total, h->s_comp);
     fill_u32_kernel<<<grid_for(cap, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_keys[0], nkeys, cap);
@@ -543,10 +592,10 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     dim3 grid(gp.ntx * gp.nty, npairs);
     if (h->native_fft)
         splat_zfft_kernel<true><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
-                                                                        gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->chunk, h->xycap, h->zcap);
+                                                                        gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS);
     else
         splat_zfft_kernel<false><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
-                                                                         gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->chunk, h->xycap, h->zcap);
+                                                                         gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS);
     ++h->launches;
     CU(cudaGetLastError());
     int rc = transform_and_accumulate(h, nf, h->native_fft, tv);

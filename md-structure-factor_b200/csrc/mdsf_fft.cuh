@@ -166,11 +166,13 @@ __device__ __forceinline__ void fft_stage(double* __restrict__ sre, double* __re
     const int nbf = n / R;
     const int tws = n / L;
     const int items = nfft * nbf;
+    const bool p2 = ((M & (M - 1)) == 0) && ((nbf & (nbf - 1)) == 0);   // power-of-two stage: shifts, no divides
+    const int lM = __ffs(M) - 1, lnbf = __ffs(nbf) - 1;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        int f, bf;
-        if (ZPASS) { f = it / nbf; bf = it - f * nbf; }
+        int f, bf, b, n2;
+        if (ZPASS) { if (p2) { f = it >> lnbf; bf = it & (nbf - 1); } else { f = it / nbf; bf = it - f * nbf; } }
         else       { bf = it >> logw; f = it & (nfft - 1); }
-        const int b = bf / M, n2 = bf - b * M;
+        if (p2) { b = bf >> lM; n2 = bf & (M - 1); } else { b = bf / M; n2 = bf - b * M; }
         const int base = b * L + n2;
         double xr[R], xi[R];
         if (IN == IO_GLOBAL) {

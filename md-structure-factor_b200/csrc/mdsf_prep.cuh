@@ -13,12 +13,36 @@ template <typename P> __device__ __forceinline__ P add_rn(P a, P b);
 template <> __device__ __forceinline__ float  add_rn<float>(float a, float b)   { return __fadd_rn(a, b); }
 template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
 
+// (image, tile, slab) pairs of one atom: for every periodic image (sx,sy) of the stamp's xy
+// rectangle, every tile it overlaps, every z slab it touches.  emit_pairs_kernel walks the same loops.
+__device__ __forceinline__ unsigned count_pairs(const AtomRec& rec, const GridParams& gp, const TypeTable& tt) {
+    const int Ax = tt.halfw[rec.type * 3], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
+    unsigned total = 0;
+    for (int sx = -1; sx <= 1; ++sx) {
+        int xlo, xhi;
+        stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
+        if (xhi <= xlo) continue;
+        const int ntx = (xhi - 1 - sx * gp.n[0]) / gp.tx - (xlo - sx * gp.n[0]) / gp.tx + 1;
+        for (int sy = -1; sy <= 1; ++sy) {
+            int ylo, yhi;
+            stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
+            if (yhi <= ylo) continue;
+            const int nty = (yhi - 1 - sy * gp.n[1]) / gp.ty - (ylo - sy * gp.n[1]) / gp.ty + 1;
+            int shlo, shhi, kA, kB;
+            const unsigned sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
+            total += (unsigned)(ntx * nty * __popc(sm));
+        }
+    }
+    return total;
+}
+
 template <typename C, typename P>
 __global__ void __launch_bounds__(256)
 prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], rewritten in place
                   const int* __restrict__ type_id,   // [natoms]
                   AtomRec* __restrict__ recs,        // [nframes][natoms]
                   unsigned* __restrict__ pair_count, // [nframes*natoms]
+                  double* __restrict__ tables,       // [nframes][tstride] per-atom Gaussian factor tables
                   GridParams gp, TypeTable tt, BatchScales sc, int nframes,
                   long long wrap_lo, long long wrap_hi, int* __restrict__ err_flag)
 {
@@ -31,7 +55,6 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
         const int t = type_id[a];
         AtomRec rec;
         rec.type = t;
-        unsigned tiles[2] = {0u, 0u};
         bool bad = false;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -54,15 +77,41 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
             if (ir - A < -gp.nb || ir + A > gp.n[d] + gp.nb) bad = true;
             rec.r[d] = rd;
             rec.ir[d] = ir;
-            if (d < 2 && !bad) tiles[d] = stamp_tiles_1d(ir, A, gp.n[d], d == 0 ? gp.tx : gp.ty);
         }
         recs[idx] = rec;
-        if (bad) { atomicExch(err_flag, 1); pair_count[idx] = 0; }
-        else pair_count[idx] = tiles[0] * tiles[1];
+        if (bad) { atomicExch(err_flag, 1); pair_count[idx] = 0; continue; }
+        pair_count[idx] = count_pairs(rec, gp, tt);
+        if (!gp.separable) continue;
+        // One-dimensional Gaussian factors of this atom's stamp (dens.py:299-308 factorised):
+        //   exp(-|c|^2/(2s^2)) = EX[i] * EY[j] * C_type[i][j] * EZ[k]/amp, with
+        //   EX[i] = exp(-(cxx bx_i^2 + 2 gxy bx_i by_0)/(2s^2)),  EY[j] = exp(-(cyy by_j^2 - 2 gxy (j dy) bx_0)/(2s^2)),
+        //   EZ[k] = Nel/s^3 exp(-czz bz_k^2/(2s^2)),  C[i][j] = exp(-2 gxy dx dy i j/(2s^2)) (per type, host-built).
+        // b = r - (i - B)*dr with the product rounded on its own, as numpy does (dens.py:252-256,299).
+        {
+            const int Ax = tt.halfw[t * 3], Ay = tt.halfw[t * 3 + 1], Az = tt.halfw[t * 3 + 2];
+            const double t2 = tt.two_sig2[t], amp = tt.amp[t];
+            double* T = tables + (long long)f * gp.tstride + tt.toff[a];
+            const double bx0 = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax), gp.dr[0]));
+            const double by0 = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay), gp.dr[1]));
+            for (int i = 0; i < 2 * Ax; ++i) {
+                const double b = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax + i), gp.dr[0]));
+                T[i] = exp(-(gp.cxx * b * b + 2.0 * gp.gxy * b * by0) / t2);
+            }
+            T += 2 * Ax;
+            for (int j = 0; j < 2 * Ay; ++j) {
+                const double b = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay + j), gp.dr[1]));
+                T[j] = exp(-(gp.cyy * b * b - 2.0 * gp.gxy * ((double)j * gp.dr[1]) * bx0) / t2);
+            }
+            T += 2 * Ay;
+            for (int k = 0; k < 2 * Az; ++k) {
+                const double b = __dsub_rn(rec.r[2], __dmul_rn((double)(rec.ir[2] - Az + k), gp.dr[2]));
+                T[k] = amp * exp(-(gp.czz * b * b) / t2);
+            }
+        }
     }
 }
 
-// ---- K2a: emit (key = frame*ntiles + tile, payload = atom | sx | sy) at scanned offsets ------
+// ---- K2a: emit (key = (frame*ntiles + tile)*nslab + slab, payload = atom | sx | sy) at scanned offsets
 __global__ void __launch_bounds__(256)
 emit_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ pair_count,
                   const unsigned* __restrict__ pair_off, unsigned* __restrict__ keys,
@@ -76,7 +125,7 @@ emit_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         const int f = (int)(idx / gp.natoms);
         const int a = (int)(idx - (long long)f * gp.natoms);
         const AtomRec rec = recs[idx];
-        const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1];
+        const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
         unsigned o = pair_off[idx];
         for (int sx = -1; sx <= 1; ++sx) {
             int xlo, xhi;
@@ -90,11 +139,16 @@ emit_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 const int ty0 = (ylo - sy * gp.n[1]) / gp.ty, ty1 = (yhi - 1 - sy * gp.n[1]) / gp.ty;
                 const unsigned payload = (unsigned)a | ((unsigned)(sx + 1) << MDSF_ATOM_BITS) |
                                          ((unsigned)(sy + 1) << (MDSF_ATOM_BITS + 2));
+                int shlo, shhi, kA, kB;
+                const unsigned sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
                 for (int tX = tx0; tX <= tx1; ++tX)
                     for (int tY = ty0; tY <= ty1; ++tY) {
-                        keys[o] = (unsigned)(f * ntiles + tX * gp.nty + tY);
-                        vals[o] = payload;
-                        ++o;
+                        const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
+                        for (unsigned m = sm; m; m &= m - 1) {
+                            keys[o] = kbase + (unsigned)(__ffs(m) - 1);
+                            vals[o] = payload;
+                            ++o;
+                        }
                     }
             }
         }

@@ -24,13 +24,15 @@
 #define MDSF_OWNERS 128            // owner threads per part = columns * slabs
 
 struct PairSlot {
-    double rx, ry, rz;     // atom coordinate (float64 value of the coords dtype)
+    double rx, ry, rz;     // atom coordinate (general-ucell path only)
     int px0, py0, pz0;     // padded-grid index of the first clipped column / first z cell
     int type;
     unsigned rect;         // cx0 | w << 8 | cy0 << 16 | h << 24   (tile-relative clip rectangle)
     short nz, kA, kB, pad0;// 2*Az; k < kA: low padding, kA <= k < kB: cell, k >= kB: high padding
     int shlo, shhi;        // destination z = pz0 + k + shlo (low padding) / + shhi (high padding)
-    int offxy, offz;       // table offsets
+    unsigned tbase;        // offset of the atom's factor tables (frame block included, in doubles / 1)
+    short i0, j0;          // stamp index of the first clipped column (for the cross-term table)
+    short twoAx, twoAy;
 };
 
 __device__ __forceinline__ void part_barrier(int part) {
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(256, MDSF_SPLAT_MINBLOCKS)
 splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ vals,
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
                   double2* __restrict__ dens_dump, GridParams gp, TypeTable tt, FftPlan zplan,
-                  const double2* __restrict__ twz, int chunk, int xycap, int zcap)
+                  const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS)
 {
     extern __shared__ double smem[];
     const int ncol = gp.tx * gp.ty;
@@ -59,41 +61,41 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     double* twr = tile_im + (size_t)ncol * nzp;               // [nz] z twiddles (fused FFT only)
     double* twi = twr + (FUSE_ZFFT ? nz : 0);
     double* tables = twi + (FUSE_ZFFT ? nz : 0);
-    const size_t tbl_per_part = (size_t)chunk * (xycap + zcap);
-    double* tblxy = tables + part * tbl_per_part;             // [chunk*xycap]
-    double* tblz = tblxy + (size_t)chunk * xycap;             // [chunk*zcap]
+    const size_t tbl_per_part = (size_t)chunk << logS;        // per pair: [EX: tx][EY: ty][EZ: 2Az] in a 2^logS stride
+    double* tbl = tables + part * tbl_per_part;
     PairSlot* slots_all = reinterpret_cast<PairSlot*>(tables + 2 * tbl_per_part);
     unsigned* hit_all = reinterpret_cast<unsigned*>(slots_all + 2 * chunk);
-    int* scan_all = reinterpret_cast<int*>(hit_all + 2 * 4 * MDSF_OWNERS);
     PairSlot* slots = slots_all + part * chunk;               // [chunk]
-    unsigned* hitT = hit_all + part * 4 * MDSF_OWNERS;        // [4 warps of pairs][owner]
-    int* scan_tmp = scan_all + part * 16;                     // warp totals + chunk totals
+    unsigned* hitT = hit_all + part * 4 * 32;                 // [4 warps of pairs][column]
 
     double* mytile = part ? tile_im : tile_re;
-    for (int i = threadIdx.x; i < 2 * ncol * nzp; i += blockDim.x) tile_re[i] = 0.0;
+    {
+        double2* z2 = reinterpret_cast<double2*>(tile_re);
+        for (int i = threadIdx.x; i < ncol * nzp; i += blockDim.x) z2[i] = make_double2(0.0, 0.0);
+    }
     if (FUSE_ZFFT) load_twiddles(twr, twi, twz, nz);
     __syncthreads();
 
     const int f = 2 * q + part;
-    const unsigned lbeg = tile_start[f * ntiles + tile], lend = tile_start[f * ntiles + tile + 1];
-
-    // ---- ownership: owner o = slab * ncol + column; slab s covers z in [s*zs, (s+1)*zs)
-    const int nslab = MDSF_OWNERS / ncol;
-    const int zs = (nz + nslab - 1) / nslab;
+    // ---- ownership: owner o = slab * ncol + column; slab s covers z in [s*zs, (s+1)*zs).
+    // The tile's pair list is sorted by slab (K2), so an owner's hits are the pairs of ITS slab
+    // sub-list that cover its column -- no filtering, every loop iteration does real work.
+    const int nslab = gp.nslab, zs = gp.zs;
     const int mycol = pt % ncol, myslab = pt / ncol;
+    const unsigned kbase = (unsigned)(f * ntiles + tile) * (unsigned)nslab;
+    const unsigned lbeg = tile_start[kbase], lend = tile_start[kbase + nslab];
+    const unsigned sbeg = tile_start[kbase + myslab], send = tile_start[kbase + myslab + 1];
     const int mycx = mycol / gp.ty, mycy = mycol % gp.ty;
     const int zlo = myslab * zs, zhi = min(zlo + zs, nz);
     const bool owner_valid = X0 + mycx < gp.n[0] && Y0 + mycy < gp.n[1] && zlo < zhi;
     double* col = mytile + (size_t)mycol * nzp;
-    const int colbits = ncol;                                  // owner words: 32/ncol slabs per 32-bit word
-    const int slabs_per_word = 32 / colbits;
 
-    for (unsigned cb = lbeg; cb < lend; cb += chunk) {
+    for (unsigned cb = lbeg; cb < ((gp.debug_skip & 16) ? lbeg : lend); cb += chunk) {
         const int npair = (int)min((unsigned)chunk, lend - cb);
         // ---------------- A0: clip one pair per thread
-        unsigned colmask = 0, slabmask = 0; int nxy = 0, nzc = 0;
-        PairSlot s;
+        unsigned colmask = 0;
         if (pt < npair) {
+            PairSlot s;
             const unsigned v = vals[cb + pt];
             const int a = (int)(v & (MDSF_MAX_ATOMS - 1));
             const int sx = (int)((v >> MDSF_ATOM_BITS) & 3u) - 1, sy = (int)((v >> (MDSF_ATOM_BITS + 2)) & 3u) - 1;
@@ -112,107 +114,65 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             s.pz0 = rec.ir[2] - Az;
             s.type = rec.type;
             s.rect = (unsigned)cx0 | ((unsigned)w << 8) | ((unsigned)cy0 << 16) | ((unsigned)h << 24);
-            const int nzr = 2 * Az;
-            const int kA = min(max(-s.pz0, 0), nzr), kB = min(max(nz - s.pz0, 0), nzr);
-            s.nz = (short)nzr; s.kA = (short)kA; s.kB = (short)kB; s.pad0 = 0;
-            // fold (dens.py:95-107): padding cells move by -+N_z, except in the 8 corner regions
-            // whose z block is chosen by the y side: there the shift is +-Nborder when sy != sz
-            const bool corner = (sx != 0 && sy != 0 && gp.fold_mode == 0);
-            s.shlo = (corner && sy != -1) ? gp.nb : nz;
-            s.shhi = (corner && sy != 1) ? -gp.nb : -nz;
-            nxy = w * h; nzc = (nxy > 0) ? nzr : 0;
-            if (nxy > 0) {
+            int kA, kB;
+            (void)image_slabmask(rec.ir[2], Az, sx, sy, nz, gp.nb, gp.fold_mode, zs, s.shlo, s.shhi, kA, kB);
+            s.nz = (short)(2 * Az); s.kA = (short)kA; s.kB = (short)kB; s.pad0 = 0;
+            s.tbase = (unsigned)((long long)f * gp.tstride + tt.toff[a]);
+            s.i0 = (short)(s.px0 - (rec.ir[0] - Ax)); s.j0 = (short)(s.py0 - (rec.ir[1] - Ay));
+            s.twoAx = (short)(2 * Ax); s.twoAy = (short)(2 * Ay);
+            if (w * h > 0)
                 for (int cx = cx0; cx < cx0 + w; ++cx)
                     colmask |= (((h >= 32) ? 0xffffffffu : ((1u << h) - 1u)) << (cx * gp.ty + cy0));
-                if (kA > 0) { const int a0 = s.pz0 + s.shlo, a1 = s.pz0 + kA - 1 + s.shlo;
-                              for (int sl = a0 / zs; sl <= a1 / zs; ++sl) slabmask |= 1u << sl; }
-                if (kB > kA) { const int a0 = s.pz0 + kA, a1 = s.pz0 + kB - 1;
-                               for (int sl = a0 / zs; sl <= a1 / zs; ++sl) slabmask |= 1u << sl; }
-                if (nzr > kB) { const int a0 = s.pz0 + kB + s.shhi, a1 = s.pz0 + nzr - 1 + s.shhi;
-                                for (int sl = a0 / zs; sl <= a1 / zs; ++sl) slabmask |= 1u << sl; }
-            }
-        }
-        // per-part exclusive scan of (nxy, nzc) over the 128 threads
-        int ixy = nxy, iz = nzc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t1 = __shfl_up_sync(0xffffffffu, ixy, d), t2 = __shfl_up_sync(0xffffffffu, iz, d);
-            if (lane >= d) { ixy += t1; iz += t2; }
-        }
-        if (lane == 31) { scan_tmp[pw * 2] = ixy; scan_tmp[pw * 2 + 1] = iz; }
-        // ballot transpose of the 32 x 128 (pair x owner) hit matrix of this warp:
-        // hitT[warp][o] = pairs (bit = lane) that touch owner o, list order = bit order
-        for (int word = 0; word < MDSF_OWNERS / 32; ++word) {
-            unsigned ow = 0;                                   // this pair's hits on owners [32*word, 32*word+32)
-            for (int j = 0; j < slabs_per_word; ++j)
-                if ((slabmask >> (word * slabs_per_word + j)) & 1u) ow |= colmask << (j * colbits);
-            unsigned mine = 0;
-#pragma unroll 8
-            for (int c = 0; c < 32; ++c) {
-                const unsigned b = __ballot_sync(0xffffffffu, (ow >> c) & 1u);
-                if (lane == c) mine = b;
-            }
-            hitT[pw * MDSF_OWNERS + word * 32 + lane] = mine;
-        }
-        part_barrier(part);
-        int bxy = 0, bz = 0;
-        for (int wv = 0; wv < pw; ++wv) { bxy += scan_tmp[wv * 2]; bz += scan_tmp[wv * 2 + 1]; }
-        if (pt < npair) {
-            s.offxy = bxy + ixy - nxy; s.offz = bz + iz - nzc;
             slots[pt] = s;
         }
-        if (pt == 127) { scan_tmp[8] = bxy + ixy; scan_tmp[9] = bz + iz; }
+        // ballot transpose of the 32 x ncol (pair x column) hit matrix of this warp:
+        // hitT[warp][c] = pairs (bit = lane) whose image covers column c; bit order = list order
+        {
+            unsigned mine = 0;
+            for (int c = 0; c < ncol; ++c) {
+                const unsigned b = __ballot_sync(0xffffffffu, (colmask >> c) & 1u);
+                if (lane == c) mine = b;
+            }
+            hitT[pw * 32 + lane] = mine;
+        }
         part_barrier(part);
-        const int totxy = scan_tmp[8], totz = scan_tmp[9];
 
-        // ---------------- A1: dense evaluation of the Gaussian factor tables
-        if (gp.separable) {
-            for (int e = pt; e < totxy + totz; e += 128) {
-                const bool isz = e >= totxy;
-                const int ee = isz ? e - totxy : e;
-                int lo = 0, hi = npair - 1;       // last slot whose offset <= ee
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    const int o = isz ? slots[mid].offz : slots[mid].offxy;
-                    if (o <= ee) lo = mid; else hi = mid - 1;
-                }
-                const PairSlot& p = slots[lo];
-                const double t2 = tt.two_sig2[p.type];
-                if (!isz) {
-                    const int hh = (int)(p.rect >> 24);
-                    const int li = ee - p.offxy;
-                    const int lx = li / hh, ly = li - lx * hh;
-                    // b = r - (i - B)*dr with the product rounded on its own (dens.py:252-256,299)
-                    const double bx = __dsub_rn(p.rx, __dmul_rn((double)(p.px0 + lx), gp.dr[0]));
-                    const double by = __dsub_rn(p.ry, __dmul_rn((double)(p.py0 + ly), gp.dr[1]));
-                    const double c0 = gp.u[0] * bx + gp.u[3] * by;     // sum_m ucell[m][0] b_m (dens.py:301)
-                    const double c1 = gp.u[1] * bx + gp.u[4] * by;
-                    tblxy[ee] = exp(-(c0 * c0 + c1 * c1) / t2);
-                } else {
-                    const int k = ee - p.offz;
-                    const double bzv = __dsub_rn(p.rz, __dmul_rn((double)(p.pz0 + k), gp.dr[2]));
-                    const double c2 = gp.u[8] * bzv;
-                    tblz[ee] = tt.amp[p.type] * exp(-(c2 * c2) / t2);
-                }
+        // ---------------- A1: stage the pairs' factor tables (built per atom by K1) in shared memory
+        if (gp.separable && !(gp.debug_skip & 4)) {
+            const int S = 1 << logS;
+            for (int e = pt; e < (npair << logS); e += 128) {
+                const int i = e >> logS, sub = e & (S - 1);
+                const PairSlot& p = slots[i];
+                const int w = (int)((p.rect >> 8) & 0xff), hh = (int)(p.rect >> 24);
+                int src = -1;
+                if (sub < gp.tx) { if (sub < w) src = p.i0 + sub; }
+                else if (sub < gp.tx + gp.ty) { if (sub - gp.tx < hh) src = p.twoAx + p.j0 + (sub - gp.tx); }
+                else if (sub - gp.tx - gp.ty < p.nz) src = p.twoAx + p.twoAy + (sub - gp.tx - gp.ty);
+                if (src >= 0) tbl[e] = atom_tables[(size_t)p.tbase + src];
             }
             part_barrier(part);
         }
 
         // ---------------- B: every owner adds its hits, in list order, into cells only it writes
-        if (owner_valid) {
+        if (owner_valid && !(gp.debug_skip & 1)) {
             const int nwarp_used = (npair + 31) >> 5;
             for (int wv = 0; wv < nwarp_used; ++wv) {
-                unsigned m = hitT[wv * MDSF_OWNERS + pt];
+                // pairs [lo, hi) of this warp-of-pairs belong to my slab
+                const int lo = max((int)(sbeg - cb) - wv * 32, 0), hi = min((int)(send - cb) - wv * 32, 32);
+                if (hi <= lo) continue;
+                unsigned m = hitT[wv * 32 + mycol] & (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
                 while (m) {
                     const int i = wv * 32 + __ffs(m) - 1;
                     m &= m - 1;
                     const PairSlot& p = slots[i];
-                    const int cx0 = (int)(p.rect & 0xff), cy0 = (int)((p.rect >> 16) & 0xff), hh = (int)(p.rect >> 24);
+                    const int cx0 = (int)(p.rect & 0xff), cy0 = (int)((p.rect >> 16) & 0xff);
                     const int lx = mycx - cx0, ly = mycy - cy0;
                     const int pz0 = p.pz0, kA = p.kA, kB = p.kB, nzr = p.nz;
                     if (gp.separable) {
-                        const double exy = tblxy[p.offxy + lx * hh + ly];
-                        const double* ez = tblz + p.offz;
+                        const double* T = tbl + ((size_t)i << logS);
+                        double exy = T[lx] * T[gp.tx + ly];
+                        if (tt.ctab != nullptr) exy *= tt.ctab[tt.ctab_off[p.type] + (p.i0 + lx) * p.twoAy + (p.j0 + ly)];
+                        const double* ez = T + gp.tx + gp.ty;
                         {   // cell
                             const int ka = max(kA, zlo - pz0), kb = min(kB, zhi - pz0);
                             for (int k = ka; k < kb; ++k) { const int cz = pz0 + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k]; }
@@ -262,9 +222,10 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             }
         }
     }
-    if (FUSE_ZFFT) fft_tile_z(tile_re, tile_im, twr, twi, zplan, ncol, nzp, gp.pad_shift);
-    for (int c = 0; c < ncol; ++c) {
-        const int x = X0 + c / gp.ty, y = Y0 + c % gp.ty;
+    if (FUSE_ZFFT && !(gp.debug_skip & 2)) fft_tile_z(tile_re, tile_im, twr, twi, zplan, ncol, nzp, gp.pad_shift);
+    const int lty = __ffs(gp.ty) - 1;                     // tx, ty are powers of two
+    for (int c = 0; c < ((gp.debug_skip & 8) ? 0 : ncol); ++c) {
+        const int x = X0 + (c >> lty), y = Y0 + (c & (gp.ty - 1));
         if (x < gp.n[0] && y < gp.n[1]) {
             double2* dst = vol + (((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz;
             for (int z = threadIdx.x; z < nz; z += blockDim.x) {
