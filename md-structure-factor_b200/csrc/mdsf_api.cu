@@ -183,6 +183,9 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     }
     if (cfg->ntypes < 1 || !cfg->amp || !cfg->two_sig2 || !cfg->halfw) return fail(MDSF_EINVAL, "type tables missing");
     if (cfg->nborder < 0) return fail(MDSF_EINVAL, "negative Nborder");
+    if (cfg->ntypes > 2048) return fail(MDSF_EINVAL, "more than 2048 distinct labels");
+    for (int t = 0; t < cfg->ntypes * 3; ++t)
+        if (2 * cfg->halfw[t] > MDSF_MAX_STAMP) return fail(MDSF_EINVAL, "stamp of %d cells exceeds %d", 2 * cfg->halfw[t], MDSF_MAX_STAMP);
     for (int t = 0; t < cfg->ntypes * 3; ++t)
         if (cfg->halfw[t] < 0 || cfg->halfw[t] > cfg->nborder) return fail(MDSF_EINVAL, "half width %d outside [0, Nborder=%d]", cfg->halfw[t], cfg->nborder);
     if (cfg->coord_dtype != MDSF_F32 && cfg->coord_dtype != MDSF_F64) return fail(MDSF_EINVAL, "bad coord_dtype");
@@ -440,7 +443,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     while ((1 << h->logS) < g0.tx + g0.ty + zmax) ++h->logS;
     const size_t tile_b = (size_t)2 * g0.tx * g0.ty * g0.nzp * 8 + (h->native_fft ? (size_t)2 * g0.n[2] * 8 : 0);
     int chunk = 128;
-    auto smem_for = [&](int c) { return tile_b + ((size_t)2 * c * 8 << h->logS) + (size_t)2 * c * sizeof(PairSlot) + 2 * 4 * 32 * 4 + 64; };
+    auto smem_for = [&](int c) { return tile_b + ((size_t)2 * c * 8 << h->logS) + (size_t)2 * c * (sizeof(PairInfo) + 24) + 2 * 4 * 32 * 4 + 64; };
     const size_t soft = tile_b <= 80 * 1024 ? 112 * 1024 : kMaxSmem;    // two CTAs per SM when the tile allows
     while (chunk > 32 && smem_for(chunk) > soft) chunk -= 32;
     if (smem_for(chunk) > (size_t)kMaxSmem) return fail(MDSF_EINVAL, "splat tile does not fit shared memory (%zu bytes)", smem_for(chunk));

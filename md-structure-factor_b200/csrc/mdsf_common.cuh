@@ -45,6 +45,8 @@ struct AtomRec {
     double r[3];   // coordinate as float64 (value of the coords-dtype number)
     int ir[3];     // trunc(r/dr)  (dens.py:285)
     int type;
+    unsigned tbase;   // offset of this atom's factor tables (frame block included), in doubles
+    unsigned pad_;
 };
 
 struct BatchScales {

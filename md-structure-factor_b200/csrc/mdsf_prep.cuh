@@ -55,6 +55,8 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
         const int t = type_id[a];
         AtomRec rec;
         rec.type = t;
+        rec.tbase = (unsigned)((long long)f * gp.tstride + tt.toff[a]);
+        rec.pad_ = 0;
         bool bad = false;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -90,7 +92,7 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
         {
             const int Ax = tt.halfw[t * 3], Ay = tt.halfw[t * 3 + 1], Az = tt.halfw[t * 3 + 2];
             const double t2 = tt.two_sig2[t], amp = tt.amp[t];
-            double* T = tables + (long long)f * gp.tstride + tt.toff[a];
+            double* T = tables + rec.tbase;
             const double bx0 = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax), gp.dr[0]));
             const double by0 = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay), gp.dr[1]));
             for (int i = 0; i < 2 * Ax; ++i) {

@@ -5,14 +5,15 @@
 // frame 2q+1 -> imaginary part; threads 0..127 serve the real part, 128..255 the imaginary
 // part).  Every thread OWNS the cells of one column inside one z slab; nobody else ever writes
 // them, so the accumulation needs no atomics and no barriers, and its order is the order of the
-// sorted pair list: the density is bitwise reproducible.  The list (K2) is consumed in chunks:
-//   A0  one thread per pair: clip the atom image against the tile, work out which owners
-//       (column x slab) it touches; a ballot transpose turns the per-pair owner masks into
-//       per-owner hit lists that keep list order;
-//   A1  the Gaussian factors are evaluated densely, one table entry per thread:
-//       exy[pair][column] = exp(-(c0^2+c1^2)/(2 sigma^2)),  ez[pair][k] = Nel/sigma^3 exp(-c2^2/(2 sigma^2));
-//   B   every owner walks ITS hits and adds exy*ez[k] into its cells.  The periodic fold (incl.
-//       the corner rule of dens.py:107) is an index shift per z segment; no padded array exists.
+// sorted pair list: the density is bitwise reproducible.  The tile's list (K2, sorted by slab) is
+// consumed in chunks:
+//   A  one thread per pair: clip the atom image against the tile, fetch the slice of the atom's
+//      one-dimensional Gaussian factor tables (built once per atom by K1) that the tile needs into
+//      shared memory, publish 16 bytes of geometry; a ballot transpose turns the per-pair column
+//      masks into per-column hit lists that keep list order;
+//   B  every owner walks the hits of ITS slab sub-list that cover ITS column and adds
+//      EX[i]*EY[j]*C[i][j]*EZ[k] into its cells.  The periodic fold (incl. the corner rule of
+//      dens.py:107) is an index shift per z segment; no padded array exists.
 // Afterwards the tile is transformed along z in place (native FFT path) and stored.
 #pragma once
 #include "mdsf_common.cuh"
@@ -22,18 +23,14 @@
 #define MDSF_SPLAT_MINBLOCKS 2
 #endif
 #define MDSF_OWNERS 128            // owner threads per part = columns * slabs
+#define MDSF_MAX_STAMP 1023        // 2*A must fit 10 bits of the packed pair info
 
-struct PairSlot {
-    double rx, ry, rz;     // atom coordinate (general-ucell path only)
-    int px0, py0, pz0;     // padded-grid index of the first clipped column / first z cell
-    int type;
-    unsigned rect;         // cx0 | w << 8 | cy0 << 16 | h << 24   (tile-relative clip rectangle)
-    short nz, kA, kB, pad0;// 2*Az; k < kA: low padding, kA <= k < kB: cell, k >= kB: high padding
-    int shlo, shhi;        // destination z = pz0 + k + shlo (low padding) / + shhi (high padding)
-    unsigned tbase;        // offset of the atom's factor tables (frame block included, in doubles / 1)
-    short i0, j0;          // stamp index of the first clipped column (for the cross-term table)
-    short twoAx, twoAy;
-};
+// what phase B needs to know about a pair, one 16-byte shared-memory load
+//   x: cx0 | w << 8 | cy0 << 16 | h << 24          tile-relative clip rectangle
+//   y: pz0                                          padded-grid index of the first z cell
+//   z: kA | kB << 10 | nz << 20 | lowB << 30 | highB << 31   z segments; *B: shift is Nborder, not N_z
+//   w: i0 | j0 << 10 | type << 20                   stamp index of the first clipped column (cross-term table)
+typedef int4 PairInfo;
 
 __device__ __forceinline__ void part_barrier(int part) {
     asm volatile("bar.sync %0, %1;" ::"r"(part + 1), "r"(128) : "memory");
@@ -54,6 +51,16 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     const int X0 = (tile / gp.nty) * gp.tx, Y0 = (tile % gp.nty) * gp.ty;
     const int part = threadIdx.x >> 7, pt = threadIdx.x & 127, lane = threadIdx.x & 31, pw = pt >> 5;
     const int nz = gp.n[2];
+    const int f = 2 * q + part;
+
+    // ---- ownership: owner o = slab * ncol + column; slab s covers z in [s*zs, (s+1)*zs).
+    // The tile's pair list is sorted by slab (K2), so an owner's hits are the pairs of ITS slab
+    // sub-list that cover its column -- no filtering, every loop iteration does real work.
+    const int nslab = gp.nslab, zs = gp.zs;
+    const int mycol = pt % ncol, myslab = pt / ncol;
+    const unsigned kbase = (unsigned)(f * ntiles + tile) * (unsigned)nslab;
+    const unsigned lbeg = tile_start[kbase], lend = (gp.debug_skip & 16) ? lbeg : tile_start[kbase + nslab];
+    const unsigned sbeg = tile_start[kbase + myslab], send = tile_start[kbase + myslab + 1];
 
     // ---- shared memory carve-up
     double* tile_re = smem;                                   // [ncol][nzp]  frame 2q
@@ -63,10 +70,10 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     double* tables = twi + (FUSE_ZFFT ? nz : 0);
     const size_t tbl_per_part = (size_t)chunk << logS;        // per pair: [EX: tx][EY: ty][EZ: 2Az] in a 2^logS stride
     double* tbl = tables + part * tbl_per_part;
-    PairSlot* slots_all = reinterpret_cast<PairSlot*>(tables + 2 * tbl_per_part);
-    unsigned* hit_all = reinterpret_cast<unsigned*>(slots_all + 2 * chunk);
-    PairSlot* slots = slots_all + part * chunk;               // [chunk]
-    unsigned* hitT = hit_all + part * 4 * 32;                 // [4 warps of pairs][column]
+    double* rxyz = tables + 2 * tbl_per_part + (size_t)part * chunk * 3;     // general-ucell path only
+    PairInfo* info_all = reinterpret_cast<PairInfo*>(tables + 2 * tbl_per_part + (size_t)2 * chunk * 3);
+    PairInfo* info = info_all + part * chunk;
+    unsigned* hitT = reinterpret_cast<unsigned*>(info_all + 2 * chunk) + part * 4 * 32;   // [4 warps of pairs][column]
 
     double* mytile = part ? tile_im : tile_re;
     {
@@ -76,26 +83,18 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     if (FUSE_ZFFT) load_twiddles(twr, twi, twz, nz);
     __syncthreads();
 
-    const int f = 2 * q + part;
-    // ---- ownership: owner o = slab * ncol + column; slab s covers z in [s*zs, (s+1)*zs).
-    // The tile's pair list is sorted by slab (K2), so an owner's hits are the pairs of ITS slab
-    // sub-list that cover its column -- no filtering, every loop iteration does real work.
-    const int nslab = gp.nslab, zs = gp.zs;
-    const int mycol = pt % ncol, myslab = pt / ncol;
-    const unsigned kbase = (unsigned)(f * ntiles + tile) * (unsigned)nslab;
-    const unsigned lbeg = tile_start[kbase], lend = tile_start[kbase + nslab];
-    const unsigned sbeg = tile_start[kbase + myslab], send = tile_start[kbase + myslab + 1];
-    const int mycx = mycol / gp.ty, mycy = mycol % gp.ty;
+    const int lty = __ffs(gp.ty) - 1;                         // tx, ty are powers of two
+    const int mycx = mycol >> lty, mycy = mycol & (gp.ty - 1);
     const int zlo = myslab * zs, zhi = min(zlo + zs, nz);
     const bool owner_valid = X0 + mycx < gp.n[0] && Y0 + mycy < gp.n[1] && zlo < zhi;
     double* col = mytile + (size_t)mycol * nzp;
+    const int S = 1 << logS;
 
-    for (unsigned cb = lbeg; cb < ((gp.debug_skip & 16) ? lbeg : lend); cb += chunk) {
+    for (unsigned cb = lbeg; cb < lend; cb += chunk) {
         const int npair = (int)min((unsigned)chunk, lend - cb);
-        // ---------------- A0: clip one pair per thread
+        // ---------------- A: one pair per thread
         unsigned colmask = 0;
         if (pt < npair) {
-            PairSlot s;
             const unsigned v = vals[cb + pt];
             const int a = (int)(v & (MDSF_MAX_ATOMS - 1));
             const int sx = (int)((v >> MDSF_ATOM_BITS) & 3u) - 1, sy = (int)((v >> (MDSF_ATOM_BITS + 2)) & 3u) - 1;
@@ -108,22 +107,46 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             const int cx0 = max(xlo - sx * gp.n[0] - X0, 0), cx1 = min(xhi - sx * gp.n[0] - X0, gp.tx);
             const int cy0 = max(ylo - sy * gp.n[1] - Y0, 0), cy1 = min(yhi - sy * gp.n[1] - Y0, gp.ty);
             const int w = max(cx1 - cx0, 0), h = max(cy1 - cy0, 0);
-            s.rx = rec.r[0]; s.ry = rec.r[1]; s.rz = rec.r[2];
-            s.px0 = X0 + cx0 + sx * gp.n[0];
-            s.py0 = Y0 + cy0 + sy * gp.n[1];
-            s.pz0 = rec.ir[2] - Az;
-            s.type = rec.type;
-            s.rect = (unsigned)cx0 | ((unsigned)w << 8) | ((unsigned)cy0 << 16) | ((unsigned)h << 24);
-            int kA, kB;
-            (void)image_slabmask(rec.ir[2], Az, sx, sy, nz, gp.nb, gp.fold_mode, zs, s.shlo, s.shhi, kA, kB);
-            s.nz = (short)(2 * Az); s.kA = (short)kA; s.kB = (short)kB; s.pad0 = 0;
-            s.tbase = (unsigned)((long long)f * gp.tstride + tt.toff[a]);
-            s.i0 = (short)(s.px0 - (rec.ir[0] - Ax)); s.j0 = (short)(s.py0 - (rec.ir[1] - Ay));
-            s.twoAx = (short)(2 * Ax); s.twoAy = (short)(2 * Ay);
+            const int i0 = X0 + cx0 + sx * gp.n[0] - (rec.ir[0] - Ax);       // stamp index of the first clipped column
+            const int j0 = Y0 + cy0 + sy * gp.n[1] - (rec.ir[1] - Ay);
+            int shlo, shhi, kA, kB;
+            (void)image_slabmask(rec.ir[2], Az, sx, sy, nz, gp.nb, gp.fold_mode, zs, shlo, shhi, kA, kB);
+            PairInfo pi;
+            pi.x = cx0 | (w << 8) | (cy0 << 16) | (h << 24);
+            pi.y = rec.ir[2] - Az;
+            pi.z = kA | (kB << 10) | ((2 * Az) << 20) | ((shlo != nz) ? (1 << 30) : 0) | ((shhi != -nz) ? (int)(1u << 31) : 0);
+            pi.w = i0 | (j0 << 10) | (rec.type << 20);
+            info[pt] = pi;
             if (w * h > 0)
                 for (int cx = cx0; cx < cx0 + w; ++cx)
                     colmask |= (((h >= 32) ? 0xffffffffu : ((1u << h) - 1u)) << (cx * gp.ty + cy0));
-            slots[pt] = s;
+            if (gp.separable) {
+                // slice of the atom's factor tables this tile needs: EX[i0..i0+w), EY[j0..j0+h), EZ[0..2Az)
+                if (!(gp.debug_skip & 4)) {
+                    const double* T = atom_tables + rec.tbase;
+                    double* dst = tbl + ((size_t)pt << logS);
+                    if (S <= 16) {              // issue every load before the first store
+                        double vv[16];
+#pragma unroll
+                        for (int sidx = 0; sidx < 16; ++sidx) {
+                            int src = -1;
+                            if (sidx < gp.tx) { if (sidx < w) src = i0 + sidx; }
+                            else if (sidx < gp.tx + gp.ty) { if (sidx - gp.tx < h) src = 2 * Ax + j0 + (sidx - gp.tx); }
+                            else if (sidx - gp.tx - gp.ty < 2 * Az) src = 2 * (Ax + Ay) + (sidx - gp.tx - gp.ty);
+                            vv[sidx] = (src >= 0 && sidx < S) ? T[src] : 0.0;
+                        }
+#pragma unroll
+                        for (int sidx = 0; sidx < 16; ++sidx) if (sidx < S) dst[sidx] = vv[sidx];
+                    } else {
+                        for (int sidx = 0; sidx < w; ++sidx) dst[sidx] = T[i0 + sidx];
+                        for (int sidx = 0; sidx < h; ++sidx) dst[gp.tx + sidx] = T[2 * Ax + j0 + sidx];
+#pragma unroll 4
+                        for (int sidx = 0; sidx < 2 * Az; ++sidx) dst[gp.tx + gp.ty + sidx] = T[2 * (Ax + Ay) + sidx];
+                    }
+                }
+            } else {
+                rxyz[pt * 3] = rec.r[0]; rxyz[pt * 3 + 1] = rec.r[1]; rxyz[pt * 3 + 2] = rec.r[2];
+            }
         }
         // ballot transpose of the 32 x ncol (pair x column) hit matrix of this warp:
         // hitT[warp][c] = pairs (bit = lane) whose image covers column c; bit order = list order
@@ -137,22 +160,6 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         }
         part_barrier(part);
 
-        // ---------------- A1: stage the pairs' factor tables (built per atom by K1) in shared memory
-        if (gp.separable && !(gp.debug_skip & 4)) {
-            const int S = 1 << logS;
-            for (int e = pt; e < (npair << logS); e += 128) {
-                const int i = e >> logS, sub = e & (S - 1);
-                const PairSlot& p = slots[i];
-                const int w = (int)((p.rect >> 8) & 0xff), hh = (int)(p.rect >> 24);
-                int src = -1;
-                if (sub < gp.tx) { if (sub < w) src = p.i0 + sub; }
-                else if (sub < gp.tx + gp.ty) { if (sub - gp.tx < hh) src = p.twoAx + p.j0 + (sub - gp.tx); }
-                else if (sub - gp.tx - gp.ty < p.nz) src = p.twoAx + p.twoAy + (sub - gp.tx - gp.ty);
-                if (src >= 0) tbl[e] = atom_tables[(size_t)p.tbase + src];
-            }
-            part_barrier(part);
-        }
-
         // ---------------- B: every owner adds its hits, in list order, into cells only it writes
         if (owner_valid && !(gp.debug_skip & 1)) {
             const int nwarp_used = (npair + 31) >> 5;
@@ -164,39 +171,47 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 while (m) {
                     const int i = wv * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    const PairSlot& p = slots[i];
-                    const int cx0 = (int)(p.rect & 0xff), cy0 = (int)((p.rect >> 16) & 0xff);
-                    const int lx = mycx - cx0, ly = mycy - cy0;
-                    const int pz0 = p.pz0, kA = p.kA, kB = p.kB, nzr = p.nz;
+                    const PairInfo pi = info[i];
+                    const int lx = mycx - (pi.x & 0xff), ly = mycy - ((pi.x >> 16) & 0xff);
+                    const int pz0 = pi.y, kA = pi.z & 1023, kB = (pi.z >> 10) & 1023, nzr = (pi.z >> 20) & 1023;
+                    const int shlo = (pi.z & (1 << 30)) ? gp.nb : nz, shhi = (pi.z < 0) ? -gp.nb : -nz;
                     if (gp.separable) {
                         const double* T = tbl + ((size_t)i << logS);
                         double exy = T[lx] * T[gp.tx + ly];
-                        if (tt.ctab != nullptr) exy *= tt.ctab[tt.ctab_off[p.type] + (p.i0 + lx) * p.twoAy + (p.j0 + ly)];
+                        if (tt.ctab != nullptr) {
+                            const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
+                            exy *= tt.ctab[tt.ctab_off[type] + (i0 + lx) * 2 * tt.halfw[type * 3 + 1] + (j0 + ly)];
+                        }
                         const double* ez = T + gp.tx + gp.ty;
                         {   // cell
                             const int ka = max(kA, zlo - pz0), kb = min(kB, zhi - pz0);
                             for (int k = ka; k < kb; ++k) { const int cz = pz0 + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k]; }
                         }
                         if (kA > 0) {   // low padding
-                            const int sh = pz0 + p.shlo, ka = max(0, zlo - sh), kb = min(kA, zhi - sh);
+                            const int sh = pz0 + shlo, ka = max(0, zlo - sh), kb = min(kA, zhi - sh);
                             for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k]; }
                         }
                         if (nzr > kB) { // high padding
-                            const int sh = pz0 + p.shhi, ka = max(kB, zlo - sh), kb = min(nzr, zhi - sh);
+                            const int sh = pz0 + shhi, ka = max(kB, zlo - sh), kb = min(nzr, zhi - sh);
                             for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k]; }
                         }
                     } else {
                         // general ucell: one exp per cell, exactly the reference's expression
-                        const double bx = __dsub_rn(p.rx, __dmul_rn((double)(p.px0 + lx), gp.dr[0]));
-                        const double by = __dsub_rn(p.ry, __dmul_rn((double)(p.py0 + ly), gp.dr[1]));
-                        const double t2 = tt.two_sig2[p.type], amp = tt.amp[p.type];
+                        const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
+                        const int Ax = tt.halfw[type * 3], Ay = tt.halfw[type * 3 + 1];
+                        const double rx = rxyz[i * 3], ry = rxyz[i * 3 + 1], rz = rxyz[i * 3 + 2];
+                        // padded-grid index of my column: p = ir - A + stamp index, ir = trunc(r/dr) as in K1
+                        const int px = (int)(rx / gp.dr[0]) - Ax + i0 + lx, py = (int)(ry / gp.dr[1]) - Ay + j0 + ly;
+                        const double bx = __dsub_rn(rx, __dmul_rn((double)px, gp.dr[0]));
+                        const double by = __dsub_rn(ry, __dmul_rn((double)py, gp.dr[1]));
+                        const double t2 = tt.two_sig2[type], amp = tt.amp[type];
 #pragma unroll 1
                         for (int seg = 0; seg < 3; ++seg) {
-                            const int sh = pz0 + (seg == 0 ? 0 : (seg == 1 ? p.shlo : p.shhi));
+                            const int sh = pz0 + (seg == 0 ? 0 : (seg == 1 ? shlo : shhi));
                             const int k0 = seg == 0 ? kA : (seg == 1 ? 0 : kB), k1 = seg == 0 ? kB : (seg == 1 ? kA : nzr);
                             const int ka = max(k0, zlo - sh), kb = min(k1, zhi - sh);
                             for (int k = ka; k < kb; ++k) {
-                                const double bzv = __dsub_rn(p.rz, __dmul_rn((double)(pz0 + k), gp.dr[2]));
+                                const double bzv = __dsub_rn(rz, __dmul_rn((double)(pz0 + k), gp.dr[2]));
                                 const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
                                 const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
                                 const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
@@ -215,7 +230,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     if (dens_dump != nullptr) {
         for (int i = threadIdx.x; i < ncol * nz; i += blockDim.x) {
             const int c = i / nz, z = i - c * nz;
-            const int x = X0 + c / gp.ty, y = Y0 + c % gp.ty;
+            const int x = X0 + (c >> lty), y = Y0 + (c & (gp.ty - 1));
             if (x < gp.n[0] && y < gp.n[1]) {
                 const int a = c * nzp + z + (z >> gp.pad_shift);
                 dens_dump[(((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + z] = make_double2(tile_re[a], tile_im[a]);
@@ -223,14 +238,17 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         }
     }
     if (FUSE_ZFFT && !(gp.debug_skip & 2)) fft_tile_z(tile_re, tile_im, twr, twi, zplan, ncol, nzp, gp.pad_shift);
-    const int lty = __ffs(gp.ty) - 1;                     // tx, ty are powers of two
-    for (int c = 0; c < ((gp.debug_skip & 8) ? 0 : ncol); ++c) {
-        const int x = X0 + (c >> lty), y = Y0 + (c & (gp.ty - 1));
-        if (x < gp.n[0] && y < gp.n[1]) {
-            double2* dst = vol + (((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz;
-            for (int z = threadIdx.x; z < nz; z += blockDim.x) {
-                const int a = c * nzp + z + (z >> gp.pad_shift);
-                dst[z] = make_double2(tile_re[a], tile_im[a]);
+    if (!(gp.debug_skip & 8)) {
+        // thread <-> z, loop over the tile's columns: 16-byte stores, one contiguous run per column
+        for (int z = threadIdx.x; z < nz; z += blockDim.x) {
+            const int a0 = z + (z >> gp.pad_shift);
+            const int ymax = min(gp.ty, gp.n[1] - Y0);
+            for (int cx = 0; cx < gp.tx; ++cx) {
+                const int x = X0 + cx;
+                if (x >= gp.n[0]) break;
+                double2* dst = vol + (((long long)q * gp.n[0] + x) * gp.n[1] + Y0) * nz + z;
+                int a = (cx << lty) * nzp + a0;
+                for (int cy = 0; cy < ymax; ++cy, a += nzp, dst += nz) *dst = make_double2(tile_re[a], tile_im[a]);
             }
         }
     }

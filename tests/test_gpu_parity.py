@@ -192,3 +192,39 @@ def _smooth(n):
         while n % p == 0:
             n //= p
     return n == 1
+
+
+def test_cli_lattice_mode_gives_bragg_peaks_only(mdsf, tmp_path, monkeypatch):
+    """Known-answer test the reference offers as a CLI mode (main_gromacs.py -LX -LY -LZ): a simple
+    cubic lattice of 4x4x4 R3 particles in the 100 A box, grid 40^3 (commensurate) -> S(q) vanishes
+    except where all three indices are multiples of 4."""
+    import importlib
+    monkeypatch.chdir(tmp_path)
+    cli = importlib.import_module("main_gromacs")
+    assert cli.main(["-LX", "4", "-LY", "4", "-LZ", "4", "-SR", "2.5", "-ct", "90"]) == 0
+    z = np.load("lattice_4_4_4.npz")
+    assert tuple(z["N"]) == (40, 40, 40) and sorted(np.load("lattice_4_4_4.npz").files) == sorted(["sf", "sfplt", "L", "N", "kgrid", "kgridplt"])
+    sf = z["sf"]
+    on = np.zeros(sf.shape, dtype=bool)
+    on[::4, ::4, ::4] = True
+    assert sf[on].min() > 0
+    assert sf[~on].max() < 1e-20 * sf[on].max()
+
+
+def test_full_size_c2_frame_against_oracle(mdsf):
+    """One full-size frame of the benchmark workload (105 456 atoms, 256^3): bit-exact cell indices,
+    density and S(q) against the CPU oracle (takes ~5 s of numpy)."""
+    w = __import__("workloads")
+    wl = w.get("c2")
+    coords = w.jitter_frames(wl["base"], wl["box"], 1, wl["jitter"], wl["seed0"])
+    dims = wl["box"][None, :].copy()
+    c = dict(coords=coords, dims=dims, typ=wl["typ"], rad=wl["rad"], ucell=wl["ucell"], sres=wl["sres"])
+    got = run_engine(mdsf, c, "native", batch=2)
+    taps = {}
+    r = coords.copy()
+    ref = orc.structure_factor(r, dims.copy(), wl["typ"], wl["rad"], wl["ucell"], wl["sres"], taps=taps)
+    assert np.array_equal(got["coords_after"], r)
+    assert np.array_equal(got["ir"][0].astype(np.int64), taps["ir"][0])
+    assert np.abs(got["d1"][0] - taps["d1"][0]).max() <= 1e-13 * taps["d1"][0].max()
+    rel, norm = sf_errors(got["sf"], ref["sf"])
+    assert rel <= 1e-5 and norm <= 1e-12, (rel, norm)

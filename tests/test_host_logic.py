@@ -1,0 +1,140 @@
+"""CPU tests of the host side of the drop-in boundary (no GPU, no compute calls): the numpy parts
+of dens.py against the reference's golden outputs, the C ABI surface, the loaders, workloads."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mdsf_b200
+from tests.helpers import CASES, GOLDEN, ROOT, load_case
+
+dens = mdsf_b200.dens
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mdsf.h")).read()
+    declared = sorted(set(re.findall(r"\b(mdsf_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 20
+    lib = mdsf_b200.native.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(mdsf_b200.native.EXPORTS) == declared
+    assert lib.mdsf_abi_version() == mdsf_b200.native.ABI_VERSION
+
+
+def test_config_struct_matches_header_layout():
+    # 2 + 3 + 1 int32 (24 B) | 3+3+9 doubles (120 B) | int32 + pad | 3 pointers | 8 int32 | 7 reserved
+    cfg = mdsf_b200.native.Config
+    assert cfg.dr.offset == 24 and cfg.box.offset == 48 and cfg.ucell.offset == 72
+    assert cfg.ntypes.offset == 144 and cfg.amp.offset == 152 and cfg.halfw.offset == 168
+    assert cfg.coord_dtype.offset == 176 and ctypes.sizeof(cfg) == 240
+
+
+def test_no_cuda_device_fails_loudly_instead_of_falling_back():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mdsf_b200.native.MdsfError) as ei:
+        mdsf_b200.native.Engine((8, 8, 8), 2, (1, 1, 1), (8, 8, 8), np.eye(3), [1.0], [1.0], [[2, 2, 2]], np.float32, np.float32)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_grid_borders_and_k_lattices_match_reference(name):
+    c = load_case(name)
+    L = np.average(c["dims"], axis=0)
+    assert L.dtype == c["ref_L"].dtype and np.array_equal(L, c["ref_L"])
+    n, dr = dens._grid(L, c["sres"])
+    assert np.array_equal(n, c["ref_N"]) and dr.dtype == np.float64
+    kgrid, kplt = dens._k_lattices(c["ref_sf"].shape, L)
+    assert np.array_equal(kgrid, c["ref_kgrid"])
+    assert np.array_equal(kplt[..., :3], c["ref_kgridplt"][..., :3])
+    assert np.array_equal(dens.get_dplot(c["ref_sf"]), c["ref_sfplt"])
+
+
+def test_remap_grid_tcl_and_get_dplot_match_reference_helpers():
+    z = np.load(os.path.join(GOLDEN, "helpers.npz"))
+    i = 0
+    while "fold%d_d0" % i in z.files:
+        n = z["fold%d_nb" % i]
+        b = int(n[3])
+        des = [[0, b, int(n[d]) - b, int(n[d])] for d in range(3)]
+        ori = [[0, b, b + int(n[d]), 2 * b + int(n[d])] for d in range(3)]
+        assert np.abs(dens.remap_grid_tcl(z["fold%d_d0" % i], des, ori) - z["fold%d_d1" % i]).max() < 1e-13
+        i += 1
+    i = 0
+    while "dplot%d_in" % i in z.files:
+        assert np.array_equal(dens.get_dplot(z["dplot%d_in" % i]), z["dplot%d_out" % i])
+        i += 1
+
+
+def test_rescale_helper_is_in_place_and_matches_golden():
+    c = load_case("mono_f32")
+    r = c["coords"].copy()
+    out, L = dens.rescale(r, c["dims"])
+    assert out is r and np.array_equal(L, c["ref_L"])
+    from oracle import dens_oracle as orc
+    r2 = c["coords"].copy()
+    orc.rescale_frames(r2, c["dims"])
+    assert np.array_equal(r, r2)
+
+
+def test_radii_table_is_a_superset_with_reference_values(tmp_path):
+    rad = dens.load_radii(os.path.join(ROOT, "md-structure-factor_b200", "radii.txt"))
+    for lab, val in {"H": (1.0, 0.53), "C": (6.0, 0.70), "O": (8.0, 0.60), "N": (7.0, 0.56), "NA": (11.0, 2.27),
+                     "R3": (1.0, 0.90), "C145": (6.0, 0.67), "OES": (8.0, 0.48), "H146": (1.0, 0.53)}.items():
+        assert rad[lab] == val
+    for c in CASES:   # every label the golden cases use has the value the reference's table gave
+        for lab, val in load_case(c)["rad"].items():
+            assert rad[lab] == val
+    p = tmp_path / "r.txt"
+    p.write_text("1 H 53\n8\tO\t60\n1 H 99\n")
+    assert dens.load_radii(str(p)) == {"H": (1.0, 0.99), "O": (8.0, 0.60)}     # later rows win
+    assert set(dens.get_borders({"H": (1.0, 0.53)}, np.ones(3), ["H"]).keys()) == {"H"}
+
+
+def test_large_system_wrap_quirk_range():
+    assert dens._wrapped_atoms(5, 999999) == (0, 999999)
+    assert dens._wrapped_atoms(5, 1000000) == (0, 5)
+    assert dens._wrapped_atoms(3000000, 4000000) == (0, 0)          # imax == nframes: the branch never fires
+    assert dens._wrapped_atoms(2500000, 4000000) == (2000000, 2500000)
+
+
+def test_module_knobs_exist_like_the_reference():
+    for attr in ("USE_BETTER_RESOLUTION", "PRINT_DETAILS", "RANDOM_NOISE", "Nspatialgrid", "theta", "PRECISION", "dtyp",
+                 "load_radii", "get_borders", "rescale", "remap_grid_tcl", "get_dplot", "compute_sf"):
+        assert hasattr(dens, attr)
+    assert dens.PRECISION == 1.0e-24 and dens.dtyp is np.float64
+
+
+def test_load_gro_and_traj_npz_layout(tmp_path):
+    lt = mdsf_b200.load_traj
+    gro = tmp_path / "w.gro"
+    gro.write_text("two waters\n    6\n"
+                   "    1WATER  OW1    1   0.126   1.624   1.679\n    1WATER  HW2    2   0.190   1.661   1.747\n"
+                   "    1WATER  HW3    3   0.177   1.568   1.613\n    2WATER  OW1    4   1.275   0.053   0.622\n"
+                   "    2WATER  HW2    5   1.337   0.002   0.680\n    2WATER  HW3    6   1.326   0.120   0.568\n"
+                   "   1.82060   1.82060   1.82060\n")
+    assert lt.load_gro(str(gro)) == ["OW1", "HW2", "HW3", "OW1", "HW2", "HW3"]     # the reference's own unit test
+    names, xyz, box = lt.read_gro(str(gro))
+    assert xyz.dtype == np.float32 and xyz.shape == (6, 3) and np.allclose(box, 18.206)
+    assert np.allclose(xyz[0], [1.26, 16.24, 16.79])
+    lt.process_gro_mdtraj(str(gro), str(gro), str(tmp_path / "out_w_traj"))
+    z = np.load(str(tmp_path / "out_w_traj.npz"))
+    assert sorted(z.files) == ["coords", "dims", "mass", "name", "typ"]
+    assert z["coords"].shape == (1, 6, 3) and z["coords"].dtype == np.float32 and z["dims"].shape == (1, 3)
+    assert list(z["typ"]) == names                                                  # typ = atom NAMES (load_traj.py:110)
+
+
+def test_workloads_are_deterministic_and_inside_the_box():
+    w = __import__("workloads")
+    c = w.get("tiny")
+    a = w.jitter_frames(c["base"], c["box"], 2, c["jitter"], c["seed0"])
+    b = w.jitter_frames(c["base"], c["box"], 2, c["jitter"], c["seed0"])
+    assert np.array_equal(a, b) and a.dtype == np.float32
+    assert (a > 0).all() and (a < c["box"]).all()
+    c2 = w.get("c2")
+    assert c2["base"].shape == (105456, 3) and tuple(dens._grid(c2["box"], c2["sres"])[0]) == (256, 256, 256)
+    assert w.algorithmic_bytes_per_frame((256, 256, 256), 105456) == 105456 * 16 + 16 * 256 ** 3 + 16 * 256 * 256 * 129
