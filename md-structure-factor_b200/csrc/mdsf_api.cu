@@ -218,7 +218,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     const bool want_native = cfg->fft_mode != MDSF_FFT_CUFFT;
     for (int d = 0; d < 3; ++d) {
         const char* env = getenv(d == 2 ? "MDSF_RADIX_LOG2_Z" : "MDSF_RADIX_LOG2_XY");
-        int max_log2 = env ? atoi(env) : (d == 2 ? 3 : 4);
+        int max_log2 = env ? atoi(env) : 4;
         if (max_log2 < 1 || max_log2 > 4) max_log2 = 4;
         int rc = build_axis(h->ax[d], gp.n[d], want_native, max_log2);
         if (rc) return rc;
