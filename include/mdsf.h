@@ -37,6 +37,9 @@ enum { MDSF_F32 = 0, MDSF_F64 = 1 };
 enum { MDSF_FOLD_REFERENCE = 0,   /* reproduce the corner rule of dens.py:107 (default) */
        MDSF_FOLD_PERIODIC = 1 };  /* mathematically periodic fold                       */
 enum { MDSF_FFT_AUTO = 0, MDSF_FFT_NATIVE = 1, MDSF_FFT_CUFFT = 2 };
+enum { MDSF_SPLAT_AUTO = 0,      /* scatter when stamps are small, owner otherwise                    */
+       MDSF_SPLAT_OWNER = 1,     /* owner-computes column tiles in shared memory, fp64 accumulation   */
+       MDSF_SPLAT_SCATTER = 2 }; /* slab-pipelined 64-bit fixed-point integer reductions (L2-resident) */
 
 typedef struct mdsf_handle mdsf_handle;
 
@@ -62,7 +65,8 @@ typedef struct mdsf_config {
     int32_t batch_frames;    /* frames per device batch (even, >= 2); 0 = pick automatically  */
     int32_t tile_x, tile_y;  /* splat tile in columns; 0 = pick automatically                 */
     int32_t keep_density;    /* keep per-frame densities of the last batch for the debug tap  */
-    int32_t reserved[7];
+    int32_t splat_mode;      /* MDSF_SPLAT_*                                                  */
+    int32_t reserved[6];
 } mdsf_config;
 
 /* Create / destroy an engine.  Replaces the allocations of dens.py:237-263. */
@@ -117,6 +121,7 @@ int mdsf_debug_density(mdsf_handle* h, int64_t frame, double* d1_out /* [Nx][Ny]
 int64_t mdsf_kernel_launches(const mdsf_handle* h);
 int64_t mdsf_frames_done(const mdsf_handle* h);
 const char* mdsf_fft_path(const mdsf_handle* h);
+const char* mdsf_splat_path(const mdsf_handle* h);   /* "owner" / "scatter" (valid after mdsf_set_atoms) */
 int mdsf_batch_frames(const mdsf_handle* h);
 /* Record CUDA events around every stage of subsequent batches; query the accumulated
  * per-stage device milliseconds: out[0..5] = copy, prep+bin, splat+zfft, y pass, x pass+accumulate

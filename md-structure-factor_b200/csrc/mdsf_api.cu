@@ -19,6 +19,7 @@
 #include "mdsf_fft.cuh"
 #include "mdsf_prep.cuh"
 #include "mdsf_splat.cuh"
+#include "mdsf_scatter.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
@@ -73,6 +74,14 @@ struct mdsf_handle {
     unsigned* d_toff = nullptr;
     std::vector<double> two_host;
     int logS = 4;
+    // scatter (fixed-point, slab-pipelined) splat mode
+    bool scatter = false;
+    int want_mode = 0;                // 0 auto, 1 owner, 2 scatter
+    SlabParams sp{};
+    unsigned long long* d_acc = nullptr;
+    unsigned *d_slab_count = nullptr, *d_slab_start = nullptr, *d_slab_cursor = nullptr, *d_entries = nullptr;
+    long long entries_cap = 0;
+    int zcol = 16;
     int* d_type = nullptr;
     void* d_stage[kSlots]{};
     AtomRec* d_recs = nullptr;
@@ -204,6 +213,9 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     for (int d = 0; d < 3; ++d) { gp.n[d] = cfg->n[d]; gp.dr[d] = cfg->dr[d]; gp.box[d] = cfg->box[d]; }
     for (int i = 0; i < 9; ++i) gp.u[i] = cfg->ucell[i];
     gp.nb = cfg->nborder;
+    h->want_mode = cfg->splat_mode;
+    if (getenv("MDSF_SPLAT_MODE")) h->want_mode = atoi(getenv("MDSF_SPLAT_MODE"));
+    if (h->want_mode < 0 || h->want_mode > 2) return fail(MDSF_EINVAL, "splat mode must be 0 (auto), 1 (owner) or 2 (scatter)");
     gp.debug_skip = getenv("MDSF_SPLAT_SKIP") ? atoi(getenv("MDSF_SPLAT_SKIP")) : 0;
     gp.fold_mode = cfg->fold_mode;
     // z decouples when ucell[2][0]=ucell[2][1]=0 (b_z feeds only c_2) and ucell[0][2]=ucell[1][2]=0
@@ -353,6 +365,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaFuncSetAttribute(fft_x_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     }
+    CU(cudaFuncSetAttribute(zpass_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(splat_zfft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(splat_zfft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     *out = h;
@@ -364,7 +377,7 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->cufft_plan) cufftDestroy(h->cufft_plan);
-    void* bufs[] = {h->d_ctab, h->d_ctab_off, h->d_toff, h->d_tables, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1], h->d_recs, h->d_cnt,
+    void* bufs[] = {h->d_acc, h->d_slab_count, h->d_slab_start, h->d_slab_cursor, h->d_entries, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_tables, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1], h->d_recs, h->d_cnt,
                     h->d_off, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_tile_start, h->d_cub,
                     h->d_vol, h->d_dump, h->d_P, h->d_sf, h->d_err};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -428,6 +441,51 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     }
     if (tstride * h->F >= (1LL << 32)) return fail(MDSF_EINVAL, "factor tables overflow 32-bit offsets; lower batch_frames");
     h->gp.tstride = tstride;
+    // ---- splat mode: small stamps -> fixed-point scatter into L2-resident slabs; large stamps -> owner tiles
+    {
+        double terms = 0, amax = 0;
+        for (int64_t a = 0; a < natoms; ++a) {
+            const int* hw = &h->halfw_host[type_id[a] * 3];
+            terms += 8.0 * hw[0] * hw[1] * hw[2];
+        }
+        h->scatter = h->want_mode == 2 || (h->want_mode == 0 && terms / (double)natoms <= 2048.0);
+        if (h->scatter) {
+            if ((long long)natoms * h->F >= (1LL << MDSF_ENTRY_BITS)) return fail(MDSF_EINVAL, "natoms*batch_frames exceeds 2^30 in scatter mode");
+            std::vector<double> amp(nt);
+            CU(cudaMemcpy(amp.data(), h->d_amp, sizeof(double) * nt, cudaMemcpyDeviceToHost));
+            for (int t = 0; t < nt; ++t) amax = std::max(amax, amp[t]);
+            int e = 0;
+            (void)std::frexp(amax, &e);                   // amax < 2^e
+            h->sp.scale = std::ldexp(1.0, 52 - e);
+            h->sp.inv_scale = std::ldexp(1.0, e - 52);
+            const int npairs = h->F / 2;
+            const double per_plane = (double)npairs * g0.n[1] * g0.n[2] * 16.0;
+            const double budget = (getenv("MDSF_SLAB_MB") ? atof(getenv("MDSF_SLAB_MB")) : 32.0) * 1048576.0;
+            int X = (int)std::floor(budget / per_plane);
+            X = std::max(1, std::min(X, std::min(g0.n[0], 1023)));
+            h->sp.X = X;
+            h->sp.nslabs = (g0.n[0] + X - 1) / X;
+            if (h->sp.nslabs > 4096) return fail(MDSF_EINVAL, "too many slabs");
+            long long cap = 0;
+            std::vector<long long> sb(nt, 1);
+            for (int t = 0; t < nt; ++t) {
+                const int A = h->halfw_host[t * 3], N = g0.n[0];
+                for (int ir = A - g0.nb; ir <= N + g0.nb - A; ++ir) sb[t] = std::max<long long>(sb[t], stamp_tiles_1d(ir, A, N, X));
+            }
+            for (int64_t a = 0; a < natoms; ++a) cap += sb[type_id[a]];
+            h->entries_cap = cap * h->F;
+            if (h->entries_cap >= (1LL << 32) - 2) return fail(MDSF_EINVAL, "slab entry capacity overflows 32 bits");
+            const size_t acc_cells = (size_t)npairs * X * g0.n[1] * g0.n[2];
+            CU(cudaMalloc(&h->d_acc, acc_cells * 16));
+            CU(cudaMemset(h->d_acc, 0, acc_cells * 16));
+            CU(cudaMalloc(&h->d_slab_count, sizeof(unsigned) * (h->sp.nslabs + 1)));
+            CU(cudaMalloc(&h->d_slab_start, sizeof(unsigned) * (h->sp.nslabs + 1)));
+            CU(cudaMalloc(&h->d_slab_cursor, sizeof(unsigned) * (h->sp.nslabs + 1)));
+            CU(cudaMalloc(&h->d_entries, sizeof(unsigned) * std::max(1LL, h->entries_cap)));
+            h->zcol = 16;
+            while (h->zcol > 1 && (size_t)2 * h->zcol * g0.nzp * 8 > 96 * 1024) h->zcol >>= 1;
+        }
+    }
     h->natoms = natoms;
     h->gp.natoms = (int)natoms;
     h->maxpairs_frame = maxpairs;
@@ -573,6 +631,29 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     }
     CU(cudaEventRecord(h->ev_back[slot], h->s_back));
 
+    const int npairs = (nf + 1) / 2;
+    if (h->scatter) {
+        // K2s: counting sort of atom images by x slab (order inside a bin is irrelevant: integer adds commute)
+        const long long total = (long long)nf * h->natoms;
+        const SlabParams& sp = h->sp;
+        CU(cudaMemsetAsync(h->d_slab_count, 0, sizeof(unsigned) * (sp.nslabs + 1), h->s_comp));
+        bin_slabs_kernel<0><<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_count, nullptr, gp, h->tt, sp, nf);
+        scan_slabs_kernel<<<1, 1024, 0, h->s_comp>>>(h->d_slab_count, h->d_slab_start, h->d_slab_cursor, sp.nslabs);
+        bin_slabs_kernel<1><<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_cursor, h->d_entries, gp, h->tt, sp, nf);
+        h->launches += 3;
+        if (tv) CU(cudaEventRecord(tv[2], h->s_comp));
+        // K3s/K3z per slab: scatter into the L2-resident accumulator, then z pass out of it
+        const FftPlan zplan = h->native_fft ? h->ax[2].plan : FftPlan{gp.n[2], 0, {0}};
+        const size_t zsm = (size_t)2 * h->zcol * gp.nzp * 8 + (size_t)2 * gp.n[2] * 8;
+        for (int s = 0; s < sp.nslabs; ++s) {
+            scatter_slab_kernel<<<h->nsm * 4, 256, 0, h->s_comp>>>(h->d_recs, h->d_entries, h->d_slab_start, h->d_tables, h->d_acc, gp, h->tt, sp, s);
+            const int xcount = std::min(sp.X, gp.n[0] - s * sp.X);
+            dim3 zgrid((unsigned)(((long long)xcount * gp.n[1] + h->zcol - 1) / h->zcol), npairs);
+            zpass_slab_kernel<<<zgrid, 256, zsm, h->s_comp>>>((longlong2*)h->d_acc, h->d_vol, h->d_dump, zplan, h->ax[2].d_tw, gp, sp, s, h->zcol, h->d_err);
+            h->launches += 2;
+        }
+        CU(cudaGetLastError());
+    } else {
     // deterministic binning: scan -> emit -> stable radix sort by (frame, tile) -> list starts
     const long long total = (long long)nf * h->natoms;
     const long long cap = h->maxpairs_frame * nf;
@@ -591,7 +672,6 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     if (tv) CU(cudaEventRecord(tv[2], h->s_comp));
 
     // splat (+ fused z FFT on the native path)
-    const int npairs = (nf + 1) / 2;
     dim3 grid(gp.ntx * gp.nty, npairs);
     if (h->native_fft)
         splat_zfft_kernel<true><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
@@ -601,7 +681,8 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
                                                                          gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS);
     ++h->launches;
     CU(cudaGetLastError());
-    int rc = transform_and_accumulate(h, nf, h->native_fft, tv);
+    }
+    int rc = transform_and_accumulate(h, nf, h->native_fft, tv);   // z pass already done on the native path
     if (rc) return rc;
     CU(cudaEventRecord(h->ev_free[slot], h->s_comp));
     if (tv) { CU(cudaEventRecord(tv[5], h->s_comp)); ++h->timed_batches; }
@@ -659,6 +740,11 @@ extern "C" int mdsf_sync(mdsf_handle* h) {
     CU(cudaStreamSynchronize(h->s_copy));
     CU(cudaStreamSynchronize(h->s_comp));
     CU(cudaStreamSynchronize(h->s_back));
+    if (*h->h_err == 2) {
+        *h->h_err = 0;
+        cudaMemset(h->d_err, 0, sizeof(int));
+        return fail(MDSF_ERANGE, "fixed-point density accumulator overflow (> 2048 peak amplitudes in one cell); use splat mode 1 (owner)");
+    }
     if (*h->h_err) {
         *h->h_err = 0;
         cudaMemset(h->d_err, 0, sizeof(int));
@@ -742,6 +828,7 @@ extern "C" int mdsf_debug_density(mdsf_handle* h, int64_t frame, double* d1_out)
 extern "C" int64_t mdsf_kernel_launches(const mdsf_handle* h) { return h ? h->launches : 0; }
 extern "C" int64_t mdsf_frames_done(const mdsf_handle* h) { return h ? h->frames_done : 0; }
 extern "C" const char* mdsf_fft_path(const mdsf_handle* h) { return (h && h->native_fft) ? "native" : "cufft"; }
+extern "C" const char* mdsf_splat_path(const mdsf_handle* h) { return (h && h->scatter) ? "scatter" : "owner"; }
 extern "C" int mdsf_batch_frames(const mdsf_handle* h) { return h ? h->F : 0; }
 extern "C" int mdsf_enable_timing(mdsf_handle* h, int32_t on) {
     if (!h) return fail(MDSF_EINVAL, "null handle");

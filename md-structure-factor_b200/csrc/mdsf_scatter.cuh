@@ -1,0 +1,239 @@
+// K3 (sparse-stamp regime): slab-pipelined fixed-point scatter splat + z pass.
+//
+// Replaces the per-atom Python loop dens.py:283-308 and the fold dens.py:86-108 when stamps are
+// small (a few cells wide, dr >~ 1 A: every BASELINE config except the dr~0.3 A one).  There the
+// density is sparse (c2: 0.4 Gaussian terms per cell) and the work is bookkeeping, not arithmetic,
+// so the design minimises bookkeeping:
+//   * the volume is processed in SLABS of X consecutive x planes (all y, all z, all frame pairs of
+//     the batch), small enough (tens of MB) to stay resident in the 126 MB L2;
+//   * atoms are binned by slab with a counting sort (K2s) -- order inside a bin is irrelevant, see below;
+//   * scatter_slab_kernel: one thread per (atom image, column of its stamp): EX[i]*EY[j]*C[i][j]*EZ[k]
+//     from the per-atom factor tables of K1, converted to 64-bit FIXED POINT and added with integer
+//     `red.global.add.u64` into the slab accumulator.  Integer addition is associative and
+//     commutative, so the result is bitwise deterministic whatever the order of the adds -- the grid
+//     is not built from float atomics.  The periodic fold (incl. the corner rule of dens.py:107) is an
+//     index map;
+//   * zpass_slab_kernel: reads the slab accumulator (L2 hits), clears it, converts to fp64, runs the z
+//     FFT in shared memory and writes the complex pair volume: the density never travels to HBM.
+// Fixed point: LSB = 2^(e-52) with 2^e >= max_t Nel/sigma^3, i.e. 2^-52 of the largest peak amplitude
+// (finer than an fp64 ulp of any cell near a peak); a cell can hold 2048 peak amplitudes; overflow is
+// detected in the z pass and reported.  Measured L2 throughput of the integer reductions on B200:
+// 210 G adds/s into a <= 64 MB buffer (tools/micro/atom_bench.cu), 73 G adds/s once the buffer spills.
+#pragma once
+#include "mdsf_common.cuh"
+#include "mdsf_fft.cuh"
+
+struct SlabParams {
+    int X;               // x planes per slab
+    int nslabs;
+    double scale;        // 2^(52-e): value -> fixed point
+    double inv_scale;    // 2^(e-52)
+};
+
+// entry of a slab bin: (frame*natoms + atom) | (sx+1) << 30
+#define MDSF_ENTRY_BITS 30
+
+// ---- K2s: counting sort of atom images by slab ------------------------------------------------
+// pass 0 counts, pass 1 fills (cursor = exclusive scan of the counts, advanced atomically)
+template <int PASS>
+__global__ void __launch_bounds__(256)
+bin_slabs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ valid, unsigned* __restrict__ count_or_cursor,
+                 unsigned* __restrict__ entries, GridParams gp, TypeTable tt, SlabParams sp, int nframes)
+{
+    const long long total = (long long)nframes * gp.natoms;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (valid[idx] == 0) continue;
+        const AtomRec rec = recs[idx];
+        const int Ax = tt.halfw[rec.type * 3];
+        for (int sx = -1; sx <= 1; ++sx) {
+            int xlo, xhi;
+            stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
+            if (xhi <= xlo) continue;
+            const int s0 = (xlo - sx * gp.n[0]) / sp.X, s1 = (xhi - 1 - sx * gp.n[0]) / sp.X;
+            for (int s = s0; s <= s1; ++s) {
+                const unsigned pos = atomicAdd(&count_or_cursor[s], 1u);
+                if (PASS == 1) entries[pos] = (unsigned)idx | ((unsigned)(sx + 1) << MDSF_ENTRY_BITS);
+            }
+        }
+    }
+}
+
+// exclusive scan of nslabs counts (nslabs <= 4096) -> start[0..nslabs], cursor[0..nslabs) = start
+__global__ void __launch_bounds__(1024)
+scan_slabs_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ start, unsigned* __restrict__ cursor, int nslabs)
+{
+    __shared__ unsigned part[1024];
+    const int per = (nslabs + 1023) / 1024;
+    unsigned local = 0;
+    for (int i = 0; i < per; ++i) { const int s = threadIdx.x * per + i; if (s < nslabs) local += count[s]; }
+    part[threadIdx.x] = local;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned v = threadIdx.x >= d ? part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = part[threadIdx.x] - local;
+    for (int i = 0; i < per; ++i) {
+        const int s = threadIdx.x * per + i;
+        if (s < nslabs) { start[s] = run; cursor[s] = run; run += count[s]; }
+    }
+    if (threadIdx.x == 1023) start[nslabs] = part[1023];
+}
+
+// ---- K3s: scatter the atom images of ONE slab into its fixed-point accumulator ----------------
+// acc layout: [pair][x local][y][z][part] int64 (a complex128-shaped cell: re = frame 2q, im = frame 2q+1)
+#define MDSF_SC_ENTRIES 64
+__global__ void __launch_bounds__(256)
+scatter_slab_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ entries,
+                    const unsigned* __restrict__ slab_start, const double* __restrict__ atom_tables,
+                    unsigned long long* __restrict__ acc, GridParams gp, TypeTable tt, SlabParams sp, int slab)
+{
+    __shared__ int s_off[MDSF_SC_ENTRIES + 1];
+    __shared__ int4 s_a[MDSF_SC_ENTRIES];     // x: tbase  y: type | sx+1 << 16 | part << 18   z: pair  w: nrows | i_first << 10 | xl_first << 20
+    __shared__ int4 s_b[MDSF_SC_ENTRIES];     // x: ir_y - Ay   y: ir_z - Az   z: 2Ay   w: 2Az
+    __shared__ double s_r[MDSF_SC_ENTRIES * 3];
+    const unsigned beg = slab_start[slab], end = slab_start[slab + 1];
+    const int X0 = slab * sp.X;
+    const int nx = gp.n[0], ny = gp.n[1], nz = gp.n[2];
+    for (unsigned cb = beg + blockIdx.x * MDSF_SC_ENTRIES; cb < end; cb += gridDim.x * MDSF_SC_ENTRIES) {
+        const int ne = (int)min((unsigned)MDSF_SC_ENTRIES, end - cb);
+        __syncthreads();
+        if (threadIdx.x < ne) {
+            const unsigned ent = entries[cb + threadIdx.x];
+            const unsigned idx = ent & ((1u << MDSF_ENTRY_BITS) - 1u);
+            const int sx = (int)(ent >> MDSF_ENTRY_BITS) - 1;
+            const AtomRec rec = recs[idx];
+            const int f = (int)(idx / (unsigned)gp.natoms);
+            const int Ax = tt.halfw[rec.type * 3], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
+            int xlo, xhi;
+            stamp_segment(rec.ir[0], Ax, nx, sx, xlo, xhi);
+            // rows of this image inside the slab: destination planes [X0, X0+X)
+            const int c0 = max(xlo - sx * nx, X0), c1 = min(xhi - sx * nx, min(X0 + sp.X, nx));
+            const int nrows = max(c1 - c0, 0);
+            const int i_first = c0 + sx * nx - (rec.ir[0] - Ax);
+            s_a[threadIdx.x] = make_int4((int)rec.tbase, rec.type | ((sx + 1) << 16) | ((f & 1) << 18), f >> 1,
+                                         nrows | (i_first << 10) | ((c0 - X0) << 20));
+            s_b[threadIdx.x] = make_int4(rec.ir[1] - Ay, rec.ir[2] - Az, 2 * Ay, 2 * Az);
+            if (!gp.separable) { s_r[threadIdx.x * 3] = rec.r[0]; s_r[threadIdx.x * 3 + 1] = rec.r[1]; s_r[threadIdx.x * 3 + 2] = rec.r[2]; }
+            s_off[threadIdx.x + 1] = nrows * 2 * Ay;
+        }
+        if (threadIdx.x == 0) s_off[0] = 0;
+        __syncthreads();
+        if (threadIdx.x < 32) {          // inclusive scan of <= 64 column counts by one warp
+            int v0 = threadIdx.x < ne ? s_off[threadIdx.x + 1] : 0;
+            int v1 = threadIdx.x + 32 < ne ? s_off[threadIdx.x + 33] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t0 = __shfl_up_sync(0xffffffffu, v0, d), t1 = __shfl_up_sync(0xffffffffu, v1, d);
+                if ((int)threadIdx.x >= d) { v0 += t0; v1 += t1; }
+            }
+            const int tot0 = __shfl_sync(0xffffffffu, v0, 31);
+            if (threadIdx.x < ne) s_off[threadIdx.x + 1] = v0;
+            if (threadIdx.x + 32 < ne) s_off[threadIdx.x + 33] = v1 + tot0;
+        }
+        __syncthreads();
+        const int total = s_off[ne];
+        for (int v = threadIdx.x; v < total; v += blockDim.x) {
+            int lo = 0, hi = ne - 1;          // entry e with s_off[e] <= v < s_off[e+1]
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= v) lo = mid; else hi = mid - 1; }
+            const int4 a = s_a[lo], b = s_b[lo];
+            const int twoAy = b.z, nzr = b.w;
+            const int local = v - s_off[lo];
+            const int r = local / twoAy, j = local - r * twoAy;
+            const int type = a.y & 0xffff, sx = ((a.y >> 16) & 3) - 1, part = (a.y >> 18) & 1;
+            const int i = ((a.w >> 10) & 1023) + r, xl = (a.w >> 20) + r;
+            // y image of this column
+            const int py = b.x + j;
+            const int sy = py < 0 ? -1 : (py >= ny ? 1 : 0);
+            const int cy = py - sy * ny;
+            const bool corner = (sx != 0 && sy != 0 && gp.fold_mode == 0);
+            const int shlo = (corner && sy != -1) ? gp.nb : nz, shhi = (corner && sy != 1) ? -gp.nb : -nz;
+            unsigned long long* colp = acc + ((((size_t)a.z * sp.X + xl) * ny + cy) * (size_t)nz) * 2 + part;
+            const int pz0 = b.y;
+            if (gp.separable) {
+                const double* T = atom_tables + (unsigned)a.x;
+                const int twoAx = 2 * tt.halfw[type * 3];
+                double exy = T[i] * T[twoAx + j];
+                if (tt.ctab != nullptr) exy *= tt.ctab[tt.ctab_off[type] + i * twoAy + j];
+                exy *= sp.scale;
+                const double* ez = T + twoAx + twoAy;
+                for (int k = 0; k < nzr; ++k) {
+                    const int pz = pz0 + k;
+                    const int cz = pz < 0 ? pz + shlo : (pz >= nz ? pz + shhi : pz);
+                    const long long q = __double2ll_rn(exy * ez[k]);
+                    atomicAdd(colp + 2 * (size_t)cz, (unsigned long long)q);
+                }
+            } else {
+                // general ucell: one exp per cell, exactly the reference's expression (dens.py:299-308)
+                const double rx = s_r[lo * 3], ry = s_r[lo * 3 + 1], rz = s_r[lo * 3 + 2];
+                const int Ax = tt.halfw[type * 3];
+                const int px = (int)(rx / gp.dr[0]) - Ax + i;
+                const double bx = __dsub_rn(rx, __dmul_rn((double)px, gp.dr[0]));
+                const double by = __dsub_rn(ry, __dmul_rn((double)py, gp.dr[1]));
+                const double t2 = tt.two_sig2[type], amp = tt.amp[type] * sp.scale;
+                for (int k = 0; k < nzr; ++k) {
+                    const int pz = pz0 + k;
+                    const int cz = pz < 0 ? pz + shlo : (pz >= nz ? pz + shhi : pz);
+                    const double bzv = __dsub_rn(rz, __dmul_rn((double)pz, gp.dr[2]));
+                    const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
+                    const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
+                    const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
+                    const long long q = __double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2));
+                    atomicAdd(colp + 2 * (size_t)cz, (unsigned long long)q);
+                }
+            }
+        }
+    }
+}
+
+// ---- K3z: slab accumulator -> fp64 -> z FFT -> complex pair volume; clears the accumulator ------
+// grid = (column groups of the slab, pairs); ncol consecutive (x,y) columns are contiguous.
+__global__ void __launch_bounds__(256)
+zpass_slab_kernel(longlong2* __restrict__ acc, double2* __restrict__ vol, double2* __restrict__ dens_dump,
+                  FftPlan plan, const double2* __restrict__ tw, GridParams gp, SlabParams sp, int slab,
+                  int ncol, int* __restrict__ err_flag)
+{
+    extern __shared__ double smem[];
+    const int nz = gp.n[2], nzp = gp.nzp, pad = gp.pad_shift;
+    double* sre = smem;
+    double* sim = sre + (size_t)ncol * nzp;
+    double* twr = sim + (size_t)ncol * nzp;
+    double* twi = twr + nz;
+    if (plan.nstages > 0) load_twiddles(twr, twi, tw, nz);
+    const int X0 = slab * sp.X;
+    const int xcount = min(sp.X, gp.n[0] - X0);
+    const long long slab_cols = (long long)xcount * gp.n[1];
+    const long long col0 = (long long)blockIdx.x * ncol;
+    const int nc = (int)min((long long)ncol, slab_cols - col0);
+    const int q = blockIdx.y;
+    longlong2* src = acc + ((long long)q * sp.X * gp.n[1] + col0) * nz;
+    double2* dst = vol + (((long long)q * gp.n[0] + X0) * gp.n[1] + col0) * nz;
+    bool overflow = false;
+    for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
+        const int c = i / nz, z = i - c * nz;
+        const longlong2 v = src[i];
+        src[i] = make_longlong2(0, 0);
+        overflow |= (v.x > (1LL << 62)) | (v.x < -(1LL << 62)) | (v.y > (1LL << 62)) | (v.y < -(1LL << 62));
+        const int a = c * nzp + z + (z >> pad);
+        sre[a] = (double)v.x * sp.inv_scale; sim[a] = (double)v.y * sp.inv_scale;
+    }
+    if (overflow) atomicExch(err_flag, 2);
+    __syncthreads();
+    if (dens_dump != nullptr) {
+        double2* dd = dens_dump + (((long long)q * gp.n[0] + X0) * gp.n[1] + col0) * nz;
+        for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
+            const int c = i / nz, z = i - c * nz;
+            const int a = c * nzp + z + (z >> pad);
+            dd[i] = make_double2(sre[a], sim[a]);
+        }
+    }
+    fft_tile_z(sre, sim, twr, twi, plan, nc, nzp, pad);
+    for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
+        const int c = i / nz, z = i - c * nz;
+        const int a = c * nzp + z + (z >> pad);
+        dst[i] = make_double2(sre[a], sim[a]);
+    }
+}

@@ -34,6 +34,7 @@ FOLD_MODE = "reference"   # "reference": reproduce the corner rule of reference 
 WRITE_BACK_COORDS = True  # the reference rescales/wraps ``r`` in place; keep that side effect
 DEVICE = 0                # CUDA device ordinal used by compute_sf
 FFT_MODE = "auto"         # "auto" | "native" | "cufft"
+SPLAT_MODE = "auto"       # "auto" | "owner" (fp64 owner-computes tiles) | "scatter" (fixed-point slab scatter)
 BATCH_FRAMES = 0          # frames per device batch (0 = automatic)
 SAVE_COMPRESSED = True    # np.savez_compressed like the reference; False writes an uncompressed npz
 LAST_RUN = {}             # filled by compute_sf: grid, batch size, FFT path, kernel launches
@@ -152,7 +153,7 @@ def _k_lattices(shape, L):
 
 
 def make_engine(L_mean, typ, rad, ucell, Sres, coord_dtype, arith_dtype, keep_density=False, device=None,
-                batch_frames=None, fft_mode=None, tile=(0, 0), fold_mode=None):
+                batch_frames=None, fft_mode=None, tile=(0, 0), fold_mode=None, splat_mode=None):
     """Build the GPU engine for one call: everything that is frame-invariant (dens.py:181-231).
 
     Returns (engine, N, dr).  Raises KeyError for labels missing from ``rad`` like the reference."""
@@ -166,7 +167,8 @@ def make_engine(L_mean, typ, rad, ucell, Sres, coord_dtype, arith_dtype, keep_de
     halfw = np.array([bdict[l].astype(int) for l in labels])                    # dens.py:287
     fold = {"reference": _native.FOLD_REFERENCE, "periodic": _native.FOLD_PERIODIC}[fold_mode or FOLD_MODE]
     fft = {"auto": _native.FFT_AUTO, "native": _native.FFT_NATIVE, "cufft": _native.FFT_CUFFT}[fft_mode or FFT_MODE]
-    eng = _native.Engine(n, nborder, dr, L_mean, ucell, amp, two_sig2, halfw, coord_dtype, arith_dtype,
+    splat = {"auto": _native.SPLAT_AUTO, "owner": _native.SPLAT_OWNER, "scatter": _native.SPLAT_SCATTER}[splat_mode or SPLAT_MODE]
+    eng = _native.Engine(n, nborder, dr, L_mean, ucell, amp, two_sig2, halfw, coord_dtype, arith_dtype, splat_mode=splat,
                          fold_mode=fold, fft_mode=fft, batch_frames=BATCH_FRAMES if batch_frames is None else batch_frames,
                          tile=tile, keep_density=keep_density, device=DEVICE if device is None else device)
     eng.set_atoms(type_ids)
@@ -224,7 +226,7 @@ def compute_sf(r, L, typ, out_filename, rad, ucell, Sres):
         print(dtyp)
         print((int(n[0]), int(n[1]), int(n[2]) / 2 + 1))
         print("Calculating Structure factor for ", natoms, " atoms over ", nframes, " timesteps. \n", "Progress: ")
-        print("GPU engine: batch of %d frames, %s FFT, border %d cells" % (eng.batch_frames, eng.fft_path, nborder))
+        print("GPU engine: batch of %d frames, %s splat, %s FFT, border %d cells" % (eng.batch_frames, eng.splat_path, eng.fft_path, nborder))
 
         if RANDOM_NOISE > 0:
             print("*" * 80)
@@ -240,7 +242,7 @@ def compute_sf(r, L, typ, out_filename, rad, ucell, Sres):
             eng.push_frames(r, scale.astype(np.float64), (lo, hi), write_back=WRITE_BACK_COORDS)
         sf = eng.read_sf()
         LAST_RUN.clear()
-        LAST_RUN.update(N=n.copy(), dr=dr.copy(), Nborder=nborder, batch_frames=eng.batch_frames, fft=eng.fft_path,
+        LAST_RUN.update(N=n.copy(), dr=dr.copy(), Nborder=nborder, batch_frames=eng.batch_frames, fft=eng.fft_path, splat=eng.splat_path,
                         kernel_launches=eng.kernel_launches, frames=eng.frames_done)
     finally:
         eng.close()

@@ -16,12 +16,14 @@ ABI_VERSION = 1
 F32, F64 = 0, 1
 FOLD_REFERENCE, FOLD_PERIODIC = 0, 1
 FFT_AUTO, FFT_NATIVE, FFT_CUFFT = 0, 1, 2
+SPLAT_AUTO, SPLAT_OWNER, SPLAT_SCATTER = 0, 1, 2
 
 EXPORTS = [
     "mdsf_create", "mdsf_destroy", "mdsf_set_atoms", "mdsf_host_alloc", "mdsf_host_free",
     "mdsf_host_register", "mdsf_host_unregister", "mdsf_push_frames", "mdsf_push_density", "mdsf_sync",
     "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
-    "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_batch_frames",
+    "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_splat_path",
+    "mdsf_batch_frames",
     "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_timer_start", "mdsf_timer_stop", "mdsf_last_error",
     "mdsf_abi_version",
 ]
@@ -40,7 +42,7 @@ class Config(C.Structure):
         ("amp", C.POINTER(C.c_double)), ("two_sig2", C.POINTER(C.c_double)), ("halfw", C.POINTER(C.c_int32)),
         ("coord_dtype", C.c_int32), ("arith_dtype", C.c_int32), ("fold_mode", C.c_int32), ("fft_mode", C.c_int32),
         ("batch_frames", C.c_int32), ("tile_x", C.c_int32), ("tile_y", C.c_int32), ("keep_density", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("splat_mode", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -77,6 +79,7 @@ def load():
         "mdsf_kernel_launches": (i64, [vp]),
         "mdsf_frames_done": (i64, [vp]),
         "mdsf_fft_path": (C.c_char_p, [vp]),
+        "mdsf_splat_path": (C.c_char_p, [vp]),
         "mdsf_batch_frames": (C.c_int, [vp]),
         "mdsf_enable_timing": (C.c_int, [vp, i32]),
         "mdsf_stage_ms": (C.c_int, [vp, dp, C.POINTER(i64)]),
@@ -121,7 +124,7 @@ class Engine:
 
     def __init__(self, n, nborder, dr, box, ucell, amp, two_sig2, halfw, coord_dtype, arith_dtype,
                  fold_mode=FOLD_REFERENCE, fft_mode=FFT_AUTO, batch_frames=0, tile=(0, 0), keep_density=False,
-                 device=0):
+                 device=0, splat_mode=SPLAT_AUTO):
         self._lib = load()
         self._h = C.c_void_p()
         self.n = tuple(int(v) for v in n)
@@ -150,6 +153,7 @@ class Engine:
         cfg.batch_frames = int(batch_frames)
         cfg.tile_x, cfg.tile_y = int(tile[0]), int(tile[1])
         cfg.keep_density = 1 if keep_density else 0
+        cfg.splat_mode = int(splat_mode)
         _check(self._lib.mdsf_create(C.byref(cfg), C.byref(self._h)))
         self.natoms = 0
         self._finalizer = weakref.finalize(self, self._lib.mdsf_destroy, C.c_void_p(self._h.value))
@@ -242,6 +246,10 @@ class Engine:
     @property
     def fft_path(self):
         return self._lib.mdsf_fft_path(self._h).decode()
+
+    @property
+    def splat_path(self):
+        return self._lib.mdsf_splat_path(self._h).decode()
 
     @property
     def batch_frames(self):

@@ -21,7 +21,7 @@ def mdsf():
     return mdsf_b200
 
 
-def run_engine(mdsf, c, fft_mode, batch=0, tile=(0, 0), fold=None, keep=True):
+def run_engine(mdsf, c, fft_mode, batch=0, tile=(0, 0), fold=None, keep=True, splat="auto"):
     """Push a golden case through the engine; returns dict(sf, ir, d1, coords_after, N)."""
     dens = mdsf.dens
     r = c["coords"].copy()
@@ -30,8 +30,8 @@ def run_engine(mdsf, c, fft_mode, batch=0, tile=(0, 0), fold=None, keep=True):
     L = np.average(dims, axis=0)
     scale = (L / dims).astype(np.float64)
     eng, n, dr, nb = dens.make_engine(L, c["typ"], c["rad"], c["ucell"], c["sres"], r.dtype, arith, keep_density=keep,
-                                      batch_frames=batch, fft_mode=fft_mode, tile=tile, fold_mode=fold)
-    out = dict(N=n, dr=dr, ir=[], d1=[], fft=eng.fft_path)
+                                      batch_frames=batch, fft_mode=fft_mode, tile=tile, fold_mode=fold, splat_mode=splat)
+    out = dict(N=n, dr=dr, ir=[], d1=[], fft=eng.fft_path, splat=eng.splat_path)
     try:
         T = r.shape[0]
         F = eng.batch_frames
@@ -51,12 +51,13 @@ def run_engine(mdsf, c, fft_mode, batch=0, tile=(0, 0), fold=None, keep=True):
     return out
 
 
+@pytest.mark.parametrize("splat", ["owner", "scatter"])
 @pytest.mark.parametrize("fft_mode", ["native", "cufft"])
 @pytest.mark.parametrize("name", CASES)
-def test_engine_matches_reference_golden(mdsf, name, fft_mode):
+def test_engine_matches_reference_golden(mdsf, name, fft_mode, splat):
     c = load_case(name)
-    got = run_engine(mdsf, c, fft_mode)
-    assert got["fft"] == fft_mode
+    got = run_engine(mdsf, c, fft_mode, splat=splat)
+    assert got["fft"] == fft_mode and got["splat"] == splat
     assert got["launches"] > 0
     assert np.array_equal(got["N"], c["ref_N"])
     # rescale + wrap: bit-exact in the coords dtype
@@ -110,22 +111,24 @@ def test_atom_far_outside_box_is_reported(mdsf, tmp_path):
     assert ei.value.code == -3
 
 
-def test_bitwise_reproducible_and_batch_invariant(mdsf):
+@pytest.mark.parametrize("splat", ["owner", "scatter"])
+def test_bitwise_reproducible_and_batch_invariant(mdsf, splat):
     c = load_case("mono_f32")
-    a = run_engine(mdsf, c, "native", batch=2)
-    b = run_engine(mdsf, c, "native", batch=2)
+    a = run_engine(mdsf, c, "native", batch=2, splat=splat)
+    b = run_engine(mdsf, c, "native", batch=2, splat=splat)
     assert np.array_equal(a["sf"], b["sf"])                     # deterministic: no float atomics anywhere
     assert all(np.array_equal(x, y) for x, y in zip(a["d1"], b["d1"]))
-    d = run_engine(mdsf, c, "native", batch=4, tile=(2, 2))
-    assert all(np.array_equal(x, y) for x, y in zip(a["d1"], d["d1"]))   # tile shape does not change the sums
+    d = run_engine(mdsf, c, "native", batch=4, tile=(2, 2), splat=splat)
+    assert all(np.array_equal(x, y) for x, y in zip(a["d1"], d["d1"]))   # tile shape / batch do not change the sums
     rel, norm = sf_errors(d["sf"], a["sf"])
     assert norm <= 1e-14
 
 
-def test_periodic_fold_switch_differs_only_in_corners(mdsf):
+@pytest.mark.parametrize("splat", ["owner", "scatter"])
+def test_periodic_fold_switch_differs_only_in_corners(mdsf, splat):
     c = load_case("corner_na_f64")
-    ref = run_engine(mdsf, c, "native", fold="reference")
-    per = run_engine(mdsf, c, "native", fold="periodic")
+    ref = run_engine(mdsf, c, "native", fold="reference", splat=splat)
+    per = run_engine(mdsf, c, "native", fold="periodic", splat=splat)
     taps = {}
     r = c["coords"].copy()
     orc.structure_factor(r, c["dims"].copy(), c["typ"], c["rad"], c["ucell"], c["sres"], fold_mode="periodic", taps=taps)
@@ -134,14 +137,15 @@ def test_periodic_fold_switch_differs_only_in_corners(mdsf):
     assert abs(per["d1"][0].sum() - ref["d1"][0].sum()) <= 1e-10 * ref["d1"][0].sum()
 
 
-def test_general_ucell_uses_full_expression(mdsf):
+@pytest.mark.parametrize("splat", ["owner", "scatter"])
+def test_general_ucell_uses_full_expression(mdsf, splat):
     c = load_case("gas_f64_ortho")
     c = dict(c)
     c["ucell"] = np.array([[1.0, 0.0, 0.0], [0.3, 0.9, 0.1], [0.05, 0.2, 0.95]])
     taps = {}
     r = c["coords"].copy()
     ref = orc.structure_factor(r, c["dims"].copy(), c["typ"], c["rad"], c["ucell"], c["sres"], taps=taps)
-    got = run_engine(mdsf, c, "native")
+    got = run_engine(mdsf, c, "native", splat=splat)
     d1 = np.stack(got["d1"])
     assert np.abs(d1 - np.stack(taps["d1"])).max() <= 1e-13 * np.stack(taps["d1"]).max()
     rel, norm = sf_errors(got["sf"], ref["sf"])
@@ -211,7 +215,8 @@ def test_cli_lattice_mode_gives_bragg_peaks_only(mdsf, tmp_path, monkeypatch):
     assert sf[~on].max() < 1e-20 * sf[on].max()
 
 
-def test_full_size_c2_frame_against_oracle(mdsf):
+@pytest.mark.parametrize("splat", ["owner", "scatter"])
+def test_full_size_c2_frame_against_oracle(mdsf, splat):
     """One full-size frame of the benchmark workload (105 456 atoms, 256^3): bit-exact cell indices,
     density and S(q) against the CPU oracle (takes ~5 s of numpy)."""
     w = __import__("workloads")
@@ -219,7 +224,7 @@ def test_full_size_c2_frame_against_oracle(mdsf):
     coords = w.jitter_frames(wl["base"], wl["box"], 1, wl["jitter"], wl["seed0"])
     dims = wl["box"][None, :].copy()
     c = dict(coords=coords, dims=dims, typ=wl["typ"], rad=wl["rad"], ucell=wl["ucell"], sres=wl["sres"])
-    got = run_engine(mdsf, c, "native", batch=2)
+    got = run_engine(mdsf, c, "native", batch=2, splat=splat)
     taps = {}
     r = coords.copy()
     ref = orc.structure_factor(r, dims.copy(), wl["typ"], wl["rad"], wl["ucell"], wl["sres"], taps=taps)
