@@ -82,6 +82,8 @@ struct mdsf_handle {
     unsigned *d_slab_count = nullptr, *d_slab_start = nullptr, *d_slab_cursor = nullptr, *d_entries = nullptr;
     long long entries_cap = 0;
     int zcol = 16;
+    size_t acc_cells = 0;
+    int pipe_grid = 0;
     int* d_type = nullptr;
     void* d_stage[kSlots]{};
     AtomRec* d_recs = nullptr;
@@ -365,7 +367,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaFuncSetAttribute(fft_x_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     }
-    CU(cudaFuncSetAttribute(zpass_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 8192));
     CU(cudaFuncSetAttribute(splat_zfft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(splat_zfft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     *out = h;
@@ -476,14 +478,20 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
             h->entries_cap = cap * h->F;
             if (h->entries_cap >= (1LL << 32) - 2) return fail(MDSF_EINVAL, "slab entry capacity overflows 32 bits");
             const size_t acc_cells = (size_t)npairs * X * g0.n[1] * g0.n[2];
-            CU(cudaMalloc(&h->d_acc, acc_cells * 16));
-            CU(cudaMemset(h->d_acc, 0, acc_cells * 16));
+            h->acc_cells = acc_cells;
+            CU(cudaMalloc(&h->d_acc, acc_cells * 16 * 2));          // double buffered: scatter(s) || z pass(s-1)
+            CU(cudaMemset(h->d_acc, 0, acc_cells * 16 * 2));
             CU(cudaMalloc(&h->d_slab_count, sizeof(unsigned) * (h->sp.nslabs + 1)));
             CU(cudaMalloc(&h->d_slab_start, sizeof(unsigned) * (h->sp.nslabs + 1)));
             CU(cudaMalloc(&h->d_slab_cursor, sizeof(unsigned) * (h->sp.nslabs + 1)));
             CU(cudaMalloc(&h->d_entries, sizeof(unsigned) * std::max(1LL, h->entries_cap)));
             h->zcol = 16;
-            while (h->zcol > 1 && (size_t)2 * h->zcol * g0.nzp * 8 > 96 * 1024) h->zcol >>= 1;
+            while (h->zcol > 1 && (size_t)2 * h->zcol * g0.nzp * 8 > 80 * 1024) h->zcol >>= 1;
+            int per_sm = 0;
+            const size_t zsm = (size_t)2 * h->zcol * g0.nzp * 8 + (size_t)2 * g0.n[2] * 8;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slab_pipeline_kernel, 256, zsm));
+            if (per_sm < 1) return fail(MDSF_EINVAL, "slab pipeline kernel does not fit on an SM");
+            h->pipe_grid = per_sm * h->nsm;
         }
     }
     h->natoms = natoms;
@@ -637,21 +645,24 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
         const long long total = (long long)nf * h->natoms;
         const SlabParams& sp = h->sp;
         CU(cudaMemsetAsync(h->d_slab_count, 0, sizeof(unsigned) * (sp.nslabs + 1), h->s_comp));
-        bin_slabs_kernel<0><<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_count, nullptr, gp, h->tt, sp, nf);
+        bin_slabs_kernel<0><<<h->nsm * 4, 256, sizeof(unsigned) * 2 * sp.nslabs, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_count, nullptr, gp, h->tt, sp, nf);
         scan_slabs_kernel<<<1, 1024, 0, h->s_comp>>>(h->d_slab_count, h->d_slab_start, h->d_slab_cursor, sp.nslabs);
-        bin_slabs_kernel<1><<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_cursor, h->d_entries, gp, h->tt, sp, nf);
+        bin_slabs_kernel<1><<<h->nsm * 4, 256, sizeof(unsigned) * 2 * sp.nslabs, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_cursor, h->d_entries, gp, h->tt, sp, nf);
         h->launches += 3;
         if (tv) CU(cudaEventRecord(tv[2], h->s_comp));
-        // K3s/K3z per slab: scatter into the L2-resident accumulator, then z pass out of it
-        const FftPlan zplan = h->native_fft ? h->ax[2].plan : FftPlan{gp.n[2], 0, {0}};
-        const size_t zsm = (size_t)2 * h->zcol * gp.nzp * 8 + (size_t)2 * gp.n[2] * 8;
-        for (int s = 0; s < sp.nslabs; ++s) {
-            scatter_slab_kernel<<<h->nsm * 4, 256, 0, h->s_comp>>>(h->d_recs, h->d_entries, h->d_slab_start, h->d_tables, h->d_acc, gp, h->tt, sp, s);
-            const int xcount = std::min(sp.X, gp.n[0] - s * sp.X);
-            dim3 zgrid((unsigned)(((long long)xcount * gp.n[1] + h->zcol - 1) / h->zcol), npairs);
-            zpass_slab_kernel<<<zgrid, 256, zsm, h->s_comp>>>((longlong2*)h->d_acc, h->d_vol, h->d_dump, zplan, h->ax[2].d_tw, gp, sp, s, h->zcol, h->d_err);
-            h->launches += 2;
-        }
+        // K3s/K3z: persistent cooperative kernel, scatter(s) overlapped with the z pass of slab s-1
+        FftPlan zplan = h->native_fft ? h->ax[2].plan : FftPlan{gp.n[2], 0, {0}};
+        size_t zsm = (size_t)2 * h->zcol * gp.nzp * 8 + (size_t)2 * gp.n[2] * 8;
+        const double2* twz = h->ax[2].d_tw;
+        GridParams gpl = gp;
+        TypeTable ttl = h->tt;
+        SlabParams spl = sp;
+        int np = npairs, ncol = h->zcol;
+        size_t cells = h->acc_cells;
+        void* args[] = {&h->d_recs, &h->d_entries, &h->d_slab_start, &h->d_tables, &h->d_acc, &cells, &h->d_vol, &h->d_dump,
+                        &zplan, &twz, &gpl, &ttl, &spl, &np, &ncol, &h->d_err};
+        CU(cudaLaunchCooperativeKernel((void*)slab_pipeline_kernel, dim3(h->pipe_grid), dim3(256), args, zsm, h->s_comp));
+        ++h->launches;
         CU(cudaGetLastError());
     } else {
     // deterministic binning: scan -> emit -> stable radix sort by (frame, tile) -> list starts

@@ -7,13 +7,13 @@
 //   * the volume is processed in SLABS of X consecutive x planes (all y, all z, all frame pairs of
 //     the batch), small enough (tens of MB) to stay resident in the 126 MB L2;
 //   * atoms are binned by slab with a counting sort (K2s) -- order inside a bin is irrelevant, see below;
-//   * scatter_slab_kernel: one thread per (atom image, column of its stamp): EX[i]*EY[j]*C[i][j]*EZ[k]
+//   * slab_pipeline_kernel / scatter_chunk: one thread per (atom image, column of its stamp): EX[i]*EY[j]*C[i][j]*EZ[k]
 //     from the per-atom factor tables of K1, converted to 64-bit FIXED POINT and added with integer
 //     `red.global.add.u64` into the slab accumulator.  Integer addition is associative and
 //     commutative, so the result is bitwise deterministic whatever the order of the adds -- the grid
 //     is not built from float atomics.  The periodic fold (incl. the corner rule of dens.py:107) is an
 //     index map;
-//   * zpass_slab_kernel: reads the slab accumulator (L2 hits), clears it, converts to fp64, runs the z
+//   * slab_pipeline_kernel / zpass_item: reads the slab accumulator (L2 hits), clears it, converts to fp64, runs the z
 //     FFT in shared memory and writes the complex pair volume: the density never travels to HBM.
 // Fixed point: LSB = 2^(e-52) with 2^e >= max_t Nel/sigma^3, i.e. 2^-52 of the largest peak amplitude
 // (finer than an fp64 ulp of any cell near a peak); a cell can hold 2048 peak amplitudes; overflow is
@@ -21,6 +21,7 @@
 // 210 G adds/s into a <= 64 MB buffer (tools/micro/atom_bench.cu), 73 G adds/s once the buffer spills.
 #pragma once
 #include "mdsf_common.cuh"
+#include <cooperative_groups.h>
 #include "mdsf_fft.cuh"
 
 struct SlabParams {
@@ -40,9 +41,17 @@ __global__ void __launch_bounds__(256)
 bin_slabs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ valid, unsigned* __restrict__ count_or_cursor,
                  unsigned* __restrict__ entries, GridParams gp, TypeTable tt, SlabParams sp, int nframes)
 {
+    // One block handles a contiguous range of (frame, atom) records.  Slab counters are first
+    // accumulated in shared memory; one global atomic per (block, slab) then reserves the block's
+    // range, so the hot global counters see gridDim.x adds instead of one per atom image.
+    extern __shared__ unsigned s_cnt[];            // [nslabs] counts, then [nslabs] block bases (PASS 1)
+    unsigned* s_base = s_cnt + sp.nslabs;
     const long long total = (long long)nframes * gp.natoms;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
+    const long long per_block = (total + gridDim.x - 1) / gridDim.x;
+    const long long lo = blockIdx.x * per_block, hi = min(total, lo + per_block);
+    for (int i = threadIdx.x; i < sp.nslabs; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (long long idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
         if (valid[idx] == 0) continue;
         const AtomRec rec = recs[idx];
         const int Ax = tt.halfw[rec.type * 3];
@@ -51,10 +60,28 @@ bin_slabs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ 
             stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
             if (xhi <= xlo) continue;
             const int s0 = (xlo - sx * gp.n[0]) / sp.X, s1 = (xhi - 1 - sx * gp.n[0]) / sp.X;
-            for (int s = s0; s <= s1; ++s) {
-                const unsigned pos = atomicAdd(&count_or_cursor[s], 1u);
-                if (PASS == 1) entries[pos] = (unsigned)idx | ((unsigned)(sx + 1) << MDSF_ENTRY_BITS);
-            }
+            for (int s = s0; s <= s1; ++s) atomicAdd(&s_cnt[s], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < sp.nslabs; i += blockDim.x) {
+        const unsigned c = s_cnt[i];
+        if (c) { const unsigned base = atomicAdd(&count_or_cursor[i], c); if (PASS == 1) s_base[i] = base; }
+        if (PASS == 1) s_cnt[i] = 0;
+    }
+    if (PASS == 0) return;
+    __syncthreads();
+    for (long long idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
+        if (valid[idx] == 0) continue;
+        const AtomRec rec = recs[idx];
+        const int Ax = tt.halfw[rec.type * 3];
+        for (int sx = -1; sx <= 1; ++sx) {
+            int xlo, xhi;
+            stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
+            if (xhi <= xlo) continue;
+            const int s0 = (xlo - sx * gp.n[0]) / sp.X, s1 = (xhi - 1 - sx * gp.n[0]) / sp.X;
+            for (int s = s0; s <= s1; ++s)
+                entries[s_base[s] + atomicAdd(&s_cnt[s], 1u)] = (unsigned)idx | ((unsigned)(sx + 1) << MDSF_ENTRY_BITS);
         }
     }
 }
@@ -83,157 +110,212 @@ scan_slabs_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ sta
     if (threadIdx.x == 1023) start[nslabs] = part[1023];
 }
 
-// ---- K3s: scatter the atom images of ONE slab into its fixed-point accumulator ----------------
+// ---- K3s: scatter one chunk of <= 64 atom images of a slab into its fixed-point accumulator ------
 // acc layout: [pair][x local][y][z][part] int64 (a complex128-shaped cell: re = frame 2q, im = frame 2q+1)
 #define MDSF_SC_ENTRIES 64
-__global__ void __launch_bounds__(256)
-scatter_slab_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ entries,
-                    const unsigned* __restrict__ slab_start, const double* __restrict__ atom_tables,
-                    unsigned long long* __restrict__ acc, GridParams gp, TypeTable tt, SlabParams sp, int slab)
+struct ScatterSmem {
+    int off[MDSF_SC_ENTRIES + 1];
+    int4 a[MDSF_SC_ENTRIES];     // x: tbase  y: type | sx+1 << 16 | part << 18   z: pair  w: nrows | i_first << 10 | xl_first << 20
+    int4 b[MDSF_SC_ENTRIES];     // x: ir_y - Ay   y: ir_z - Az   z: 2Ay   w: 2Az
+    double r[MDSF_SC_ENTRIES * 3];
+};
+
+__device__ __forceinline__ void scatter_chunk(ScatterSmem& sm, const AtomRec* __restrict__ recs, const unsigned* __restrict__ entries,
+                                              unsigned cb, int ne, const double* __restrict__ atom_tables,
+                                              unsigned long long* __restrict__ acc, const GridParams& gp, const TypeTable& tt,
+                                              const SlabParams& sp, int slab)
 {
-    __shared__ int s_off[MDSF_SC_ENTRIES + 1];
-    __shared__ int4 s_a[MDSF_SC_ENTRIES];     // x: tbase  y: type | sx+1 << 16 | part << 18   z: pair  w: nrows | i_first << 10 | xl_first << 20
-    __shared__ int4 s_b[MDSF_SC_ENTRIES];     // x: ir_y - Ay   y: ir_z - Az   z: 2Ay   w: 2Az
-    __shared__ double s_r[MDSF_SC_ENTRIES * 3];
-    const unsigned beg = slab_start[slab], end = slab_start[slab + 1];
     const int X0 = slab * sp.X;
     const int nx = gp.n[0], ny = gp.n[1], nz = gp.n[2];
-    for (unsigned cb = beg + blockIdx.x * MDSF_SC_ENTRIES; cb < end; cb += gridDim.x * MDSF_SC_ENTRIES) {
-        const int ne = (int)min((unsigned)MDSF_SC_ENTRIES, end - cb);
-        __syncthreads();
-        if (threadIdx.x < ne) {
-            const unsigned ent = entries[cb + threadIdx.x];
-            const unsigned idx = ent & ((1u << MDSF_ENTRY_BITS) - 1u);
-            const int sx = (int)(ent >> MDSF_ENTRY_BITS) - 1;
-            const AtomRec rec = recs[idx];
-            const int f = (int)(idx / (unsigned)gp.natoms);
-            const int Ax = tt.halfw[rec.type * 3], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
-            int xlo, xhi;
-            stamp_segment(rec.ir[0], Ax, nx, sx, xlo, xhi);
-            // rows of this image inside the slab: destination planes [X0, X0+X)
-            const int c0 = max(xlo - sx * nx, X0), c1 = min(xhi - sx * nx, min(X0 + sp.X, nx));
-            const int nrows = max(c1 - c0, 0);
-            const int i_first = c0 + sx * nx - (rec.ir[0] - Ax);
-            s_a[threadIdx.x] = make_int4((int)rec.tbase, rec.type | ((sx + 1) << 16) | ((f & 1) << 18), f >> 1,
-                                         nrows | (i_first << 10) | ((c0 - X0) << 20));
-            s_b[threadIdx.x] = make_int4(rec.ir[1] - Ay, rec.ir[2] - Az, 2 * Ay, 2 * Az);
-            if (!gp.separable) { s_r[threadIdx.x * 3] = rec.r[0]; s_r[threadIdx.x * 3 + 1] = rec.r[1]; s_r[threadIdx.x * 3 + 2] = rec.r[2]; }
-            s_off[threadIdx.x + 1] = nrows * 2 * Ay;
-        }
-        if (threadIdx.x == 0) s_off[0] = 0;
-        __syncthreads();
-        if (threadIdx.x < 32) {          // inclusive scan of <= 64 column counts by one warp
-            int v0 = threadIdx.x < ne ? s_off[threadIdx.x + 1] : 0;
-            int v1 = threadIdx.x + 32 < ne ? s_off[threadIdx.x + 33] : 0;
+    if (threadIdx.x < ne) {
+        const unsigned ent = entries[cb + threadIdx.x];
+        const unsigned idx = ent & ((1u << MDSF_ENTRY_BITS) - 1u);
+        const int sx = (int)(ent >> MDSF_ENTRY_BITS) - 1;
+        const AtomRec rec = recs[idx];
+        const int f = (int)(idx / (unsigned)gp.natoms);
+        const int Ax = tt.halfw[rec.type * 3], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
+        int xlo, xhi;
+        stamp_segment(rec.ir[0], Ax, nx, sx, xlo, xhi);
+        // rows of this image inside the slab: destination planes [X0, X0+X)
+        const int c0 = max(xlo - sx * nx, X0), c1 = min(xhi - sx * nx, min(X0 + sp.X, nx));
+        const int nrows = max(c1 - c0, 0);
+        const int i_first = c0 + sx * nx - (rec.ir[0] - Ax);
+        sm.a[threadIdx.x] = make_int4((int)rec.tbase, rec.type | ((sx + 1) << 16) | ((f & 1) << 18), f >> 1,
+                                      nrows | (i_first << 10) | ((c0 - X0) << 20));
+        sm.b[threadIdx.x] = make_int4(rec.ir[1] - Ay, rec.ir[2] - Az, 2 * Ay, 2 * Az);
+        if (!gp.separable) { sm.r[threadIdx.x * 3] = rec.r[0]; sm.r[threadIdx.x * 3 + 1] = rec.r[1]; sm.r[threadIdx.x * 3 + 2] = rec.r[2]; }
+        sm.off[threadIdx.x + 1] = nrows * 2 * Ay;
+    }
+    if (threadIdx.x == 0) sm.off[0] = 0;
+    __syncthreads();
+    if (threadIdx.x < 32) {          // inclusive scan of <= 64 column counts by one warp
+        int v0 = (int)threadIdx.x < ne ? sm.off[threadIdx.x + 1] : 0;
+        int v1 = (int)threadIdx.x + 32 < ne ? sm.off[threadIdx.x + 33] : 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t0 = __shfl_up_sync(0xffffffffu, v0, d), t1 = __shfl_up_sync(0xffffffffu, v1, d);
-                if ((int)threadIdx.x >= d) { v0 += t0; v1 += t1; }
-            }
-            const int tot0 = __shfl_sync(0xffffffffu, v0, 31);
-            if (threadIdx.x < ne) s_off[threadIdx.x + 1] = v0;
-            if (threadIdx.x + 32 < ne) s_off[threadIdx.x + 33] = v1 + tot0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t0 = __shfl_up_sync(0xffffffffu, v0, d), t1 = __shfl_up_sync(0xffffffffu, v1, d);
+            if ((int)threadIdx.x >= d) { v0 += t0; v1 += t1; }
         }
-        __syncthreads();
-        const int total = s_off[ne];
-        for (int v = threadIdx.x; v < total; v += blockDim.x) {
-            int lo = 0, hi = ne - 1;          // entry e with s_off[e] <= v < s_off[e+1]
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= v) lo = mid; else hi = mid - 1; }
-            const int4 a = s_a[lo], b = s_b[lo];
-            const int twoAy = b.z, nzr = b.w;
-            const int local = v - s_off[lo];
-            const int r = local / twoAy, j = local - r * twoAy;
-            const int type = a.y & 0xffff, sx = ((a.y >> 16) & 3) - 1, part = (a.y >> 18) & 1;
-            const int i = ((a.w >> 10) & 1023) + r, xl = (a.w >> 20) + r;
-            // y image of this column
-            const int py = b.x + j;
-            const int sy = py < 0 ? -1 : (py >= ny ? 1 : 0);
-            const int cy = py - sy * ny;
-            const bool corner = (sx != 0 && sy != 0 && gp.fold_mode == 0);
-            const int shlo = (corner && sy != -1) ? gp.nb : nz, shhi = (corner && sy != 1) ? -gp.nb : -nz;
-            unsigned long long* colp = acc + ((((size_t)a.z * sp.X + xl) * ny + cy) * (size_t)nz) * 2 + part;
-            const int pz0 = b.y;
-            if (gp.separable) {
-                const double* T = atom_tables + (unsigned)a.x;
-                const int twoAx = 2 * tt.halfw[type * 3];
-                double exy = T[i] * T[twoAx + j];
-                if (tt.ctab != nullptr) exy *= tt.ctab[tt.ctab_off[type] + i * twoAy + j];
-                exy *= sp.scale;
-                const double* ez = T + twoAx + twoAy;
-                for (int k = 0; k < nzr; ++k) {
-                    const int pz = pz0 + k;
-                    const int cz = pz < 0 ? pz + shlo : (pz >= nz ? pz + shhi : pz);
-                    const long long q = __double2ll_rn(exy * ez[k]);
-                    atomicAdd(colp + 2 * (size_t)cz, (unsigned long long)q);
-                }
-            } else {
-                // general ucell: one exp per cell, exactly the reference's expression (dens.py:299-308)
-                const double rx = s_r[lo * 3], ry = s_r[lo * 3 + 1], rz = s_r[lo * 3 + 2];
-                const int Ax = tt.halfw[type * 3];
-                const int px = (int)(rx / gp.dr[0]) - Ax + i;
-                const double bx = __dsub_rn(rx, __dmul_rn((double)px, gp.dr[0]));
-                const double by = __dsub_rn(ry, __dmul_rn((double)py, gp.dr[1]));
-                const double t2 = tt.two_sig2[type], amp = tt.amp[type] * sp.scale;
-                for (int k = 0; k < nzr; ++k) {
-                    const int pz = pz0 + k;
-                    const int cz = pz < 0 ? pz + shlo : (pz >= nz ? pz + shhi : pz);
-                    const double bzv = __dsub_rn(rz, __dmul_rn((double)pz, gp.dr[2]));
-                    const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
-                    const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
-                    const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
-                    const long long q = __double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2));
-                    atomicAdd(colp + 2 * (size_t)cz, (unsigned long long)q);
-                }
+        const int tot0 = __shfl_sync(0xffffffffu, v0, 31);
+        if ((int)threadIdx.x < ne) sm.off[threadIdx.x + 1] = v0;
+        if ((int)threadIdx.x + 32 < ne) sm.off[threadIdx.x + 33] = v1 + tot0;
+    }
+    __syncthreads();
+    const int total = sm.off[ne];
+    for (int v = threadIdx.x; v < total; v += blockDim.x) {
+        int lo = 0, hi = ne - 1;          // entry e with off[e] <= v < off[e+1]
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sm.off[mid] <= v) lo = mid; else hi = mid - 1; }
+        const int4 a = sm.a[lo], b = sm.b[lo];
+        const int twoAy = b.z, nzr = b.w;
+        const int local = v - sm.off[lo];
+        const int r = local / twoAy, j = local - r * twoAy;
+        const int type = a.y & 0xffff, sx = ((a.y >> 16) & 3) - 1, part = (a.y >> 18) & 1;
+        const int i = ((a.w >> 10) & 1023) + r, xl = (a.w >> 20) + r;
+        // y image of this column
+        const int py = b.x + j;
+        const int sy = py < 0 ? -1 : (py >= ny ? 1 : 0);
+        const int cy = py - sy * ny;
+        const bool corner = (sx != 0 && sy != 0 && gp.fold_mode == 0);
+        const int shlo = (corner && sy != -1) ? gp.nb : nz, shhi = (corner && sy != 1) ? -gp.nb : -nz;
+        unsigned long long* colp = acc + ((((size_t)a.z * sp.X + xl) * ny + cy) * (size_t)nz) * 2 + part;
+        const int pz0 = b.y;
+        if (gp.separable) {
+            const double* T = atom_tables + (unsigned)a.x;
+            const int twoAx = 2 * tt.halfw[type * 3];
+            double exy = T[i] * T[twoAx + j];
+            if (tt.ctab != nullptr) exy *= tt.ctab[tt.ctab_off[type] + i * twoAy + j];
+            exy *= sp.scale;
+            const double* ez = T + twoAx + twoAy;
+            for (int k = 0; k < nzr; ++k) {
+                const int pz = pz0 + k;
+                const int cz = pz < 0 ? pz + shlo : (pz >= nz ? pz + shhi : pz);
+                const long long q = __double2ll_rn(exy * ez[k]);
+                atomicAdd(colp + 2 * (size_t)cz, (unsigned long long)q);
+            }
+        } else {
+            // general ucell: one exp per cell, exactly the reference's expression (dens.py:299-308)
+            const double rx = sm.r[lo * 3], ry = sm.r[lo * 3 + 1], rz = sm.r[lo * 3 + 2];
+            const int Ax = tt.halfw[type * 3];
+            const int px = (int)(rx / gp.dr[0]) - Ax + i;
+            const double bx = __dsub_rn(rx, __dmul_rn((double)px, gp.dr[0]));
+            const double by = __dsub_rn(ry, __dmul_rn((double)py, gp.dr[1]));
+            const double t2 = tt.two_sig2[type], amp = tt.amp[type] * sp.scale;
+            for (int k = 0; k < nzr; ++k) {
+                const int pz = pz0 + k;
+                const int cz = pz < 0 ? pz + shlo : (pz >= nz ? pz + shhi : pz);
+                const double bzv = __dsub_rn(rz, __dmul_rn((double)pz, gp.dr[2]));
+                const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
+                const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
+                const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
+                const long long q = __double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2));
+                atomicAdd(colp + 2 * (size_t)cz, (unsigned long long)q);
             }
         }
     }
+    // reductions are fire-and-forget: every thread must see its own performed before the grid-wide
+    // barrier lets the z pass read the accumulator (grid.sync() only fences from one thread per block)
+    __threadfence();
+    __syncthreads();
 }
 
-// ---- K3z: slab accumulator -> fp64 -> z FFT -> complex pair volume; clears the accumulator ------
-// grid = (column groups of the slab, pairs); ncol consecutive (x,y) columns are contiguous.
-__global__ void __launch_bounds__(256)
-zpass_slab_kernel(longlong2* __restrict__ acc, double2* __restrict__ vol, double2* __restrict__ dens_dump,
-                  FftPlan plan, const double2* __restrict__ tw, GridParams gp, SlabParams sp, int slab,
-                  int ncol, int* __restrict__ err_flag)
+// ---- K3z: one group of `ncol` columns: slab accumulator -> fp64 -> z FFT -> complex pair volume ---
+// (clears the accumulator cells it reads; ncol consecutive (x,y) columns are contiguous in memory)
+__device__ __forceinline__ void zpass_item(double* sre, double* sim, const double* twr, const double* twi,
+                                           longlong2* __restrict__ acc, double2* __restrict__ vol, double2* __restrict__ dens_dump,
+                                           const FftPlan& plan, const GridParams& gp, const SlabParams& sp, int slab, int q,
+                                           long long col0, int ncol, int* __restrict__ err_flag)
 {
-    extern __shared__ double smem[];
     const int nz = gp.n[2], nzp = gp.nzp, pad = gp.pad_shift;
-    double* sre = smem;
-    double* sim = sre + (size_t)ncol * nzp;
-    double* twr = sim + (size_t)ncol * nzp;
-    double* twi = twr + nz;
-    if (plan.nstages > 0) load_twiddles(twr, twi, tw, nz);
     const int X0 = slab * sp.X;
     const int xcount = min(sp.X, gp.n[0] - X0);
     const long long slab_cols = (long long)xcount * gp.n[1];
-    const long long col0 = (long long)blockIdx.x * ncol;
     const int nc = (int)min((long long)ncol, slab_cols - col0);
-    const int q = blockIdx.y;
     longlong2* src = acc + ((long long)q * sp.X * gp.n[1] + col0) * nz;
     double2* dst = vol + (((long long)q * gp.n[0] + X0) * gp.n[1] + col0) * nz;
     bool overflow = false;
-    for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
-        const int c = i / nz, z = i - c * nz;
-        const longlong2 v = src[i];
-        src[i] = make_longlong2(0, 0);
-        overflow |= (v.x > (1LL << 62)) | (v.x < -(1LL << 62)) | (v.y > (1LL << 62)) | (v.y < -(1LL << 62));
-        const int a = c * nzp + z + (z >> pad);
-        sre[a] = (double)v.x * sp.inv_scale; sim[a] = (double)v.y * sp.inv_scale;
+    const int total = nc * nz;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {      // 8 loads in flight per thread
+        longlong2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < total ? __ldcg(src + i) : make_longlong2(0, 0); }   // L2 only: L1 is not coherent with the reductions
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) {
+                __stcg(src + i, make_longlong2(0, 0));
+                overflow |= (v[u].x > (1LL << 62)) | (v[u].x < -(1LL << 62)) | (v[u].y > (1LL << 62)) | (v[u].y < -(1LL << 62));
+                const int c = i / nz, z = i - c * nz;
+                const int a = c * nzp + z + (z >> pad);
+                sre[a] = (double)v[u].x * sp.inv_scale; sim[a] = (double)v[u].y * sp.inv_scale;
+            }
+        }
     }
     if (overflow) atomicExch(err_flag, 2);
     __syncthreads();
     if (dens_dump != nullptr) {
         double2* dd = dens_dump + (((long long)q * gp.n[0] + X0) * gp.n[1] + col0) * nz;
-        for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int c = i / nz, z = i - c * nz;
             const int a = c * nzp + z + (z >> pad);
             dd[i] = make_double2(sre[a], sim[a]);
         }
+        __syncthreads();     // the FFT below rewrites the tile in place
     }
     fft_tile_z(sre, sim, twr, twi, plan, nc, nzp, pad);
-    for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int c = i / nz, z = i - c * nz;
         const int a = c * nzp + z + (z >> pad);
         dst[i] = make_double2(sre[a], sim[a]);
+    }
+    __threadfence();        // the cleared accumulator cells must be visible before the slab is scattered into again
+    __syncthreads();
+}
+
+// ---- persistent slab pipeline (cooperative launch, one grid-wide barrier per slab) -----------------
+// Step s scatters slab s into accumulator (s & 1) while the z pass drains slab s-1 out of accumulator
+// ((s-1) & 1): both kinds of work items share one queue, so the latency chains of the scatter
+// (entry -> atom record -> factor tables -> reductions) overlap the streaming of the z pass.
+#ifndef MDSF_PIPE_MINBLOCKS
+#define MDSF_PIPE_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, MDSF_PIPE_MINBLOCKS)
+slab_pipeline_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ entries,
+                     const unsigned* __restrict__ slab_start, const double* __restrict__ atom_tables,
+                     unsigned long long* __restrict__ acc, size_t acc_cells, double2* __restrict__ vol,
+                     double2* __restrict__ dens_dump, FftPlan zplan, const double2* __restrict__ twz,
+                     GridParams gp, TypeTable tt, SlabParams sp, int npairs, int ncol, int* __restrict__ err_flag)
+{
+    extern __shared__ double smem[];
+    __shared__ ScatterSmem ssm;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int nz = gp.n[2];
+    double* sre = smem;
+    double* sim = sre + (size_t)ncol * gp.nzp;
+    double* twr = sim + (size_t)ncol * gp.nzp;
+    double* twi = twr + nz;
+    if (zplan.nstages > 0) load_twiddles(twr, twi, twz, nz);
+    __syncthreads();
+    for (int s = 0; s <= sp.nslabs; ++s) {
+        int nB = 0, groups = 0;
+        if (s > 0) {
+            const int xcount = min(sp.X, gp.n[0] - (s - 1) * sp.X);
+            groups = (int)(((long long)xcount * gp.n[1] + ncol - 1) / ncol);
+            nB = groups * npairs;
+        }
+        unsigned beg = 0, end = 0;
+        if (s < sp.nslabs) { beg = slab_start[s]; end = slab_start[s + 1]; }
+        const int nA = (int)((end - beg + MDSF_SC_ENTRIES - 1) / MDSF_SC_ENTRIES);
+        for (int item = blockIdx.x; item < nA + nB; item += gridDim.x) {
+            if (item < nB) {
+                const int q = item / groups, g = item - q * groups;
+                zpass_item(sre, sim, twr, twi, reinterpret_cast<longlong2*>(acc + (size_t)((s - 1) & 1) * acc_cells * 2), vol, dens_dump,
+                           zplan, gp, sp, s - 1, q, (long long)g * ncol, ncol, err_flag);
+            } else {
+                const unsigned cb = beg + (unsigned)(item - nB) * MDSF_SC_ENTRIES;
+                scatter_chunk(ssm, recs, entries, cb, (int)min((unsigned)MDSF_SC_ENTRIES, end - cb), atom_tables,
+                              acc + (size_t)(s & 1) * acc_cells * 2, gp, tt, sp, s);
+            }
+        }
+        grid.sync();
     }
 }

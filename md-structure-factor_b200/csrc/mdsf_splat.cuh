@@ -236,6 +236,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 dens_dump[(((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + z] = make_double2(tile_re[a], tile_im[a]);
             }
         }
+        __syncthreads();     // the FFT below rewrites the tile in place
     }
     if (FUSE_ZFFT && !(gp.debug_skip & 2)) fft_tile_z(tile_re, tile_im, twr, twi, zplan, ncol, nzp, gp.pad_shift);
     if (!(gp.debug_skip & 8)) {
