@@ -80,9 +80,13 @@ struct mdsf_handle {
     SlabParams sp{};
     unsigned long long* d_acc = nullptr;
     unsigned *d_slab_count = nullptr, *d_slab_start = nullptr, *d_slab_cursor = nullptr, *d_entries = nullptr;
+    unsigned *d_step_start = nullptr, *d_ctl = nullptr;
+    int ring = 3;
+    int zfast = 0;                    // 16 / 8: Nz = R*R handled by the two-stage z pass with natural-order output
     long long entries_cap = 0;
     int zcol = 16;
-    size_t acc_cells = 0;
+    size_t acc_cells = 0, l2_window = 0;
+    float l2_ratio = 1.0f;
     int pipe_grid = 0;
     int* d_type = nullptr;
     void* d_stage[kSlots]{};
@@ -367,7 +371,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaFuncSetAttribute(fft_x_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     }
-    CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 8192));
+    CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 20480));
     CU(cudaFuncSetAttribute(splat_zfft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     CU(cudaFuncSetAttribute(splat_zfft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     *out = h;
@@ -379,7 +383,7 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->cufft_plan) cufftDestroy(h->cufft_plan);
-    void* bufs[] = {h->d_acc, h->d_slab_count, h->d_slab_start, h->d_slab_cursor, h->d_entries, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_tables, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1], h->d_recs, h->d_cnt,
+    void* bufs[] = {h->d_acc, h->d_slab_count, h->d_slab_start, h->d_slab_cursor, h->d_entries, h->d_step_start, h->d_ctl, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_tables, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1], h->d_recs, h->d_cnt,
                     h->d_off, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_tile_start, h->d_cub,
                     h->d_vol, h->d_dump, h->d_P, h->d_sf, h->d_err};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -462,7 +466,10 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
             h->sp.inv_scale = std::ldexp(1.0, e - 52);
             const int npairs = h->F / 2;
             const double per_plane = (double)npairs * g0.n[1] * g0.n[2] * 16.0;
-            const double budget = (getenv("MDSF_SLAB_MB") ? atof(getenv("MDSF_SLAB_MB")) : 32.0) * 1048576.0;
+            // R slab accumulators form a ring that must stay resident in L2 (measured on B200: a 17 MB ring
+            // stays resident, a 50 MB ring does not) -> default 8.4 MB per slab, ring of 3
+            const double budget = (getenv("MDSF_SLAB_MB") ? atof(getenv("MDSF_SLAB_MB")) : 8.5) * 1048576.0;
+            h->ring = getenv("MDSF_SLAB_RING") ? std::max(2, atoi(getenv("MDSF_SLAB_RING"))) : 3;
             int X = (int)std::floor(budget / per_plane);
             X = std::max(1, std::min(X, std::min(g0.n[0], 1023)));
             h->sp.X = X;
@@ -479,17 +486,47 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
             if (h->entries_cap >= (1LL << 32) - 2) return fail(MDSF_EINVAL, "slab entry capacity overflows 32 bits");
             const size_t acc_cells = (size_t)npairs * X * g0.n[1] * g0.n[2];
             h->acc_cells = acc_cells;
-            CU(cudaMalloc(&h->d_acc, acc_cells * 16 * 2));          // double buffered: scatter(s) || z pass(s-1)
-            CU(cudaMemset(h->d_acc, 0, acc_cells * 16 * 2));
+            {   // keep the accumulator slabs resident in L2: persisting window on the compute stream
+                cudaDeviceProp prop;
+                CU(cudaGetDeviceProperties(&prop, h->device));
+                const size_t want = acc_cells * 16 * h->ring;
+                const size_t carve = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
+                if (carve > 0 && getenv("MDSF_L2_PERSIST")) {      // opt-in: measured slower on B200 (it starves the y/x passes of L2)
+                    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+                    h->l2_window = std::min<size_t>(want, (size_t)prop.accessPolicyMaxWindowSize);
+                    h->l2_ratio = (float)std::min(1.0, (double)carve / (double)h->l2_window);
+                }
+            }
+            CU(cudaMalloc(&h->d_acc, acc_cells * 16 * h->ring));    // ring of slab accumulators
+            CU(cudaMemset(h->d_acc, 0, acc_cells * 16 * h->ring));
+            CU(cudaMalloc(&h->d_step_start, sizeof(unsigned) * (h->sp.nslabs + 2)));
+            CU(cudaMalloc(&h->d_ctl, sizeof(unsigned) * (2 + 2 * h->sp.nslabs)));
+            if (h->l2_window) {
+                cudaStreamAttrValue attr{};
+                attr.accessPolicyWindow.base_ptr = h->d_acc;
+                attr.accessPolicyWindow.num_bytes = h->l2_window;
+                attr.accessPolicyWindow.hitRatio = h->l2_ratio;
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                CU(cudaStreamSetAttribute(h->s_comp, cudaStreamAttributeAccessPolicyWindow, &attr));
+            }
             CU(cudaMalloc(&h->d_slab_count, sizeof(unsigned) * (h->sp.nslabs + 1)));
             CU(cudaMalloc(&h->d_slab_start, sizeof(unsigned) * (h->sp.nslabs + 1)));
             CU(cudaMalloc(&h->d_slab_cursor, sizeof(unsigned) * (h->sp.nslabs + 1)));
             CU(cudaMalloc(&h->d_entries, sizeof(unsigned) * std::max(1LL, h->entries_cap)));
-            h->zcol = 16;
+            h->zcol = MDSF_PIPE_THREADS / 16;
             while (h->zcol > 1 && (size_t)2 * h->zcol * g0.nzp * 8 > 80 * 1024) h->zcol >>= 1;
+            h->zfast = 0;
+            if (h->native_fft && h->ax[2].plan.nstages == 2 && h->ax[2].plan.radix[0] == h->ax[2].plan.radix[1] &&
+                (h->ax[2].plan.radix[0] == 16 || h->ax[2].plan.radix[0] == 8) && !getenv("MDSF_NO_ZFAST")) {
+                h->zfast = h->ax[2].plan.radix[0];
+                std::vector<int> ident(g0.n[2]);
+                for (int k = 0; k < g0.n[2]; ++k) ident[k] = k;       // this path leaves z in natural frequency order
+                CU(cudaMemcpy(h->ax[2].d_rev, ident.data(), sizeof(int) * g0.n[2], cudaMemcpyHostToDevice));
+            }
             int per_sm = 0;
             const size_t zsm = (size_t)2 * h->zcol * g0.nzp * 8 + (size_t)2 * g0.n[2] * 8;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slab_pipeline_kernel, 256, zsm));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slab_pipeline_kernel, MDSF_PIPE_THREADS, zsm));
             if (per_sm < 1) return fail(MDSF_EINVAL, "slab pipeline kernel does not fit on an SM");
             h->pipe_grid = per_sm * h->nsm;
         }
@@ -646,7 +683,9 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
         const SlabParams& sp = h->sp;
         CU(cudaMemsetAsync(h->d_slab_count, 0, sizeof(unsigned) * (sp.nslabs + 1), h->s_comp));
         bin_slabs_kernel<0><<<h->nsm * 4, 256, sizeof(unsigned) * 2 * sp.nslabs, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_count, nullptr, gp, h->tt, sp, nf);
-        scan_slabs_kernel<<<1, 1024, 0, h->s_comp>>>(h->d_slab_count, h->d_slab_start, h->d_slab_cursor, sp.nslabs);
+        scan_slabs_kernel<<<1, 1024, 0, h->s_comp>>>(h->d_slab_count, h->d_slab_start, h->d_slab_cursor, sp.nslabs, h->d_step_start,
+                                                     MDSF_SC_ENTRIES, sp.X, gp.n[0], gp.n[1], h->zcol, npairs);
+        CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(unsigned) * (2 + 2 * sp.nslabs), h->s_comp));
         bin_slabs_kernel<1><<<h->nsm * 4, 256, sizeof(unsigned) * 2 * sp.nslabs, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_cursor, h->d_entries, gp, h->tt, sp, nf);
         h->launches += 3;
         if (tv) CU(cudaEventRecord(tv[2], h->s_comp));
@@ -659,9 +698,10 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
         SlabParams spl = sp;
         int np = npairs, ncol = h->zcol;
         size_t cells = h->acc_cells;
-        void* args[] = {&h->d_recs, &h->d_entries, &h->d_slab_start, &h->d_tables, &h->d_acc, &cells, &h->d_vol, &h->d_dump,
-                        &zplan, &twz, &gpl, &ttl, &spl, &np, &ncol, &h->d_err};
-        CU(cudaLaunchCooperativeKernel((void*)slab_pipeline_kernel, dim3(h->pipe_grid), dim3(256), args, zsm, h->s_comp));
+        int ring = h->ring, zfast = h->zfast;
+        void* args[] = {&h->d_recs, &h->d_entries, &h->d_slab_start, &h->d_step_start, &h->d_ctl, &h->d_tables, &h->d_acc, &cells, &ring,
+                        &h->d_vol, &h->d_dump, &zplan, &twz, &gpl, &ttl, &spl, &np, &ncol, &zfast, &h->d_err};
+        CU(cudaLaunchCooperativeKernel((void*)slab_pipeline_kernel, dim3(h->pipe_grid), dim3(MDSF_PIPE_THREADS), args, zsm, h->s_comp));
         ++h->launches;
         CU(cudaGetLastError());
     } else {
@@ -751,6 +791,11 @@ extern "C" int mdsf_sync(mdsf_handle* h) {
     CU(cudaStreamSynchronize(h->s_copy));
     CU(cudaStreamSynchronize(h->s_comp));
     CU(cudaStreamSynchronize(h->s_back));
+    if (*h->h_err == 3) {
+        *h->h_err = 0;
+        cudaMemset(h->d_err, 0, sizeof(int));
+        return fail(MDSF_ECUDA, "slab pipeline aborted: a dependency wait exceeded its spin limit");
+    }
     if (*h->h_err == 2) {
         *h->h_err = 0;
         cudaMemset(h->d_err, 0, sizeof(int));

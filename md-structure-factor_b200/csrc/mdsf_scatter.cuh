@@ -86,9 +86,12 @@ bin_slabs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ 
     }
 }
 
-// exclusive scan of nslabs counts (nslabs <= 4096) -> start[0..nslabs], cursor[0..nslabs) = start
+// exclusive scan of nslabs counts (nslabs <= 4096) -> start[0..nslabs], cursor[0..nslabs) = start;
+// also lays out the work queue of the slab pipeline: step t holds the scatter chunks of slab t followed
+// by the z-pass items of slab t-1; step_start[t] = first item of step t (t = 0..nslabs+1)
 __global__ void __launch_bounds__(1024)
-scan_slabs_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ start, unsigned* __restrict__ cursor, int nslabs)
+scan_slabs_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ start, unsigned* __restrict__ cursor, int nslabs,
+                  unsigned* __restrict__ step_start, int chunk_entries, int X, int nx, int ny, int ncol, int npairs)
 {
     __shared__ unsigned part[1024];
     const int per = (nslabs + 1023) / 1024;
@@ -108,16 +111,45 @@ scan_slabs_kernel(const unsigned* __restrict__ count, unsigned* __restrict__ sta
         if (s < nslabs) { start[s] = run; cursor[s] = run; run += count[s]; }
     }
     if (threadIdx.x == 1023) start[nslabs] = part[1023];
+    __syncthreads();
+    // items per step (t = 0..nslabs): A(t) + B(t-1); same block-wide scan again
+    unsigned items = 0;
+    for (int i = 0; i < per + 1; ++i) {
+        const int t = threadIdx.x * (per + 1) + i;
+        if (t <= nslabs) {
+            if (t < nslabs) items += (count[t] + chunk_entries - 1) / chunk_entries;
+            if (t >= 1) { const int xc = min(X, nx - (t - 1) * X); items += (unsigned)(((long long)xc * ny + ncol - 1) / ncol) * npairs; }
+        }
+    }
+    part[threadIdx.x] = items;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned v = threadIdx.x >= d ? part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    run = part[threadIdx.x] - items;
+    for (int i = 0; i < per + 1; ++i) {
+        const int t = threadIdx.x * (per + 1) + i;
+        if (t <= nslabs) {
+            step_start[t] = run;
+            if (t < nslabs) run += (count[t] + chunk_entries - 1) / chunk_entries;
+            if (t >= 1) { const int xc = min(X, nx - (t - 1) * X); run += (unsigned)(((long long)xc * ny + ncol - 1) / ncol) * npairs; }
+        }
+    }
+    if (threadIdx.x == 1023) step_start[nslabs + 1] = part[1023];
 }
 
 // ---- K3s: scatter one chunk of <= 64 atom images of a slab into its fixed-point accumulator ------
 // acc layout: [pair][x local][y][z][part] int64 (a complex128-shaped cell: re = frame 2q, im = frame 2q+1)
-#define MDSF_SC_ENTRIES 64
+#define MDSF_SC_ENTRIES 256         // atom images per scatter work item (one per thread in the load phase)
 struct ScatterSmem {
     int off[MDSF_SC_ENTRIES + 1];
     int4 a[MDSF_SC_ENTRIES];     // x: tbase  y: type | sx+1 << 16 | part << 18   z: pair  w: nrows | i_first << 10 | xl_first << 20
     int4 b[MDSF_SC_ENTRIES];     // x: ir_y - Ay   y: ir_z - Az   z: 2Ay   w: 2Az
     double r[MDSF_SC_ENTRIES * 3];
+    int wsum[32];
 };
 
 __device__ __forceinline__ void scatter_chunk(ScatterSmem& sm, const AtomRec* __restrict__ recs, const unsigned* __restrict__ entries,
@@ -148,17 +180,16 @@ __device__ __forceinline__ void scatter_chunk(ScatterSmem& sm, const AtomRec* __
     }
     if (threadIdx.x == 0) sm.off[0] = 0;
     __syncthreads();
-    if (threadIdx.x < 32) {          // inclusive scan of <= 64 column counts by one warp
-        int v0 = (int)threadIdx.x < ne ? sm.off[threadIdx.x + 1] : 0;
-        int v1 = (int)threadIdx.x + 32 < ne ? sm.off[threadIdx.x + 33] : 0;
+    {   // block-wide inclusive scan of the <= 256 column counts (one per thread)
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int v = (int)threadIdx.x < ne ? sm.off[threadIdx.x + 1] : 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t0 = __shfl_up_sync(0xffffffffu, v0, d), t1 = __shfl_up_sync(0xffffffffu, v1, d);
-            if ((int)threadIdx.x >= d) { v0 += t0; v1 += t1; }
-        }
-        const int tot0 = __shfl_sync(0xffffffffu, v0, 31);
-        if ((int)threadIdx.x < ne) sm.off[threadIdx.x + 1] = v0;
-        if ((int)threadIdx.x + 32 < ne) sm.off[threadIdx.x + 33] = v1 + tot0;
+        for (int d = 1; d < 32; d <<= 1) { const int t0 = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t0; }
+        if (lane == 31) sm.wsum[wid] = v;
+        __syncthreads();
+        int basev = 0;
+        for (int w2 = 0; w2 < wid; ++w2) basev += sm.wsum[w2];
+        if ((int)threadIdx.x < ne) sm.off[threadIdx.x + 1] = v + basev;
     }
     __syncthreads();
     const int total = sm.off[ne];
@@ -232,8 +263,9 @@ __device__ __forceinline__ void zpass_item(double* sre, double* sim, const doubl
     const int nc = (int)min((long long)ncol, slab_cols - col0);
     longlong2* src = acc + ((long long)q * sp.X * gp.n[1] + col0) * nz;
     double2* dst = vol + (((long long)q * gp.n[0] + X0) * gp.n[1] + col0) * nz;
-    bool overflow = false;
+    long long overflow = 0;
     const int total = nc * nz;
+    const int lnz = (nz & (nz - 1)) ? -1 : __ffs(nz) - 1;        // power-of-two nz: shifts instead of divides
     for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {      // 8 loads in flight per thread
         longlong2 v[8];
 #pragma unroll
@@ -243,14 +275,14 @@ __device__ __forceinline__ void zpass_item(double* sre, double* sim, const doubl
             const int i = i0 + u * blockDim.x;
             if (i < total) {
                 __stcg(src + i, make_longlong2(0, 0));
-                overflow |= (v[u].x > (1LL << 62)) | (v[u].x < -(1LL << 62)) | (v[u].y > (1LL << 62)) | (v[u].y < -(1LL << 62));
-                const int c = i / nz, z = i - c * nz;
+                overflow |= (v[u].x ^ (v[u].x << 1)) | (v[u].y ^ (v[u].y << 1));     // bit 63 != bit 62: |value| >= 2^62
+                const int c = lnz >= 0 ? (i >> lnz) : i / nz, z = i - c * nz;
                 const int a = c * nzp + z + (z >> pad);
                 sre[a] = (double)v[u].x * sp.inv_scale; sim[a] = (double)v[u].y * sp.inv_scale;
             }
         }
     }
-    if (overflow) atomicExch(err_flag, 2);
+    if (overflow < 0) atomicExch(err_flag, 2);
     __syncthreads();
     if (dens_dump != nullptr) {
         double2* dd = dens_dump + (((long long)q * gp.n[0] + X0) * gp.n[1] + col0) * nz;
@@ -271,23 +303,128 @@ __device__ __forceinline__ void zpass_item(double* sre, double* sim, const doubl
     __syncthreads();
 }
 
-// ---- persistent slab pipeline (cooperative launch, one grid-wide barrier per slab) -----------------
-// Step s scatters slab s into accumulator (s & 1) while the z pass drains slab s-1 out of accumulator
-// ((s-1) & 1): both kinds of work items share one queue, so the latency chains of the scatter
-// (entry -> atom record -> factor tables -> reductions) overlap the streaming of the z pass.
+// ---- K3z (fast path, Nz = R*R): two radix-R stages, accumulator -> registers -> shared -> registers -> volume
+// Stage 1 reads the fixed-point cells straight into registers (coalesced: lanes = consecutive z), clears
+// them, converts, transforms and parks the result in shared memory; stage 2 transforms again and stores
+// output k2 of block k1 at z = R*k2 + k1.  Transposing the digit-reversed result of two equal radices
+// gives NATURAL frequency order, so the z axis needs no permutation table on this path.
+template <int R>
+__device__ __forceinline__ void zpass_item_fast(double* sre, double* sim, const double* twr, const double* twi,
+                                                longlong2* __restrict__ acc, double2* __restrict__ vol, double2* __restrict__ dens_dump,
+                                                const GridParams& gp, const SlabParams& sp, int slab, int q,
+                                                long long col0, int ncol, int* __restrict__ err_flag)
+{
+    constexpr int NZ = R * R;
+    const int nzp = gp.nzp, pad = gp.pad_shift;
+    const int X0 = slab * sp.X;
+    const int xcount = min(sp.X, gp.n[0] - X0);
+    const long long slab_cols = (long long)xcount * gp.n[1];
+    const int nc = (int)min((long long)ncol, slab_cols - col0);
+    longlong2* src = acc + ((long long)q * sp.X * gp.n[1] + col0) * NZ;
+    const long long vbase = (((long long)q * gp.n[0] + X0) * gp.n[1] + col0) * NZ;
+    double2* dst = vol + vbase;
+    long long overflow = 0;
+    for (int it = threadIdx.x; it < nc * R; it += blockDim.x) {
+        const int f = it / R, n2 = it - f * R;
+        longlong2 v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = __ldcg(src + f * NZ + n2 + R * j);      // L2 only: L1 is not coherent with the reductions
+        double xr[R], xi[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            __stcg(src + f * NZ + n2 + R * j, make_longlong2(0, 0));
+            overflow |= (v[j].x ^ (v[j].x << 1)) | (v[j].y ^ (v[j].y << 1));
+            xr[j] = (double)v[j].x * sp.inv_scale; xi[j] = (double)v[j].y * sp.inv_scale;
+        }
+        if (dens_dump != nullptr) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) dens_dump[vbase + f * NZ + n2 + R * j] = make_double2(xr[j], xi[j]);
+        }
+        Dft<R>::run(xr, xi, twr, twi, NZ);
+#pragma unroll
+        for (int k = 1; k < R; ++k) {
+            const double wr = twr[n2 * k], wi = twi[n2 * k];
+            const double yr = xr[k] * wr - xi[k] * wi;
+            xi[k] = xr[k] * wi + xi[k] * wr;
+            xr[k] = yr;
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int p = k * R + n2;
+            const int a = f * nzp + p + (p >> pad);
+            sre[a] = xr[k]; sim[a] = xi[k];
+        }
+    }
+    if (overflow < 0) atomicExch(err_flag, 2);
+    __syncthreads();
+    for (int it = threadIdx.x; it < nc * R; it += blockDim.x) {
+        const int f = it / R, b = it - f * R;
+        double xr[R], xi[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int p = b * R + j;
+            const int a = f * nzp + p + (p >> pad);
+            xr[j] = sre[a]; xi[j] = sim[a];
+        }
+        Dft<R>::run(xr, xi, twr, twi, NZ);
+#pragma unroll
+        for (int k = 0; k < R; ++k) dst[f * NZ + R * k + b] = make_double2(xr[k], xi[k]);
+    }
+    __threadfence();
+    __syncthreads();
+}
+
+// ---- persistent slab pipeline: static work queue + per-slab completion counters, no grid-wide barriers
+// The queue is laid out by scan_slabs_kernel: step t = scatter items of slab t, then z-pass items of slab
+// t-1.  Items are dealt round-robin (item = k*gridDim + blockIdx).  A z-pass item waits until every
+// scatter item of its slab has signalled; a scatter item of slab s waits until the z pass has drained
+// slab s-R out of its ring buffer (R slab accumulators stay resident in L2).  Every CTA walks its items in
+// increasing order and only ever waits for EARLIER items, and all CTAs are co-resident (cooperative
+// launch), so the smallest unfinished item is never blocked: no deadlock.  Spins are bounded and abort
+// the whole launch through ctl[1].  The number of items in flight (= CTAs) must stay below ring x (items
+// per slab), otherwise most CTAs spin: 2 CTAs of 256 threads per SM measured best on B200.
 #ifndef MDSF_PIPE_MINBLOCKS
 #define MDSF_PIPE_MINBLOCKS 2
 #endif
-__global__ void __launch_bounds__(256, MDSF_PIPE_MINBLOCKS)
+#ifndef MDSF_PIPE_THREADS
+#define MDSF_PIPE_THREADS 256
+#endif
+#define MDSF_PIPE_SPIN_LIMIT (1u << 24)
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// thread 0 spins until *ctr >= target (or the launch is aborted); returns false on abort
+__device__ __forceinline__ bool wait_counter(const unsigned* ctr, unsigned target, unsigned* ctl) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        int good = 1;
+        while (ld_acquire_u32(ctr) < target) {
+            __nanosleep(64);
+            if (++spins > MDSF_PIPE_SPIN_LIMIT || ld_acquire_u32(ctl + 1) != 0) { atomicExch(ctl + 1, 1u); good = 0; break; }
+        }
+        ok = good;
+    }
+    __syncthreads();
+    const bool r = ok != 0;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(MDSF_PIPE_THREADS, MDSF_PIPE_MINBLOCKS)
 slab_pipeline_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ entries,
-                     const unsigned* __restrict__ slab_start, const double* __restrict__ atom_tables,
-                     unsigned long long* __restrict__ acc, size_t acc_cells, double2* __restrict__ vol,
-                     double2* __restrict__ dens_dump, FftPlan zplan, const double2* __restrict__ twz,
-                     GridParams gp, TypeTable tt, SlabParams sp, int npairs, int ncol, int* __restrict__ err_flag)
+                     const unsigned* __restrict__ slab_start, const unsigned* __restrict__ step_start,
+                     unsigned* __restrict__ ctl,          // [0] unused, [1] abort, [2..2+n) scatter done, [2+n..2+2n) z-pass done
+                     const double* __restrict__ atom_tables, unsigned long long* __restrict__ acc, size_t acc_cells, int ring,
+                     double2* __restrict__ vol, double2* __restrict__ dens_dump, FftPlan zplan, const double2* __restrict__ twz,
+                     GridParams gp, TypeTable tt, SlabParams sp, int npairs, int ncol, int zfast, int* __restrict__ err_flag)
 {
     extern __shared__ double smem[];
     __shared__ ScatterSmem ssm;
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int nz = gp.n[2];
     double* sre = smem;
     double* sim = sre + (size_t)ncol * gp.nzp;
@@ -295,27 +432,46 @@ slab_pipeline_kernel(const AtomRec* __restrict__ recs, const unsigned* __restric
     double* twi = twr + nz;
     if (zplan.nstages > 0) load_twiddles(twr, twi, twz, nz);
     __syncthreads();
-    for (int s = 0; s <= sp.nslabs; ++s) {
-        int nB = 0, groups = 0;
-        if (s > 0) {
-            const int xcount = min(sp.X, gp.n[0] - (s - 1) * sp.X);
-            groups = (int)(((long long)xcount * gp.n[1] + ncol - 1) / ncol);
-            nB = groups * npairs;
-        }
+    unsigned* scat_done = ctl + 2;
+    unsigned* zp_done = ctl + 2 + sp.nslabs;
+    const unsigned total_items = step_start[sp.nslabs + 1];
+    int t = 0;
+    for (unsigned item = blockIdx.x; item < total_items; item += gridDim.x) {
+        while (item >= step_start[t + 1]) ++t;
+        const unsigned local = item - step_start[t];
         unsigned beg = 0, end = 0;
-        if (s < sp.nslabs) { beg = slab_start[s]; end = slab_start[s + 1]; }
-        const int nA = (int)((end - beg + MDSF_SC_ENTRIES - 1) / MDSF_SC_ENTRIES);
-        for (int item = blockIdx.x; item < nA + nB; item += gridDim.x) {
-            if (item < nB) {
-                const int q = item / groups, g = item - q * groups;
-                zpass_item(sre, sim, twr, twi, reinterpret_cast<longlong2*>(acc + (size_t)((s - 1) & 1) * acc_cells * 2), vol, dens_dump,
-                           zplan, gp, sp, s - 1, q, (long long)g * ncol, ncol, err_flag);
-            } else {
-                const unsigned cb = beg + (unsigned)(item - nB) * MDSF_SC_ENTRIES;
-                scatter_chunk(ssm, recs, entries, cb, (int)min((unsigned)MDSF_SC_ENTRIES, end - cb), atom_tables,
-                              acc + (size_t)(s & 1) * acc_cells * 2, gp, tt, sp, s);
+        if (t < sp.nslabs) { beg = slab_start[t]; end = slab_start[t + 1]; }
+        const unsigned nA = (end - beg + MDSF_SC_ENTRIES - 1) / MDSF_SC_ENTRIES;
+        if (local < nA) {
+            // ---- scatter item `local` of slab t into ring buffer t % ring
+            if (t >= ring) {
+                const int sd = t - ring;
+                const int xc = min(sp.X, gp.n[0] - sd * sp.X);
+                const unsigned need = (unsigned)(((long long)xc * gp.n[1] + ncol - 1) / ncol) * npairs;
+                if (!wait_counter(zp_done + sd, need, ctl)) break;
             }
+            const unsigned cb = beg + local * MDSF_SC_ENTRIES;
+            if (!(gp.debug_skip & 32))
+                scatter_chunk(ssm, recs, entries, cb, (int)min((unsigned)MDSF_SC_ENTRIES, end - cb), atom_tables,
+                              acc + (size_t)(t % ring) * acc_cells * 2, gp, tt, sp, t);
+            if (threadIdx.x == 0) atomicAdd(scat_done + t, 1u);
+        } else {
+            // ---- z-pass item of slab t-1
+            const int sd = t - 1;
+            const unsigned need = (slab_start[sd + 1] - slab_start[sd] + MDSF_SC_ENTRIES - 1) / MDSF_SC_ENTRIES;
+            if (!wait_counter(scat_done + sd, need, ctl)) break;
+            const int xc = min(sp.X, gp.n[0] - sd * sp.X);
+            const int groups = (int)(((long long)xc * gp.n[1] + ncol - 1) / ncol);
+            const int zi = (int)(local - nA);
+            const int q = zi / groups, g = zi - q * groups;
+            longlong2* abuf = reinterpret_cast<longlong2*>(acc + (size_t)(sd % ring) * acc_cells * 2);
+            if (!(gp.debug_skip & 64)) {
+                if (zfast == 16) zpass_item_fast<16>(sre, sim, twr, twi, abuf, vol, dens_dump, gp, sp, sd, q, (long long)g * ncol, ncol, err_flag);
+                else if (zfast == 8) zpass_item_fast<8>(sre, sim, twr, twi, abuf, vol, dens_dump, gp, sp, sd, q, (long long)g * ncol, ncol, err_flag);
+                else zpass_item(sre, sim, twr, twi, abuf, vol, dens_dump, zplan, gp, sp, sd, q, (long long)g * ncol, ncol, err_flag);
+            }
+            if (threadIdx.x == 0) atomicAdd(zp_done + sd, 1u);
         }
-        grid.sync();
     }
+    if (threadIdx.x == 0 && ld_acquire_u32(ctl + 1) != 0) atomicExch(err_flag, 3);
 }
