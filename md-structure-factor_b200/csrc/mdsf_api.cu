@@ -367,6 +367,10 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         };
         pick(gp.n[1], h->Wy, h->thr_y);
         pick(gp.n[0], h->Wx, h->thr_x);
+        if (getenv("MDSF_WY")) h->Wy = atoi(getenv("MDSF_WY"));
+        if (getenv("MDSF_WX")) h->Wx = atoi(getenv("MDSF_WX"));
+        if (getenv("MDSF_THR_Y")) h->thr_y = atoi(getenv("MDSF_THR_Y"));
+        if (getenv("MDSF_THR_X")) h->thr_x = atoi(getenv("MDSF_THR_X"));
         CU(cudaFuncSetAttribute(fft_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_x_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -447,6 +451,15 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     }
     if (tstride * h->F >= (1LL << 32)) return fail(MDSF_EINVAL, "factor tables overflow 32-bit offsets; lower batch_frames");
     h->gp.tstride = tstride;
+    // Nz = R*R: the z pass runs as two radix-R stages whose (transposed) output is in natural frequency order
+    h->zfast = 0;
+    if (h->native_fft && h->ax[2].plan.nstages == 2 && h->ax[2].plan.radix[0] == h->ax[2].plan.radix[1] &&
+        (h->ax[2].plan.radix[0] == 16 || h->ax[2].plan.radix[0] == 8) && !getenv("MDSF_NO_ZFAST")) {
+        h->zfast = h->ax[2].plan.radix[0];
+        std::vector<int> ident(g0.n[2]);
+        for (int k = 0; k < g0.n[2]; ++k) ident[k] = k;
+        CU(cudaMemcpy(h->ax[2].d_rev, ident.data(), sizeof(int) * g0.n[2], cudaMemcpyHostToDevice));
+    }
     // ---- splat mode: small stamps -> fixed-point scatter into L2-resident slabs; large stamps -> owner tiles
     {
         double terms = 0, amax = 0;
@@ -520,14 +533,6 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
             CU(cudaMalloc(&h->d_entries, sizeof(unsigned) * std::max(1LL, h->entries_cap)));
             h->zcol = MDSF_PIPE_THREADS / 16;
             while (h->zcol > 1 && (size_t)2 * h->zcol * g0.nzp * 8 > 80 * 1024) h->zcol >>= 1;
-            h->zfast = 0;
-            if (h->native_fft && h->ax[2].plan.nstages == 2 && h->ax[2].plan.radix[0] == h->ax[2].plan.radix[1] &&
-                (h->ax[2].plan.radix[0] == 16 || h->ax[2].plan.radix[0] == 8) && !getenv("MDSF_NO_ZFAST")) {
-                h->zfast = h->ax[2].plan.radix[0];
-                std::vector<int> ident(g0.n[2]);
-                for (int k = 0; k < g0.n[2]; ++k) ident[k] = k;       // this path leaves z in natural frequency order
-                CU(cudaMemcpy(h->ax[2].d_rev, ident.data(), sizeof(int) * g0.n[2], cudaMemcpyHostToDevice));
-            }
             int per_sm = 0;
             const size_t zsm = (size_t)2 * h->zcol * g0.nzp * 8 + (size_t)2 * g0.n[2] * 8;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slab_pipeline_kernel, MDSF_PIPE_THREADS, zsm));
@@ -602,7 +607,7 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             while (ncol > 1 && (size_t)2 * ncol * gp.nzp * 8 > 96 * 1024) ncol >>= 1;
             const size_t sm = (size_t)2 * ncol * gp.nzp * 8 + (size_t)2 * gp.n[2] * 8;
             dim3 grid((unsigned)((ncolumns + ncol - 1) / ncol), npairs);
-            fft_z_kernel<<<grid, 256, sm, h->s_comp>>>(h->d_vol, h->ax[2].plan, h->ax[2].d_tw, ncolumns, ncol, gp.nzp, gp.pad_shift);
+            fft_z_kernel<<<grid, 256, sm, h->s_comp>>>(h->d_vol, h->ax[2].plan, h->ax[2].d_tw, ncolumns, ncol, gp.nzp, gp.pad_shift, h->zfast);
             ++h->launches;
         }
         if (tv) CU(cudaEventRecord(tv[3], h->s_comp));
@@ -730,10 +735,10 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     dim3 grid(gp.ntx * gp.nty, npairs);
     if (h->native_fft)
         splat_zfft_kernel<true><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
-                                                                        gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS);
+                                                                        gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast);
     else
         splat_zfft_kernel<false><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
-                                                                         gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS);
+                                                                         gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast);
     ++h->launches;
     CU(cudaGetLastError());
     }

@@ -289,7 +289,9 @@ __device__ __forceinline__ void load_twiddles(double* twr, double* twi, const do
     }
 }
 
+#ifndef MDSF_PASS_THREADS
 #define MDSF_PASS_THREADS 128
+#endif
 #ifndef MDSF_PASS_MINBLOCKS
 #define MDSF_PASS_MINBLOCKS 4
 #endif
@@ -300,7 +302,7 @@ __device__ __forceinline__ void load_twiddles(double* twr, double* twi, const do
 // the same stages inside splat_zfft_kernel without the load.
 __global__ void __launch_bounds__(256)
 fft_z_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw,
-             long long ncolumns, int ncol, int nzp, int pad)
+             long long ncolumns, int ncol, int nzp, int pad, int zfast)
 {
     extern __shared__ double smem[];
     const int nz = plan.n;
@@ -322,7 +324,9 @@ fft_z_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict_
     fft_tile_z(sre, sim, twr, twi, plan, nc, nzp, pad);
     for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
         const int c = i / nz, z = i - c * nz;
-        const int a = c * nzp + z + (z >> pad);
+        // Nz = R*R engines keep z in natural frequency order: frequency z sits at position (z % R)*R + z / R
+        const int p = zfast ? (z % zfast) * zfast + z / zfast : z;
+        const int a = c * nzp + p + (p >> pad);
         base[i] = make_double2(sre[a], sim[a]);
     }
 }

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256, MDSF_SPLAT_MINBLOCKS)
 splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ vals,
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
                   double2* __restrict__ dens_dump, GridParams gp, TypeTable tt, FftPlan zplan,
-                  const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS)
+                  const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS, int zfast)
 {
     extern __shared__ double smem[];
     const int ncol = gp.tx * gp.ty;
@@ -237,6 +237,37 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             }
         }
         __syncthreads();     // the FFT below rewrites the tile in place
+    }
+    if (FUSE_ZFFT && zfast && !(gp.debug_skip & 2)) {
+        // Nz = R*R: first radix-R stage in place in shared memory, second stage from shared memory straight
+        // to the volume.  Output k2 of block k1 goes to z = R*k2 + k1: the transposed digit-reversed order of
+        // two equal radices is the natural frequency order, and lanes (k1) write contiguous 16-byte cells.
+        const int R = zfast;
+        fft_stage_dispatch<true, IO_SMEM, IO_SMEM>(R, tile_re, tile_im, twr, twi, nz, nz, ncol, nzp, 1, gp.pad_shift, 0,
+                                                   GlobalTile{nullptr, 0, 0}, nullptr, false);
+        __syncthreads();
+        for (int it = threadIdx.x; it < ncol * R; it += blockDim.x) {
+            const int fcol = it / R, b = it - fcol * R;
+            const int x = X0 + (fcol >> lty), y = Y0 + (fcol & (gp.ty - 1));
+            if (x >= gp.n[0] || y >= gp.n[1]) continue;
+            double2* dst = vol + (((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + b;
+            if (R == 16) {
+                double xr[16], xi[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const int p = b * 16 + j; const int a = fcol * nzp + p + (p >> gp.pad_shift); xr[j] = tile_re[a]; xi[j] = tile_im[a]; }
+                Dft<16>::run(xr, xi, twr, twi, nz);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) dst[16 * k] = make_double2(xr[k], xi[k]);
+            } else {
+                double xr[8], xi[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int p = b * 8 + j; const int a = fcol * nzp + p + (p >> gp.pad_shift); xr[j] = tile_re[a]; xi[j] = tile_im[a]; }
+                Dft<8>::run(xr, xi, twr, twi, nz);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dst[8 * k] = make_double2(xr[k], xi[k]);
+            }
+        }
+        return;
     }
     if (FUSE_ZFFT && !(gp.debug_skip & 2)) fft_tile_z(tile_re, tile_im, twr, twi, zplan, ncol, nzp, gp.pad_shift);
     if (!(gp.debug_skip & 8)) {

@@ -5,8 +5,5 @@ run() { echo "== $1"; shift; env "$@" timeout 300 python bench.py --steps 10 --w
 import json,sys
 d=json.loads(sys.stdin.readline()); print('frames/s %.0f  e2e %.0f  stages(ms/step):'%(d['value'],d['e2e']['value']), {k:round(v,3) for k,v in d['stage_ms_per_step'].items()}, d['config'].get('splat'))"; }
 run c2_auto X=1
+run c2_nozfast MDSF_NO_ZFAST=1
 EXTRA="--splat scatter" run c2_scatter X=1
-EXTRA="--workload c1 --frames-per-step 64 --pool 64" run c1_auto X=1
-EXTRA="--workload c1 --frames-per-step 64 --pool 64" run c1_auto_17mb MDSF_SLAB_MB=17
-EXTRA="--workload c1 --frames-per-step 64 --pool 64" run c1_auto_4mb MDSF_SLAB_MB=4
-EXTRA="--workload c1 --frames-per-step 32 --pool 64" run c1_auto_f32 X=1
