@@ -65,22 +65,30 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     // ---- shared memory carve-up
     double* tile_re = smem;                                   // [ncol][nzp]  frame 2q
     double* tile_im = tile_re + (size_t)ncol * nzp;           // [ncol][nzp]  frame 2q+1
-    double* twr = tile_im + (size_t)ncol * nzp;               // [nz] z twiddles (fused FFT only)
-    double* twi = twr + (FUSE_ZFFT ? nz : 0);
-    double* tables = twi + (FUSE_ZFFT ? nz : 0);
+    double* tables = tile_im + (size_t)ncol * nzp;
     const size_t tbl_per_part = (size_t)chunk << logS;        // per pair: [EX: tx][EY: ty][EZ: 2Az] in a 2^logS stride
     double* tbl = tables + part * tbl_per_part;
-    double* rxyz = tables + 2 * tbl_per_part + (size_t)part * chunk * 3;     // general-ucell path only
-    PairInfo* info_all = reinterpret_cast<PairInfo*>(tables + 2 * tbl_per_part + (size_t)2 * chunk * 3);
+    double* rxyz = tbl;                                       // general-ucell path keeps r here instead (3 doubles per pair)
+    double* twr = tables;                                     // z twiddles reuse the table region once the splat is done
+    double* twi = twr + nz;
+    PairInfo* info_all = reinterpret_cast<PairInfo*>(tables + 2 * tbl_per_part);
     PairInfo* info = info_all + part * chunk;
     unsigned* hitT = reinterpret_cast<unsigned*>(info_all + 2 * chunk) + part * 4 * 32;   // [4 warps of pairs][column]
 
     double* mytile = part ? tile_im : tile_re;
+    // the first chunk's list entries and atom records are requested before the tile is cleared, the next
+    // chunk's while the current one is being accumulated: the dependent loads overlap useful work
+    unsigned pf_v = 0;
+    AtomRec pf_rec;
+    pf_rec.type = 0;
+    if (lbeg < lend && pt < (int)min((unsigned)chunk, lend - lbeg)) {
+        pf_v = vals[lbeg + pt];
+        pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
+    }
     {
         double2* z2 = reinterpret_cast<double2*>(tile_re);
         for (int i = threadIdx.x; i < ncol * nzp; i += blockDim.x) z2[i] = make_double2(0.0, 0.0);
     }
-    if (FUSE_ZFFT) load_twiddles(twr, twi, twz, nz);
     __syncthreads();
 
     const int lty = __ffs(gp.ty) - 1;                         // tx, ty are powers of two
@@ -95,10 +103,9 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         // ---------------- A: one pair per thread
         unsigned colmask = 0;
         if (pt < npair) {
-            const unsigned v = vals[cb + pt];
-            const int a = (int)(v & (MDSF_MAX_ATOMS - 1));
+            const unsigned v = pf_v;
             const int sx = (int)((v >> MDSF_ATOM_BITS) & 3u) - 1, sy = (int)((v >> (MDSF_ATOM_BITS + 2)) & 3u) - 1;
-            const AtomRec rec = recs[(long long)f * gp.natoms + a];
+            const AtomRec rec = pf_rec;
             const int Ax = tt.halfw[rec.type * 3], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
             int xlo, xhi, ylo, yhi;
             stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
@@ -159,6 +166,10 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             hitT[pw * 32 + lane] = mine;
         }
         part_barrier(part);
+        if (cb + chunk < lend && pt < (int)min((unsigned)chunk, lend - cb - chunk)) {      // prefetch the next chunk
+            pf_v = vals[cb + chunk + pt];
+            pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
+        }
 
         // ---------------- B: every owner adds its hits, in list order, into cells only it writes
         if (owner_valid && !(gp.debug_skip & 1)) {
@@ -226,6 +237,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         part_barrier(part);
     }
     __syncthreads();
+    if (FUSE_ZFFT) { load_twiddles(twr, twi, twz, nz); __syncthreads(); }
 
     if (dens_dump != nullptr) {
         for (int i = threadIdx.x; i < ncol * nz; i += blockDim.x) {
