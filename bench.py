@@ -37,8 +37,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--frames-per-step", type=int, default=16)
-    ap.add_argument("--pool", type=int, default=32, help="distinct synthetic frames cycled through")
+    ap.add_argument("--frames-per-step", type=int, default=32)
+    ap.add_argument("--pool", type=int, default=64, help="distinct synthetic frames cycled through")
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fft", default="auto")
@@ -264,6 +264,15 @@ def main():
         dom = max(kern, key=kern.get)
         dom_ms = kern[dom] / max(nbatch, 1)                      # average duration of one launch of that stage
         achieved = alg_frame * F / (dom_ms * 1e-3) / 1e9
+        traffic = None          # dram bytes per launch of that kernel from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic_%s.json" % args.workload)
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            key = {"splat_zfft": "splat_zfft", "fft_y": "fft_y_kernel", "fft_x_accum": "fft_x_accum_kernel"}.get(dom, dom)
+            for kname, kv in tj.get("kernels", {}).items():
+                if key in kname:
+                    traffic = kv["dram_bytes_per_launch"] * F / kv["frames_per_launch"]
         step_gbs = alg_frame * value / world / 1e9
         out = {
             "metric": "trajectory frames/sec into 3D S(q)", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -277,7 +286,7 @@ def main():
                     "d2h_bytes_per_step": sf_bytes // K, "note": "pinned host frames -> Engine.push_frames; S(q) read once per job"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": alg_frame, "frames_per_launch": F,
                          "kernel_ms_per_launch": dom_ms, "whole_step_GBps": step_gbs, "whole_step_frac": step_gbs / peak},
             "stage_ms_per_step": {k: v / max(nbatch, 1) for k, v in stage.items()},

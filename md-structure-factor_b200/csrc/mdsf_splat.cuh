@@ -173,11 +173,11 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
 
         // ---------------- B: every owner adds its hits, in list order, into cells only it writes
         if (owner_valid && !(gp.debug_skip & 1)) {
-            const int nwarp_used = (npair + 31) >> 5;
-            for (int wv = 0; wv < nwarp_used; ++wv) {
-                // pairs [lo, hi) of this warp-of-pairs belong to my slab
-                const int lo = max((int)(sbeg - cb) - wv * 32, 0), hi = min((int)(send - cb) - wv * 32, 32);
-                if (hi <= lo) continue;
+            // my slab's pairs inside this chunk are [r0, r1); every owner starts at ITS first warp-of-pairs, so
+            // the lanes of a warp (two slabs x 16 columns) all have work in the same loop iteration
+            const int r0 = max((int)(sbeg - cb), 0), r1 = min((int)(send - cb), npair);
+            for (int wv = r0 >> 5; wv <= (r1 - 1) >> 5 && r1 > r0; ++wv) {
+                const int lo = max(r0 - wv * 32, 0), hi = min(r1 - wv * 32, 32);
                 unsigned m = hitT[wv * 32 + mycol] & (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
                 while (m) {
                     const int i = wv * 32 + __ffs(m) - 1;

@@ -1,9 +1,7 @@
 #!/bin/sh
-mkdir -p gpurun_out
 if [ "$1" != "nopytest" ]; then timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3; fi
 run() { echo "== $1"; shift; env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu $EXTRA | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline()); print('frames/s %.0f  e2e %.0f  stages(ms/step):'%(d['value'],d['e2e']['value']), {k:round(v,3) for k,v in d['stage_ms_per_step'].items()}, d['config'].get('splat'))"; }
-run c2_auto X=1
-run c2_nozfast MDSF_NO_ZFAST=1
-EXTRA="--splat scatter" run c2_scatter X=1
+run c2 X=1
+EXTRA="--workload c1 --frames-per-step 64 --pool 64 --splat owner" run c1_owner X=1
