@@ -39,7 +39,9 @@ enum { MDSF_FOLD_REFERENCE = 0,   /* reproduce the corner rule of dens.py:107 (d
 enum { MDSF_FFT_AUTO = 0, MDSF_FFT_NATIVE = 1, MDSF_FFT_CUFFT = 2 };
 enum { MDSF_SPLAT_AUTO = 0,      /* scatter when stamps are small, owner otherwise                    */
        MDSF_SPLAT_OWNER = 1,     /* owner-computes column tiles in shared memory, fp64 accumulation   */
-       MDSF_SPLAT_SCATTER = 2 }; /* slab-pipelined 64-bit fixed-point integer reductions (L2-resident) */
+       MDSF_SPLAT_SCATTER = 2,   /* slab-pipelined 64-bit fixed-point integer reductions (L2-resident) */
+       MDSF_SPLAT_TILE = 3 };    /* column tiles in shared memory, one thread per (atom image, column),
+                                    64-bit fixed-point integer shared-memory atomics, fused z FFT       */
 
 typedef struct mdsf_handle mdsf_handle;
 
@@ -121,7 +123,7 @@ int mdsf_debug_density(mdsf_handle* h, int64_t frame, double* d1_out /* [Nx][Ny]
 int64_t mdsf_kernel_launches(const mdsf_handle* h);
 int64_t mdsf_frames_done(const mdsf_handle* h);
 const char* mdsf_fft_path(const mdsf_handle* h);
-const char* mdsf_splat_path(const mdsf_handle* h);   /* "owner" / "scatter" (valid after mdsf_set_atoms) */
+const char* mdsf_splat_path(const mdsf_handle* h);   /* "owner" / "scatter" / "tile" (valid after mdsf_set_atoms) */
 int mdsf_batch_frames(const mdsf_handle* h);
 /* Record CUDA events around every stage of subsequent batches; query the accumulated
  * per-stage device milliseconds: out[0..5] = copy, prep+bin, splat+zfft, y pass, x pass+accumulate

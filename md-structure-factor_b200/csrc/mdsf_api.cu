@@ -75,8 +75,8 @@ struct mdsf_handle {
     std::vector<double> two_host;
     int logS = 4;
     // scatter (fixed-point, slab-pipelined) splat mode
-    bool scatter = false;
-    int want_mode = 0;                // 0 auto, 1 owner, 2 scatter
+    bool scatter = false, tile_atomic = false;
+    int want_mode = 0;                // 0 auto, 1 owner, 2 scatter, 3 tile (shared-memory fixed-point atomics)
     SlabParams sp{};
     unsigned long long* d_acc = nullptr;
     unsigned *d_slab_count = nullptr, *d_slab_start = nullptr, *d_slab_cursor = nullptr, *d_entries = nullptr;
@@ -221,7 +221,8 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     gp.nb = cfg->nborder;
     h->want_mode = cfg->splat_mode;
     if (getenv("MDSF_SPLAT_MODE")) h->want_mode = atoi(getenv("MDSF_SPLAT_MODE"));
-    if (h->want_mode < 0 || h->want_mode > 2) return fail(MDSF_EINVAL, "splat mode must be 0 (auto), 1 (owner) or 2 (scatter)");
+    if (h->want_mode < 0 || h->want_mode > 3) return fail(MDSF_EINVAL, "splat mode must be 0 (auto), 1 (owner), 2 (scatter) or 3 (tile)");
+    h->tile_atomic = h->want_mode == 3 || (h->want_mode == 0 && !getenv("MDSF_AUTO_OWNER"));
     gp.debug_skip = getenv("MDSF_SPLAT_SKIP") ? atoi(getenv("MDSF_SPLAT_SKIP")) : 0;
     gp.fold_mode = cfg->fold_mode;
     // z decouples when ucell[2][0]=ucell[2][1]=0 (b_z feeds only c_2) and ucell[0][2]=ucell[1][2]=0
@@ -279,6 +280,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     if ((gp.tx & (gp.tx - 1)) || (gp.ty & (gp.ty - 1))) return fail(MDSF_EINVAL, "tile sizes must be powers of two");
     gp.nslab = 128 / (gp.tx * gp.ty);
     gp.zs = (gp.n[2] + gp.nslab - 1) / gp.nslab;
+    if (h->tile_atomic) { gp.nslab = 1; gp.zs = gp.n[2]; }     // no owners, no z slabs: one list per tile
     gp.ntx = (gp.n[0] + gp.tx - 1) / gp.tx;
     gp.nty = (gp.n[1] + gp.ty - 1) / gp.ty;
 
@@ -305,6 +307,14 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     CU(cudaMemcpy(h->d_amp, cfg->amp, sizeof(double) * nt, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_two, cfg->two_sig2, sizeof(double) * nt, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_halfw, cfg->halfw, sizeof(int) * nt * 3, cudaMemcpyHostToDevice));
+    {
+        double amax = 0;
+        for (int t = 0; t < nt; ++t) amax = std::max(amax, cfg->amp[t]);
+        int e = 0;
+        (void)std::frexp(amax, &e);                       // amax < 2^e
+        gp.fx_scale = std::ldexp(1.0, 52 - e);
+        gp.fx_inv = std::ldexp(1.0, e - 52);
+    }
     h->halfw_host.assign(cfg->halfw, cfg->halfw + nt * 3);
     h->two_host.assign(cfg->two_sig2, cfg->two_sig2 + nt);
     h->tt.amp = h->d_amp; h->tt.two_sig2 = h->d_two; h->tt.halfw = h->d_halfw;
@@ -376,8 +386,10 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     }
     CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 20480));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     *out = h;
     return MDSF_OK;
 }
@@ -472,6 +484,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
         // also take the large-stamp regime, where 2^30 reductions per frame would be hopeless
         const double mean_terms = terms / (double)natoms;
         h->scatter = h->want_mode == 2 || (h->want_mode == 0 && mean_terms > 200.0 && mean_terms <= 4096.0);
+        if (h->scatter) h->tile_atomic = false;
         if (h->scatter) {
             if ((long long)natoms * h->F >= (1LL << MDSF_ENTRY_BITS)) return fail(MDSF_EINVAL, "natoms*batch_frames exceeds 2^30 in scatter mode");
             std::vector<double> amp(nt);
@@ -556,7 +569,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     const size_t tile_b = (size_t)2 * g0.tx * g0.ty * g0.nzp * 8;
     int chunk = 128;
     // tables (also hold r in the general-ucell path and the z twiddles after the splat), pair info, hit masks
-    auto smem_for = [&](int c) { return tile_b + std::max((size_t)2 * c * 8 << h->logS, (size_t)2 * g0.n[2] * 8) + (size_t)2 * c * sizeof(PairInfo) + 2 * 4 * 32 * 4 + 64; };
+    auto smem_for = [&](int c) { return tile_b + std::max((size_t)2 * c * 8 << h->logS, (size_t)2 * g0.n[2] * 8) + (size_t)2 * c * sizeof(PairInfo) + 2 * 4 * 32 * 4 + (size_t)2 * (c + 8) * 4 + 64; };
     const size_t soft = tile_b <= 80 * 1024 ? 113 * 1024 : kMaxSmem;    // two CTAs per SM when the tile allows
     while (chunk > 32 && smem_for(chunk) > soft) chunk -= 32;
     if (smem_for(chunk) > (size_t)kMaxSmem) return fail(MDSF_EINVAL, "splat tile does not fit shared memory (%zu bytes)", smem_for(chunk));
@@ -734,12 +747,11 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
 
     // splat (+ fused z FFT on the native path)
     dim3 grid(gp.ntx * gp.nty, npairs);
-    if (h->native_fft)
-        splat_zfft_kernel<true><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
-                                                                        gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast);
-    else
-        splat_zfft_kernel<false><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, h->d_dump,
-                                                                         gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast);
+#define MDSF_SPLAT_LAUNCH(FUSE, ATOM)                                                                                     \
+    splat_zfft_kernel<FUSE, ATOM><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, \
+        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->d_err)
+    if (h->native_fft) { if (h->tile_atomic) MDSF_SPLAT_LAUNCH(true, true); else MDSF_SPLAT_LAUNCH(true, false); }
+    else               { if (h->tile_atomic) MDSF_SPLAT_LAUNCH(false, true); else MDSF_SPLAT_LAUNCH(false, false); }
     ++h->launches;
     CU(cudaGetLastError());
     }
@@ -894,7 +906,7 @@ extern "C" int mdsf_debug_density(mdsf_handle* h, int64_t frame, double* d1_out)
 extern "C" int64_t mdsf_kernel_launches(const mdsf_handle* h) { return h ? h->launches : 0; }
 extern "C" int64_t mdsf_frames_done(const mdsf_handle* h) { return h ? h->frames_done : 0; }
 extern "C" const char* mdsf_fft_path(const mdsf_handle* h) { return (h && h->native_fft) ? "native" : "cufft"; }
-extern "C" const char* mdsf_splat_path(const mdsf_handle* h) { return (h && h->scatter) ? "scatter" : "owner"; }
+extern "C" const char* mdsf_splat_path(const mdsf_handle* h) { return (h && h->scatter) ? "scatter" : ((h && h->tile_atomic) ? "tile" : "owner"); }
 extern "C" int mdsf_batch_frames(const mdsf_handle* h) { return h ? h->F : 0; }
 extern "C" int mdsf_enable_timing(mdsf_handle* h, int32_t on) {
     if (!h) return fail(MDSF_EINVAL, "null handle");

@@ -29,6 +29,7 @@ struct GridParams {
     // separable case: |c|^2 = cxx bx^2 + cyy by^2 + 2 gxy bx by + czz bz^2
     double cxx, cyy, gxy, czz;
     long long tstride;  // doubles of per-atom factor tables per frame
+    double fx_scale, fx_inv;   // fixed-point scale 2^(52-e) and its inverse (tile-atomic / scatter modes)
 };
 
 struct TypeTable {

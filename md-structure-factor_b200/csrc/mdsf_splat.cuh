@@ -36,12 +36,16 @@ __device__ __forceinline__ void part_barrier(int part) {
     asm volatile("bar.sync %0, %1;" ::"r"(part + 1), "r"(128) : "memory");
 }
 
-template <bool FUSE_ZFFT>
+// ATOMIC = true is the "tile" splat mode: phase B has no owners, one thread per (pair, column) adds its
+// terms with 64-bit FIXED-POINT integer atomics into the shared-memory tile (integer addition commutes, so
+// the result is still bitwise deterministic); the tile is converted to fp64 in place before the z FFT.
+template <bool FUSE_ZFFT, bool ATOMIC>
 __global__ void __launch_bounds__(256, MDSF_SPLAT_MINBLOCKS)
 splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ vals,
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
                   double2* __restrict__ dens_dump, GridParams gp, TypeTable tt, FftPlan zplan,
-                  const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS, int zfast)
+                  const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS, int zfast,
+                  int* __restrict__ err_flag)
 {
     extern __shared__ double smem[];
     const int ncol = gp.tx * gp.ty;
@@ -57,7 +61,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     // The tile's pair list is sorted by slab (K2), so an owner's hits are the pairs of ITS slab
     // sub-list that cover its column -- no filtering, every loop iteration does real work.
     const int nslab = gp.nslab, zs = gp.zs;
-    const int mycol = pt % ncol, myslab = pt / ncol;
+    const int mycol = pt % ncol, myslab = ATOMIC ? 0 : pt / ncol;
     const unsigned kbase = (unsigned)(f * ntiles + tile) * (unsigned)nslab;
     const unsigned lbeg = tile_start[kbase], lend = (gp.debug_skip & 16) ? lbeg : tile_start[kbase + nslab];
     const unsigned sbeg = tile_start[kbase + myslab], send = tile_start[kbase + myslab + 1];
@@ -74,6 +78,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     PairInfo* info_all = reinterpret_cast<PairInfo*>(tables + 2 * tbl_per_part);
     PairInfo* info = info_all + part * chunk;
     unsigned* hitT = reinterpret_cast<unsigned*>(info_all + 2 * chunk) + part * 4 * 32;   // [4 warps of pairs][column]
+    int* voff = reinterpret_cast<int*>(reinterpret_cast<unsigned*>(info_all + 2 * chunk) + 2 * 4 * 32) + part * (chunk + 8);   // ATOMIC: visit offsets
 
     double* mytile = part ? tile_im : tile_re;
     // the first chunk's list entries and atom records are requested before the tile is cleared, the next
@@ -155,9 +160,22 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 rxyz[pt * 3] = rec.r[0]; rxyz[pt * 3 + 1] = rec.r[1]; rxyz[pt * 3 + 2] = rec.r[2];
             }
         }
-        // ballot transpose of the 32 x ncol (pair x column) hit matrix of this warp:
-        // hitT[warp][c] = pairs (bit = lane) whose image covers column c; bit order = list order
-        {
+        int nvis = 0;
+        if (ATOMIC) {
+            // inclusive scan of the pairs' column counts over the part's 128 threads -> voff[i+1]
+            nvis = __popc(colmask);
+            int v = nvis;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t0 = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t0; }
+            if (lane == 31) voff[chunk + 1 + pw] = v;
+            part_barrier(part);
+            int basev = 0;
+            for (int w2 = 0; w2 < pw; ++w2) basev += voff[chunk + 1 + w2];
+            if (pt < chunk) voff[pt + 1] = v + basev;
+            if (pt == 0) voff[0] = 0;
+        } else {
+            // ballot transpose of the 32 x ncol (pair x column) hit matrix of this warp:
+            // hitT[warp][c] = pairs (bit = lane) whose image covers column c; bit order = list order
             unsigned mine = 0;
             for (int c = 0; c < ncol; ++c) {
                 const unsigned b = __ballot_sync(0xffffffffu, (colmask >> c) & 1u);
@@ -171,8 +189,58 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
         }
 
+        // ---------------- B (tile mode): one thread per (pair, column), fixed-point integer atomics
+        if (ATOMIC && !(gp.debug_skip & 1)) {
+            unsigned long long* itile = reinterpret_cast<unsigned long long*>(mytile);
+            const int total = voff[npair];
+            for (int v = pt; v < total; v += 128) {
+                int lo = 0, hi = npair - 1;               // pair i with voff[i] <= v < voff[i+1]
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (voff[mid] <= v) lo = mid; else hi = mid - 1; }
+                const PairInfo pi = info[lo];
+                const int hh = (pi.x >> 24) & 0xff;
+                const int local = v - voff[lo];
+                const int lx = local / hh, ly = local - lx * hh;
+                const int cx = (pi.x & 0xff) + lx, cy = ((pi.x >> 16) & 0xff) + ly;
+                if (X0 + cx >= gp.n[0] || Y0 + cy >= gp.n[1]) continue;
+                const int pz0 = pi.y, kA = pi.z & 1023, kB = (pi.z >> 10) & 1023, nzr = (pi.z >> 20) & 1023;
+                const int shlo = (pi.z & (1 << 30)) ? gp.nb : nz, shhi = (pi.z < 0) ? -gp.nb : -nz;
+                unsigned long long* colp = itile + (size_t)((cx << lty) + cy) * nzp;
+                if (gp.separable) {
+                    const double* T = tbl + ((size_t)lo << logS);
+                    double exy = T[lx] * T[gp.tx + ly];
+                    if (tt.ctab != nullptr) {
+                        const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
+                        exy *= tt.ctab[tt.ctab_off[type] + (i0 + lx) * 2 * tt.halfw[type * 3 + 1] + (j0 + ly)];
+                    }
+                    exy *= gp.fx_scale;
+                    const double* ez = T + gp.tx + gp.ty;
+                    for (int k = 0; k < nzr; ++k) {
+                        const int pz = pz0 + k;
+                        const int cz = k < kA ? pz + shlo : (k < kB ? pz : pz + shhi);
+                        atomicAdd(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(exy * ez[k]));
+                    }
+                } else {
+                    const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
+                    const int Ax = tt.halfw[type * 3], Ay = tt.halfw[type * 3 + 1];
+                    const double rx = rxyz[lo * 3], ry = rxyz[lo * 3 + 1], rz = rxyz[lo * 3 + 2];
+                    const int px = (int)(rx / gp.dr[0]) - Ax + i0 + lx, py = (int)(ry / gp.dr[1]) - Ay + j0 + ly;
+                    const double bx = __dsub_rn(rx, __dmul_rn((double)px, gp.dr[0]));
+                    const double by = __dsub_rn(ry, __dmul_rn((double)py, gp.dr[1]));
+                    const double t2 = tt.two_sig2[type], amp = tt.amp[type] * gp.fx_scale;
+                    for (int k = 0; k < nzr; ++k) {
+                        const int pz = pz0 + k;
+                        const int cz = k < kA ? pz + shlo : (k < kB ? pz : pz + shhi);
+                        const double bzv = __dsub_rn(rz, __dmul_rn((double)pz, gp.dr[2]));
+                        const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
+                        const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
+                        const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
+                        atomicAdd(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2)));
+                    }
+                }
+            }
+        }
         // ---------------- B: every owner adds its hits, in list order, into cells only it writes
-        if (owner_valid && !(gp.debug_skip & 1)) {
+        if (!ATOMIC && owner_valid && !(gp.debug_skip & 1)) {
             // my slab's pairs inside this chunk are [r0, r1); every owner starts at ITS first warp-of-pairs, so
             // the lanes of a warp (two slabs x 16 columns) all have work in the same loop iteration
             const int r0 = max((int)(sbeg - cb), 0), r1 = min((int)(send - cb), npair);
@@ -237,7 +305,17 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         part_barrier(part);
     }
     __syncthreads();
-    if (FUSE_ZFFT) { load_twiddles(twr, twi, twz, nz); __syncthreads(); }
+    if (ATOMIC) {       // fixed point -> fp64, in place (overflow: |value| >= 2^62 means a cell held > 2048 peak amplitudes)
+        long long ovf = 0;
+        for (int i = threadIdx.x; i < 2 * ncol * nzp; i += blockDim.x) {
+            const long long q64 = reinterpret_cast<long long*>(tile_re)[i];
+            ovf |= q64 ^ (q64 << 1);
+            tile_re[i] = (double)q64 * gp.fx_inv;
+        }
+        if (ovf < 0) atomicExch(err_flag, 2);
+    }
+    if (FUSE_ZFFT) load_twiddles(twr, twi, twz, nz);
+    if (ATOMIC || FUSE_ZFFT) __syncthreads();
 
     if (dens_dump != nullptr) {
         for (int i = threadIdx.x; i < ncol * nz; i += blockDim.x) {

@@ -16,7 +16,7 @@ ABI_VERSION = 1
 F32, F64 = 0, 1
 FOLD_REFERENCE, FOLD_PERIODIC = 0, 1
 FFT_AUTO, FFT_NATIVE, FFT_CUFFT = 0, 1, 2
-SPLAT_AUTO, SPLAT_OWNER, SPLAT_SCATTER = 0, 1, 2
+SPLAT_AUTO, SPLAT_OWNER, SPLAT_SCATTER, SPLAT_TILE = 0, 1, 2, 3
 
 EXPORTS = [
     "mdsf_create", "mdsf_destroy", "mdsf_set_atoms", "mdsf_host_alloc", "mdsf_host_free",

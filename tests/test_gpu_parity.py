@@ -51,7 +51,7 @@ def run_engine(mdsf, c, fft_mode, batch=0, tile=(0, 0), fold=None, keep=True, sp
     return out
 
 
-@pytest.mark.parametrize("splat", ["owner", "scatter"])
+@pytest.mark.parametrize("splat", ["owner", "scatter", "tile"])
 @pytest.mark.parametrize("fft_mode", ["native", "cufft"])
 @pytest.mark.parametrize("name", CASES)
 def test_engine_matches_reference_golden(mdsf, name, fft_mode, splat):
@@ -111,7 +111,7 @@ def test_atom_far_outside_box_is_reported(mdsf, tmp_path):
     assert ei.value.code == -3
 
 
-@pytest.mark.parametrize("splat", ["owner", "scatter"])
+@pytest.mark.parametrize("splat", ["owner", "scatter", "tile"])
 def test_bitwise_reproducible_and_batch_invariant(mdsf, splat):
     c = load_case("mono_f32")
     a = run_engine(mdsf, c, "native", batch=2, splat=splat)
@@ -124,7 +124,7 @@ def test_bitwise_reproducible_and_batch_invariant(mdsf, splat):
     assert norm <= 1e-14
 
 
-@pytest.mark.parametrize("splat", ["owner", "scatter"])
+@pytest.mark.parametrize("splat", ["owner", "scatter", "tile"])
 def test_periodic_fold_switch_differs_only_in_corners(mdsf, splat):
     c = load_case("corner_na_f64")
     ref = run_engine(mdsf, c, "native", fold="reference", splat=splat)
@@ -137,7 +137,7 @@ def test_periodic_fold_switch_differs_only_in_corners(mdsf, splat):
     assert abs(per["d1"][0].sum() - ref["d1"][0].sum()) <= 1e-10 * ref["d1"][0].sum()
 
 
-@pytest.mark.parametrize("splat", ["owner", "scatter"])
+@pytest.mark.parametrize("splat", ["owner", "scatter", "tile"])
 def test_general_ucell_uses_full_expression(mdsf, splat):
     c = load_case("gas_f64_ortho")
     c = dict(c)
@@ -215,7 +215,7 @@ def test_cli_lattice_mode_gives_bragg_peaks_only(mdsf, tmp_path, monkeypatch):
     assert sf[~on].max() < 1e-20 * sf[on].max()
 
 
-@pytest.mark.parametrize("splat", ["owner", "scatter"])
+@pytest.mark.parametrize("splat", ["owner", "scatter", "tile"])
 def test_full_size_c2_frame_against_oracle(mdsf, splat):
     """One full-size frame of the benchmark workload (105 456 atoms, 256^3): bit-exact cell indices,
     density and S(q) against the CPU oracle (takes ~5 s of numpy)."""
