@@ -1,5 +1,5 @@
 #!/bin/sh
-run() { echo "== $1"; shift; env "$@" timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu $EXTRA | python -c "
+run() { echo "== $1"; shift; env "$@" timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu --splat tile --frames-per-step 16 --pool 32 | python -c "
 import json,sys
-d=json.loads(sys.stdin.readline()); print('frames/s %.0f  stages(ms/step16):'%(d['value']), {k:round(v,3) for k,v in d['stage_ms_per_step'].items()})"; }
-for s in 0 32 64 96 ; do run "skip=$s" MDSF_SPLAT_SKIP=$s; done
+d=json.loads(sys.stdin.readline()); print('frames/s %.0f  splat %.3f'%(d['value'], d['stage_ms_per_step']['splat_zfft']))"; }
+for s in 0 1 2 4 5 16 18 ; do run "skip=$s" MDSF_SPLAT_SKIP=$s; done
