@@ -479,11 +479,9 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
             const int* hw = &h->halfw_host[type_id[a] * 3];
             terms += 8.0 * hw[0] * hw[1] * hw[2];
         }
-        // measured on B200: very small stamps (c2: 64 cells) are quickest through the owner tiles,
-        // mid-size stamps (c1: ~800 cells per atom on average) through the fixed-point scatter; the owner tiles
-        // also take the large-stamp regime, where 2^30 reductions per frame would be hopeless
-        const double mean_terms = terms / (double)natoms;
-        h->scatter = h->want_mode == 2 || (h->want_mode == 0 && mean_terms > 200.0 && mean_terms <= 4096.0);
+        // measured on B200: the shared-memory fixed-point tile mode wins for small and
+        // mid-size stamps (c2: 64 cells, c1: ~800 cells per atom); scatter and owner stay selectable
+        h->scatter = h->want_mode == 2;
         if (h->scatter) h->tile_atomic = false;
         if (h->scatter) {
             if ((long long)natoms * h->F >= (1LL << MDSF_ENTRY_BITS)) return fail(MDSF_EINVAL, "natoms*batch_frames exceeds 2^30 in scatter mode");

@@ -233,3 +233,39 @@ def test_full_size_c2_frame_against_oracle(mdsf, splat):
     assert np.abs(got["d1"][0] - taps["d1"][0]).max() <= 1e-13 * taps["d1"][0].max()
     rel, norm = sf_errors(got["sf"], ref["sf"])
     assert rel <= 1e-5 and norm <= 1e-12, (rel, norm)
+
+
+@pytest.mark.parametrize("workload", ["c3", "c4"])
+def test_full_size_properties_without_oracle(mdsf, workload):
+    """BASELINE-size grids (512^3 with 334k atoms, 768^3 with 1M atoms) through size-independent
+    properties: additivity over frames (sf is a plain sum, reference dens.py:318), bitwise reproducibility,
+    and the normalisation identity of the reference (comment at dens.py:309): the DC bin of one frame is
+    (sum of the density)^2 = (electrons * (2 pi)^1.5 / (dr_x dr_y dr_z |det ucell|))^2 (the Gaussians live in
+    lattice coordinates, so a monoclinic cell stretches them by 1/sin(theta))."""
+    w = __import__("workloads")
+    wl = w.get(workload)
+    coords = w.jitter_frames(wl["base"], wl["box"], 2, wl["jitter"], wl["seed0"])
+    dens = mdsf.dens
+
+    def run(frames):
+        eng, n, dr, nb = dens.make_engine(wl["box"], wl["typ"], wl["rad"], wl["ucell"], wl["sres"], np.float32, np.float32,
+                                          batch_frames=2)
+        try:
+            r = frames.copy()
+            eng.push_frames(r, np.ones((r.shape[0], 3)))
+            return eng.read_sf(), dr
+        finally:
+            eng.close()
+
+    both, dr = run(coords)
+    assert tuple(both.shape) == (wl["grid"][0], wl["grid"][1], wl["grid"][2] // 2 + 1)
+    again, _ = run(coords)
+    assert np.array_equal(both, again)
+    a, _ = run(coords[:1])
+    b, _ = run(coords[1:])
+    rel = np.abs(both - (a + b)).max() / both.max()
+    assert rel <= 1e-13, rel
+    electrons = sum(wl["rad"][t][0] for t in wl["typ"])
+    expect = (electrons * (2 * np.pi) ** 1.5 / (float(np.prod(dr)) * abs(np.linalg.det(wl["ucell"])))) ** 2
+    assert abs(a[0, 0, 0] / expect - 1) < 2e-3
+    assert a.min() >= 0
