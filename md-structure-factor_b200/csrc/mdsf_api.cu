@@ -567,7 +567,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     const size_t tile_b = (size_t)2 * g0.tx * g0.ty * g0.nzp * 8;
     int chunk = 128;
     // tables (also hold r in the general-ucell path and the z twiddles after the splat), pair info, hit masks
-    auto smem_for = [&](int c) { return tile_b + std::max((size_t)2 * c * 8 << h->logS, (size_t)2 * g0.n[2] * 8) + (size_t)2 * c * sizeof(PairInfo) + 2 * 4 * 32 * 4 + (size_t)2 * (c + 8) * 4 + 64; };
+    auto smem_for = [&](int c) { return tile_b + std::max((size_t)2 * c * 8 << h->logS, (size_t)2 * g0.n[2] * 8) + (size_t)2 * c * sizeof(PairInfo) + 2 * 4 * 32 * 4 + (size_t)2 * (c + 8) * 4 + (size_t)2 * c * g0.tx * g0.ty + 64; };
     const size_t soft = tile_b <= 80 * 1024 ? 113 * 1024 : kMaxSmem;    // two CTAs per SM when the tile allows
     while (chunk > 32 && smem_for(chunk) > soft) chunk -= 32;
     if (smem_for(chunk) > (size_t)kMaxSmem) return fail(MDSF_EINVAL, "splat tile does not fit shared memory (%zu bytes)", smem_for(chunk));

@@ -79,6 +79,8 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     PairInfo* info = info_all + part * chunk;
     unsigned* hitT = reinterpret_cast<unsigned*>(info_all + 2 * chunk) + part * 4 * 32;   // [4 warps of pairs][column]
     int* voff = reinterpret_cast<int*>(reinterpret_cast<unsigned*>(info_all + 2 * chunk) + 2 * 4 * 32) + part * (chunk + 8);   // ATOMIC: visit offsets
+    unsigned char* vpair = reinterpret_cast<unsigned char*>(reinterpret_cast<int*>(reinterpret_cast<unsigned*>(info_all + 2 * chunk) + 2 * 4 * 32) + 2 * (chunk + 8))
+                           + (size_t)part * chunk * ncol;      // ATOMIC: visit -> pair (chunk <= 128 pairs, <= ncol visits each)
 
     double* mytile = part ? tile_im : tile_re;
     // the first chunk's list entries and atom records are requested before the tile is cleared, the next
@@ -173,6 +175,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             for (int w2 = 0; w2 < pw; ++w2) basev += voff[chunk + 1 + w2];
             if (pt < chunk) voff[pt + 1] = v + basev;
             if (pt == 0) voff[0] = 0;
+            for (int u = 0; u < nvis; ++u) vpair[v + basev - nvis + u] = (unsigned char)pt;
         } else {
             // ballot transpose of the 32 x ncol (pair x column) hit matrix of this warp:
             // hitT[warp][c] = pairs (bit = lane) whose image covers column c; bit order = list order
@@ -194,8 +197,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             unsigned long long* itile = reinterpret_cast<unsigned long long*>(mytile);
             const int total = voff[npair];
             for (int v = pt; v < total; v += 128) {
-                int lo = 0, hi = npair - 1;               // pair i with voff[i] <= v < voff[i+1]
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (voff[mid] <= v) lo = mid; else hi = mid - 1; }
+                const int lo = vpair[v];                  // pair i with voff[i] <= v < voff[i+1]
                 const PairInfo pi = info[lo];
                 const int hh = (pi.x >> 24) & 0xff;
                 const int local = v - voff[lo];
@@ -305,7 +307,9 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         part_barrier(part);
     }
     __syncthreads();
-    if (ATOMIC) {       // fixed point -> fp64, in place (overflow: |value| >= 2^62 means a cell held > 2048 peak amplitudes)
+    // tile mode on the fast z path converts fixed point -> fp64 inside the first FFT stage instead
+    const bool fused_convert = ATOMIC && FUSE_ZFFT && zfast && dens_dump == nullptr && !(gp.debug_skip & 2);
+    if (ATOMIC && !fused_convert) {   // fixed point -> fp64, in place (overflow: |value| >= 2^62: a cell held > 2048 peak amplitudes)
         long long ovf = 0;
         for (int i = threadIdx.x; i < 2 * ncol * nzp; i += blockDim.x) {
             const long long q64 = reinterpret_cast<long long*>(tile_re)[i];
@@ -333,8 +337,47 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         // to the volume.  Output k2 of block k1 goes to z = R*k2 + k1: the transposed digit-reversed order of
         // two equal radices is the natural frequency order, and lanes (k1) write contiguous 16-byte cells.
         const int R = zfast;
-        fft_stage_dispatch<true, IO_SMEM, IO_SMEM>(R, tile_re, tile_im, twr, twi, nz, nz, ncol, nzp, 1, gp.pad_shift, 0,
-                                                   GlobalTile{nullptr, 0, 0}, nullptr, false);
+        if (fused_convert && R == 16) {
+            // stage 1 written out: load the int64 cells, check overflow, convert, radix-16, twiddle, store fp64 in place
+            long long ovf = 0;
+            for (int it = threadIdx.x; it < ncol * 16; it += blockDim.x) {
+                const int fcol = it >> 4, n2 = it & 15;
+                double xr[16], xi[16];
+                int addr[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int p = n2 + 16 * j;
+                    addr[j] = fcol * nzp + p + (p >> gp.pad_shift);
+                    const long long qr = reinterpret_cast<long long*>(tile_re)[addr[j]], qi = reinterpret_cast<long long*>(tile_im)[addr[j]];
+                    ovf |= (qr ^ (qr << 1)) | (qi ^ (qi << 1));
+                    xr[j] = (double)qr * gp.fx_inv; xi[j] = (double)qi * gp.fx_inv;
+                }
+                Dft<16>::run(xr, xi, twr, twi, nz);
+#pragma unroll
+                for (int k = 1; k < 16; ++k) {
+                    const double wr = twr[n2 * k], wi = twi[n2 * k];
+                    const double yr = xr[k] * wr - xi[k] * wi;
+                    xi[k] = xr[k] * wi + xi[k] * wr;
+                    xr[k] = yr;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { tile_re[addr[k]] = xr[k]; tile_im[addr[k]] = xi[k]; }
+            }
+            if (ovf < 0) atomicExch(err_flag, 2);
+        } else {
+            if (fused_convert) {      // radix 8: plain conversion pass, then the generic stage
+                long long ovf = 0;
+                for (int i = threadIdx.x; i < 2 * ncol * nzp; i += blockDim.x) {
+                    const long long q64 = reinterpret_cast<long long*>(tile_re)[i];
+                    ovf |= q64 ^ (q64 << 1);
+                    tile_re[i] = (double)q64 * gp.fx_inv;
+                }
+                if (ovf < 0) atomicExch(err_flag, 2);
+                __syncthreads();
+            }
+            fft_stage_dispatch<true, IO_SMEM, IO_SMEM>(R, tile_re, tile_im, twr, twi, nz, nz, ncol, nzp, 1, gp.pad_shift, 0,
+                                                       GlobalTile{nullptr, 0, 0}, nullptr, false);
+        }
         __syncthreads();
         for (int it = threadIdx.x; it < ncol * R; it += blockDim.x) {
             const int fcol = it / R, b = it - fcol * R;
