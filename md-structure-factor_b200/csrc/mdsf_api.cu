@@ -635,6 +635,15 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             const size_t sm = (size_t)3 * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
             int logw = 0; while ((1 << logw) < h->Wx) ++logw;
             dim3 grid((gp.n[2] + h->Wx - 1) / h->Wx, gp.n[1]);
+            const FftPlan& xp = h->ax[0].plan;
+            const bool fast = xp.nstages == 2 && xp.radix[0] == xp.radix[1] && (gp.n[0] / xp.radix[0]) * h->Wx == h->thr_x &&
+                              (xp.radix[0] == 16 || xp.radix[0] == 8) && !getenv("MDSF_NO_XFAST");
+            const size_t smf = (size_t)2 * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
+            if (fast && xp.radix[0] == 16)
+                fft_x_accum_fast_kernel<16, 16><<<grid, h->thr_x, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
+            else if (fast)
+                fft_x_accum_fast_kernel<8, 8><<<grid, h->thr_x, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
+            else
             fft_x_accum_kernel<<<grid, h->thr_x, sm, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].plan, h->ax[0].d_tw,
                                                                       gp.n[0], gp.n[1], gp.n[2], h->Wx, logw, npairs);
             ++h->launches;

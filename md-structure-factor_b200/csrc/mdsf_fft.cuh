@@ -386,6 +386,71 @@ fft_x_accum_kernel(double2* __restrict__ vol, double* __restrict__ P, FftPlan pl
     }
 }
 
+// ------------------------------------------------------------------ x pass, two-stage fast path (Nx = R1*R2)
+// Same data flow as fft_x_accum_kernel, written out for plans with exactly two stages whose butterfly count
+// per tile equals the block size (Nx/R1 * W == Nx/R2 * W == blockDim): every thread owns ONE butterfly per
+// stage, so the |C|^2 sums of its R2 outputs stay in registers across the pairs of the batch and P sees a
+// single read-modify-write straight from registers (no accumulator tile in shared memory).
+template <int R1, int R2>
+__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_PASS_MINBLOCKS)
+fft_x_accum_fast_kernel(double2* __restrict__ vol, double* __restrict__ P, const double2* __restrict__ tw,
+                        int ny, int nz, int logw, int npairs)
+{
+    constexpr int NX = R1 * R2;
+    extern __shared__ double smem[];
+    const int W = 1 << logw;
+    double* sre = smem;
+    double* sim = sre + (size_t)NX * W;
+    double* twr = sim + (size_t)NX * W;
+    double* twi = twr + NX;
+    load_twiddles(twr, twi, tw, NX);
+    const int z0 = blockIdx.x * W;
+    const int y = blockIdx.y;
+    const long long xstride = (long long)ny * nz;
+    const long long off = (long long)y * nz + z0;
+    const int f = threadIdx.x & (W - 1), bf = threadIdx.x >> logw;      // column, butterfly index (same for both stages)
+    const bool ok = z0 + f < nz;
+    double acc[R2];
+#pragma unroll
+    for (int k = 0; k < R2; ++k) acc[k] = 0.0;
+    for (int q = 0; q < npairs; ++q) {
+        const double2* base = vol + (long long)q * NX * xstride + off + f;
+        {   // stage 1: points n2 + R2*j (n2 = bf), straight from global memory
+            double xr[R1], xi[R1];
+#pragma unroll
+            for (int j = 0; j < R1; ++j) {
+                double2 v = make_double2(0.0, 0.0);
+                if (ok) v = base[(long long)(bf + R2 * j) * xstride];
+                xr[j] = v.x; xi[j] = v.y;
+            }
+            Dft<R1>::run(xr, xi, twr, twi, NX);
+#pragma unroll
+            for (int k = 1; k < R1; ++k) {
+                const double wr = twr[bf * k], wi = twi[bf * k];
+                const double yr = xr[k] * wr - xi[k] * wi;
+                xi[k] = xr[k] * wi + xi[k] * wr;
+                xr[k] = yr;
+            }
+            __syncthreads();                       // previous pair's stage 2 has finished reading the tile
+#pragma unroll
+            for (int k = 0; k < R1; ++k) { const int a = ((k * R2 + bf) << logw) + f; sre[a] = xr[k]; sim[a] = xi[k]; }
+        }
+        __syncthreads();
+        {   // stage 2: block b = bf holds points b*R2 + j; outputs stay at b*R2 + k (position space)
+            double xr[R2], xi[R2];
+#pragma unroll
+            for (int j = 0; j < R2; ++j) { const int a = ((bf * R2 + j) << logw) + f; xr[j] = sre[a]; xi[j] = sim[a]; }
+            Dft<R2>::run(xr, xi, twr, twi, NX);
+#pragma unroll
+            for (int k = 0; k < R2; ++k) acc[k] += xr[k] * xr[k] + xi[k] * xi[k];
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int k = 0; k < R2; ++k) P[(long long)(bf * R2 + k) * xstride + off + f] += acc[k];
+    }
+}
+
 // ------------------------------------------------------------------ library-FFT path helper
 // P += sum_q |vol_q|^2 after a cuFFT Z2Z (grids whose sizes have prime factors > 13)
 __global__ void accumulate_power_kernel(const double2* __restrict__ vol, double* __restrict__ P,
