@@ -627,6 +627,14 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             const size_t sm = (size_t)2 * gp.n[1] * h->Wy * 8 + (size_t)2 * gp.n[1] * 8;
             dim3 grid((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0], npairs);
             int logw = 0; while ((1 << logw) < h->Wy) ++logw;
+            const FftPlan& yp = h->ax[1].plan;
+            const bool fast = yp.nstages == 2 && yp.radix[0] == yp.radix[1] && (gp.n[1] / yp.radix[0]) * h->Wy == h->thr_y &&
+                              (yp.radix[0] == 16 || yp.radix[0] == 8) && !getenv("MDSF_NO_YFAST");
+            if (fast && yp.radix[0] == 16)
+                fft_y_fast_kernel<16, 16><<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw);
+            else if (fast)
+                fft_y_fast_kernel<8, 8><<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw);
+            else
             fft_y_kernel<<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy, logw);
             ++h->launches;
         }

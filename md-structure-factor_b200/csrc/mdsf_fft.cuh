@@ -386,6 +386,57 @@ fft_x_accum_kernel(double2* __restrict__ vol, double* __restrict__ P, FftPlan pl
     }
 }
 
+// ------------------------------------------------------------------ y pass, two-stage fast path (Ny = R1*R2)
+// grid = (z chunks, Nx, pairs), one butterfly per thread and stage; in place on the volume.
+template <int R1, int R2>
+__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_PASS_MINBLOCKS)
+fft_y_fast_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, int nx, int nz, int logw)
+{
+    constexpr int NY = R1 * R2;
+    extern __shared__ double smem[];
+    const int W = 1 << logw;
+    double* sre = smem;
+    double* sim = sre + (size_t)NY * W;
+    double* twr = sim + (size_t)NY * W;
+    double* twi = twr + NY;
+    load_twiddles(twr, twi, tw, NY);
+    const int z0 = blockIdx.x * W;
+    const int f = threadIdx.x & (W - 1), bf = threadIdx.x >> logw;
+    const bool ok = z0 + f < nz;
+    double2* base = vol + (((long long)blockIdx.z * nx + blockIdx.y) * NY) * (long long)nz + z0 + f;
+    {
+        double xr[R1], xi[R1];
+#pragma unroll
+        for (int j = 0; j < R1; ++j) {
+            double2 v = make_double2(0.0, 0.0);
+            if (ok) v = base[(long long)(bf + R2 * j) * nz];
+            xr[j] = v.x; xi[j] = v.y;
+        }
+        Dft<R1>::run(xr, xi, twr, twi, NY);
+        __syncthreads();                           // twiddle table is in shared memory
+#pragma unroll
+        for (int k = 1; k < R1; ++k) {
+            const double wr = twr[bf * k], wi = twi[bf * k];
+            const double yr = xr[k] * wr - xi[k] * wi;
+            xi[k] = xr[k] * wi + xi[k] * wr;
+            xr[k] = yr;
+        }
+#pragma unroll
+        for (int k = 0; k < R1; ++k) { const int a = ((k * R2 + bf) << logw) + f; sre[a] = xr[k]; sim[a] = xi[k]; }
+    }
+    __syncthreads();
+    {
+        double xr[R2], xi[R2];
+#pragma unroll
+        for (int j = 0; j < R2; ++j) { const int a = ((bf * R2 + j) << logw) + f; xr[j] = sre[a]; xi[j] = sim[a]; }
+        Dft<R2>::run(xr, xi, twr, twi, NY);
+        if (ok) {
+#pragma unroll
+            for (int k = 0; k < R2; ++k) base[(long long)(bf * R2 + k) * nz] = make_double2(xr[k], xi[k]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ x pass, two-stage fast path (Nx = R1*R2)
 // Same data flow as fft_x_accum_kernel, written out for plans with exactly two stages whose butterfly count
 // per tile equals the block size (Nx/R1 * W == Nx/R2 * W == blockDim): every thread owns ONE butterfly per
@@ -413,6 +464,7 @@ fft_x_accum_fast_kernel(double2* __restrict__ vol, double* __restrict__ P, const
     double acc[R2];
 #pragma unroll
     for (int k = 0; k < R2; ++k) acc[k] = 0.0;
+    __syncthreads();                               // twiddle table is in shared memory
     for (int q = 0; q < npairs; ++q) {
         const double2* base = vol + (long long)q * NX * xstride + off + f;
         {   // stage 1: points n2 + R2*j (n2 = bf), straight from global memory
