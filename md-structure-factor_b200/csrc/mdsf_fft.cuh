@@ -295,6 +295,9 @@ __device__ __forceinline__ void load_twiddles(double* twr, double* twi, const do
 #ifndef MDSF_PASS_MINBLOCKS
 #define MDSF_PASS_MINBLOCKS 4
 #endif
+#ifndef MDSF_FAST_MINBLOCKS
+#define MDSF_FAST_MINBLOCKS 5          // two-stage kernels: 5 CTAs/SM (102 registers) measured best on B200
+#endif
 
 // ------------------------------------------------------------------ z pass (stand-alone)
 // grid = (column groups, pairs).  A group is `ncol` consecutive (x,y) columns, contiguous in
@@ -389,7 +392,7 @@ fft_x_accum_kernel(double2* __restrict__ vol, double* __restrict__ P, FftPlan pl
 // ------------------------------------------------------------------ y pass, two-stage fast path (Ny = R1*R2)
 // grid = (z chunks, Nx, pairs), one butterfly per thread and stage; in place on the volume.
 template <int R1, int R2>
-__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_PASS_MINBLOCKS)
+__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_FAST_MINBLOCKS)
 fft_y_fast_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, int nx, int nz, int logw)
 {
     constexpr int NY = R1 * R2;
@@ -443,7 +446,7 @@ fft_y_fast_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, int
 // stage, so the |C|^2 sums of its R2 outputs stay in registers across the pairs of the batch and P sees a
 // single read-modify-write straight from registers (no accumulator tile in shared memory).
 template <int R1, int R2>
-__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_PASS_MINBLOCKS)
+__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_FAST_MINBLOCKS)
 fft_x_accum_fast_kernel(double2* __restrict__ vol, double* __restrict__ P, const double2* __restrict__ tw,
                         int ny, int nz, int logw, int npairs)
 {
