@@ -32,6 +32,18 @@
 //   w: i0 | j0 << 10 | type << 20                   stamp index of the first clipped column (cross-term table)
 typedef int4 PairInfo;
 
+// 64-bit fixed-point add into shared memory from two NATIVE 32-bit atomics (a 64-bit shared-memory
+// atomicAdd compiles to a compare-and-swap loop).  The low-word add returns the old value, so exactly the
+// adds that wrap the low word see a carry; the high word receives hi + carry.  The final 64-bit value is
+// the exact integer sum whatever the interleaving, i.e. still bitwise deterministic.  v must be >= 0.
+__device__ __forceinline__ void smem_add_u64(unsigned long long* cell, unsigned long long v) {
+    unsigned* w = reinterpret_cast<unsigned*>(cell);
+    const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    const unsigned old = atomicAdd(w, lo);
+    const unsigned carry = (old + lo) < lo ? 1u : 0u;
+    if (hi | carry) atomicAdd(w + 1, hi + carry);
+}
+
 __device__ __forceinline__ void part_barrier(int part) {
     asm volatile("bar.sync %0, %1;" ::"r"(part + 1), "r"(128) : "memory");
 }
@@ -219,7 +231,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                     for (int k = 0; k < nzr; ++k) {
                         const int pz = pz0 + k;
                         const int cz = k < kA ? pz + shlo : (k < kB ? pz : pz + shhi);
-                        atomicAdd(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(exy * ez[k]));
+                        smem_add_u64(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(exy * ez[k]));
                     }
                 } else {
                     const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
@@ -236,7 +248,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                         const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
                         const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
                         const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
-                        atomicAdd(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2)));
+                        smem_add_u64(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2)));
                     }
                 }
             }

@@ -4,4 +4,4 @@ run() { echo "== $1"; shift; env "$@" timeout 300 python bench.py --steps 10 --w
 import json,sys
 d=json.loads(sys.stdin.readline()); print('frames/s %.0f  e2e %.0f  stages(ms/step):'%(d['value'],d['e2e']['value']), {k:round(v,3) for k,v in d['stage_ms_per_step'].items()}, d['config'].get('splat'))"; }
 run c2 X=1
-run c2_noyfast MDSF_NO_YFAST=1
+EXTRA="--workload c1 --frames-per-step 64 --pool 64" run c1 X=1
