@@ -150,7 +150,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 // slice of the atom's factor tables this tile needs: EX[i0..i0+w), EY[j0..j0+h), EZ[0..2Az)
                 if (!(gp.debug_skip & 4)) {
                     const double* T = atom_tables + rec.tbase;
-                    double* dst = tbl + ((size_t)pt << logS);
+                    double* dst = tbl + pt;                 // transposed: entry sidx of pair pt at tbl[sidx*chunk + pt] (conflict-free)
                     if (S <= 16) {              // issue every load before the first store
                         double vv[16];
 #pragma unroll
@@ -162,12 +162,12 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                             vv[sidx] = (src >= 0 && sidx < S) ? T[src] : 0.0;
                         }
 #pragma unroll
-                        for (int sidx = 0; sidx < 16; ++sidx) if (sidx < S) dst[sidx] = vv[sidx];
+                        for (int sidx = 0; sidx < 16; ++sidx) if (sidx < S) dst[sidx * chunk] = vv[sidx];
                     } else {
-                        for (int sidx = 0; sidx < w; ++sidx) dst[sidx] = T[i0 + sidx];
-                        for (int sidx = 0; sidx < h; ++sidx) dst[gp.tx + sidx] = T[2 * Ax + j0 + sidx];
+                        for (int sidx = 0; sidx < w; ++sidx) dst[sidx * chunk] = T[i0 + sidx];
+                        for (int sidx = 0; sidx < h; ++sidx) dst[(gp.tx + sidx) * chunk] = T[2 * Ax + j0 + sidx];
 #pragma unroll 4
-                        for (int sidx = 0; sidx < 2 * Az; ++sidx) dst[gp.tx + gp.ty + sidx] = T[2 * (Ax + Ay) + sidx];
+                        for (int sidx = 0; sidx < 2 * Az; ++sidx) dst[(gp.tx + gp.ty + sidx) * chunk] = T[2 * (Ax + Ay) + sidx];
                     }
                 }
             } else {
@@ -220,18 +220,18 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 const int shlo = (pi.z & (1 << 30)) ? gp.nb : nz, shhi = (pi.z < 0) ? -gp.nb : -nz;
                 unsigned long long* colp = itile + (size_t)((cx << lty) + cy) * nzp;
                 if (gp.separable) {
-                    const double* T = tbl + ((size_t)lo << logS);
-                    double exy = T[lx] * T[gp.tx + ly];
+                    const double* T = tbl + lo;
+                    double exy = T[lx * chunk] * T[(gp.tx + ly) * chunk];
                     if (tt.ctab != nullptr) {
                         const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
                         exy *= tt.ctab[tt.ctab_off[type] + (i0 + lx) * 2 * tt.halfw[type * 3 + 1] + (j0 + ly)];
                     }
                     exy *= gp.fx_scale;
-                    const double* ez = T + gp.tx + gp.ty;
+                    const double* ez = T + (gp.tx + gp.ty) * chunk;
                     for (int k = 0; k < nzr; ++k) {
                         const int pz = pz0 + k;
                         const int cz = k < kA ? pz + shlo : (k < kB ? pz : pz + shhi);
-                        smem_add_u64(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(exy * ez[k]));
+                        smem_add_u64(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(exy * ez[k * chunk]));
                     }
                 } else {
                     const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
@@ -269,24 +269,24 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                     const int pz0 = pi.y, kA = pi.z & 1023, kB = (pi.z >> 10) & 1023, nzr = (pi.z >> 20) & 1023;
                     const int shlo = (pi.z & (1 << 30)) ? gp.nb : nz, shhi = (pi.z < 0) ? -gp.nb : -nz;
                     if (gp.separable) {
-                        const double* T = tbl + ((size_t)i << logS);
-                        double exy = T[lx] * T[gp.tx + ly];
+                        const double* T = tbl + i;
+                        double exy = T[lx * chunk] * T[(gp.tx + ly) * chunk];
                         if (tt.ctab != nullptr) {
                             const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
                             exy *= tt.ctab[tt.ctab_off[type] + (i0 + lx) * 2 * tt.halfw[type * 3 + 1] + (j0 + ly)];
                         }
-                        const double* ez = T + gp.tx + gp.ty;
+                        const double* ez = T + (gp.tx + gp.ty) * chunk;
                         {   // cell
                             const int ka = max(kA, zlo - pz0), kb = min(kB, zhi - pz0);
-                            for (int k = ka; k < kb; ++k) { const int cz = pz0 + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = pz0 + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * chunk]; }
                         }
                         if (kA > 0) {   // low padding
                             const int sh = pz0 + shlo, ka = max(0, zlo - sh), kb = min(kA, zhi - sh);
-                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * chunk]; }
                         }
                         if (nzr > kB) { // high padding
                             const int sh = pz0 + shhi, ka = max(kB, zlo - sh), kb = min(nzr, zhi - sh);
-                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * chunk]; }
                         }
                     } else {
                         // general ucell: one exp per cell, exactly the reference's expression
