@@ -330,7 +330,17 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         }
         if (ovf < 0) atomicExch(err_flag, 2);
     }
-    if (FUSE_ZFFT) load_twiddles(twr, twi, twz, nz);
+    if (FUSE_ZFFT) {
+        if (fused_convert && zfast == 16) {
+            // stage-1 twiddles laid out [k][n2] (w^(n2 k) at k*16 + n2): lanes walk n2, so the reads are conflict-free
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+                const double2 w = twz[(i >> 4) * (i & 15)];
+                twr[i] = w.x; twi[i] = w.y;
+            }
+        } else {
+            load_twiddles(twr, twi, twz, nz);
+        }
+    }
     if (ATOMIC || FUSE_ZFFT) __syncthreads();
 
     if (dens_dump != nullptr) {
@@ -367,7 +377,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 Dft<16>::run(xr, xi, twr, twi, nz);
 #pragma unroll
                 for (int k = 1; k < 16; ++k) {
-                    const double wr = twr[n2 * k], wi = twi[n2 * k];
+                    const double wr = twr[k * 16 + n2], wi = twi[k * 16 + n2];
                     const double yr = xr[k] * wr - xi[k] * wi;
                     xi[k] = xr[k] * wi + xi[k] * wr;
                     xr[k] = yr;
