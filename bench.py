@@ -247,7 +247,7 @@ def main():
     for i in range(K):
         step_host(W + i)
     finish()
-    sf = eng.read_sf() if rank == 0 or world == 1 else None
+    sf = eng.read_sf(pinned=True) if rank == 0 or world == 1 else None
     if sf is None:
         eng.sync()
     e2e_s = time.perf_counter() - t0

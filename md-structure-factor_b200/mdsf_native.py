@@ -207,8 +207,10 @@ class Engine:
     def sync(self):
         _check(self._lib.mdsf_sync(self._h))
 
-    def read_sf(self):
-        out = np.empty((self.n[0], self.n[1], self.n[2] // 2 + 1), dtype=np.float64)
+    def read_sf(self, pinned=False):
+        """sf (Nx, Ny, Nz/2+1) float64; ``pinned=True`` lands it in page-locked memory (faster device->host copy)."""
+        shape = (self.n[0], self.n[1], self.n[2] // 2 + 1)
+        out = pinned_empty(shape, np.float64) if pinned else np.empty(shape, dtype=np.float64)
         _check(self._lib.mdsf_read_sf(self._h, _dptr(out)))
         return out
 
