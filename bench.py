@@ -180,6 +180,7 @@ def main():
     frame_bytes = natoms * 12
     sf_shape = (int(n[0]), int(n[1]), int(n[2]) // 2 + 1)
     red = torch.empty(sf_shape, dtype=torch.float64, device="cuda:%d" % local)
+    sf_host = native.pinned_empty(sf_shape, np.float64)          # destination of the final S(q) read-out
 
     def step_device(i):
         s = (i * F) % (pool_n - F + 1)
@@ -247,7 +248,7 @@ def main():
     for i in range(K):
         step_host(W + i)
     finish()
-    sf = eng.read_sf(pinned=True) if rank == 0 or world == 1 else None
+    sf = eng.read_sf(out=sf_host) if rank == 0 or world == 1 else None
     if sf is None:
         eng.sync()
     e2e_s = time.perf_counter() - t0

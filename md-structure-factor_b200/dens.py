@@ -240,7 +240,7 @@ def compute_sf(r, L, typ, out_filename, rad, ucell, Sres):
         else:
             lo, hi = _wrapped_atoms(nframes, natoms)
             eng.push_frames(r, scale.astype(np.float64), (lo, hi), write_back=WRITE_BACK_COORDS)
-        sf = eng.read_sf(pinned=True)
+        sf = eng.read_sf()
         LAST_RUN.clear()
         LAST_RUN.update(N=n.copy(), dr=dr.copy(), Nborder=nborder, batch_frames=eng.batch_frames, fft=eng.fft_path, splat=eng.splat_path,
                         kernel_launches=eng.kernel_launches, frames=eng.frames_done)

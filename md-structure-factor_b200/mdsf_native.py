@@ -207,10 +207,13 @@ class Engine:
     def sync(self):
         _check(self._lib.mdsf_sync(self._h))
 
-    def read_sf(self, pinned=False):
-        """sf (Nx, Ny, Nz/2+1) float64; ``pinned=True`` lands it in page-locked memory (faster device->host copy)."""
+    def read_sf(self, out=None):
+        """sf (Nx, Ny, Nz/2+1) float64, into ``out`` if given (e.g. a pinned_empty buffer for a faster copy)."""
         shape = (self.n[0], self.n[1], self.n[2] // 2 + 1)
-        out = pinned_empty(shape, np.float64) if pinned else np.empty(shape, dtype=np.float64)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
         _check(self._lib.mdsf_read_sf(self._h, _dptr(out)))
         return out
 
