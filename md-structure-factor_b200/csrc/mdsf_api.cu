@@ -73,7 +73,8 @@ struct mdsf_handle {
     int *d_halfw = nullptr, *d_ctab_off = nullptr;
     unsigned* d_toff = nullptr;
     std::vector<double> two_host;
-    int logS = 4;
+    int logS = 4, zstage = 1023;
+    bool ez_global = false;
     // scatter (fixed-point, slab-pipelined) splat mode
     bool scatter = false, tile_atomic = false;
     int want_mode = 0;                // 0 auto, 1 owner, 2 scatter, 3 tile (shared-memory fixed-point atomics)
@@ -198,7 +199,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     }
     if (cfg->ntypes < 1 || !cfg->amp || !cfg->two_sig2 || !cfg->halfw) return fail(MDSF_EINVAL, "type tables missing");
     if (cfg->nborder < 0) return fail(MDSF_EINVAL, "negative Nborder");
-    if (cfg->ntypes > 2048) return fail(MDSF_EINVAL, "more than 2048 distinct labels");
+    if (cfg->ntypes > 1024) return fail(MDSF_EINVAL, "more than 1024 distinct labels");
     for (int t = 0; t < cfg->ntypes * 3; ++t)
         if (2 * cfg->halfw[t] > MDSF_MAX_STAMP) return fail(MDSF_EINVAL, "stamp of %d cells exceeds %d", 2 * cfg->halfw[t], MDSF_MAX_STAMP);
     for (int t = 0; t < cfg->ntypes * 3; ++t)
@@ -386,10 +387,14 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     }
     CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 20480));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     *out = h;
     return MDSF_OK;
 }
@@ -562,8 +567,19 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     while ((1LL << h->sort_bits) <= nkeys) ++h->sort_bits;
 
     // splat shared-memory budget -> pairs per chunk; per-pair table stride 2^logS >= tx + ty + max 2Az
+    // stamps taller than `zstage` cells (rare heavy ions next to light atoms) keep EZ in global memory, so they do
+    // not inflate every pair's slot
+    h->zstage = zmax;
+    if (zmax > 16) {
+        long long tall = 0;
+        for (int64_t a = 0; a < natoms; ++a) tall += 2 * h->halfw_host[type_id[a] * 3 + 2] > 16;
+        if (tall * 4 < natoms) h->zstage = 16;
+    }
+    if (getenv("MDSF_ZSTAGE")) h->zstage = atoi(getenv("MDSF_ZSTAGE"));
+    h->ez_global = zmax > h->zstage;
+    const int zslot = std::max(1, std::min(zmax, h->zstage));
     h->logS = 0;
-    while ((1 << h->logS) < g0.tx + g0.ty + zmax) ++h->logS;
+    while ((1 << h->logS) < g0.tx + g0.ty + zslot) ++h->logS;
     const size_t tile_b = (size_t)2 * g0.tx * g0.ty * g0.nzp * 8;
     int chunk = 128;
     // tables (also hold r in the general-ucell path and the z twiddles after the splat), pair info, hit masks
@@ -762,11 +778,19 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
 
     // splat (+ fused z FFT on the native path)
     dim3 grid(gp.ntx * gp.nty, npairs);
-#define MDSF_SPLAT_LAUNCH(FUSE, ATOM)                                                                                     \
-    splat_zfft_kernel<FUSE, ATOM><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, \
-        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->d_err)
-    if (h->native_fft) { if (h->tile_atomic) MDSF_SPLAT_LAUNCH(true, true); else MDSF_SPLAT_LAUNCH(true, false); }
-    else               { if (h->tile_atomic) MDSF_SPLAT_LAUNCH(false, true); else MDSF_SPLAT_LAUNCH(false, false); }
+#define MDSF_SPLAT_LAUNCH(FUSE, ATOM, EZG)                                                                                \
+    splat_zfft_kernel<FUSE, ATOM, EZG><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, \
+        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err)
+    switch ((h->native_fft ? 4 : 0) | (h->tile_atomic ? 2 : 0) | (h->ez_global ? 1 : 0)) {
+        case 0: MDSF_SPLAT_LAUNCH(false, false, false); break;
+        case 1: MDSF_SPLAT_LAUNCH(false, false, true); break;
+        case 2: MDSF_SPLAT_LAUNCH(false, true, false); break;
+        case 3: MDSF_SPLAT_LAUNCH(false, true, true); break;
+        case 4: MDSF_SPLAT_LAUNCH(true, false, false); break;
+        case 5: MDSF_SPLAT_LAUNCH(true, false, true); break;
+        case 6: MDSF_SPLAT_LAUNCH(true, true, false); break;
+        default: MDSF_SPLAT_LAUNCH(true, true, true); break;
+    }
     ++h->launches;
     CU(cudaGetLastError());
     }

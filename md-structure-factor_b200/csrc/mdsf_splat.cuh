@@ -51,13 +51,14 @@ __device__ __forceinline__ void part_barrier(int part) {
 // ATOMIC = true is the "tile" splat mode: phase B has no owners, one thread per (pair, column) adds its
 // terms with 64-bit FIXED-POINT integer atomics into the shared-memory tile (integer addition commutes, so
 // the result is still bitwise deterministic); the tile is converted to fp64 in place before the z FFT.
-template <bool FUSE_ZFFT, bool ATOMIC>
+// EZG = true compiles the path for stamps taller than `zstage` (EZ read from global memory in phase B).
+template <bool FUSE_ZFFT, bool ATOMIC, bool EZG>
 __global__ void __launch_bounds__(256, MDSF_SPLAT_MINBLOCKS)
 splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ vals,
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
                   double2* __restrict__ dens_dump, GridParams gp, TypeTable tt, FftPlan zplan,
                   const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS, int zfast,
-                  int* __restrict__ err_flag)
+                  int zstage, int* __restrict__ err_flag)
 {
     extern __shared__ double smem[];
     const int ncol = gp.tx * gp.ty;
@@ -141,7 +142,9 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             pi.x = cx0 | (w << 8) | (cy0 << 16) | (h << 24);
             pi.y = rec.ir[2] - Az;
             pi.z = kA | (kB << 10) | ((2 * Az) << 20) | ((shlo != nz) ? (1 << 30) : 0) | ((shhi != -nz) ? (int)(1u << 31) : 0);
-            pi.w = i0 | (j0 << 10) | (rec.type << 20);
+            // stamps taller than zstage cells do not stage EZ: phase B reads it from the atom's table in global memory
+            const bool ez_global = EZG && 2 * Az > zstage;
+            pi.w = i0 | (j0 << 10) | (rec.type << 20) | (ez_global ? (int)(1u << 31) : 0);
             info[pt] = pi;
             if (w * h > 0)
                 for (int cx = cx0; cx < cx0 + w; ++cx)
@@ -158,16 +161,19 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                             int src = -1;
                             if (sidx < gp.tx) { if (sidx < w) src = i0 + sidx; }
                             else if (sidx < gp.tx + gp.ty) { if (sidx - gp.tx < h) src = 2 * Ax + j0 + (sidx - gp.tx); }
-                            else if (sidx - gp.tx - gp.ty < 2 * Az) src = 2 * (Ax + Ay) + (sidx - gp.tx - gp.ty);
+                            else if (!ez_global && sidx - gp.tx - gp.ty < 2 * Az) src = 2 * (Ax + Ay) + (sidx - gp.tx - gp.ty);
                             vv[sidx] = (src >= 0 && sidx < S) ? T[src] : 0.0;
                         }
+                        if (ez_global) vv[gp.tx + gp.ty] = __longlong_as_double((long long)rec.tbase + 2 * (Ax + Ay));
 #pragma unroll
                         for (int sidx = 0; sidx < 16; ++sidx) if (sidx < S) dst[sidx * chunk] = vv[sidx];
                     } else {
                         for (int sidx = 0; sidx < w; ++sidx) dst[sidx * chunk] = T[i0 + sidx];
                         for (int sidx = 0; sidx < h; ++sidx) dst[(gp.tx + sidx) * chunk] = T[2 * Ax + j0 + sidx];
+                        if (ez_global) dst[(gp.tx + gp.ty) * chunk] = __longlong_as_double((long long)rec.tbase + 2 * (Ax + Ay));
+                        else
 #pragma unroll 4
-                        for (int sidx = 0; sidx < 2 * Az; ++sidx) dst[(gp.tx + gp.ty + sidx) * chunk] = T[2 * (Ax + Ay) + sidx];
+                            for (int sidx = 0; sidx < 2 * Az; ++sidx) dst[(gp.tx + gp.ty + sidx) * chunk] = T[2 * (Ax + Ay) + sidx];
                     }
                 }
             } else {
@@ -223,18 +229,20 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                     const double* T = tbl + lo;
                     double exy = T[lx * chunk] * T[(gp.tx + ly) * chunk];
                     if (tt.ctab != nullptr) {
-                        const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
+                        const int type = (pi.w >> 20) & 1023, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
                         exy *= tt.ctab[tt.ctab_off[type] + (i0 + lx) * 2 * tt.halfw[type * 3 + 1] + (j0 + ly)];
                     }
                     exy *= gp.fx_scale;
                     const double* ez = T + (gp.tx + gp.ty) * chunk;
+                    int ezs = chunk;                          // stride of the EZ entries (compile-time chunk stride when !EZG)
+                    if (EZG && pi.w < 0) { ez = atom_tables + __double_as_longlong(ez[0]); ezs = 1; }
                     for (int k = 0; k < nzr; ++k) {
                         const int pz = pz0 + k;
                         const int cz = k < kA ? pz + shlo : (k < kB ? pz : pz + shhi);
-                        smem_add_u64(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(exy * ez[k * chunk]));
+                        smem_add_u64(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(exy * ez[k * ezs]));
                     }
                 } else {
-                    const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
+                    const int type = (pi.w >> 20) & 1023, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
                     const int Ax = tt.halfw[type * 3], Ay = tt.halfw[type * 3 + 1];
                     const double rx = rxyz[lo * 3], ry = rxyz[lo * 3 + 1], rz = rxyz[lo * 3 + 2];
                     const int px = (int)(rx / gp.dr[0]) - Ax + i0 + lx, py = (int)(ry / gp.dr[1]) - Ay + j0 + ly;
@@ -272,25 +280,27 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                         const double* T = tbl + i;
                         double exy = T[lx * chunk] * T[(gp.tx + ly) * chunk];
                         if (tt.ctab != nullptr) {
-                            const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
+                            const int type = (pi.w >> 20) & 1023, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
                             exy *= tt.ctab[tt.ctab_off[type] + (i0 + lx) * 2 * tt.halfw[type * 3 + 1] + (j0 + ly)];
                         }
                         const double* ez = T + (gp.tx + gp.ty) * chunk;
+                        int ezs = chunk;
+                        if (EZG && pi.w < 0) { ez = atom_tables + __double_as_longlong(ez[0]); ezs = 1; }
                         {   // cell
                             const int ka = max(kA, zlo - pz0), kb = min(kB, zhi - pz0);
-                            for (int k = ka; k < kb; ++k) { const int cz = pz0 + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * chunk]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = pz0 + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * ezs]; }
                         }
                         if (kA > 0) {   // low padding
                             const int sh = pz0 + shlo, ka = max(0, zlo - sh), kb = min(kA, zhi - sh);
-                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * chunk]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * ezs]; }
                         }
                         if (nzr > kB) { // high padding
                             const int sh = pz0 + shhi, ka = max(kB, zlo - sh), kb = min(nzr, zhi - sh);
-                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * chunk]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * ezs]; }
                         }
                     } else {
                         // general ucell: one exp per cell, exactly the reference's expression
-                        const int type = pi.w >> 20, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
+                        const int type = (pi.w >> 20) & 1023, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
                         const int Ax = tt.halfw[type * 3], Ay = tt.halfw[type * 3 + 1];
                         const double rx = rxyz[i * 3], ry = rxyz[i * 3 + 1], rz = rxyz[i * 3 + 2];
                         // padded-grid index of my column: p = ir - A + stamp index, ir = trunc(r/dr) as in K1
