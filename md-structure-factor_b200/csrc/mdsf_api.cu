@@ -733,7 +733,6 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     const int npairs = (nf + 1) / 2;
     if (h->scatter) {
         // K2s: counting sort of atom images by x slab (order inside a bin is irrelevant: integer adds commute)
-        const long long total = (long long)nf * h->natoms;
         const SlabParams& sp = h->sp;
         CU(cudaMemsetAsync(h->d_slab_count, 0, sizeof(unsigned) * (sp.nslabs + 1), h->s_comp));
         bin_slabs_kernel<0><<<h->nsm * 4, 256, sizeof(unsigned) * 2 * sp.nslabs, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_count, nullptr, gp, h->tt, sp, nf);

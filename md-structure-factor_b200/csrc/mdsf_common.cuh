@@ -96,11 +96,3 @@ __host__ __device__ inline unsigned image_slabmask(int irz, int Az, int sx, int 
     if (nzr > kB) for (int sl = (pz0 + kB + shhi) / zs; sl <= (pz0 + nzr - 1 + shhi) / zs; ++sl) m |= 1u << sl;
     return m;
 }
-
-// destination z of padded index pz for an image with x side sx and y side sy (dens.py:95-107)
-__device__ __forceinline__ int fold_z(int pz, int nz, int nb, bool corner_xy, int sy, int fold_mode) {
-    int sz = pz < 0 ? -1 : (pz >= nz ? 1 : 0);
-    if (sz == 0) return pz;
-    if (fold_mode == 0 && corner_xy && sz != sy) return pz + (sz < 0 ? nb : -nb);
-    return pz - sz * nz;
-}
