@@ -69,7 +69,7 @@ struct mdsf_handle {
     bool slot_used[kSlots]{};
     int next_slot = 0;
     // device buffers
-    double *d_amp = nullptr, *d_two = nullptr, *d_ctab = nullptr, *d_tables = nullptr;
+    double *d_amp = nullptr, *d_two = nullptr, *d_ctab = nullptr, *d_tables = nullptr;     // d_tables: alias of the current set
     int *d_halfw = nullptr, *d_ctab_off = nullptr;
     unsigned* d_toff = nullptr;
     std::vector<double> two_host;
@@ -91,6 +91,19 @@ struct mdsf_handle {
     int pipe_grid = 0;
     int* d_type = nullptr;
     void* d_stage[kSlots]{};
+    // outputs of the prep/bin stage; two sets so that prep+bin of batch b+1 (stream s_prep) overlap the
+    // splat/FFT kernels of batch b (stream s_comp).  The d_* names below alias the set of the current batch.
+    struct PrepSet {
+        AtomRec* recs = nullptr;
+        unsigned *cnt = nullptr, *off = nullptr, *keys[2]{}, *vals[2]{}, *tile_start = nullptr;
+        double* tables = nullptr;
+        void* cub = nullptr;
+        cudaEvent_t ev_binned = nullptr, ev_consumed = nullptr;
+        bool used = false;
+    } sets[2];
+    int nsets = 1;
+    long long batch_counter = 0;
+    cudaStream_t s_prep = nullptr;
     AtomRec* d_recs = nullptr;
     unsigned *d_cnt = nullptr, *d_off = nullptr;
     unsigned *d_keys[2]{}, *d_vals[2]{};
@@ -355,6 +368,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     CU(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_back, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_prep, cudaStreamNonBlocking));
     for (int s = 0; s < kSlots; ++s) {
         CU(cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_free[s], cudaEventDisableTiming));
@@ -404,11 +418,17 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->cufft_plan) cufftDestroy(h->cufft_plan);
-    void* bufs[] = {h->d_acc, h->d_slab_count, h->d_slab_start, h->d_slab_cursor, h->d_entries, h->d_step_start, h->d_ctl, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_tables, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1], h->d_recs, h->d_cnt,
-                    h->d_off, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_tile_start, h->d_cub,
+    void* bufs[] = {h->d_acc, h->d_slab_count, h->d_slab_start, h->d_slab_cursor, h->d_entries, h->d_step_start, h->d_ctl, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1],
                     h->d_vol, h->d_dump, h->d_P, h->d_sf, h->d_err};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int d = 0; d < 3; ++d) { if (h->ax[d].d_tw) cudaFree(h->ax[d].d_tw); if (h->ax[d].d_rev) cudaFree(h->ax[d].d_rev); }
+    for (auto& ps : h->sets) {
+        void* pb[] = {ps.recs, ps.cnt, ps.off, ps.keys[0], ps.keys[1], ps.vals[0], ps.vals[1], ps.tile_start, ps.tables, ps.cub};
+        for (void* b : pb) if (b) cudaFree(b);
+        if (ps.ev_binned) cudaEventDestroy(ps.ev_binned);
+        if (ps.ev_consumed) cudaEventDestroy(ps.ev_consumed);
+    }
+    if (h->s_prep) cudaStreamDestroy(h->s_prep);
     if (h->h_err) cudaFreeHost(h->h_err);
     for (int s = 0; s < kSlots; ++s) {
         if (h->ev_h2d[s]) cudaEventDestroy(h->ev_h2d[s]);
@@ -593,23 +613,34 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     CU(cudaMalloc(&h->d_type, sizeof(int) * natoms));
     CU(cudaMemcpy(h->d_type, type_id, sizeof(int) * natoms, cudaMemcpyHostToDevice));
     for (int s = 0; s < kSlots; ++s) CU(cudaMalloc(&h->d_stage[s], h->csize * 3 * natoms * h->F));
-    CU(cudaMalloc(&h->d_recs, sizeof(AtomRec) * natoms * h->F));
     CU(cudaMalloc(&h->d_toff, sizeof(unsigned) * natoms));
     CU(cudaMemcpy(h->d_toff, toff.data(), sizeof(unsigned) * natoms, cudaMemcpyHostToDevice));
     h->tt.toff = h->d_toff;
-    CU(cudaMalloc(&h->d_tables, sizeof(double) * std::max(1LL, tstride * h->F)));
-    CU(cudaMalloc(&h->d_cnt, sizeof(unsigned) * natoms * h->F));
-    CU(cudaMalloc(&h->d_off, sizeof(unsigned) * natoms * h->F));
-    for (int i = 0; i < 2; ++i) {
-        CU(cudaMalloc(&h->d_keys[i], sizeof(unsigned) * std::max(1LL, cap)));
-        CU(cudaMalloc(&h->d_vals[i], sizeof(unsigned) * std::max(1LL, cap)));
+    h->nsets = (h->scatter || getenv("MDSF_ONE_STREAM")) ? 1 : 2;
+    {
+        size_t b1 = 0, b2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, b1, (unsigned*)nullptr, (unsigned*)nullptr, (long long)natoms * h->F, h->s_comp);
+        cub::DeviceRadixSort::SortPairs(nullptr, b2, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, cap, 0, h->sort_bits, h->s_comp);
+        h->cub_bytes = std::max(b1, b2) + 256;
     }
-    CU(cudaMalloc(&h->d_tile_start, sizeof(unsigned) * (nkeys + 2)));
-    size_t b1 = 0, b2 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, b1, h->d_cnt, h->d_off, (long long)natoms * h->F, h->s_comp);
-    cub::DeviceRadixSort::SortPairs(nullptr, b2, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], cap, 0, h->sort_bits, h->s_comp);
-    h->cub_bytes = std::max(b1, b2) + 256;
-    CU(cudaMalloc(&h->d_cub, h->cub_bytes));
+    for (int p = 0; p < h->nsets; ++p) {
+        mdsf_handle::PrepSet& ps = h->sets[p];
+        CU(cudaMalloc(&ps.recs, sizeof(AtomRec) * natoms * h->F));
+        CU(cudaMalloc(&ps.tables, sizeof(double) * std::max(1LL, tstride * h->F)));
+        CU(cudaMalloc(&ps.cnt, sizeof(unsigned) * natoms * h->F));
+        CU(cudaMalloc(&ps.off, sizeof(unsigned) * natoms * h->F));
+        if (!h->scatter) {
+            for (int i = 0; i < 2; ++i) {
+                CU(cudaMalloc(&ps.keys[i], sizeof(unsigned) * std::max(1LL, cap)));
+                CU(cudaMalloc(&ps.vals[i], sizeof(unsigned) * std::max(1LL, cap)));
+            }
+            CU(cudaMalloc(&ps.tile_start, sizeof(unsigned) * (nkeys + 2)));
+            CU(cudaMalloc(&ps.cub, h->cub_bytes));
+        }
+        CU(cudaEventCreateWithFlags(&ps.ev_binned, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ps.ev_consumed, cudaEventDisableTiming));
+    }
+    h->d_recs = h->sets[0].recs; h->d_tables = h->sets[0].tables; h->d_cnt = h->sets[0].cnt; h->d_off = h->sets[0].off;
     return MDSF_OK;
 }
 
@@ -689,9 +720,9 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
 }
 
 template <typename C, typename P>
-static void launch_prep(mdsf_handle* h, void* stage, const BatchScales& sc, int nf, long long wlo, long long whi) {
+static void launch_prep(mdsf_handle* h, cudaStream_t st, void* stage, const BatchScales& sc, int nf, long long wlo, long long whi) {
     const long long total = (long long)nf * h->natoms;
-    prep_atoms_kernel<C, P><<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(
+    prep_atoms_kernel<C, P><<<grid_for(total, 256, h->nsm), 256, 0, st>>>(
         (C*)stage, h->d_type, h->d_recs, h->d_cnt, h->d_tables, h->gp, h->tt, sc, nf, wlo, whi, h->d_err);
 }
 
@@ -705,25 +736,38 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
         CU(cudaStreamWaitEvent(h->s_copy, h->ev_free[slot], 0));
         CU(cudaStreamWaitEvent(h->s_copy, h->ev_back[slot], 0));
     }
+    // prep/bin outputs of this batch go to set p; with two sets they are produced on s_prep while the
+    // previous batch is still in its splat/FFT kernels on s_comp
+    const int p = (int)(h->batch_counter++ % h->nsets);
+    mdsf_handle::PrepSet& ps = h->sets[p];
+    cudaStream_t sp = h->nsets == 2 ? h->s_prep : h->s_comp;
+    h->d_recs = ps.recs; h->d_cnt = ps.cnt; h->d_off = ps.off; h->d_tables = ps.tables;
+    h->d_keys[0] = ps.keys[0]; h->d_keys[1] = ps.keys[1]; h->d_vals[0] = ps.vals[0]; h->d_vals[1] = ps.vals[1];
+    h->d_tile_start = ps.tile_start; h->d_cub = ps.cub;
     cudaEvent_t* tv = nullptr;
     if (h->timing) {
-        for (int i = 0; i < 6; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tev.push_back(e); }
-        tv = &h->tev[h->tev.size() - 6];
+        for (int i = 0; i < 7; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tev.push_back(e); }
+        tv = &h->tev[h->tev.size() - 7];
         CU(cudaEventRecord(tv[0], h->s_copy));
     }
     CU(cudaMemcpyAsync(h->d_stage[slot], src, bytes, cudaMemcpyDefault, h->s_copy));
     CU(cudaEventRecord(h->ev_h2d[slot], h->s_copy));
-    CU(cudaStreamWaitEvent(h->s_comp, h->ev_h2d[slot], 0));
-    if (tv) CU(cudaEventRecord(tv[1], h->s_comp));
+    CU(cudaStreamWaitEvent(sp, h->ev_h2d[slot], 0));
+    if (ps.used && h->nsets == 2) CU(cudaStreamWaitEvent(sp, ps.ev_consumed, 0));     // the splat of batch b-2 has read this set
+    // start after the splat of batch b-1: prep+bin then overlap its HBM-bound y/x passes instead of fighting the
+    // issue-bound splat kernel for the SMs
+    if (h->nsets == 2 && h->sets[1 - p].used && !getenv("MDSF_PREP_EARLY")) CU(cudaStreamWaitEvent(sp, h->sets[1 - p].ev_consumed, 0));
+    if (tv) CU(cudaEventRecord(tv[1], sp));
 
     BatchScales sc;
     for (int f = 0; f < nf; ++f) for (int d = 0; d < 3; ++d) sc.a[f][d] = scale[f * 3 + d];
     const bool c32 = h->cfg.coord_dtype == MDSF_F32, p32 = h->cfg.arith_dtype == MDSF_F32;
-    if (c32 && p32) launch_prep<float, float>(h, h->d_stage[slot], sc, nf, wlo, whi);
-    else if (c32) launch_prep<float, double>(h, h->d_stage[slot], sc, nf, wlo, whi);
-    else launch_prep<double, double>(h, h->d_stage[slot], sc, nf, wlo, whi);
+    if (c32 && p32) launch_prep<float, float>(h, sp, h->d_stage[slot], sc, nf, wlo, whi);
+    else if (c32) launch_prep<float, double>(h, sp, h->d_stage[slot], sc, nf, wlo, whi);
+    else launch_prep<double, double>(h, sp, h->d_stage[slot], sc, nf, wlo, whi);
     ++h->launches;
-    CU(cudaEventRecord(h->ev_prep[slot], h->s_comp));
+    CU(cudaEventRecord(h->ev_prep[slot], sp));
+    CU(cudaEventRecord(h->ev_free[slot], sp));          // the staging slot is only read (and rewritten) by K1
     if (write_back) {
         CU(cudaStreamWaitEvent(h->s_back, h->ev_prep[slot], 0));
         CU(cudaMemcpyAsync(src, h->d_stage[slot], bytes, cudaMemcpyDefault, h->s_back));
@@ -741,7 +785,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
         CU(cudaMemsetAsync(h->d_ctl, 0, sizeof(unsigned) * (2 + 2 * sp.nslabs), h->s_comp));
         bin_slabs_kernel<1><<<h->nsm * 4, 256, sizeof(unsigned) * 2 * sp.nslabs, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_slab_cursor, h->d_entries, gp, h->tt, sp, nf);
         h->launches += 3;
-        if (tv) CU(cudaEventRecord(tv[2], h->s_comp));
+        if (tv) { CU(cudaEventRecord(tv[2], h->s_comp)); CU(cudaEventRecord(tv[6], h->s_comp)); }
         // K3s/K3z: persistent cooperative kernel, scatter(s) overlapped with the z pass of slab s-1
         FftPlan zplan = h->native_fft ? h->ax[2].plan : FftPlan{gp.n[2], 0, {0}};
         size_t zsm = (size_t)2 * h->zcol * gp.nzp * 8 + (size_t)2 * gp.n[2] * 8;
@@ -764,16 +808,21 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     // an odd batch gets a phantom last frame with empty lists (imaginary part of the last pair)
     const unsigned nkeys = (unsigned)((nf + (nf & 1)) * gp.ntx * gp.nty * gp.nslab);
     size_t cb = h->cub_bytes;
-    cub::DeviceScan::ExclusiveSum(h->d_cub, cb, h->d_cnt, h->d_off, total, h->s_comp);
-    fill_u32_kernel<<<grid_for(cap, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_keys[0], nkeys, cap);
-    emit_pairs_kernel<<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_recs, h->d_cnt, h->d_off, h->d_keys[0], h->d_vals[0], gp, h->tt, nf);
+    cub::DeviceScan::ExclusiveSum(h->d_cub, cb, h->d_cnt, h->d_off, total, sp);
+    fill_u32_kernel<<<grid_for(cap, 256, h->nsm), 256, 0, sp>>>(h->d_keys[0], nkeys, cap);
+    emit_pairs_kernel<<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(h->d_recs, h->d_cnt, h->d_off, h->d_keys[0], h->d_vals[0], gp, h->tt, nf);
     int bits = 1;
     while ((1LL << bits) <= (long long)nkeys) ++bits;
     cb = h->cub_bytes;
-    cub::DeviceRadixSort::SortPairs(h->d_cub, cb, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], cap, 0, bits, h->s_comp);
-    tile_starts_kernel<<<grid_for(cap + 1, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_keys[1], cap, nkeys, h->d_tile_start);
+    cub::DeviceRadixSort::SortPairs(h->d_cub, cb, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], cap, 0, bits, sp);
+    tile_starts_kernel<<<grid_for(cap + 1, 256, h->nsm), 256, 0, sp>>>(h->d_keys[1], cap, nkeys, h->d_tile_start);
     h->launches += 3;
-    if (tv) CU(cudaEventRecord(tv[2], h->s_comp));
+    if (tv) CU(cudaEventRecord(tv[2], sp));
+    if (h->nsets == 2) {
+        CU(cudaEventRecord(ps.ev_binned, sp));
+        CU(cudaStreamWaitEvent(h->s_comp, ps.ev_binned, 0));
+    }
+    if (tv) CU(cudaEventRecord(tv[6], h->s_comp));
 
     // splat (+ fused z FFT on the native path)
     dim3 grid(gp.ntx * gp.nty, npairs);
@@ -792,10 +841,11 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     }
     ++h->launches;
     CU(cudaGetLastError());
+    if (h->nsets == 2) CU(cudaEventRecord(ps.ev_consumed, h->s_comp));
     }
+    ps.used = true;
     int rc = transform_and_accumulate(h, nf, h->native_fft, tv);   // z pass already done on the native path
     if (rc) return rc;
-    CU(cudaEventRecord(h->ev_free[slot], h->s_comp));
     if (tv) { CU(cudaEventRecord(tv[5], h->s_comp)); ++h->timed_batches; }
     h->slot_used[slot] = true;
     h->frames_done += nf;
@@ -849,6 +899,7 @@ extern "C" int mdsf_sync(mdsf_handle* h) {
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->s_comp));
     CU(cudaStreamSynchronize(h->s_copy));
+    CU(cudaStreamSynchronize(h->s_prep));
     CU(cudaStreamSynchronize(h->s_comp));
     CU(cudaStreamSynchronize(h->s_back));
     if (*h->h_err == 3) {
@@ -961,13 +1012,17 @@ extern "C" int mdsf_stage_ms(mdsf_handle* h, double* out6, int64_t* batches) {
     CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
     for (int i = 0; i < 6; ++i) out6[i] = 0;
-    const size_t nb = h->tev.size() / 6;
+    const size_t nb = h->tev.size() / 7;
     for (size_t b = 0; b < nb; ++b) {
-        cudaEvent_t* tv = &h->tev[b * 6];
+        // tv: 0 copy start (s_copy), 1 prep start, 2 binned (prep stream), 6 splat start, 3 splat done, 4 y done, 5 end (s_comp)
+        cudaEvent_t* tv = &h->tev[b * 7];
         float ms;
         CU(cudaEventElapsedTime(&ms, tv[0], tv[1])); out6[0] += ms;     // copy (overlaps the previous batch's kernels)
-        for (int i = 1; i < 5; ++i) { CU(cudaEventElapsedTime(&ms, tv[i], tv[i + 1])); out6[i] += ms; }
-        CU(cudaEventElapsedTime(&ms, tv[1], tv[5])); out6[5] += ms;     // compute-stream time of the batch
+        CU(cudaEventElapsedTime(&ms, tv[1], tv[2])); out6[1] += ms;     // prep + bin (overlaps the previous batch when two sets)
+        CU(cudaEventElapsedTime(&ms, tv[6], tv[3])); out6[2] += ms;
+        CU(cudaEventElapsedTime(&ms, tv[3], tv[4])); out6[3] += ms;
+        CU(cudaEventElapsedTime(&ms, tv[4], tv[5])); out6[4] += ms;
+        CU(cudaEventElapsedTime(&ms, tv[6], tv[5])); out6[5] += ms;     // compute-stream time of the batch
     }
     if (batches) *batches = (int64_t)nb;
     return MDSF_OK;
