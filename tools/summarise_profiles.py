@@ -55,9 +55,15 @@ st = bench['stage_ms_per_step']
 with open('profiles/r01_launches_c2.md', 'w') as f:
     f.write('# Round 1 - ncu launch list, c2 (256^3, 105456 atoms), %d frames per step, %s splat mode\n\n' % (F, bench['config']['splat']))
     f.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv python bench.py --steps 3 --warmup 2 --no-cpu`.\n')
+    main3 = sum(st[k] for k in ('splat_zfft', 'fft_y', 'fft_x_accum'))
+    ncu3 = {k: sum(v[1] for n, v in agg.items() if k in n) for k in ('splat_zfft', 'fft_y', 'fft_x_accum')}
     f.write('Times are cold-cache and serialised under the profiler: compare SHARES with the CUDA-event stage times of the un-profiled\n'
-            'bench (profiles/r01_bench_c2.json): splat_zfft %.0f %%, fft_y %.0f %%, fft_x_accum %.0f %%, prep+bin %.0f %%.\n\n'
-            % tuple(100 * st[k] / st['total'] for k in ('splat_zfft', 'fft_y', 'fft_x_accum', 'prep_bin')))
+            'bench (profiles/r01_bench_c2.json). Among the three compute-stream kernels: splat_zfft %.0f %% (ncu %.0f %%), fft_y %.0f %% (ncu %.0f %%), '
+            'fft_x_accum %.0f %% (ncu %.0f %%).\nprep+bin (prep_atoms, scan, emit, radix sort, tile starts) runs on its own stream underneath the '
+            'previous batch\'s y/x passes; its event span (%.2f ms) includes that waiting, its serialised ncu time is %.2f ms per step.\n\n'
+            % (100 * st['splat_zfft'] / main3, 100 * ncu3['splat_zfft'] / sum(ncu3.values()), 100 * st['fft_y'] / main3, 100 * ncu3['fft_y'] / sum(ncu3.values()),
+               100 * st['fft_x_accum'] / main3, 100 * ncu3['fft_x_accum'] / sum(ncu3.values()), st['prep_bin'],
+               (tot - sum(ncu3.values())) / 1e6 / 3))
     f.write('| kernel | launches | total us | share | grid | block |\n|---|---|---|---|---|---|\n')
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write('| %s | %d | %.1f | %.1f%% | %s | %s |\n' % (k, v[0], v[1] / 1e3, 100 * v[1] / tot, v[2], v[3]))
