@@ -269,3 +269,117 @@ def test_full_size_properties_without_oracle(mdsf, workload):
     expect = (electrons * (2 * np.pi) ** 1.5 / (float(np.prod(dr)) * abs(np.linalg.det(wl["ucell"])))) ** 2
     assert abs(a[0, 0, 0] / expect - 1) < 2e-3
     assert a.min() >= 0
+
+
+def _engine_for(mdsf, c, batch, **kw):
+    r = c["coords"].copy()
+    dims = c["dims"]
+    arith = np.float32 if (r.dtype == np.float32 and dims.dtype == np.float32) else np.float64
+    L = np.average(dims, axis=0)
+    scale = (L / dims).astype(np.float64)
+    eng, n, dr, nb = mdsf.dens.make_engine(L, c["typ"], c["rad"], c["ucell"], c["sres"], r.dtype, arith, batch_frames=batch, **kw)
+    return eng, r, scale
+
+
+def test_ragged_last_batch_empty_push_and_reset(mdsf):
+    """3 frames in batches of 2 (ragged last batch of one frame, i.e. half a complex pair), an empty push,
+    reset() and partial sums.  sf is a plain sum over frames (reference dens.py:318)."""
+    c = load_case("mono_f32")
+    eng, r, scale = _engine_for(mdsf, c, 2)
+    try:
+        wr = mdsf.dens._wrapped_atoms(r.shape[0], r.shape[1])
+        eng.push_frames(r[0:0], scale[0:0], wr)                  # nothing to do, not an error
+        assert eng.frames_done == 0 and not eng.read_sf().any()
+        eng.push_frames(r.copy(), scale, wr)
+        full = eng.read_sf()
+        rel, norm = sf_errors(full, c["ref_sf"])
+        assert rel <= 1e-5 and norm <= 1e-12, (rel, norm)
+        eng.reset()
+        assert eng.frames_done == 0 and not eng.read_sf().any()
+        eng.push_frames(r[:1].copy(), scale[:1], wr)
+        a = eng.read_sf()
+        eng.reset()
+        eng.push_frames(r[1:].copy(), scale[1:], wr)
+        b = eng.read_sf()
+        assert np.abs(full - (a + b)).max() <= 1e-13 * full.max()
+        eng.reset()
+        eng.push_frames(r.copy(), scale, wr)                     # same frames after a reset: bitwise the same
+        assert np.array_equal(eng.read_sf(), full)
+    finally:
+        eng.close()
+
+
+def test_device_pageable_and_pinned_inputs_agree(mdsf):
+    """mdsf_push_frames takes pinned, pageable or device pointers (cudaMemcpyDefault); the result is bitwise the same."""
+    import torch
+    c = load_case("mono_f32")
+    eng, r, scale = _engine_for(mdsf, c, 2)
+    try:
+        wr = mdsf.dens._wrapped_atoms(r.shape[0], r.shape[1])
+        eng.push_frames(r.copy(), scale, wr)
+        ref = eng.read_sf()
+        pinned = mdsf.native.pinned_empty(r.shape, r.dtype)
+        pinned[...] = r
+        eng.reset()
+        eng.push_frames(pinned, scale, wr)
+        assert np.array_equal(eng.read_sf(), ref)
+        dev = torch.from_numpy(r.copy()).cuda()
+        eng.reset()
+        eng.push_frames_ptr(dev.data_ptr(), r.shape[0], scale, wr)
+        assert np.array_equal(eng.read_sf(), ref)
+        # the S(q) grid can also stay on the device (mdsf_export_sf_device)
+        out = torch.empty(ref.shape, dtype=torch.float64, device="cuda")
+        eng.export_sf_device(out.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ref)
+    finally:
+        eng.close()
+
+
+def test_two_handles_are_independent(mdsf):
+    """One handle per (GPU, stream set); interleaved calls on two handles do not disturb each other."""
+    ca, cb = load_case("mono_f32"), load_case("gas_f64_ortho")
+    ea, ra, sa = _engine_for(mdsf, ca, 2)
+    eb, rb, sb = _engine_for(mdsf, cb, 2, splat_mode="owner")
+    try:
+        ea.push_frames(ra[:2].copy(), sa[:2], mdsf.dens._wrapped_atoms(3, ra.shape[1]))
+        eb.push_frames(rb.copy(), sb, mdsf.dens._wrapped_atoms(2, rb.shape[1]))
+        ea.push_frames(ra[2:].copy(), sa[2:], mdsf.dens._wrapped_atoms(3, ra.shape[1]))
+        rel_b, norm_b = sf_errors(eb.read_sf(), cb["ref_sf"])
+        rel_a, norm_a = sf_errors(ea.read_sf(), ca["ref_sf"])
+        assert rel_a <= 1e-5 and norm_a <= 1e-12 and rel_b <= 1e-5 and norm_b <= 1e-12
+    finally:
+        ea.close()
+        eb.close()
+
+
+def test_million_atom_wrap_quirk_cell_indices(mdsf):
+    """At >= 1e6 atoms the reference's PBC pass only touches the first `nframes` atoms (dens.py:213-221); the
+    engine reproduces that: wrapped coordinates and cell indices bit-exact against the oracle's restatement."""
+    rng = np.random.default_rng(77)
+    na, T, L = 1_000_003, 2, 200.0
+    box = np.array([L, L, L], dtype=np.float32)
+    r = rng.uniform(1.0, L - 1.0, size=(T, na, 3)).astype(np.float32)
+    r[0, 0] = (-3.0, L + 2.0, 5.0)          # atoms 0 and 1 (< nframes) are wrapped ...
+    r[1, 1] = (L + 0.5, -0.25, L)
+    r[0, 5] = (-0.4, 7.0, L + 0.3)          # ... atom 5 is not: it lands in the padding as in the reference
+    r[1, 999_999] = (L + 0.3, -0.2, 3.0)
+    typ = np.array(["H"] * na)
+    rad = {"H": (1.0, 0.53)}
+    lo, hi = orc.wrapped_atom_range(T, na)
+    assert (lo, hi) == (0, T) == tuple(mdsf.dens._wrapped_atoms(T, na))
+    eng, n, dr, nb = mdsf.dens.make_engine(box, typ, rad, np.eye(3), 2.0, np.float32, np.float32, batch_frames=2)
+    try:
+        got = r.copy()
+        eng.push_frames(got, np.ones((T, 3)), (lo, hi), write_back=True)
+        eng.sync()
+        want = r.copy()
+        orc.wrap_frames(want, box)
+        assert np.array_equal(got, want)
+        assert not np.array_equal(want, r) and np.array_equal(want[0, 5], r[0, 5])
+        for t in range(T):
+            assert np.array_equal(eng.debug_cell_indices(t).astype(np.int64), orc.cell_indices(want[t], dr))
+        sf = eng.read_sf()
+        assert np.isfinite(sf).all() and sf[0, 0, 0] > 0
+    finally:
+        eng.close()
