@@ -385,19 +385,27 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         h->cufft_batch = npairs;
     } else {
         // y / x pass tiles: [n][W] complex in shared memory
-        auto pick = [&](int n, int& W, int& thr) {
+        // short axes: [n][8] tiles, 128 threads, 4+ CTAs per SM.  Long axes keep the 128-byte rows and take 256
+        // threads (two CTAs per SM) or 512 (one) instead of narrowing the tile (c3: x pass 6.8 -> 5.5 ms).
+        auto pick = [&](int n, int& W, int& thr, int arrays) {
+            const size_t one = (size_t)n * 8 * 8 * arrays + (size_t)n * 16;       // [n][8] tile(s) + twiddles
             W = 8;
-            while (W > 1 && (size_t)n * W * 24 + (size_t)n * 16 > 100 * 1024) W >>= 1;
             thr = MDSF_PASS_THREADS;
+            if (one > 100 * 1024) thr = one <= 110 * 1024 ? 256 : 512;
+            while (W > 1 && (size_t)n * W * 8 * arrays + (size_t)n * 16 > (size_t)kMaxSmem - 2048) W >>= 1;
         };
-        pick(gp.n[1], h->Wy, h->thr_y);
-        pick(gp.n[0], h->Wx, h->thr_x);
+        pick(gp.n[1], h->Wy, h->thr_y, 2);
+        pick(gp.n[0], h->Wx, h->thr_x, 3);
         if (getenv("MDSF_WY")) h->Wy = atoi(getenv("MDSF_WY"));
         if (getenv("MDSF_WX")) h->Wx = atoi(getenv("MDSF_WX"));
         if (getenv("MDSF_THR_Y")) h->thr_y = atoi(getenv("MDSF_THR_Y"));
         if (getenv("MDSF_THR_X")) h->thr_x = atoi(getenv("MDSF_THR_X"));
-        CU(cudaFuncSetAttribute(fft_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CU(cudaFuncSetAttribute(fft_x_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_y_kernel<128, MDSF_PASS_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_y_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_y_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_x_accum_kernel<128, MDSF_PASS_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_x_accum_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_x_accum_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     }
     CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 20480));
@@ -675,14 +683,18 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             dim3 grid((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0], npairs);
             int logw = 0; while ((1 << logw) < h->Wy) ++logw;
             const FftPlan& yp = h->ax[1].plan;
-            const bool fast = yp.nstages == 2 && yp.radix[0] == yp.radix[1] && (gp.n[1] / yp.radix[0]) * h->Wy == h->thr_y &&
+            const bool fast = yp.nstages == 2 && yp.radix[0] == yp.radix[1] && (gp.n[1] / yp.radix[0]) * h->Wy == h->thr_y && h->thr_y == MDSF_PASS_THREADS &&
                               (yp.radix[0] == 16 || yp.radix[0] == 8) && !getenv("MDSF_NO_YFAST");
             if (fast && yp.radix[0] == 16)
                 fft_y_fast_kernel<16, 16><<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw);
             else if (fast)
                 fft_y_fast_kernel<8, 8><<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw);
+            else if (h->thr_y == 512)
+                fft_y_kernel<512, 1><<<grid, 512, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy, logw);
+            else if (h->thr_y == 256)
+                fft_y_kernel<256, 2><<<grid, 256, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy, logw);
             else
-            fft_y_kernel<<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy, logw);
+                fft_y_kernel<128, MDSF_PASS_MINBLOCKS><<<grid, 128, sm, h->s_comp>>>(h->d_vol, h->ax[1].plan, h->ax[1].d_tw, gp.n[0], gp.n[1], gp.n[2], h->Wy, logw);
             ++h->launches;
         }
         if (tv) CU(cudaEventRecord(tv[4], h->s_comp));
@@ -691,16 +703,22 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             int logw = 0; while ((1 << logw) < h->Wx) ++logw;
             dim3 grid((gp.n[2] + h->Wx - 1) / h->Wx, gp.n[1]);
             const FftPlan& xp = h->ax[0].plan;
-            const bool fast = xp.nstages == 2 && xp.radix[0] == xp.radix[1] && (gp.n[0] / xp.radix[0]) * h->Wx == h->thr_x &&
+            const bool fast = xp.nstages == 2 && xp.radix[0] == xp.radix[1] && (gp.n[0] / xp.radix[0]) * h->Wx == h->thr_x && h->thr_x == MDSF_PASS_THREADS &&
                               (xp.radix[0] == 16 || xp.radix[0] == 8) && !getenv("MDSF_NO_XFAST");
             const size_t smf = (size_t)2 * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
             if (fast && xp.radix[0] == 16)
                 fft_x_accum_fast_kernel<16, 16><<<grid, h->thr_x, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
             else if (fast)
                 fft_x_accum_fast_kernel<8, 8><<<grid, h->thr_x, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
+            else if (h->thr_x == 512)
+                fft_x_accum_kernel<512, 1><<<grid, 512, sm, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].plan, h->ax[0].d_tw,
+                                                                         gp.n[0], gp.n[1], gp.n[2], h->Wx, logw, npairs);
+            else if (h->thr_x == 256)
+                fft_x_accum_kernel<256, 2><<<grid, 256, sm, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].plan, h->ax[0].d_tw,
+                                                                         gp.n[0], gp.n[1], gp.n[2], h->Wx, logw, npairs);
             else
-            fft_x_accum_kernel<<<grid, h->thr_x, sm, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].plan, h->ax[0].d_tw,
-                                                                      gp.n[0], gp.n[1], gp.n[2], h->Wx, logw, npairs);
+                fft_x_accum_kernel<128, MDSF_PASS_MINBLOCKS><<<grid, 128, sm, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].plan, h->ax[0].d_tw,
+                                                                                           gp.n[0], gp.n[1], gp.n[2], h->Wx, logw, npairs);
             ++h->launches;
         }
     } else {

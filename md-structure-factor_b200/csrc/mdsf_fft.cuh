@@ -336,7 +336,9 @@ fft_z_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict_
 
 // ------------------------------------------------------------------ y pass, in place
 // grid = (z chunks, Nx, pairs); tile = [Ny][W] at fixed x; rows are W*16 contiguous bytes.
-__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_PASS_MINBLOCKS)
+// THR x MINB: 128 x 4 for short axes ([n][8] tiles <= 36 KB); 256 x 2 / 512 x 1 keep 128-byte rows on long axes.
+template <int THR, int MINB>
+__global__ void __launch_bounds__(THR, MINB)
 fft_y_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw,
              int nx, int ny, int nz, int W, int logw)
 {
@@ -359,7 +361,8 @@ fft_y_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict_
 // grid = (z chunks, Ny); tile = [Nx][W] at fixed y; loops over the pairs of the batch, keeps
 // sum_q |C_q|^2 in shared memory and adds it to the resident fp64 accumulator P with one
 // read-modify-write per batch (dens.py:315-318).
-__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_PASS_MINBLOCKS)
+template <int THR, int MINB>
+__global__ void __launch_bounds__(THR, MINB)
 fft_x_accum_kernel(double2* __restrict__ vol, double* __restrict__ P, FftPlan plan,
                    const double2* __restrict__ tw, int nx, int ny, int nz, int W, int logw, int npairs)
 {
