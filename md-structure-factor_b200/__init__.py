@@ -16,6 +16,7 @@ if _HERE not in sys.path:
 
 import mdsf_native as native  # noqa: E402
 import dens  # noqa: E402
+import npz_writer  # noqa: E402
 import load_traj  # noqa: E402
 import sf_distributed as distributed  # noqa: E402
 

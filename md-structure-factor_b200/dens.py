@@ -17,6 +17,7 @@ import math
 import numpy as np
 
 import mdsf_native as _native
+import npz_writer
 
 USE_BETTER_RESOLUTION = True
 PRINT_DETAILS = True
@@ -37,6 +38,7 @@ FFT_MODE = "auto"         # "auto" | "native" | "cufft"
 SPLAT_MODE = "auto"       # "auto" | "owner" (fp64 owner-computes tiles) | "tile" / "scatter" (deterministic fixed-point accumulation)
 BATCH_FRAMES = 0          # frames per device batch (0 = automatic)
 SAVE_COMPRESSED = True    # np.savez_compressed like the reference; False writes an uncompressed npz
+PARALLEL_NPZ = True       # deflate the npz members on all host cores (same container, np.load reads it); False = numpy's writer
 LAST_RUN = {}             # filled by compute_sf: grid, batch size, FFT path, kernel launches
 
 _BUFFSIZE = 1000000       # reference dens.py:206
@@ -180,8 +182,11 @@ def finish_sf(sf, L, n, out_filename):
     sfplt = get_dplot(sf)
     kgrid, kgridplt = _k_lattices(sf.shape, L)
     kgridplt[:, :, :, 3] = sfplt
-    save = np.savez_compressed if SAVE_COMPRESSED else np.savez
-    save(out_filename, sf=sf, sfplt=sfplt, L=L, N=n, kgrid=kgrid, kgridplt=kgridplt)
+    if PARALLEL_NPZ:      # same zip-of-npy container as np.savez_compressed, deflated on all cores (npz_writer.py)
+        npz_writer.savez_parallel(out_filename, compressed=SAVE_COMPRESSED, sf=sf, sfplt=sfplt, L=L, N=n, kgrid=kgrid, kgridplt=kgridplt)
+    else:
+        save = np.savez_compressed if SAVE_COMPRESSED else np.savez
+        save(out_filename, sf=sf, sfplt=sfplt, L=L, N=n, kgrid=kgrid, kgridplt=kgridplt)
 
 
 def compute_sf(r, L, typ, out_filename, rad, ucell, Sres):

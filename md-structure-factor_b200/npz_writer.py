@@ -1,0 +1,142 @@
+"""Parallel writer for the reference's ``.npz`` artefacts.
+
+The reference ends ``compute_sf`` with ``np.savez_compressed(out, sf, sfplt, L, N, kgrid, kgridplt)``
+(dens.py:346): one zlib stream per array on one core -- 28 s for a 256^3 run whose GPU loop takes
+0.2 s, and ~8 GB through zlib at 512^3.  This module writes the SAME container (a zip archive of
+``<key>.npy`` members, deflate, readable by ``np.load`` and by the reference's plot2d.py) but
+compresses every member as independent chunks on a thread pool (zlib releases the GIL):
+
+* a member's bytes (npy header + C-ordered data) are cut into ``CHUNK`` byte pieces;
+* each piece is deflated on its own (raw deflate, level 6 like numpy) and ended with
+  ``Z_SYNC_FLUSH`` -- an empty stored block that byte-aligns the stream without setting the
+  final-block bit; only the last piece ends with ``Z_FINISH``.  The concatenation is one valid
+  deflate stream (pieces never reference each other's history);
+* CRC-32 runs over the raw bytes on the calling thread while the workers compress;
+* zip64 records are written whenever a size or offset needs them (kgridplt is 4.2 GB at 512^3).
+
+Only the standard library and numpy are used; nothing here touches the GPU.
+"""
+import io
+import os
+import struct
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+CHUNK = 8 << 20          # raw bytes per independently compressed piece
+LEVEL = 6                # zlib default, what np.savez_compressed uses
+ZIP64_LIMIT = 0xFFFFFFFF
+
+
+def _npy_header(arr):
+    """The bytes np.save would put in front of ``arr`` (format 1.0/2.0/3.0 as numpy picks)."""
+    buf = io.BytesIO()
+    d = np.lib.format.header_data_from_array_1_0(arr)
+    try:
+        np.lib.format.write_array_header_1_0(buf, d)
+    except ValueError:                      # header too long for format 1.0
+        buf = io.BytesIO()
+        np.lib.format.write_array_header_2_0(buf, d)
+    return buf.getvalue()
+
+
+def _deflate_piece(args):
+    view, last, level = args
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
+    return c.compress(view) + c.flush(zlib.Z_FINISH if last else zlib.Z_SYNC_FLUSH)
+
+
+def _pieces(header, data, chunk):
+    """memoryviews over header + data in pieces of ``chunk`` bytes (the header rides with the first piece)."""
+    total = len(header) + len(data)
+    if total <= chunk:
+        yield bytes(header) + bytes(data)
+        return
+    first = chunk - len(header)
+    yield bytes(header) + bytes(data[:first])
+    for off in range(first, len(data), chunk):
+        yield data[off:off + chunk]
+
+
+def savez_parallel(file, compressed=True, threads=None, chunk=CHUNK, level=LEVEL, force_zip64=False, **arrays):
+    """``np.savez_compressed(file, **arrays)`` with the deflate work spread over ``threads`` cores
+    (``compressed=False``: stored members, like ``np.savez``).  ``file`` gets ``.npz`` appended when missing,
+    as numpy does."""
+    if not isinstance(file, (str, os.PathLike)):
+        raise TypeError("savez_parallel writes to a path")
+    file = os.fspath(file)
+    if not file.endswith(".npz"):
+        file += ".npz"
+    threads = threads or min(32, os.cpu_count() or 1)
+    method = 8 if compressed else 0
+    central = []
+    with open(file, "wb") as fh, ThreadPoolExecutor(max_workers=threads) as pool:
+        for key, val in arrays.items():
+            arr = np.asanyarray(val)
+            if arr.dtype.hasobject:
+                raise TypeError("object arrays are not supported")
+            if arr.flags.f_contiguous and not arr.flags.c_contiguous:
+                data_arr = arr.T                                   # np.save writes Fortran arrays transposed
+            else:
+                data_arr = np.ascontiguousarray(arr)
+            header = _npy_header(arr)
+            data = memoryview(data_arr.reshape(-1).view(np.uint8)) if data_arr.size else memoryview(b"")
+            name = (key + ".npy").encode("utf-8")
+            raw_size = len(header) + len(data)
+            zip64 = force_zip64 or raw_size >= ZIP64_LIMIT or fh.tell() >= ZIP64_LIMIT
+            offset = fh.tell()
+            # local header with the sizes still unknown: written again once the member is complete
+            extra = struct.pack("<HHQQ", 1, 16, 0, 0) if zip64 else b""
+            fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 45 if zip64 else 20, 0x800, method, 0, 0x21, 0, 0, 0, len(name), len(extra)))
+            fh.write(name)
+            fh.write(extra)
+            crc, csize = 0, 0
+            views = list(_pieces(header, data, chunk))
+            if compressed:
+                jobs = pool.map(_deflate_piece, [(v, i == len(views) - 1, level) for i, v in enumerate(views)])
+                for v, blob in zip(views, jobs):
+                    crc = zlib.crc32(v, crc)
+                    fh.write(blob)
+                    csize += len(blob)
+            else:
+                for v in views:
+                    crc = zlib.crc32(v, crc)
+                    fh.write(v)
+                    csize += len(v)
+            end = fh.tell()
+            fh.seek(offset)
+            if zip64:
+                extra = struct.pack("<HHQQ", 1, 16, raw_size, csize)
+                fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 45, 0x800, method, 0, 0x21, crc, ZIP64_LIMIT, ZIP64_LIMIT, len(name), len(extra)))
+            else:
+                fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0x800, method, 0, 0x21, crc, csize, raw_size, len(name), 0))
+            fh.write(name)
+            fh.write(extra)
+            fh.seek(end)
+            central.append((name, method, crc, csize, raw_size, offset, zip64))
+        # central directory
+        cd_start = fh.tell()
+        for name, method, crc, csize, raw_size, offset, zip64 in central:
+            fields = b""
+            if zip64 or offset >= ZIP64_LIMIT:
+                fields = struct.pack("<QQQ", raw_size, csize, offset)
+                extra = struct.pack("<HH", 1, len(fields)) + fields
+                fh.write(struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 45, 45, 0x800, method, 0, 0x21, crc, ZIP64_LIMIT, ZIP64_LIMIT,
+                                     len(name), len(extra), 0, 0, 0, 0o600 << 16, ZIP64_LIMIT))
+            else:
+                extra = b""
+                fh.write(struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 20, 20, 0x800, method, 0, 0x21, crc, csize, raw_size,
+                                     len(name), 0, 0, 0, 0, 0o600 << 16, offset))
+            fh.write(name)
+            fh.write(extra)
+        cd_size = fh.tell() - cd_start
+        n = len(central)
+        if any(c[6] for c in central) or cd_start >= ZIP64_LIMIT or n >= 0xFFFF:
+            z64_end = fh.tell()
+            fh.write(struct.pack("<IQHHIIQQQQ", 0x06064B50, 44, 45, 45, 0, 0, n, n, cd_size, cd_start))
+            fh.write(struct.pack("<IIQI", 0x07064B50, 0, z64_end, 1))
+            fh.write(struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, min(n, 0xFFFF), min(n, 0xFFFF), min(cd_size, ZIP64_LIMIT), ZIP64_LIMIT, 0))
+        else:
+            fh.write(struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, n, n, cd_size, cd_start, 0))
+    return file

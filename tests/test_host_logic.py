@@ -138,3 +138,30 @@ def test_workloads_are_deterministic_and_inside_the_box():
     c2 = w.get("c2")
     assert c2["base"].shape == (105456, 3) and tuple(dens._grid(c2["box"], c2["sres"])[0]) == (256, 256, 256)
     assert w.algorithmic_bytes_per_frame((256, 256, 256), 105456) == 105456 * 16 + 16 * 256 ** 3 + 16 * 256 * 256 * 129
+
+
+def test_parallel_npz_writer_matches_numpy_container(tmp_path):
+    """npz_writer.savez_parallel writes what np.savez_compressed writes (reference dens.py:346): same keys, dtypes,
+    shapes and values through np.load, valid CRCs, also with many small chunks, zip64 records, Fortran order, 0-d,
+    empty and stored members."""
+    import zipfile
+    import npz_writer
+    rng = np.random.default_rng(5)
+    arrays = dict(sf=rng.random((12, 10, 7)), sfplt=rng.random((10, 8, 13)), L=np.array([1.5, 2.5, 3.5], dtype=np.float32),
+                  N=np.array([12, 10, 12]), kgrid=np.zeros((12, 10, 7, 4)), kgridplt=np.asfortranarray(rng.random((10, 8, 13, 4))),
+                  scalar=np.float64(3.25), empty=np.zeros((0, 3)), names=np.array(["OW", "HW1", "HW2"]))
+    ref = str(tmp_path / "ref.npz")
+    np.savez_compressed(ref, **arrays)
+    want = np.load(ref)
+    for kw in (dict(), dict(chunk=1000, threads=3), dict(chunk=777, force_zip64=True), dict(compressed=False), dict(compressed=False, force_zip64=True)):
+        out = npz_writer.savez_parallel(str(tmp_path / "par"), **kw, **arrays)
+        assert out.endswith("par.npz")
+        with zipfile.ZipFile(out) as zf:
+            assert zf.testzip() is None
+            assert sorted(zf.namelist()) == sorted(k + ".npy" for k in arrays)
+            assert all(i.compress_type == (zipfile.ZIP_STORED if kw.get("compressed") is False else zipfile.ZIP_DEFLATED) for i in zf.infolist())
+        got = np.load(out)
+        assert sorted(got.files) == sorted(want.files)
+        for k in want.files:
+            assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
+            assert got[k].flags.f_contiguous == want[k].flags.f_contiguous
