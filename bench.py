@@ -12,7 +12,8 @@ splat, 3-D FFT, |F|^2 accumulation) over one batch of ``--frames-per-step`` synt
 * ``roofline``: SURVEY 8(d) algorithmic bytes x frames/s of the whole step vs the measured HBM peak, with the
                dominant kernel's own figure (its CUDA-event launch duration) beside it.
 * ``cpu_baseline``: the numpy restatement of the reference's loop (oracle/, kind "port") on a
-               bounded sample of the same workload, on this box's host cores.
+               bounded sample of the same workload, on one host core (the reference is a serial loop).
+``--impl reference`` times that same port on ALL host cores (one frame per worker process and step).
 Multi-GPU (torchrun, one rank per GPU): frames shard across ranks with no data-path collective
 (weak scaling: every rank runs the same per-GPU work) and one NCCL reduce of the partial S(q)
 closes the timed region; the time is the max over ranks.
@@ -42,6 +43,8 @@ def parse():
     ap.add_argument("--pool", type=int, default=64, help="distinct synthetic frames cycled through")
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (0 = all host cores)")
+    ap.add_argument("--ref-budget", type=float, default=200.0, help="reference arm: stop timing after this many seconds")
     ap.add_argument("--fft", default="auto")
     ap.add_argument("--tile", default="0x0")
     ap.add_argument("--splat", default="auto")
@@ -116,25 +119,59 @@ def cpu_port_frames_per_s(wl, nframes):
     return 1.0 / per_frame, per_frame
 
 
+_REF_WL = None
+
+
+def _ref_worker(args):
+    """One frame of the workload through the oracle port in a worker process; returns the frame-loop seconds."""
+    name, seed = args
+    global _REF_WL
+    from importlib import import_module
+    from oracle import dens_oracle as orc
+    workloads = import_module("workloads")
+    if _REF_WL is None or _REF_WL[0] != name:
+        _REF_WL = (name, workloads.get(name))
+    wl = _REF_WL[1]
+    coords = workloads.jitter_frames(wl["base"], wl["box"], 1, wl["jitter"], wl["seed0"] + seed)
+    dims = wl["box"][None, :]
+    stamps = []
+    t0 = time.perf_counter()
+    orc.structure_factor(coords, dims, wl["typ"], wl["rad"], wl["ucell"], wl["sres"], frame_callback=lambda t: stamps.append(time.perf_counter()))
+    return stamps[-1] - t0
+
+
 def run_reference_arm(args, wl, rank):
+    """The reference's CPU path (its numpy restatement in oracle/: the reference is Python and /root/reference does not
+    exist on the GPU box) on ALL host cores: the reference itself is one serial loop, frames are independent, so one
+    step = one frame per worker process, timed by wall clock."""
     if rank != 0:
         return
-    total = args.steps + args.warmup
-    fps_list = []
-    for i in range(total):
-        fps, sec = cpu_port_frames_per_s(wl, 1)
-        if i >= args.warmup:
-            fps_list.append(sec)
-    ms = 1e3 * float(np.mean(fps_list))
-    value = 1e3 / ms
-    base = {"kind": "port", "cores": 1, "value": value, "unit": "frames/s",
-            "sample": "%d steps of 1 frame of %s through oracle/dens_oracle.py (numpy restatement of reference dens.py:277-321; "
-                      "the reference is Python and cannot travel to this box)" % (args.steps, args.workload)}
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    procs = args.ref_procs or (os.cpu_count() or 1)
+    t_begin = time.perf_counter()
+    times, single = [], []
+    with ProcessPoolExecutor(max_workers=procs, mp_context=mp.get_context("fork")) as pool:
+        for i in range(args.steps + args.warmup):
+            t0 = time.perf_counter()
+            secs = list(pool.map(_ref_worker, [(args.workload, i * procs + k) for k in range(procs)]))
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+                single.extend(secs)
+            if len(times) >= 3 and time.perf_counter() - t_begin > args.ref_budget:
+                break
+    ms = 1e3 * float(np.mean(times))
+    value = procs * 1e3 / ms
+    base = {"kind": "port", "cores": procs, "value": value, "unit": "frames/s",
+            "sample": "%d timed steps (of %d asked; %.0f s budget) of %d frames of %s, one per worker process, through oracle/dens_oracle.py "
+                      "(numpy restatement of reference dens.py:277-321); %.2f s per frame inside a worker"
+                      % (len(times), args.steps, args.ref_budget, procs, args.workload, float(np.mean(single)))}
     print(json.dumps({
         "impl": "reference", "metric": "trajectory frames/sec into 3D S(q)", "value": value, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "frames_per_step": 1},
+        "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "frames_per_step": procs},
         "cpu_baseline": base, "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores": os.cpu_count()}))
 
