@@ -99,6 +99,12 @@ int mdsf_host_unregister(void* p);
 int mdsf_push_frames(mdsf_handle* h, void* coords, int64_t nframes, const double* scale,
                      int64_t wrap_lo, int64_t wrap_hi, int32_t write_back);
 
+/* Streaming loaders (load_traj.NpzFrameStream -> dens.compute_sf_stream) reuse their pinned chunk buffers:
+ * mdsf_input_mark() returns a ticket behind every host<->device copy queued so far, mdsf_input_wait() blocks
+ * until those copies are done (the frames themselves may still be in the splat / FFT kernels). */
+int mdsf_input_mark(mdsf_handle* h, int64_t* ticket);
+int mdsf_input_wait(mdsf_handle* h, int64_t ticket);
+
 /* RANDOM_NOISE mode of the reference (dens.py:279-280): feed ready-made real densities
  * d1[nframes][Nx][Ny][Nz] (float64, host) straight into FFT + accumulation. */
 int mdsf_push_density(mdsf_handle* h, const double* d1, int64_t nframes);

@@ -77,6 +77,9 @@ struct mdsf_handle {
     bool ez_global = false;
     // scatter (fixed-point, slab-pipelined) splat mode
     bool scatter = false, tile_atomic = false;
+    static const int kMarks = 16;             // mdsf_input_mark / mdsf_input_wait tickets
+    cudaEvent_t mark_copy[kMarks] = {}, mark_back[kMarks] = {};
+    int64_t next_mark = 0;
     int want_mode = 0;                // 0 auto, 1 owner, 2 scatter, 3 tile (shared-memory fixed-point atomics)
     SlabParams sp{};
     unsigned long long* d_acc = nullptr;
@@ -445,6 +448,10 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
         if (h->ev_back[s]) cudaEventDestroy(h->ev_back[s]);
     }
     for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+    for (int i = 0; i < mdsf_handle::kMarks; ++i) {
+        if (h->mark_copy[i]) cudaEventDestroy(h->mark_copy[i]);
+        if (h->mark_back[i]) cudaEventDestroy(h->mark_back[i]);
+    }
     if (h->timer0) cudaEventDestroy(h->timer0);
     if (h->timer1) cudaEventDestroy(h->timer1);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
@@ -1043,6 +1050,33 @@ extern "C" int mdsf_stage_ms(mdsf_handle* h, double* out6, int64_t* batches) {
         CU(cudaEventElapsedTime(&ms, tv[6], tv[5])); out6[5] += ms;     // compute-stream time of the batch
     }
     if (batches) *batches = (int64_t)nb;
+    return MDSF_OK;
+}
+
+// Host buffers handed to mdsf_push_frames may be reused once the engine has read them (H2D copy) and, with
+// write_back, written them (D2H copy) -- long before the frames are through the pipeline.  A mark is a pair of
+// events behind everything queued on the copy / write-back streams so far.
+extern "C" int mdsf_input_mark(mdsf_handle* h, int64_t* ticket) {
+    if (!h || !ticket) return fail(MDSF_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    const int i = (int)(h->next_mark % mdsf_handle::kMarks);
+    if (!h->mark_copy[i]) {
+        CU(cudaEventCreateWithFlags(&h->mark_copy[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->mark_back[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(h->mark_copy[i], h->s_copy));
+    CU(cudaEventRecord(h->mark_back[i], h->s_back));
+    *ticket = h->next_mark++;
+    return MDSF_OK;
+}
+extern "C" int mdsf_input_wait(mdsf_handle* h, int64_t ticket) {
+    if (!h) return fail(MDSF_EINVAL, "null handle");
+    if (ticket < 0 || ticket >= h->next_mark) return fail(MDSF_EINVAL, "unknown input ticket %lld", (long long)ticket);
+    CU(cudaSetDevice(h->device));
+    if (h->next_mark - ticket > mdsf_handle::kMarks) return MDSF_OK;     // recycled: a later mark on the same streams was waited for or overwritten
+    const int i = (int)(ticket % mdsf_handle::kMarks);
+    CU(cudaEventSynchronize(h->mark_copy[i]));
+    CU(cudaEventSynchronize(h->mark_back[i]));
     return MDSF_OK;
 }
 

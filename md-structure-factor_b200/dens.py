@@ -189,6 +189,65 @@ def finish_sf(sf, L, n, out_filename):
         save(out_filename, sf=sf, sfplt=sfplt, L=L, N=n, kgrid=kgrid, kgridplt=kgridplt)
 
 
+def compute_sf_stream(frames, L, typ, out_filename, rad, ucell, Sres, first_frame=0, end_frame=None, monoclinic_theta=None,
+                      chunk_frames=None):
+    """``compute_sf`` for a frame SOURCE instead of an in-memory array (north_star: the loader streams frames into
+    pinned, double-buffered host memory overlapped with the H2D copies).
+
+    ``frames``: object with ``shape`` (T, Na, 3), ``dtype``, ``read_into(buf) -> k`` and ``skip(n)``, e.g.
+    ``load_traj.NpzFrameStream``.  ``L``: all box lengths (T, 3).  Frames ``[first_frame:end_frame]`` are used, like the
+    slice main_gromacs.py:211 passes.  ``monoclinic_theta`` (radians) applies the reference's coordinate transform
+    (main_gromacs.py:204-207) chunk by chunk -- the same two numpy expressions, so the same bits.
+    Two pinned chunk buffers alternate: while the GPU works on one, the next chunk is decoded into the other; a
+    buffer is reused as soon as its host-to-device copies are done (mdsf_input_mark / mdsf_input_wait)."""
+    global Nspatialgrid
+    T, natoms = int(frames.shape[0]), int(frames.shape[1])
+    lo_f, hi_f, _ = slice(first_frame, end_frame).indices(T)
+    dims = np.asarray(L)[lo_f:hi_f]
+    if dims.dtype not in (np.float32, np.float64):
+        dims = dims.astype(np.float64)
+    cdtype = np.dtype(frames.dtype)
+    if cdtype not in (np.float32, np.float64):
+        raise TypeError("streamed coordinates must be float32 or float64")
+    arith = np.float32 if (cdtype == np.float32 and dims.dtype == np.float32) else np.float64
+    Lm = np.average(dims, axis=0)
+    scale = (Lm / dims).astype(np.float64)
+    nframes = hi_f - lo_f
+    eng, n, dr, nborder = make_engine(Lm, typ, rad, ucell, Sres, cdtype, arith)
+    Nspatialgrid = n
+    try:
+        print("Calculating Structure factor for ", natoms, " atoms over ", nframes, " timesteps (streamed). \n", "Progress: ")
+        print("GPU engine: batch of %d frames, %s splat, %s FFT, border %d cells" % (eng.batch_frames, eng.splat_path, eng.fft_path, nborder))
+        chunk = int(chunk_frames or 2 * eng.batch_frames)
+        bufs = [_native.pinned_empty((chunk, natoms, 3), cdtype) for _ in range(2)]
+        tickets = [None, None]
+        wrap = _wrapped_atoms(nframes, natoms)
+        frames.skip(lo_f)
+        done, i = 0, 0
+        while done < nframes:
+            b = i % 2
+            if tickets[b] is not None:
+                eng.wait_input(tickets[b])          # the copies out of this buffer are done; the kernels may still run
+            k = frames.read_into(bufs[b][:min(chunk, nframes - done)])
+            if k == 0:
+                raise EOFError("frame source ended after %d of %d frames" % (done, nframes))
+            blk = bufs[b][:k]
+            if monoclinic_theta is not None:
+                blk[..., 1] = blk[..., 1] / np.sin(monoclinic_theta)
+                blk[..., 0] = blk[..., 0] - blk[..., 1] * np.cos(monoclinic_theta)
+            eng.push_frames(blk, scale[done:done + k], wrap)
+            tickets[b] = eng.mark_input()
+            done += k
+            i += 1
+        sf = eng.read_sf()
+        LAST_RUN.clear()
+        LAST_RUN.update(N=n.copy(), dr=dr.copy(), Nborder=nborder, batch_frames=eng.batch_frames, fft=eng.fft_path, splat=eng.splat_path,
+                        kernel_launches=eng.kernel_launches, frames=eng.frames_done, streamed_chunks=i, chunk_frames=chunk)
+    finally:
+        eng.close()
+    finish_sf(sf, Lm, n, out_filename)
+
+
 def compute_sf(r, L, typ, out_filename, rad, ucell, Sres):
     """
     compute 3d structure factor (same contract as the reference, dens.py:166-178)

@@ -63,3 +63,67 @@ def process_gro_mdtraj(topology_filename, trajectory_filename, output_filename):
     print("saving ", output_filename)
     save_traj_npz(output_filename, dims, coords, name, mass)
     print('done saving')
+
+
+class NpzFrameStream:
+    """Frames of a trajectory npz (reference layout, load_traj.py:110) WITHOUT loading the whole ``coords`` array.
+
+    The reference does ``traj = np.load(...); T = traj['coords']`` (main_gromacs.py:200-202): the complete
+    trajectory is inflated into pageable memory before the first frame is used.  Here the ``coords.npy`` zip
+    member is inflated incrementally, straight into the caller's (pinned) chunk buffers, so that decoding chunk
+    i+1 overlaps the GPU work on chunk i (dens.compute_sf_stream).
+
+    ``shape`` / ``dtype`` describe the full array; ``read_into(buf)`` fills ``buf[:k]`` with the next k frames and
+    returns k (0 at the end); ``skip(n)`` drops n frames."""
+
+    def __init__(self, path, key="coords"):
+        import zipfile
+        self._zip = zipfile.ZipFile(path)
+        self._fh = self._zip.open(key + ".npy")
+        fmt = np.lib.format
+        version = fmt.read_magic(self._fh)
+        if version == (1, 0):
+            shape, fortran, dtype = fmt.read_array_header_1_0(self._fh)
+        else:
+            shape, fortran, dtype = fmt.read_array_header_2_0(self._fh)
+        if fortran or len(shape) != 3 or shape[2] != 3:
+            raise ValueError("%s: coords must be a C-ordered (T, Na, 3) array, got %s" % (path, (shape,)))
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self._frame_bytes = shape[1] * 3 * self.dtype.itemsize
+        self.position = 0
+
+    def read_into(self, buf):
+        if buf.dtype != self.dtype or buf.shape[1:] != self.shape[1:] or not buf.flags.c_contiguous:
+            raise ValueError("chunk buffer must be C-contiguous %s of shape (k, %d, 3)" % (self.dtype, self.shape[1]))
+        want = min(buf.shape[0], self.shape[0] - self.position)
+        if want <= 0:
+            return 0
+        view = memoryview(buf[:want].reshape(-1).view(np.uint8))
+        got = 0
+        while got < len(view):
+            n = self._fh.readinto(view[got:])
+            if not n:
+                raise EOFError("trajectory npz ends inside frame %d" % (self.position + got // max(self._frame_bytes, 1)))
+            got += n
+        self.position += want
+        return want
+
+    def skip(self, nframes):
+        nframes = min(int(nframes), self.shape[0] - self.position)
+        left = nframes * self._frame_bytes
+        while left > 0:
+            chunk = self._fh.read(min(left, 16 << 20))
+            if not chunk:
+                raise EOFError("trajectory npz ends early")
+            left -= len(chunk)
+        self.position += max(nframes, 0)
+
+    def close(self):
+        self._fh.close()
+        self._zip.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

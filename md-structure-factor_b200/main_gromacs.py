@@ -25,6 +25,7 @@ import dens
 
 XRAY_WAVELENGTH = 1.54
 TRANSFORM_MONOCLINIC = True
+STREAM_TRAJECTORY = True     # inflate the traj npz chunk by chunk into pinned buffers, overlapped with the GPU (False: np.load it whole)
 
 
 def initialize():
@@ -124,14 +125,24 @@ def main(argv=None):
             lt.process_gro_mdtraj(top_file, traj_file, tfname)
             print('done')
         traj = np.load(tfname + ".npz")
-        T = traj['coords']
-        if TRANSFORM_MONOCLINIC and theta != 90.0:      # (radians vs 90: always true, as in the reference)
-            print("transforming coordinates to monoclinic cell (theta={0:f} deg)".format(theta * 180.0 / np.pi))
-            T[..., 1] = T[..., 1] / np.sin(theta)
-            T[..., 0] = T[..., 0] - T[..., 1] * np.cos(theta)
         rad = dens.load_radii(rad_file)
-        dens.compute_sf(T[args.first_frame:args.end_frame, ...], traj['dims'][args.first_frame:args.end_frame, ...],
-                        traj['typ'], sfname, rad, ucell, args.spatial_resolution)
+        mono = theta if (TRANSFORM_MONOCLINIC and theta != 90.0) else None      # (radians vs 90: always true, as in the reference)
+        if mono is not None:
+            print("transforming coordinates to monoclinic cell (theta={0:f} deg)".format(theta * 180.0 / np.pi))
+        if STREAM_TRAJECTORY:
+            # same result as the in-memory route below, but the coords member is inflated chunk by chunk into pinned
+            # buffers while the GPU works on the previous chunk (load_traj.NpzFrameStream, dens.compute_sf_stream)
+            import load_traj as lt
+            with lt.NpzFrameStream(tfname + ".npz") as frames:
+                dens.compute_sf_stream(frames, traj['dims'], traj['typ'], sfname, rad, ucell, args.spatial_resolution,
+                                       first_frame=args.first_frame, end_frame=args.end_frame, monoclinic_theta=mono)
+        else:
+            T = traj['coords']
+            if mono is not None:
+                T[..., 1] = T[..., 1] / np.sin(theta)
+                T[..., 0] = T[..., 0] - T[..., 1] * np.cos(theta)
+            dens.compute_sf(T[args.first_frame:args.end_frame, ...], traj['dims'][args.first_frame:args.end_frame, ...],
+                            traj['typ'], sfname, rad, ucell, args.spatial_resolution)
 
     print("reloading SF...")
     grid = np.load(sfname + ".npz")['kgridplt']

@@ -25,6 +25,7 @@ EXPORTS = [
     "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_splat_path",
     "mdsf_batch_frames",
     "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_timer_start", "mdsf_timer_stop", "mdsf_last_error",
+    "mdsf_input_mark", "mdsf_input_wait",
     "mdsf_abi_version",
 ]
 
@@ -83,6 +84,8 @@ def load():
         "mdsf_batch_frames": (C.c_int, [vp]),
         "mdsf_enable_timing": (C.c_int, [vp, i32]),
         "mdsf_stage_ms": (C.c_int, [vp, dp, C.POINTER(i64)]),
+        "mdsf_input_mark": (C.c_int, [vp, C.POINTER(C.c_int64)]),
+        "mdsf_input_wait": (C.c_int, [vp, i64]),
         "mdsf_timer_start": (C.c_int, [vp]),
         "mdsf_timer_stop": (C.c_int, [vp, dp]),
         "mdsf_last_error": (C.c_char_p, []),
@@ -206,6 +209,16 @@ class Engine:
 
     def sync(self):
         _check(self._lib.mdsf_sync(self._h))
+
+    def mark_input(self):
+        """Ticket behind every host<->device copy queued so far (see wait_input)."""
+        t = C.c_int64()
+        _check(self._lib.mdsf_input_mark(self._h, C.byref(t)))
+        return t.value
+
+    def wait_input(self, ticket):
+        """Block until the copies behind ``ticket`` are done: the host buffers pushed before it can be reused."""
+        _check(self._lib.mdsf_input_wait(self._h, int(ticket)))
 
     def read_sf(self, out=None):
         """sf (Nx, Ny, Nz/2+1) float64, into ``out`` if given (e.g. a pinned_empty buffer for a faster copy)."""

@@ -53,7 +53,7 @@ def _pieces(header, data, chunk):
     if total <= chunk:
         yield bytes(header) + bytes(data)
         return
-    first = chunk - len(header)
+    first = max(chunk - len(header), 0)
     yield bytes(header) + bytes(data[:first])
     for off in range(first, len(data), chunk):
         yield data[off:off + chunk]

@@ -383,3 +383,37 @@ def test_million_atom_wrap_quirk_cell_indices(mdsf):
         assert np.isfinite(sf).all() and sf[0, 0, 0] > 0
     finally:
         eng.close()
+
+
+def test_streamed_trajectory_equals_in_memory_compute_sf(mdsf, tmp_path):
+    """dens.compute_sf_stream (traj npz inflated chunk by chunk into two pinned buffers, monoclinic transform and frame
+    slice applied on the way, main_gromacs.py:200-212) writes the same sf npz as the in-memory compute_sf."""
+    import load_traj
+    c = load_case("mono_f32")
+    theta = 120.0 * np.pi / 180.0
+    traj = str(tmp_path / "out_x_traj")
+    load_traj.save_traj_npz(traj, c["dims"], c["coords"], c["typ"])
+    z = np.load(traj + ".npz")
+    T = z["coords"]
+    T[..., 1] = T[..., 1] / np.sin(theta)
+    T[..., 0] = T[..., 0] - T[..., 1] * np.cos(theta)
+    dens = mdsf.dens
+    dens.compute_sf(T[1:3], z["dims"][1:3], z["typ"], str(tmp_path / "mem"), c["rad"], c["ucell"], c["sres"])
+    a = np.load(str(tmp_path / "mem.npz"))
+    # one chunk of two frames = the same frame pair as the in-memory run: every array bitwise equal
+    with load_traj.NpzFrameStream(traj + ".npz") as fs:
+        dens.compute_sf_stream(fs, z["dims"], z["typ"], str(tmp_path / "str2"), c["rad"], c["ucell"], c["sres"],
+                               first_frame=1, end_frame=3, monoclinic_theta=theta, chunk_frames=2)
+    assert dens.LAST_RUN["streamed_chunks"] == 1 and dens.LAST_RUN["frames"] == 2
+    b = np.load(str(tmp_path / "str2.npz"))
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+    # one frame per chunk: both pinned buffers and the input tickets are exercised; frames are no longer paired in one
+    # complex transform, so the sum differs in the last bits only
+    with load_traj.NpzFrameStream(traj + ".npz") as fs:
+        dens.compute_sf_stream(fs, z["dims"], z["typ"], str(tmp_path / "str1"), c["rad"], c["ucell"], c["sres"],
+                               first_frame=1, end_frame=3, monoclinic_theta=theta, chunk_frames=1)
+    assert dens.LAST_RUN["streamed_chunks"] == 2 and dens.LAST_RUN["frames"] == 2
+    rel, norm = sf_errors(np.load(str(tmp_path / "str1.npz"))["sf"], a["sf"])
+    assert rel <= 1e-9 and norm <= 1e-13, (rel, norm)

@@ -165,3 +165,26 @@ def test_parallel_npz_writer_matches_numpy_container(tmp_path):
         for k in want.files:
             assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
             assert got[k].flags.f_contiguous == want[k].flags.f_contiguous
+
+
+def test_npz_frame_stream_reads_chunks_like_np_load(tmp_path):
+    """load_traj.NpzFrameStream inflates the coords member of a traj npz (reference load_traj.py:110) incrementally."""
+    import load_traj
+    import npz_writer
+    rng = np.random.default_rng(9)
+    coords = rng.normal(size=(7, 11, 3)).astype(np.float32)
+    dims = np.full((7, 3), 20.0, dtype=np.float32)
+    names = np.array(["C%d" % i for i in range(11)])
+    a = str(tmp_path / "a_traj")
+    load_traj.save_traj_npz(a, dims, coords, names)
+    b = npz_writer.savez_parallel(str(tmp_path / "b_traj"), chunk=100, dims=dims, coords=coords, name=names, mass=np.zeros(11), typ=names)
+    for path in (a + ".npz", b):
+        with load_traj.NpzFrameStream(path) as fs:
+            assert fs.shape == coords.shape and fs.dtype == coords.dtype
+            fs.skip(1)
+            buf = np.zeros((4, 11, 3), dtype=np.float32)
+            assert fs.read_into(buf) == 4 and np.array_equal(buf, coords[1:5])
+            assert fs.read_into(buf) == 2 and np.array_equal(buf[:2], coords[5:7])
+            assert fs.read_into(buf) == 0
+            with pytest.raises(ValueError):
+                fs.read_into(np.zeros((4, 11, 3), dtype=np.float64))
