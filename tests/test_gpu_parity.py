@@ -417,3 +417,39 @@ def test_streamed_trajectory_equals_in_memory_compute_sf(mdsf, tmp_path):
     assert dens.LAST_RUN["streamed_chunks"] == 2 and dens.LAST_RUN["frames"] == 2
     rel, norm = sf_errors(np.load(str(tmp_path / "str1.npz"))["sf"], a["sf"])
     assert rel <= 1e-9 and norm <= 1e-13, (rel, norm)
+
+
+def test_cli_trajectory_mode_gro_to_sf_npz(mdsf, tmp_path, monkeypatch):
+    """main_gromacs.py trajectory mode end to end (reference main_gromacs.py:188-212): topology/trajectory files ->
+    out_<name>_traj.npz (load_traj.process_gro_mdtraj; .gro parsed natively) -> monoclinic transform -> streamed
+    compute_sf -> out_<name>_sf.npz.  Checked against the oracle run on the same parsed coordinates."""
+    import importlib
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(3)
+    nmol, box_nm = 20, 1.6
+    lines = ["water, t= 0.0", "%5d" % (3 * nmol)]
+    for m in range(nmol):
+        o = rng.uniform(0.1, box_nm - 0.1, 3)
+        for k, nm in enumerate(("OW", "HW1", "HW2")):
+            p = o + (0 if k == 0 else rng.normal(0, 0.05, 3))
+            lines.append("%5d%-5s%5s%5d%8.3f%8.3f%8.3f" % (m + 1, "SOL", nm, 3 * m + k + 1, p[0], p[1], p[2]))
+    lines.append("%10.5f%10.5f%10.5f" % (box_nm, box_nm, box_nm))
+    with open("sys.gro", "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    cli = importlib.import_module("main_gromacs")
+    assert cli.main(["-top", "sys.gro", "-traj", "sys.gro", "-e", "1", "-SR", "0.8", "-ct", "120"]) == 0
+    traj = np.load("out_sys_traj.npz")
+    assert sorted(traj.files) == sorted(["dims", "coords", "name", "mass", "typ"]) and traj["coords"].shape == (1, 3 * nmol, 3)
+    assert traj["coords"].dtype == np.float32 and list(traj["typ"][:3]) == ["OW", "HW1", "HW2"]
+    theta = 120 * np.pi / 180.0
+    T = traj["coords"].copy()
+    T[..., 1] = T[..., 1] / np.sin(theta)
+    T[..., 0] = T[..., 0] - T[..., 1] * np.cos(theta)
+    ucell = np.array([[1, 0, 0], [np.cos(theta), np.sin(theta), 0], [0, 0, 1]])
+    rad = mdsf.dens.load_radii(os.path.join(os.path.dirname(cli.__file__), "radii.txt"))
+    want = orc.structure_factor(T, traj["dims"], traj["typ"], rad, ucell, 0.8)
+    got = np.load("out_sys_sf.npz")
+    assert np.array_equal(got["N"], want["N"])
+    rel, norm = sf_errors(got["sf"], want["sf"])
+    assert rel <= 1e-5 and norm <= 1e-12, (rel, norm)
+    assert np.allclose(got["sfplt"], want["sfplt"], rtol=1e-5, atol=0) and got["L"].dtype == np.float32
