@@ -131,6 +131,9 @@ int64_t mdsf_frames_done(const mdsf_handle* h);
 const char* mdsf_fft_path(const mdsf_handle* h);
 const char* mdsf_splat_path(const mdsf_handle* h);   /* "owner" / "scatter" / "tile" (valid after mdsf_set_atoms) */
 int mdsf_batch_frames(const mdsf_handle* h);
+/* Pipeline shape: returns 1 when the splat of batch b+1 overlaps the y/x passes of batch b (two pair-volume
+ * sets), else 0; sms[0], sms[1] = SMs of the splat-side / pass-side green-context partition (0, 0 = unpartitioned). */
+int mdsf_pipeline_info(const mdsf_handle* h, int32_t* sms /* [2] */);
 /* Record CUDA events around every stage of subsequent batches; query the accumulated
  * per-stage device milliseconds: out[0..5] = copy, prep+bin, splat+zfft, y pass, x pass+accumulate
  * (library path: FFT, accumulate), compute-stream total */

@@ -2,6 +2,7 @@
 // One handle = one GPU, three streams (H2D copy, compute, D2H write-back) and a double-buffered
 // coordinate staging area, so the copy of batch b+1 overlaps the kernels of batch b.
 #include <cub/cub.cuh>
+#include <cuda.h>               // green-context TYPES only: the driver entry points are fetched at run time
 #include <cuda_runtime.h>
 #include <cufft.h>
 
@@ -50,6 +51,7 @@ struct AxisPlan {
     FftPlan plan{};
     bool native = false;
     double2* d_tw = nullptr;
+    double2* d_tw16 = nullptr;  // n = 256: inter-stage twiddles of the 16x16 split in [k][n2] order (w^(n2 k) at k*16 + n2)
     int* d_rev = nullptr;     // frequency index -> position
 };
 
@@ -127,6 +129,7 @@ struct mdsf_handle {
     long long maxpairs_frame = 0;
     int chunk = 128;
     size_t splat_smem = 0;
+    int tw16_off = 0;                 // byte offset of the cp.async-prefetched stage-1 twiddle table in the splat's shared memory (0 = none)
     int sort_bits = 1;
     // y/x pass geometry
     int Wy = 16, Wx = 16, thr_y = 256, thr_x = 256;
@@ -138,7 +141,88 @@ struct mdsf_handle {
     long long timed_batches = 0;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     std::vector<int> halfw_host;
+    // overlap mode (MDSF_SM_SPLIT): the issue-bound prep/bin/splat kernels of batch b+1 run on stream s_splat
+    // while the HBM-bound y/x passes of batch b run on s_comp, each on its own pair-volume set.  With
+    // MDSF_SM_SPLIT = n > 0 the two streams belong to two green contexts that own disjoint SM partitions
+    // (n SMs for the splat side, the rest for the passes); -1 overlaps on plain streams.
+    int overlap = 0;
+    int x_async = 0;                  // MDSF_X_ASYNC: cp.async-prefetched two-stage x pass
+    int y_async = 0;                  // MDSF_Y_ASYNC: same for the y pass
+    int part_sms[2] = {0, 0};
+    cudaStream_t s_splat = nullptr;
+    double2* d_volset[2] = {nullptr, nullptr};
+    cudaEvent_t ev_splat[2]{}, ev_volfree[2]{};
+    bool vol_used[2]{};
+    CUgreenCtx gctx[2] = {nullptr, nullptr};
 };
+
+// ------------------------------------------------------------------------------------------
+// SM partitions through CUDA green contexts.  libmdsf.so does not link libcuda (it must load on a box
+// without a driver, where mdsf_create then fails with MDSF_ECUDA): the few driver entry points are
+// resolved through the runtime.
+struct GreenApi {
+    CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+    CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+    CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+    CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+    CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+    CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+    bool ok = false;
+};
+static GreenApi& green_api() {
+    static GreenApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    bool ok = true;
+    auto get = [&](const char* name, void** fn) {
+        cudaDriverEntryPointQueryResult st = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !*fn) ok = false;
+    };
+    get("cuDeviceGet", (void**)&api.DeviceGet);
+    get("cuDeviceGetDevResource", (void**)&api.DeviceGetDevResource);
+    get("cuDevSmResourceSplitByCount", (void**)&api.DevSmResourceSplitByCount);
+    get("cuDevResourceGenerateDesc", (void**)&api.DevResourceGenerateDesc);
+    get("cuGreenCtxCreate", (void**)&api.GreenCtxCreate);
+    get("cuGreenCtxDestroy", (void**)&api.GreenCtxDestroy);
+    get("cuGreenCtxStreamCreate", (void**)&api.GreenCtxStreamCreate);
+    (void)cudaGetLastError();
+    api.ok = ok;
+    return api;
+}
+#define DRV(call)                                                                             \
+    do {                                                                                      \
+        CUresult r_ = (call);                                                                 \
+        if (r_ != CUDA_SUCCESS) return fail(MDSF_ECUDA, "%s failed: driver error %d (%s:%d)", #call, (int)r_, __FILE__, __LINE__); \
+    } while (0)
+
+// two green contexts: partition 0 with (at least) want_a SMs for prep/bin/splat, partition 1 with the
+// remaining SMs for the y/x passes; one non-blocking stream in each
+static int make_partitions(mdsf_handle* h, int want_a) {
+    GreenApi& api = green_api();
+    if (!api.ok) return fail(MDSF_ECUDA, "MDSF_SM_SPLIT: this driver does not export the green-context entry points");
+    if (want_a < 8 || want_a > h->nsm - 8) return fail(MDSF_EINVAL, "MDSF_SM_SPLIT=%d: need 8 <= n <= %d", want_a, h->nsm - 8);
+    CU(cudaFree(0));                                     // primary context is active
+    CUdevice dev;
+    DRV(api.DeviceGet(&dev, h->device));
+    CUdevResource all, part[2];
+    DRV(api.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+    unsigned int nb = 1;
+    DRV(api.DevSmResourceSplitByCount(&part[0], &nb, &all, &part[1], 0, (unsigned)want_a));
+    if (nb != 1 || part[0].type != CU_DEV_RESOURCE_TYPE_SM || part[1].type != CU_DEV_RESOURCE_TYPE_SM || part[1].sm.smCount == 0)
+        return fail(MDSF_ECUDA, "MDSF_SM_SPLIT=%d: the driver could not split %u SMs that way", want_a, all.sm.smCount);
+    for (int i = 0; i < 2; ++i) {
+        CUdevResourceDesc desc;
+        DRV(api.DevResourceGenerateDesc(&desc, &part[i], 1));
+        DRV(api.GreenCtxCreate(&h->gctx[i], desc, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+        h->part_sms[i] = (int)part[i].sm.smCount;
+        CUstream st;
+        DRV(api.GreenCtxStreamCreate(&st, h->gctx[i], CU_STREAM_NON_BLOCKING, 0));
+        (i == 0 ? h->s_splat : h->s_comp) = (cudaStream_t)st;
+    }
+    return MDSF_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 static bool factorize(int n, FftPlan& plan, int max_log2 = 4) {
@@ -180,6 +264,12 @@ static int build_axis(AxisPlan& ax, int n, bool want_native, int max_log2) {
         for (int k = 0; k < n; ++k) rev[k] = digit_position(k, n, ax.plan, 0);
         CU(cudaMalloc(&ax.d_tw, sizeof(double2) * n));
         CU(cudaMemcpy(ax.d_tw, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
+        if (n == 256) {
+            std::vector<double2> t16(256);
+            for (int i = 0; i < 256; ++i) t16[i] = tw[(i >> 4) * (i & 15)];
+            CU(cudaMalloc(&ax.d_tw16, sizeof(double2) * 256));
+            CU(cudaMemcpy(ax.d_tw16, t16.data(), sizeof(double2) * 256, cudaMemcpyHostToDevice));
+        }
     } else {
         ax.plan.n = n;
         ax.plan.nstages = 0;
@@ -301,13 +391,17 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     gp.ntx = (gp.n[0] + gp.tx - 1) / gp.tx;
     gp.nty = (gp.n[1] + gp.ty - 1) / gp.ty;
 
+    // ---- pipeline shape
+    int want_split = getenv("MDSF_SM_SPLIT") ? atoi(getenv("MDSF_SM_SPLIT")) : 0;
+    if (want_split != 0 && h->native_fft && h->want_mode != 2) h->overlap = 1;
+
     // ---- batch size
     int F = cfg->batch_frames;
     if (F <= 0) {
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         const double per_pair = (double)h->ncell * 16.0 * (cfg->keep_density ? 2 : 1);
-        const double budget = std::min(8.0e9, (double)free_b * 0.25);
+        const double budget = std::min(8.0e9 * (h->overlap ? 2 : 1), (double)free_b * 0.25) / (h->overlap ? 2 : 1);
         int pairs = (int)std::max(1.0, std::floor(budget / per_pair));
         F = 2 * std::min(pairs, MDSF_MAX_BATCH / 2);
     }
@@ -359,6 +453,8 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     // ---- volumes
     const int npairs = F / 2;
     CU(cudaMalloc(&h->d_vol, sizeof(double2) * h->ncell * npairs));
+    h->d_volset[0] = h->d_vol;
+    if (h->overlap) CU(cudaMalloc(&h->d_volset[1], sizeof(double2) * h->ncell * npairs));
     if (cfg->keep_density) CU(cudaMalloc(&h->d_dump, sizeof(double2) * h->ncell * npairs));
     CU(cudaMalloc(&h->d_P, sizeof(double) * h->ncell));
     CU(cudaMemset(h->d_P, 0, sizeof(double) * h->ncell));
@@ -369,9 +465,28 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     *h->h_err = 0;
 
     CU(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    if (h->overlap && want_split > 0) {
+        int rc = make_partitions(h, want_split);
+        if (rc) return rc;
+    } else {
+        CU(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+        if (h->overlap) CU(cudaStreamCreateWithFlags(&h->s_splat, cudaStreamNonBlocking));
+    }
+    if (h->overlap)
+        for (int v = 0; v < 2; ++v) {
+            CU(cudaEventCreateWithFlags(&h->ev_splat[v], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_volfree[v], cudaEventDisableTiming));
+        }
     CU(cudaStreamCreateWithFlags(&h->s_back, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->s_prep, cudaStreamNonBlocking));
+    {
+        // prep+bin of batch b+1 run underneath the HBM-bound y/x passes of batch b; at equal priority their small
+        // kernels queue behind the passes' CTAs and finish after them (a gap before the next splat), so the prep
+        // stream gets the highest priority (MDSF_PREP_PRIO=0 restores the plain stream)
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const bool prio = !getenv("MDSF_PREP_PRIO") || atoi(getenv("MDSF_PREP_PRIO")) != 0;
+        CU(cudaStreamCreateWithPriority(&h->s_prep, cudaStreamNonBlocking, prio ? hi : 0));
+    }
     for (int s = 0; s < kSlots; ++s) {
         CU(cudaEventCreateWithFlags(&h->ev_h2d[s], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_free[s], cudaEventDisableTiming));
@@ -410,6 +525,12 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaFuncSetAttribute(fft_x_accum_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_x_accum_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_x_accum_async_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_x_accum_async_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        h->x_async = getenv("MDSF_X_ASYNC") ? atoi(getenv("MDSF_X_ASYNC")) : 0;
+        CU(cudaFuncSetAttribute(fft_y_async_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft_y_async_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        h->y_async = getenv("MDSF_Y_ASYNC") ? atoi(getenv("MDSF_Y_ASYNC")) : 0;
     }
     CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 20480));
     CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -430,9 +551,9 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     cudaDeviceSynchronize();
     if (h->cufft_plan) cufftDestroy(h->cufft_plan);
     void* bufs[] = {h->d_acc, h->d_slab_count, h->d_slab_start, h->d_slab_cursor, h->d_entries, h->d_step_start, h->d_ctl, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1],
-                    h->d_vol, h->d_dump, h->d_P, h->d_sf, h->d_err};
+                    h->d_volset[0], h->d_volset[1], h->d_dump, h->d_P, h->d_sf, h->d_err};
     for (void* b : bufs) if (b) cudaFree(b);
-    for (int d = 0; d < 3; ++d) { if (h->ax[d].d_tw) cudaFree(h->ax[d].d_tw); if (h->ax[d].d_rev) cudaFree(h->ax[d].d_rev); }
+    for (int d = 0; d < 3; ++d) { if (h->ax[d].d_tw) cudaFree(h->ax[d].d_tw); if (h->ax[d].d_tw16) cudaFree(h->ax[d].d_tw16); if (h->ax[d].d_rev) cudaFree(h->ax[d].d_rev); }
     for (auto& ps : h->sets) {
         void* pb[] = {ps.recs, ps.cnt, ps.off, ps.keys[0], ps.keys[1], ps.vals[0], ps.vals[1], ps.tile_start, ps.tables, ps.cub};
         for (void* b : pb) if (b) cudaFree(b);
@@ -456,7 +577,13 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     if (h->timer1) cudaEventDestroy(h->timer1);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_splat) cudaStreamDestroy(h->s_splat);
     if (h->s_back) cudaStreamDestroy(h->s_back);
+    for (int v = 0; v < 2; ++v) {
+        if (h->ev_splat[v]) cudaEventDestroy(h->ev_splat[v]);
+        if (h->ev_volfree[v]) cudaEventDestroy(h->ev_volfree[v]);
+        if (h->gctx[v] && green_api().ok) green_api().GreenCtxDestroy(h->gctx[v]);
+    }
     delete h;
     return MDSF_OK;
 }
@@ -620,10 +747,16 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     // tables (also hold r in the general-ucell path and the z twiddles after the splat), pair info, hit masks
     auto smem_for = [&](int c) { return tile_b + std::max((size_t)2 * c * 8 << h->logS, (size_t)2 * g0.n[2] * 8) + (size_t)2 * c * sizeof(PairInfo) + 2 * 4 * 32 * 4 + (size_t)2 * (c + 8) * 4 + (size_t)2 * c * g0.tx * g0.ty + 64; };
     const size_t soft = tile_b <= 80 * 1024 ? 113 * 1024 : kMaxSmem;    // two CTAs per SM when the tile allows
-    while (chunk > 32 && smem_for(chunk) > soft) chunk -= 32;
-    if (smem_for(chunk) > (size_t)kMaxSmem) return fail(MDSF_EINVAL, "splat tile does not fit shared memory (%zu bytes)", smem_for(chunk));
+    // Nz = 256 tile mode: the 16x16 split's inter-stage twiddles get their own 4 KB, filled by cp.async at kernel
+    // start, instead of a global -> shared copy between the splat and the FFT (one exposed round trip less per CTA)
+    const bool tw_pref = h->tile_atomic && h->native_fft && h->zfast == 16 && h->ax[2].d_tw16 && !h->cfg.keep_density &&
+                         (!getenv("MDSF_TW_PREFETCH") || atoi(getenv("MDSF_TW_PREFETCH")) != 0);
+    const size_t tw_extra = tw_pref ? 4096 + 16 : 0;
+    while (chunk > 32 && smem_for(chunk) + tw_extra > soft) chunk -= 32;
+    if (smem_for(chunk) + tw_extra > (size_t)kMaxSmem) return fail(MDSF_EINVAL, "splat tile does not fit shared memory (%zu bytes)", smem_for(chunk));
     h->chunk = chunk;
-    h->splat_smem = smem_for(chunk);
+    h->tw16_off = tw_pref ? (int)((smem_for(chunk) + 15) / 16 * 16) : 0;
+    h->splat_smem = smem_for(chunk) + tw_extra;
 
     CU(cudaMalloc(&h->d_type, sizeof(int) * natoms));
     CU(cudaMemcpy(h->d_type, type_id, sizeof(int) * natoms, cudaMemcpyHostToDevice));
@@ -684,7 +817,8 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             fft_z_kernel<<<grid, 256, sm, h->s_comp>>>(h->d_vol, h->ax[2].plan, h->ax[2].d_tw, ncolumns, ncol, gp.nzp, gp.pad_shift, h->zfast);
             ++h->launches;
         }
-        if (tv) CU(cudaEventRecord(tv[3], h->s_comp));
+        if (tv && !h->overlap) CU(cudaEventRecord(tv[3], h->s_comp));
+        if (tv) CU(cudaEventRecord(tv[7], h->s_comp));
         {
             const size_t sm = (size_t)2 * gp.n[1] * h->Wy * 8 + (size_t)2 * gp.n[1] * 8;
             dim3 grid((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0], npairs);
@@ -692,7 +826,13 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             const FftPlan& yp = h->ax[1].plan;
             const bool fast = yp.nstages == 2 && yp.radix[0] == yp.radix[1] && (gp.n[1] / yp.radix[0]) * h->Wy == h->thr_y && h->thr_y == MDSF_PASS_THREADS &&
                               (yp.radix[0] == 16 || yp.radix[0] == 8) && !getenv("MDSF_NO_YFAST");
-            if (fast && yp.radix[0] == 16)
+            const size_t sya = sm + (size_t)yp.radix[0] * h->thr_y * 16;
+            dim3 grid_a((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0]);
+            if (fast && h->y_async && yp.radix[0] == 16)
+                fft_y_async_kernel<16, 16><<<grid_a, h->thr_y, sya, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw, npairs);
+            else if (fast && h->y_async)
+                fft_y_async_kernel<8, 8><<<grid_a, h->thr_y, sya, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw, npairs);
+            else if (fast && yp.radix[0] == 16)
                 fft_y_fast_kernel<16, 16><<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw);
             else if (fast)
                 fft_y_fast_kernel<8, 8><<<grid, h->thr_y, sm, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw);
@@ -713,7 +853,12 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             const bool fast = xp.nstages == 2 && xp.radix[0] == xp.radix[1] && (gp.n[0] / xp.radix[0]) * h->Wx == h->thr_x && h->thr_x == MDSF_PASS_THREADS &&
                               (xp.radix[0] == 16 || xp.radix[0] == 8) && !getenv("MDSF_NO_XFAST");
             const size_t smf = (size_t)2 * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
-            if (fast && xp.radix[0] == 16)
+            const size_t sma = smf + (size_t)xp.radix[0] * h->thr_x * 16;     // + cp.async staging slots
+            if (fast && h->x_async && xp.radix[0] == 16)
+                fft_x_accum_async_kernel<16, 16><<<grid, h->thr_x, sma, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
+            else if (fast && h->x_async)
+                fft_x_accum_async_kernel<8, 8><<<grid, h->thr_x, sma, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
+            else if (fast && xp.radix[0] == 16)
                 fft_x_accum_fast_kernel<16, 16><<<grid, h->thr_x, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
             else if (fast)
                 fft_x_accum_fast_kernel<8, 8><<<grid, h->thr_x, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
@@ -729,7 +874,7 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             ++h->launches;
         }
     } else {
-        if (tv) CU(cudaEventRecord(tv[3], h->s_comp));
+        if (tv) { CU(cudaEventRecord(tv[3], h->s_comp)); CU(cudaEventRecord(tv[7], h->s_comp)); }
         if (npairs == h->cufft_batch) {
             CF(cufftExecZ2Z(h->cufft_plan, (cufftDoubleComplex*)h->d_vol, (cufftDoubleComplex*)h->d_vol, CUFFT_FORWARD));
         } else {   // partial last batch: zero the unused pair volumes and transform the whole batch
@@ -765,23 +910,27 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     // previous batch is still in its splat/FFT kernels on s_comp
     const int p = (int)(h->batch_counter++ % h->nsets);
     mdsf_handle::PrepSet& ps = h->sets[p];
-    cudaStream_t sp = h->nsets == 2 ? h->s_prep : h->s_comp;
+    // overlap mode: prep/bin and the splat share the in-order stream s_splat; the passes keep s_comp
+    cudaStream_t sp = h->overlap ? h->s_splat : (h->nsets == 2 ? h->s_prep : h->s_comp);
+    cudaStream_t ss = h->overlap ? h->s_splat : h->s_comp;        // stream of the splat kernel
+    const int v = h->overlap ? (int)((h->batch_counter - 1) & 1) : 0;
+    h->d_vol = h->d_volset[v];
     h->d_recs = ps.recs; h->d_cnt = ps.cnt; h->d_off = ps.off; h->d_tables = ps.tables;
     h->d_keys[0] = ps.keys[0]; h->d_keys[1] = ps.keys[1]; h->d_vals[0] = ps.vals[0]; h->d_vals[1] = ps.vals[1];
     h->d_tile_start = ps.tile_start; h->d_cub = ps.cub;
     cudaEvent_t* tv = nullptr;
     if (h->timing) {
-        for (int i = 0; i < 7; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tev.push_back(e); }
-        tv = &h->tev[h->tev.size() - 7];
+        for (int i = 0; i < 8; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); h->tev.push_back(e); }
+        tv = &h->tev[h->tev.size() - 8];
         CU(cudaEventRecord(tv[0], h->s_copy));
     }
     CU(cudaMemcpyAsync(h->d_stage[slot], src, bytes, cudaMemcpyDefault, h->s_copy));
     CU(cudaEventRecord(h->ev_h2d[slot], h->s_copy));
     CU(cudaStreamWaitEvent(sp, h->ev_h2d[slot], 0));
-    if (ps.used && h->nsets == 2) CU(cudaStreamWaitEvent(sp, ps.ev_consumed, 0));     // the splat of batch b-2 has read this set
+    if (ps.used && h->nsets == 2 && !h->overlap) CU(cudaStreamWaitEvent(sp, ps.ev_consumed, 0));     // the splat of batch b-2 has read this set
     // start after the splat of batch b-1: prep+bin then overlap its HBM-bound y/x passes instead of fighting the
     // issue-bound splat kernel for the SMs
-    if (h->nsets == 2 && h->sets[1 - p].used && !getenv("MDSF_PREP_EARLY")) CU(cudaStreamWaitEvent(sp, h->sets[1 - p].ev_consumed, 0));
+    if (h->nsets == 2 && !h->overlap && h->sets[1 - p].used && !getenv("MDSF_PREP_EARLY")) CU(cudaStreamWaitEvent(sp, h->sets[1 - p].ev_consumed, 0));
     if (tv) CU(cudaEventRecord(tv[1], sp));
 
     BatchScales sc;
@@ -843,17 +992,18 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     tile_starts_kernel<<<grid_for(cap + 1, 256, h->nsm), 256, 0, sp>>>(h->d_keys[1], cap, nkeys, h->d_tile_start);
     h->launches += 3;
     if (tv) CU(cudaEventRecord(tv[2], sp));
-    if (h->nsets == 2) {
+    if (h->nsets == 2 && !h->overlap) {
         CU(cudaEventRecord(ps.ev_binned, sp));
         CU(cudaStreamWaitEvent(h->s_comp, ps.ev_binned, 0));
     }
-    if (tv) CU(cudaEventRecord(tv[6], h->s_comp));
+    if (h->overlap && h->vol_used[v]) CU(cudaStreamWaitEvent(ss, h->ev_volfree[v], 0));   // the x pass of batch b-2 has read this volume set
+    if (tv) CU(cudaEventRecord(tv[6], ss));
 
     // splat (+ fused z FFT on the native path)
     dim3 grid(gp.ntx * gp.nty, npairs);
 #define MDSF_SPLAT_LAUNCH(FUSE, ATOM, EZG)                                                                                \
-    splat_zfft_kernel<FUSE, ATOM, EZG><<<grid, 256, h->splat_smem, h->s_comp>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, \
-        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err)
+    splat_zfft_kernel<FUSE, ATOM, EZG><<<grid, 256, h->splat_smem, ss>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, \
+        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err, h->ax[2].d_tw16, h->tw16_off)
     switch ((h->native_fft ? 4 : 0) | (h->tile_atomic ? 2 : 0) | (h->ez_global ? 1 : 0)) {
         case 0: MDSF_SPLAT_LAUNCH(false, false, false); break;
         case 1: MDSF_SPLAT_LAUNCH(false, false, true); break;
@@ -866,11 +1016,17 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     }
     ++h->launches;
     CU(cudaGetLastError());
-    if (h->nsets == 2) CU(cudaEventRecord(ps.ev_consumed, h->s_comp));
+    if (h->nsets == 2 && !h->overlap) CU(cudaEventRecord(ps.ev_consumed, h->s_comp));
+    if (h->overlap) {
+        if (tv) CU(cudaEventRecord(tv[3], ss));
+        CU(cudaEventRecord(h->ev_splat[v], ss));
+        CU(cudaStreamWaitEvent(h->s_comp, h->ev_splat[v], 0));
+    }
     }
     ps.used = true;
     int rc = transform_and_accumulate(h, nf, h->native_fft, tv);   // z pass already done on the native path
     if (rc) return rc;
+    if (h->overlap) { CU(cudaEventRecord(h->ev_volfree[v], h->s_comp)); h->vol_used[v] = true; }
     if (tv) { CU(cudaEventRecord(tv[5], h->s_comp)); ++h->timed_batches; }
     h->slot_used[slot] = true;
     h->frames_done += nf;
@@ -925,6 +1081,7 @@ extern "C" int mdsf_sync(mdsf_handle* h) {
     CU(cudaMemcpyAsync(h->h_err, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->s_comp));
     CU(cudaStreamSynchronize(h->s_copy));
     CU(cudaStreamSynchronize(h->s_prep));
+    if (h->s_splat) CU(cudaStreamSynchronize(h->s_splat));
     CU(cudaStreamSynchronize(h->s_comp));
     CU(cudaStreamSynchronize(h->s_back));
     if (*h->h_err == 3) {
@@ -1022,6 +1179,10 @@ extern "C" int64_t mdsf_frames_done(const mdsf_handle* h) { return h ? h->frames
 extern "C" const char* mdsf_fft_path(const mdsf_handle* h) { return (h && h->native_fft) ? "native" : "cufft"; }
 extern "C" const char* mdsf_splat_path(const mdsf_handle* h) { return (h && h->scatter) ? "scatter" : ((h && h->tile_atomic) ? "tile" : "owner"); }
 extern "C" int mdsf_batch_frames(const mdsf_handle* h) { return h ? h->F : 0; }
+extern "C" int mdsf_pipeline_info(const mdsf_handle* h, int32_t* sms) {
+    if (sms) { sms[0] = h ? h->part_sms[0] : 0; sms[1] = h ? h->part_sms[1] : 0; }
+    return h ? h->overlap : 0;
+}
 extern "C" int mdsf_enable_timing(mdsf_handle* h, int32_t on) {
     if (!h) return fail(MDSF_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));
@@ -1037,15 +1198,16 @@ extern "C" int mdsf_stage_ms(mdsf_handle* h, double* out6, int64_t* batches) {
     CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
     for (int i = 0; i < 6; ++i) out6[i] = 0;
-    const size_t nb = h->tev.size() / 7;
+    const size_t nb = h->tev.size() / 8;
     for (size_t b = 0; b < nb; ++b) {
-        // tv: 0 copy start (s_copy), 1 prep start, 2 binned (prep stream), 6 splat start, 3 splat done, 4 y done, 5 end (s_comp)
-        cudaEvent_t* tv = &h->tev[b * 7];
+        // tv: 0 copy start (s_copy), 1 prep start, 2 binned (prep stream), 6 splat start, 3 splat done (splat stream),
+        //     7 y start, 4 y done, 5 end (s_comp).  In overlap mode 3 -> 7 is the wait for the previous batch's x pass.
+        cudaEvent_t* tv = &h->tev[b * 8];
         float ms;
         CU(cudaEventElapsedTime(&ms, tv[0], tv[1])); out6[0] += ms;     // copy (overlaps the previous batch's kernels)
         CU(cudaEventElapsedTime(&ms, tv[1], tv[2])); out6[1] += ms;     // prep + bin (overlaps the previous batch when two sets)
         CU(cudaEventElapsedTime(&ms, tv[6], tv[3])); out6[2] += ms;
-        CU(cudaEventElapsedTime(&ms, tv[3], tv[4])); out6[3] += ms;
+        CU(cudaEventElapsedTime(&ms, tv[7], tv[4])); out6[3] += ms;
         CU(cudaEventElapsedTime(&ms, tv[4], tv[5])); out6[4] += ms;
         CU(cudaEventElapsedTime(&ms, tv[6], tv[5])); out6[5] += ms;     // compute-stream time of the batch
     }

@@ -509,6 +509,163 @@ fft_x_accum_fast_kernel(double2* __restrict__ vol, double* __restrict__ P, const
     }
 }
 
+// ------------------------------------------------------------------ x pass, two-stage, cp.async-prefetched
+// Same arithmetic as fft_x_accum_fast_kernel.  The stage-1 inputs of pair q+1 are copied global -> shared
+// memory with cp.async (16 bytes per copy, each thread copies exactly the R1 points it will consume, so no
+// barrier guards the staging buffer) while the thread runs the butterflies of pair q: every CTA always has
+// its next 32 KB in flight, which keeps the HBM queues full from few SMs (SM-partitioned pipeline) as well.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+#ifndef MDSF_XASYNC_MINBLOCKS
+#define MDSF_XASYNC_MINBLOCKS 3
+#endif
+template <int R1, int R2>
+__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_XASYNC_MINBLOCKS)
+fft_x_accum_async_kernel(const double2* __restrict__ vol, double* __restrict__ P, const double2* __restrict__ tw,
+                         int ny, int nz, int logw, int npairs)
+{
+    constexpr int NX = R1 * R2;
+    extern __shared__ double smem[];
+    const int W = 1 << logw;
+    double* sre = smem;
+    double* sim = sre + (size_t)NX * W;
+    double* twr = sim + (size_t)NX * W;
+    double* twi = twr + NX;
+    double2* stage = reinterpret_cast<double2*>(twi + NX);     // [R1][blockDim.x]: point j of thread t at stage[j*T + t]
+    const int T = blockDim.x;
+    load_twiddles(twr, twi, tw, NX);
+    const int z0 = blockIdx.x * W;
+    const int y = blockIdx.y;
+    const long long xstride = (long long)ny * nz;
+    const long long off = (long long)y * nz + z0;
+    const int f = threadIdx.x & (W - 1), bf = threadIdx.x >> logw;
+    const bool ok = z0 + f < nz;
+    double acc[R2];
+#pragma unroll
+    for (int k = 0; k < R2; ++k) acc[k] = 0.0;
+    double2* mine = stage + threadIdx.x;
+    if (ok) {
+        const double2* base = vol + off + f;
+#pragma unroll
+        for (int j = 0; j < R1; ++j) cp_async16(mine + j * T, base + (long long)(bf + R2 * j) * xstride);
+    }
+    __syncthreads();                               // twiddle table is in shared memory
+    for (int q = 0; q < npairs; ++q) {
+        {
+            double xr[R1], xi[R1];
+            cp_async_wait_all();
+#pragma unroll
+            for (int j = 0; j < R1; ++j) {
+                double2 v = make_double2(0.0, 0.0);
+                if (ok) v = mine[j * T];
+                xr[j] = v.x; xi[j] = v.y;
+            }
+            if (ok && q + 1 < npairs) {            // the slots are free again: fetch the next pair behind this one's math
+                const double2* base = vol + (long long)(q + 1) * NX * xstride + off + f;
+#pragma unroll
+                for (int j = 0; j < R1; ++j) cp_async16(mine + j * T, base + (long long)(bf + R2 * j) * xstride);
+            }
+            Dft<R1>::run(xr, xi, twr, twi, NX);
+#pragma unroll
+            for (int k = 1; k < R1; ++k) {
+                const double wr = twr[bf * k], wi = twi[bf * k];
+                const double yr = xr[k] * wr - xi[k] * wi;
+                xi[k] = xr[k] * wi + xi[k] * wr;
+                xr[k] = yr;
+            }
+            __syncthreads();                       // previous pair's stage 2 has finished reading the tile
+#pragma unroll
+            for (int k = 0; k < R1; ++k) { const int a = ((k * R2 + bf) << logw) + f; sre[a] = xr[k]; sim[a] = xi[k]; }
+        }
+        __syncthreads();
+        {
+            double xr[R2], xi[R2];
+#pragma unroll
+            for (int j = 0; j < R2; ++j) { const int a = ((bf * R2 + j) << logw) + f; xr[j] = sre[a]; xi[j] = sim[a]; }
+            Dft<R2>::run(xr, xi, twr, twi, NX);
+#pragma unroll
+            for (int k = 0; k < R2; ++k) acc[k] += xr[k] * xr[k] + xi[k] * xi[k];
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int k = 0; k < R2; ++k) P[(long long)(bf * R2 + k) * xstride + off + f] += acc[k];
+    }
+}
+
+// ------------------------------------------------------------------ y pass, two-stage, cp.async-prefetched
+// grid = (z chunks, Nx); the CTA walks the pairs of the batch at fixed (x, z chunk) and fetches the tile of pair
+// q+1 behind the butterflies of pair q (see fft_x_accum_async_kernel).  In place on the volume.
+template <int R1, int R2>
+__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_XASYNC_MINBLOCKS)
+fft_y_async_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, int nx, int nz, int logw, int npairs)
+{
+    constexpr int NY = R1 * R2;
+    extern __shared__ double smem[];
+    const int W = 1 << logw;
+    double* sre = smem;
+    double* sim = sre + (size_t)NY * W;
+    double* twr = sim + (size_t)NY * W;
+    double* twi = twr + NY;
+    double2* stage = reinterpret_cast<double2*>(twi + NY);
+    const int T = blockDim.x;
+    load_twiddles(twr, twi, tw, NY);
+    const int z0 = blockIdx.x * W;
+    const int f = threadIdx.x & (W - 1), bf = threadIdx.x >> logw;
+    const bool ok = z0 + f < nz;
+    const long long pair_stride = (long long)nx * NY * nz;
+    double2* base0 = vol + ((long long)blockIdx.y * NY) * (long long)nz + z0 + f;
+    double2* mine = stage + threadIdx.x;
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < R1; ++j) cp_async16(mine + j * T, base0 + (long long)(bf + R2 * j) * nz);
+    }
+    __syncthreads();
+    for (int q = 0; q < npairs; ++q) {
+        double2* base = base0 + (long long)q * pair_stride;
+        {
+            double xr[R1], xi[R1];
+            cp_async_wait_all();
+#pragma unroll
+            for (int j = 0; j < R1; ++j) {
+                double2 v = make_double2(0.0, 0.0);
+                if (ok) v = mine[j * T];
+                xr[j] = v.x; xi[j] = v.y;
+            }
+            if (ok && q + 1 < npairs) {
+#pragma unroll
+                for (int j = 0; j < R1; ++j) cp_async16(mine + j * T, base + pair_stride + (long long)(bf + R2 * j) * nz);
+            }
+            Dft<R1>::run(xr, xi, twr, twi, NY);
+#pragma unroll
+            for (int k = 1; k < R1; ++k) {
+                const double wr = twr[bf * k], wi = twi[bf * k];
+                const double yr = xr[k] * wr - xi[k] * wi;
+                xi[k] = xr[k] * wi + xi[k] * wr;
+                xr[k] = yr;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < R1; ++k) { const int a = ((k * R2 + bf) << logw) + f; sre[a] = xr[k]; sim[a] = xi[k]; }
+        }
+        __syncthreads();
+        {
+            double xr[R2], xi[R2];
+#pragma unroll
+            for (int j = 0; j < R2; ++j) { const int a = ((bf * R2 + j) << logw) + f; xr[j] = sre[a]; xi[j] = sim[a]; }
+            Dft<R2>::run(xr, xi, twr, twi, NY);
+            if (ok) {
+#pragma unroll
+                for (int k = 0; k < R2; ++k) base[(long long)(bf * R2 + k) * nz] = make_double2(xr[k], xi[k]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ library-FFT path helper
 // P += sum_q |vol_q|^2 after a cuFFT Z2Z (grids whose sizes have prime factors > 13)
 __global__ void accumulate_power_kernel(const double2* __restrict__ vol, double* __restrict__ P,

@@ -58,9 +58,12 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
                   double2* __restrict__ dens_dump, GridParams gp, TypeTable tt, FftPlan zplan,
                   const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS, int zfast,
-                  int zstage, int* __restrict__ err_flag)
+                  int zstage, int* __restrict__ err_flag, const double2* __restrict__ tw16, int tw16_off)
 {
     extern __shared__ double smem[];
+    // Nz = 256 tile mode: stage-1 twiddles of the 16x16 z split arrive by cp.async while the splat runs
+    double2* tw16s = reinterpret_cast<double2*>(reinterpret_cast<char*>(smem) + tw16_off);
+    if (FUSE_ZFFT && ATOMIC && tw16_off > 0) cp_async16(tw16s + threadIdx.x, tw16 + threadIdx.x);
     const int ncol = gp.tx * gp.ty;
     const int nzp = gp.nzp;
     const int ntiles = gp.ntx * gp.nty;
@@ -340,7 +343,9 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         }
         if (ovf < 0) atomicExch(err_flag, 2);
     }
-    if (FUSE_ZFFT) {
+    const bool tw_ready = FUSE_ZFFT && ATOMIC && tw16_off > 0 && fused_convert && zfast == 16;
+    if (FUSE_ZFFT && ATOMIC && tw16_off > 0) cp_async_wait_all();
+    if (FUSE_ZFFT && !tw_ready) {
         if (fused_convert && zfast == 16) {
             // stage-1 twiddles laid out [k][n2] (w^(n2 k) at k*16 + n2): lanes walk n2, so the reads are conflict-free
             for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -387,7 +392,9 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 Dft<16>::run(xr, xi, twr, twi, nz);
 #pragma unroll
                 for (int k = 1; k < 16; ++k) {
-                    const double wr = twr[k * 16 + n2], wi = twi[k * 16 + n2];
+                    double wr, wi;
+                    if (tw_ready) { const double2 w = tw16s[k * 16 + n2]; wr = w.x; wi = w.y; }
+                    else { wr = twr[k * 16 + n2]; wi = twi[k * 16 + n2]; }
                     const double yr = xr[k] * wr - xi[k] * wi;
                     xi[k] = xr[k] * wi + xi[k] * wr;
                     xr[k] = yr;

@@ -23,7 +23,7 @@ EXPORTS = [
     "mdsf_host_register", "mdsf_host_unregister", "mdsf_push_frames", "mdsf_push_density", "mdsf_sync",
     "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
     "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_splat_path",
-    "mdsf_batch_frames",
+    "mdsf_batch_frames", "mdsf_pipeline_info",
     "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_timer_start", "mdsf_timer_stop", "mdsf_last_error",
     "mdsf_input_mark", "mdsf_input_wait",
     "mdsf_abi_version",
@@ -82,6 +82,7 @@ def load():
         "mdsf_fft_path": (C.c_char_p, [vp]),
         "mdsf_splat_path": (C.c_char_p, [vp]),
         "mdsf_batch_frames": (C.c_int, [vp]),
+        "mdsf_pipeline_info": (C.c_int, [vp, C.POINTER(i32)]),
         "mdsf_enable_timing": (C.c_int, [vp, i32]),
         "mdsf_stage_ms": (C.c_int, [vp, dp, C.POINTER(i64)]),
         "mdsf_input_mark": (C.c_int, [vp, C.POINTER(C.c_int64)]),
@@ -272,6 +273,13 @@ class Engine:
     @property
     def batch_frames(self):
         return int(self._lib.mdsf_batch_frames(self._h))
+
+    @property
+    def pipeline(self):
+        """{"overlap": bool, "sms": (splat-side SMs, pass-side SMs)}; (0, 0) = no SM partition."""
+        sms = (C.c_int32 * 2)()
+        ov = self._lib.mdsf_pipeline_info(self._h, sms)
+        return {"overlap": bool(ov), "sms": (int(sms[0]), int(sms[1]))}
 
     def enable_timing(self, on=True):
         _check(self._lib.mdsf_enable_timing(self._h, 1 if on else 0))
