@@ -157,6 +157,57 @@ emit_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     }
 }
 
+// ---- K2 (tile splat mode): direct binning.  The fixed-point tile accumulation is order-independent, so the
+// lists need no stable sort: count the pairs of every (frame, tile) key with integer atomics, scan the counts
+// into list starts, and let every pair claim a slot of its list from a per-key cursor.  Replaces scan + fill +
+// emit + radix sort + list starts (0.43 ms -> 0.15 ms per 32 c2 frames, serialised ncu times).
+template <typename F>
+__device__ __forceinline__ void for_each_pair(const AtomRec& rec, int a, int f, const GridParams& gp, const TypeTable& tt, F&& fn) {
+    const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
+    const int ntiles = gp.ntx * gp.nty;
+    for (int sx = -1; sx <= 1; ++sx) {
+        int xlo, xhi;
+        stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
+        if (xhi <= xlo) continue;
+        const int tx0 = (xlo - sx * gp.n[0]) / gp.tx, tx1 = (xhi - 1 - sx * gp.n[0]) / gp.tx;
+        for (int sy = -1; sy <= 1; ++sy) {
+            int ylo, yhi;
+            stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
+            if (yhi <= ylo) continue;
+            const int ty0 = (ylo - sy * gp.n[1]) / gp.ty, ty1 = (yhi - 1 - sy * gp.n[1]) / gp.ty;
+            const unsigned payload = (unsigned)a | ((unsigned)(sx + 1) << MDSF_ATOM_BITS) |
+                                     ((unsigned)(sy + 1) << (MDSF_ATOM_BITS + 2));
+            int shlo, shhi, kA, kB;
+            const unsigned sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
+            for (int tX = tx0; tX <= tx1; ++tX)
+                for (int tY = ty0; tY <= ty1; ++tY) {
+                    const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
+                    for (unsigned m = sm; m; m &= m - 1) fn(kbase + (unsigned)(__ffs(m) - 1), payload);
+                }
+        }
+    }
+}
+
+// PLACE = false: list lengths; PLACE = true: payloads into their lists (start = scanned lengths, cursor zeroed)
+template <bool PLACE>
+__global__ void __launch_bounds__(256)
+bin_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ pair_count, unsigned* __restrict__ counter,
+                 const unsigned* __restrict__ start, unsigned* __restrict__ vals, GridParams gp, TypeTable tt, int nframes)
+{
+    const long long total = (long long)nframes * gp.natoms;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (pair_count[idx] == 0) continue;
+        const int f = (int)(idx / gp.natoms);
+        const int a = (int)(idx - (long long)f * gp.natoms);
+        const AtomRec rec = recs[idx];
+        for_each_pair(rec, a, f, gp, tt, [&](unsigned key, unsigned payload) {
+            if (PLACE) vals[start[key] + atomicAdd(counter + key, 1u)] = payload;
+            else atomicAdd(counter + key, 1u);
+        });
+    }
+}
+
 __global__ void fill_u32_kernel(unsigned* __restrict__ p, unsigned v, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) p[i] = v;
