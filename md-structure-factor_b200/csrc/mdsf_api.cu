@@ -130,7 +130,6 @@ struct mdsf_handle {
     long long maxpairs_frame = 0;
     int chunk = 128;
     size_t splat_smem = 0;
-    int splat_tpc = 4;                // consecutive tiles per splat CTA (cross-tile prefetch of lists and records); MDSF_TPC
     bool direct_bin = false;          // tile mode: counting-sort binning with atomics instead of the stable radix sort
     int tw16_off = 0;                 // byte offset of the cp.async-prefetched stage-1 twiddle table in the splat's shared memory (0 = none)
     int sort_bits = 1;
@@ -768,7 +767,6 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     CU(cudaMemcpy(h->d_toff, toff.data(), sizeof(unsigned) * natoms, cudaMemcpyHostToDevice));
     h->tt.toff = h->d_toff;
     h->nsets = (h->scatter || getenv("MDSF_ONE_STREAM")) ? 1 : 2;
-    if (getenv("MDSF_TPC")) h->splat_tpc = std::max(1, atoi(getenv("MDSF_TPC")));
     h->direct_bin = h->tile_atomic && !h->scatter && (!getenv("MDSF_DIRECT_BIN") || atoi(getenv("MDSF_DIRECT_BIN")) != 0);
     {
         size_t b1 = 0, b2 = 0;
@@ -1017,11 +1015,10 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     if (tv) CU(cudaEventRecord(tv[6], ss));
 
     // splat (+ fused z FFT on the native path)
-    const int tpc = std::max(1, h->splat_tpc);
-    dim3 grid((gp.ntx * gp.nty + tpc - 1) / tpc, npairs);
+    dim3 grid(gp.ntx * gp.nty, npairs);
 #define MDSF_SPLAT_LAUNCH(FUSE, ATOM, EZG)                                                                                \
     splat_zfft_kernel<FUSE, ATOM, EZG><<<grid, 256, h->splat_smem, ss>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, \
-        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err, h->ax[2].d_tw16, h->tw16_off, tpc)
+        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err, h->ax[2].d_tw16, h->tw16_off)
     switch ((h->native_fft ? 4 : 0) | (h->tile_atomic ? 2 : 0) | (h->ez_global ? 1 : 0)) {
         case 0: MDSF_SPLAT_LAUNCH(false, false, false); break;
         case 1: MDSF_SPLAT_LAUNCH(false, false, true); break;

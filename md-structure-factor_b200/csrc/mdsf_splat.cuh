@@ -58,7 +58,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
                   double2* __restrict__ dens_dump, GridParams gp, TypeTable tt, FftPlan zplan,
                   const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS, int zfast,
-                  int zstage, int* __restrict__ err_flag, const double2* __restrict__ tw16, int tw16_off, int tpc)
+                  int zstage, int* __restrict__ err_flag, const double2* __restrict__ tw16, int tw16_off)
 {
     extern __shared__ double smem[];
     // Nz = 256 tile mode: stage-1 twiddles of the 16x16 z split arrive by cp.async while the splat runs
@@ -67,20 +67,11 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     const int ncol = gp.tx * gp.ty;
     const int nzp = gp.nzp;
     const int ntiles = gp.ntx * gp.nty;
-    const int q = blockIdx.y;
+    const int tile = blockIdx.x, q = blockIdx.y;
+    const int X0 = (tile / gp.nty) * gp.tx, Y0 = (tile % gp.nty) * gp.ty;
     const int part = threadIdx.x >> 7, pt = threadIdx.x & 127, lane = threadIdx.x & 31, pw = pt >> 5;
     const int nz = gp.n[2];
     const int f = 2 * q + part;
-    // A CTA walks `tpc` consecutive tiles of its frame pair.  The dependent chain list bounds -> list entries ->
-    // atom records of tile i+1 is requested while tile i is accumulated and transformed, so a new tile starts
-    // with its first chunk already in registers (one CTA per tile leaves three global round trips exposed).
-    const int tile_first = blockIdx.x * tpc, tile_last = min(tile_first + tpc, ntiles);
-    unsigned n_lbeg = 0, n_lend = 0;
-    unsigned pf_v = 0;
-    AtomRec pf_rec;
-    pf_rec.type = 0;
-    for (int tile = tile_first; tile < tile_last; ++tile) {
-    const int X0 = (tile / gp.nty) * gp.tx, Y0 = (tile % gp.nty) * gp.ty;
 
     // ---- ownership: owner o = slab * ncol + column; slab s covers z in [s*zs, (s+1)*zs).
     // The tile's pair list is sorted by slab (K2), so an owner's hits are the pairs of ITS slab
@@ -88,13 +79,8 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     const int nslab = gp.nslab, zs = gp.zs;
     const int mycol = pt % ncol, myslab = ATOMIC ? 0 : pt / ncol;
     const unsigned kbase = (unsigned)(f * ntiles + tile) * (unsigned)nslab;
-    const bool first_tile = tile == tile_first, has_next = tile + 1 < tile_last;
-    const unsigned lbeg = first_tile ? tile_start[kbase] : n_lbeg;
-    const unsigned lend = (gp.debug_skip & 16) ? lbeg : (first_tile ? tile_start[kbase + nslab] : n_lend);
-    const unsigned sbeg = ATOMIC ? lbeg : tile_start[kbase + myslab], send = ATOMIC ? lend : tile_start[kbase + myslab + 1];
-    if (has_next) { n_lbeg = tile_start[kbase + nslab]; n_lend = tile_start[kbase + 2 * nslab]; }
-    if (gp.debug_skip & 16) n_lend = n_lbeg;
-    bool nv_issued = false;
+    const unsigned lbeg = tile_start[kbase], lend = (gp.debug_skip & 16) ? lbeg : tile_start[kbase + nslab];
+    const unsigned sbeg = tile_start[kbase + myslab], send = tile_start[kbase + myslab + 1];
 
     // ---- shared memory carve-up
     double* tile_re = smem;                                   // [ncol][nzp]  frame 2q
@@ -115,7 +101,10 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     double* mytile = part ? tile_im : tile_re;
     // the first chunk's list entries and atom records are requested before the tile is cleared, the next
     // chunk's while the current one is being accumulated: the dependent loads overlap useful work
-    if (first_tile && lbeg < lend && pt < (int)min((unsigned)chunk, lend - lbeg)) {
+    unsigned pf_v = 0;
+    AtomRec pf_rec;
+    pf_rec.type = 0;
+    if (lbeg < lend && pt < (int)min((unsigned)chunk, lend - lbeg)) {
         pf_v = vals[lbeg + pt];
         pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
     }
@@ -219,14 +208,9 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             hitT[pw * 32 + lane] = mine;
         }
         part_barrier(part);
-        if (cb + chunk < lend) {
-            if (pt < (int)min((unsigned)chunk, lend - cb - chunk)) {      // prefetch the next chunk
-                pf_v = vals[cb + chunk + pt];
-                pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
-            }
-        } else if (has_next) {                                           // last chunk: list entries of the next tile
-            if (n_lbeg < n_lend && pt < (int)min((unsigned)chunk, n_lend - n_lbeg)) pf_v = vals[n_lbeg + pt];
-            nv_issued = true;
+        if (cb + chunk < lend && pt < (int)min((unsigned)chunk, lend - cb - chunk)) {      // prefetch the next chunk
+            pf_v = vals[cb + chunk + pt];
+            pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
         }
 
         // ---------------- B (tile mode): one thread per (pair, column), fixed-point integer atomics
@@ -347,10 +331,6 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         }
         part_barrier(part);
     }
-    if (has_next && n_lbeg < n_lend && pt < (int)min((unsigned)chunk, n_lend - n_lbeg)) {   // atom records of the next tile's first chunk
-        if (!nv_issued) pf_v = vals[n_lbeg + pt];
-        pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
-    }
     __syncthreads();
     // tile mode on the fast z path converts fixed point -> fp64 inside the first FFT stage instead
     const bool fused_convert = ATOMIC && FUSE_ZFFT && zfast && dens_dump == nullptr && !(gp.debug_skip & 2);
@@ -459,7 +439,8 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 for (int k = 0; k < 8; ++k) dst[8 * k] = make_double2(xr[k], xi[k]);
             }
         }
-    } else {
+        return;
+    }
     if (FUSE_ZFFT && !(gp.debug_skip & 2)) fft_tile_z(tile_re, tile_im, twr, twi, zplan, ncol, nzp, gp.pad_shift);
     if (!(gp.debug_skip & 8)) {
         // thread <-> z, loop over the tile's columns: 16-byte stores, one contiguous run per column
@@ -474,8 +455,5 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 for (int cy = 0; cy < ymax; ++cy, a += nzp, dst += nz) *dst = make_double2(tile_re[a], tile_im[a]);
             }
         }
-    }
-    }
-    if (has_next) __syncthreads();       // the next tile clears the buffers this one's last stage still reads
     }
 }
