@@ -39,8 +39,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--frames-per-step", type=int, default=32)
-    ap.add_argument("--pool", type=int, default=64, help="distinct synthetic frames cycled through")
+    ap.add_argument("--frames-per-step", type=int, default=64)
+    ap.add_argument("--pool", type=int, default=128, help="distinct synthetic frames cycled through")
     ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (0 = all host cores)")
@@ -324,6 +324,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "grid": list(wl["grid"]), "atoms": natoms,
                        "frames_per_step": F, "pool_frames": pool_n, "fft": eng.fft_path, "splat": eng.splat_path, "Nborder": nb,
+                       "pipeline": eng.pipeline,
                        "l2": "per-step working set (%.0f MB of pair volumes + accumulator) exceeds the 126 MB L2; no explicit flush"
                              % ((F // 2) * np.prod(wl["grid"]) * 16 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes,

@@ -114,6 +114,7 @@ struct mdsf_handle {
     unsigned *d_cnt = nullptr, *d_off = nullptr;
     unsigned *d_keys[2]{}, *d_vals[2]{};
     unsigned* d_tile_start = nullptr;
+    unsigned* d_counter = nullptr;
     void* d_cub = nullptr;
     size_t cub_bytes = 0;
     double2* d_vol = nullptr;
@@ -899,7 +900,7 @@ template <typename C, typename P>
 static void launch_prep(mdsf_handle* h, cudaStream_t st, void* stage, const BatchScales& sc, int nf, long long wlo, long long whi) {
     const long long total = (long long)nf * h->natoms;
     prep_atoms_kernel<C, P><<<grid_for(total, 256, h->nsm), 256, 0, st>>>(
-        (C*)stage, h->d_type, h->d_recs, h->d_cnt, h->d_tables, h->gp, h->tt, sc, nf, wlo, whi, h->d_err);
+        (C*)stage, h->d_type, h->d_recs, h->d_cnt, h->d_tables, h->gp, h->tt, sc, nf, wlo, whi, h->d_err, h->direct_bin ? h->d_counter : nullptr);
 }
 
 static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, long long wlo, long long whi, int write_back) {
@@ -941,6 +942,11 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
 
     BatchScales sc;
     for (int f = 0; f < nf; ++f) for (int d = 0; d < 3; ++d) sc.a[f][d] = scale[f * 3 + d];
+    h->d_counter = ps.counter;
+    if (h->direct_bin) {      // list lengths are counted by K1 itself; [nkeys+1] lengths, then [nkeys+1] cursors
+        const unsigned nk = (unsigned)((nf + (nf & 1)) * gp.ntx * gp.nty * gp.nslab);
+        CU(cudaMemsetAsync(ps.counter, 0, sizeof(unsigned) * 2 * (nk + 1), sp));
+    }
     const bool c32 = h->cfg.coord_dtype == MDSF_F32, p32 = h->cfg.arith_dtype == MDSF_F32;
     if (c32 && p32) launch_prep<float, float>(h, sp, h->d_stage[slot], sc, nf, wlo, whi);
     else if (c32) launch_prep<float, double>(h, sp, h->d_stage[slot], sc, nf, wlo, whi);
@@ -990,11 +996,9 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     size_t cb = h->cub_bytes;
     if (h->direct_bin) {
         // tile mode: order inside a list is irrelevant (integer adds commute) -> counting sort with atomics
-        CU(cudaMemsetAsync(ps.counter, 0, sizeof(unsigned) * 2 * (nkeys + 1), sp));
-        bin_pairs_kernel<false><<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(h->d_recs, h->d_cnt, ps.counter, nullptr, nullptr, gp, h->tt, nf);
         cub::DeviceScan::ExclusiveSum(h->d_cub, cb, ps.counter, h->d_tile_start, (long long)nkeys + 1, sp);
         bin_pairs_kernel<true><<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(h->d_recs, h->d_cnt, ps.counter + nkeys + 1, h->d_tile_start, h->d_vals[1], gp, h->tt, nf);
-        h->launches += 2;
+        h->launches += 1;
     } else {
     cub::DeviceScan::ExclusiveSum(h->d_cub, cb, h->d_cnt, h->d_off, total, sp);
     fill_u32_kernel<<<grid_for(cap, 256, h->nsm), 256, 0, sp>>>(h->d_keys[0], nkeys, cap);

@@ -36,6 +36,35 @@ __device__ __forceinline__ unsigned count_pairs(const AtomRec& rec, const GridPa
     return total;
 }
 
+template <typename F>
+__device__ __forceinline__ void for_each_pair(const AtomRec& rec, int a, int f, const GridParams& gp, const TypeTable& tt, F&& fn) {
+    const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
+    const int ntiles = gp.ntx * gp.nty;
+    for (int sx = -1; sx <= 1; ++sx) {
+        int xlo, xhi;
+        stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
+        if (xhi <= xlo) continue;
+        const int tx0 = (xlo - sx * gp.n[0]) / gp.tx, tx1 = (xhi - 1 - sx * gp.n[0]) / gp.tx;
+        for (int sy = -1; sy <= 1; ++sy) {
+            int ylo, yhi;
+            stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
+            if (yhi <= ylo) continue;
+            const int ty0 = (ylo - sy * gp.n[1]) / gp.ty, ty1 = (yhi - 1 - sy * gp.n[1]) / gp.ty;
+            const unsigned payload = (unsigned)a | ((unsigned)(sx + 1) << MDSF_ATOM_BITS) |
+                                     ((unsigned)(sy + 1) << (MDSF_ATOM_BITS + 2));
+            int shlo, shhi, kA, kB;
+            const unsigned sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
+            for (int tX = tx0; tX <= tx1; ++tX)
+                for (int tY = ty0; tY <= ty1; ++tY) {
+                    const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
+                    for (unsigned m = sm; m; m &= m - 1) fn(kbase + (unsigned)(__ffs(m) - 1), payload);
+                }
+        }
+    }
+}
+
+#define MDSF_PREP_STAGE 512        // doubles of factor tables one warp stages in shared memory (c2: 32 atoms x 12)
+
 template <typename C, typename P>
 __global__ void __launch_bounds__(256)
 prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], rewritten in place
@@ -44,55 +73,87 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
                   unsigned* __restrict__ pair_count, // [nframes*natoms]
                   double* __restrict__ tables,       // [nframes][tstride] per-atom Gaussian factor tables
                   GridParams gp, TypeTable tt, BatchScales sc, int nframes,
-                  long long wrap_lo, long long wrap_hi, int* __restrict__ err_flag)
+                  long long wrap_lo, long long wrap_hi, int* __restrict__ err_flag,
+                  unsigned* __restrict__ tile_counter /* direct binning: list lengths per (frame, tile) key, or nullptr */)
 {
+    // A lane's record (48 B) and factor tables (16 (Ax+Ay+Az) B) are contiguous with its neighbours' in global memory
+    // but strided across the lanes of a store instruction; both are staged per warp in shared memory and written
+    // out as whole 256-byte rows (the strided form touched every 32-byte sector four times).
+    __shared__ double s_tab[8][MDSF_PREP_STAGE];
+    __shared__ double s_rec[8][32 * 6];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long total = (long long)nframes * gp.natoms;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+    const long long nloop = (total + 31) / 32 * 32;                       // whole warps stay in the loop together
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < nloop;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int f = (int)(idx / gp.natoms);
-        const int a = (int)(idx - (long long)f * gp.natoms);
-        C* src = coords + idx * 3;
-        const int t = type_id[a];
-        AtomRec rec;
+        const bool live = idx < total;
+        const int f = live ? (int)(idx / gp.natoms) : 0;
+        const int a = live ? (int)(idx - (long long)f * gp.natoms) : 0;
+        const int t = live ? type_id[a] : 0;
+        AtomRec rec{};
         rec.type = t;
-        rec.tbase = (unsigned)((long long)f * gp.tstride + tt.toff[a]);
+        rec.tbase = live ? (unsigned)((long long)f * gp.tstride + tt.toff[a]) : 0u;
         rec.pad_ = 0;
         bool bad = false;
+        if (live) {
+            C* src = coords + idx * 3;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            // rc[it,:,i] *= a[it,i]   (dens.py:58)
-            C r = (C)mul_rn<P>((P)src[d], (P)sc.a[f][d]);
-            if (a >= wrap_lo && a < wrap_hi) {
-                const P L = (P)gp.box[d];
-                // np.where(r < L, r, r - L) then np.where(r > 0, r, r + L)   (dens.py:211-212)
-                if (!((P)r < L)) r = (C)add_rn<P>((P)r, -L);
-                if (!((P)r > (P)0)) r = (C)add_rn<P>((P)r, L);
+            for (int d = 0; d < 3; ++d) {
+                // rc[it,:,i] *= a[it,i]   (dens.py:58)
+                C r = (C)mul_rn<P>((P)src[d], (P)sc.a[f][d]);
+                if (a >= wrap_lo && a < wrap_hi) {
+                    const P L = (P)gp.box[d];
+                    // np.where(r < L, r, r - L) then np.where(r > 0, r, r + L)   (dens.py:211-212)
+                    if (!((P)r < L)) r = (C)add_rn<P>((P)r, -L);
+                    if (!((P)r > (P)0)) r = (C)add_rn<P>((P)r, L);
+                }
+                src[d] = r;
+                const double rd = (double)r;
+                const double q = rd / gp.dr[d];            // IEEE fp64 divide, as numpy (dens.py:285)
+                const int A = tt.halfw[t * 3 + d];
+                int ir = 0;
+                if (!(q > -2147483000.0 && q < 2147483000.0)) bad = true;   // also catches NaN
+                else ir = (int)q;                          // astype(int): truncation toward zero
+                // the stamp [ir-A, ir+A) must stay inside the padded grid [-B, N+B)  (dens.py:292-297)
+                if (ir - A < -gp.nb || ir + A > gp.n[d] + gp.nb) bad = true;
+                rec.r[d] = rd;
+                rec.ir[d] = ir;
             }
-            src[d] = r;
-            const double rd = (double)r;
-            const double q = rd / gp.dr[d];            // IEEE fp64 divide, as numpy (dens.py:285)
-            const int A = tt.halfw[t * 3 + d];
-            int ir = 0;
-            if (!(q > -2147483000.0 && q < 2147483000.0)) bad = true;   // also catches NaN
-            else ir = (int)q;                          // astype(int): truncation toward zero
-            // the stamp [ir-A, ir+A) must stay inside the padded grid [-B, N+B)  (dens.py:292-297)
-            if (ir - A < -gp.nb || ir + A > gp.n[d] + gp.nb) bad = true;
-            rec.r[d] = rd;
-            rec.ir[d] = ir;
         }
-        recs[idx] = rec;
-        if (bad) { atomicExch(err_flag, 1); pair_count[idx] = 0; continue; }
-        pair_count[idx] = count_pairs(rec, gp, tt);
-        if (!gp.separable) continue;
+        {   // records: 6 eight-byte words per lane -> 192 contiguous words per warp
+            const double* w = reinterpret_cast<const double*>(&rec);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s_rec[warp][lane * 6 + i] = w[i];
+            __syncwarp();
+            const long long idx0 = idx - lane;
+            const int nvalid = (int)min(32LL, total - idx0) * 6;
+            double* dst = reinterpret_cast<double*>(recs + idx0);
+            for (int j = lane; j < nvalid; j += 32) dst[j] = s_rec[warp][j];
+            __syncwarp();
+        }
+        unsigned npairs = 0;
+        if (live && bad) atomicExch(err_flag, 1);
+        const bool ok = live && !bad;
+        if (ok) {
+            if (tile_counter != nullptr) for_each_pair(rec, a, f, gp, tt, [&](unsigned key, unsigned) { atomicAdd(tile_counter + key, 1u); ++npairs; });
+            else npairs = count_pairs(rec, gp, tt);
+        }
+        if (live) pair_count[idx] = npairs;
+        if (!gp.separable) continue;                       // warp-uniform
         // One-dimensional Gaussian factors of this atom's stamp (dens.py:299-308 factorised):
         //   exp(-|c|^2/(2s^2)) = EX[i] * EY[j] * C_type[i][j] * EZ[k]/amp, with
         //   EX[i] = exp(-(cxx bx_i^2 + 2 gxy bx_i by_0)/(2s^2)),  EY[j] = exp(-(cyy by_j^2 - 2 gxy (j dy) bx_0)/(2s^2)),
         //   EZ[k] = Nel/s^3 exp(-czz bz_k^2/(2s^2)),  C[i][j] = exp(-2 gxy dx dy i j/(2s^2)) (per type, host-built).
         // b = r - (i - B)*dr with the product rounded on its own, as numpy does (dens.py:252-256,299).
-        {
-            const int Ax = tt.halfw[t * 3], Ay = tt.halfw[t * 3 + 1], Az = tt.halfw[t * 3 + 2];
+        const int Ax = tt.halfw[t * 3], Ay = tt.halfw[t * 3 + 1], Az = tt.halfw[t * 3 + 2];
+        const unsigned size = ok ? (unsigned)(2 * (Ax + Ay + Az)) : 0u;
+        const unsigned base = __reduce_min_sync(0xffffffffu, ok ? rec.tbase : 0xffffffffu);
+        const unsigned off = ok ? rec.tbase - base : 0u;
+        const unsigned span = __reduce_max_sync(0xffffffffu, off + size);
+        const bool staged = span <= MDSF_PREP_STAGE;       // false where a warp straddles two frames or holds heavy ions
+        if (ok) {
             const double t2 = tt.two_sig2[t], amp = tt.amp[t];
-            double* T = tables + rec.tbase;
+            double* T = staged ? &s_tab[warp][off] : tables + rec.tbase;
             const double bx0 = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax), gp.dr[0]));
             const double by0 = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay), gp.dr[1]));
             for (int i = 0; i < 2 * Ax; ++i) {
@@ -110,6 +171,13 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
                 T[k] = amp * exp(-(gp.czz * b * b) / t2);
             }
         }
+        __syncwarp();
+        if (staged && span > 0) {
+            // tables of atoms the stamp check rejected (holes inside the span) receive stale staging data; nobody reads them
+            double* dst = tables + base;
+            for (unsigned j = lane; j < span; j += 32) dst[j] = s_tab[warp][j];
+        }
+        __syncwarp();
     }
 }
 
@@ -161,33 +229,6 @@ emit_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
 // lists need no stable sort: count the pairs of every (frame, tile) key with integer atomics, scan the counts
 // into list starts, and let every pair claim a slot of its list from a per-key cursor.  Replaces scan + fill +
 // emit + radix sort + list starts (0.43 ms -> 0.15 ms per 32 c2 frames, serialised ncu times).
-template <typename F>
-__device__ __forceinline__ void for_each_pair(const AtomRec& rec, int a, int f, const GridParams& gp, const TypeTable& tt, F&& fn) {
-    const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
-    const int ntiles = gp.ntx * gp.nty;
-    for (int sx = -1; sx <= 1; ++sx) {
-        int xlo, xhi;
-        stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
-        if (xhi <= xlo) continue;
-        const int tx0 = (xlo - sx * gp.n[0]) / gp.tx, tx1 = (xhi - 1 - sx * gp.n[0]) / gp.tx;
-        for (int sy = -1; sy <= 1; ++sy) {
-            int ylo, yhi;
-            stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
-            if (yhi <= ylo) continue;
-            const int ty0 = (ylo - sy * gp.n[1]) / gp.ty, ty1 = (yhi - 1 - sy * gp.n[1]) / gp.ty;
-            const unsigned payload = (unsigned)a | ((unsigned)(sx + 1) << MDSF_ATOM_BITS) |
-                                     ((unsigned)(sy + 1) << (MDSF_ATOM_BITS + 2));
-            int shlo, shhi, kA, kB;
-            const unsigned sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
-            for (int tX = tx0; tX <= tx1; ++tX)
-                for (int tY = ty0; tY <= ty1; ++tY) {
-                    const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
-                    for (unsigned m = sm; m; m &= m - 1) fn(kbase + (unsigned)(__ffs(m) - 1), payload);
-                }
-        }
-    }
-}
-
 // PLACE = false: list lengths; PLACE = true: payloads into their lists (start = scanned lengths, cursor zeroed)
 template <bool PLACE>
 __global__ void __launch_bounds__(256)

@@ -453,3 +453,46 @@ def test_cli_trajectory_mode_gro_to_sf_npz(mdsf, tmp_path, monkeypatch):
     rel, norm = sf_errors(got["sf"], want["sf"])
     assert rel <= 1e-5 and norm <= 1e-12, (rel, norm)
     assert np.allclose(got["sfplt"], want["sfplt"], rtol=1e-5, atol=0) and got["L"].dtype == np.float32
+
+
+def _many_batches(mdsf, env, name="tiny", grid=None, nframes=23, batch=4):
+    """S(q) of a multi-batch job under the engine knobs in `env` (read when the handle is created)."""
+    workloads = __import__("workloads")
+    knobs = ("MDSF_SM_SPLIT", "MDSF_X_ASYNC", "MDSF_Y_ASYNC", "MDSF_DIRECT_BIN", "MDSF_TW_PREFETCH", "MDSF_PREP_PRIO")
+    saved = {k: os.environ.pop(k, None) for k in knobs}
+    os.environ.update(env)
+    try:
+        wl = workloads.get(name)
+        if grid:
+            wl["sres"] = float(wl["box"][0]) / grid * (1 + 1e-6)
+        coords = workloads.jitter_frames(wl["base"], wl["box"], nframes, wl["jitter"], wl["seed0"])
+        eng, n, dr, nb = mdsf.dens.make_engine(wl["box"], wl["typ"], wl["rad"], wl["ucell"], wl["sres"], np.float32, np.float32,
+                                               batch_frames=batch, splat_mode="tile")
+        try:
+            eng.push_frames(coords, np.ones((nframes, 3)), write_back=False)
+            eng.sync()
+            return eng.read_sf(), eng.pipeline
+        finally:
+            eng.close()
+    finally:
+        for k in knobs:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
+
+
+@pytest.mark.parametrize("grid", [None, 64, 256])
+def test_pipeline_variants_are_bitwise_identical(mdsf, grid):
+    """The performance knobs change scheduling, not arithmetic: counting-sort vs radix-sort binning, the cp.async
+    x/y passes, the prefetched z twiddles, the overlapped pipeline and its green-context SM partition all give
+    bitwise the S(q) of the plain serial pipeline over many (ragged) batches."""
+    base, info = _many_batches(mdsf, {"MDSF_DIRECT_BIN": "0", "MDSF_X_ASYNC": "0", "MDSF_TW_PREFETCH": "0", "MDSF_PREP_PRIO": "0"}, grid=grid)
+    assert not info["overlap"] and info["sms"] == (0, 0)
+    assert np.all(np.isfinite(base)) and base.max() > 0
+    for env in ({}, {"MDSF_X_ASYNC": "1", "MDSF_Y_ASYNC": "1"}, {"MDSF_SM_SPLIT": "-1"}, {"MDSF_SM_SPLIT": "96", "MDSF_Y_ASYNC": "1"}):
+        sf, info = _many_batches(mdsf, env, grid=grid)
+        assert np.array_equal(sf, base), env
+        if env.get("MDSF_SM_SPLIT") == "96":
+            assert info["overlap"] and info["sms"][0] >= 96 and info["sms"][1] > 0 and sum(info["sms"]) <= 148
+        elif "MDSF_SM_SPLIT" in env:
+            assert info["overlap"] and info["sms"] == (0, 0)

@@ -2,6 +2,7 @@
 """Turn gpurun_out/{prof_r01_c2.ncu-rep, launches.csv, bench_default.json} into the committed summaries
 under profiles/ (run here, no GPU needed)."""
 import collections, csv, json, shutil, subprocess
+PEAK = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs'] / 1e3      # TB/s, driver-written for this pod
 raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_r01_c2.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h, units = rows[0], rows[1]
@@ -35,10 +36,10 @@ for k, d in summ.items():
     b = tobytes(d['dram__bytes_read.sum'], d['dram__bytes_read.sum_unit']) + tobytes(d['dram__bytes_write.sum'], d['dram__bytes_write.sum_unit'])
     ms = d['gpu__time_duration.sum'] * {'ms': 1, 'us': 1e-3, 's': 1e3}.get(d['gpu__time_duration.sum_unit'], 1)
     tr[k] = {'dram_bytes_per_launch': b, 'frames_per_launch': F}
-    lines.append('| %s | %.2f | %.3f | %.2f | %.0f %% |' % (k, b / 1e9, ms, b / 1e9 / ms, 100 * b / 1e9 / ms / 6.5408))
+    lines.append('| %s | %.2f | %.3f | %.2f | %.0f %% |' % (k, b / 1e9, ms, b / 1e9 / ms, 100 * b / 1e9 / ms / PEAK))
 head = ('# Round 1 - ncu --set full, c2 (256^3, 105456 atoms), %d frames per launch, %s splat mode\n\n'
         'Command: `ncu --set full --clock-control none --import-source on -k regex:"splat_zfft|fft_y|fft_x" -s 3 -c 3 python bench.py --steps 2 --warmup 1 --no-cpu`\n'
-        '(the .ncu-rep itself is not committed: 40 MB).\n\n| kernel | DRAM GB / launch | ms (under ncu) | TB/s | of measured 6.54 TB/s |\n|---|---|---|---|---|\n' % (F, bench['config']['splat'])
+        '(the .ncu-rep itself is not committed: 40 MB).\n\n| kernel | DRAM GB / launch | ms (under ncu) | TB/s | of measured %.2f TB/s |\n|---|---|---|---|---|\n' % (F, bench['config']['splat'], PEAK)
         + '\n'.join(lines) + '\n\nThe y and x passes are HBM-bound; the fused splat + z pass writes the pair volumes once and is bound by instruction\n'
         'issue / dependent-load latency of its per-tile phases, not by HBM.\n\n')
 open('profiles/r01_ncu_c2_kernels.md', 'w').write(head + '\n'.join(out) + '\n')
@@ -59,7 +60,7 @@ with open('profiles/r01_launches_c2.md', 'w') as f:
     ncu3 = {k: sum(v[1] for n, v in agg.items() if k in n) for k in ('splat_zfft', 'fft_y', 'fft_x_accum')}
     f.write('Times are cold-cache and serialised under the profiler: compare SHARES with the CUDA-event stage times of the un-profiled\n'
             'bench (profiles/r01_bench_c2.json). Among the three compute-stream kernels: splat_zfft %.0f %% (ncu %.0f %%), fft_y %.0f %% (ncu %.0f %%), '
-            'fft_x_accum %.0f %% (ncu %.0f %%).\nprep+bin (prep_atoms, scan, emit, radix sort, tile starts) runs on its own stream underneath the '
+            'fft_x_accum %.0f %% (ncu %.0f %%).\nprep+bin (prep_atoms, bin_pairs x2, scan) runs on its own stream underneath the '
             'previous batch\'s y/x passes; its event span (%.2f ms) includes that waiting, its serialised ncu time is %.2f ms per step.\n\n'
             % (100 * st['splat_zfft'] / main3, 100 * ncu3['splat_zfft'] / sum(ncu3.values()), 100 * st['fft_y'] / main3, 100 * ncu3['fft_y'] / sum(ncu3.values()),
                100 * st['fft_x_accum'] / main3, 100 * ncu3['fft_x_accum'] / sum(ncu3.values()), st['prep_bin'],
