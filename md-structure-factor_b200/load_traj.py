@@ -6,7 +6,32 @@ reference load_traj.py:110).  Decoding of binary trajectories still goes through
 installed (a native XTC/TRR reader is listed as the next row in SURVEY section 8f); .gro files are
 parsed here directly.
 """
+import ctypes
+import os
+
 import numpy as np
+
+import npz_writer
+
+TRAJ_PIECE = 1 << 20      # raw bytes per independently deflated piece of a traj npz member (about one c2 frame)
+IO_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmdsf_io.so")
+IO_EXPORTS = ["mdsf_io_inflate_pieces", "mdsf_io_abi_version"]
+_io = None
+
+
+def _io_lib():
+    """libmdsf_io.so (include/mdsf_io.h): built by csrc/build.sh next to this file."""
+    global _io
+    if _io is None:
+        if not os.path.exists(IO_LIB_PATH):
+            raise ImportError("%s is missing: run md-structure-factor_b200/csrc/build.sh" % IO_LIB_PATH)
+        lib = ctypes.CDLL(IO_LIB_PATH)
+        p64 = ctypes.POINTER(ctypes.c_int64)
+        lib.mdsf_io_inflate_pieces.restype = ctypes.c_int
+        lib.mdsf_io_inflate_pieces.argtypes = [ctypes.c_int, ctypes.c_int64, p64, p64, ctypes.POINTER(ctypes.c_void_p), p64, ctypes.c_int]
+        lib.mdsf_io_abi_version.restype = ctypes.c_int
+        _io = lib
+    return _io
 
 
 def load_gro(gro):
@@ -39,7 +64,9 @@ def save_traj_npz(output_filename, dims, coords, name, mass=None):
     """Write the traj npz exactly as the reference does (load_traj.py:110): typ = atom names."""
     name = np.asarray(name)
     mass = np.zeros(len(name)) if mass is None else np.asarray(mass)
-    np.savez_compressed(output_filename, dims=dims, coords=coords, name=name, mass=mass, typ=name)
+    # same container and keys as np.savez_compressed; deflated on all cores, with a piece index so that
+    # NpzFrameStream can inflate ``coords`` on all cores as well
+    npz_writer.savez_parallel(output_filename, chunk=TRAJ_PIECE, dims=dims, coords=coords, name=name, mass=mass, typ=name)
 
 
 def process_gro_mdtraj(topology_filename, trajectory_filename, output_filename):
@@ -76,7 +103,7 @@ class NpzFrameStream:
     ``shape`` / ``dtype`` describe the full array; ``read_into(buf)`` fills ``buf[:k]`` with the next k frames and
     returns k (0 at the end); ``skip(n)`` drops n frames."""
 
-    def __init__(self, path, key="coords"):
+    def __init__(self, path, key="coords", threads=None):
         import zipfile
         self._zip = zipfile.ZipFile(path)
         self._fh = self._zip.open(key + ".npy")
@@ -91,6 +118,55 @@ class NpzFrameStream:
         self.shape, self.dtype = tuple(shape), np.dtype(dtype)
         self._frame_bytes = shape[1] * 3 * self.dtype.itemsize
         self.position = 0
+        # Members written by npz_writer.savez_parallel (our load_traj) carry a piece index: the deflate stream is a
+        # chain of independently compressed pieces, so they are inflated on all cores straight from the file
+        # (os.pread + zlib release the GIL).  Anything else (np.savez_compressed output) is inflated sequentially.
+        self._index = npz_writer.read_piece_index(path, key + ".npy")
+        self.parallel = self._index is not None
+        if self.parallel:
+            self._io = _io_lib()
+            self._data0 = self._index["raw_size"] - int(np.prod(shape)) * self.dtype.itemsize     # npy header bytes
+            self._fd = os.open(path, os.O_RDONLY)
+            self._threads = int(threads or 0)
+            self._edge = {}                # piece -> inflated bytes of a piece that straddles two reads
+
+    def _read_parallel(self, view):
+        """Fill ``view`` (a writable byte view of the caller's chunk buffer) with the member bytes that follow the
+        current position: pieces inside the range are inflated straight into it, on all cores, by libmdsf_io."""
+        ix = self._index
+        lo = self._data0 + self.position * self._frame_bytes
+        hi = lo + len(view)
+        starts, lens = ix["raw_start"], ix["raw_len"]
+        first = max(int(np.searchsorted(starts, lo, side="right")) - 1, 0)
+        last = max(int(np.searchsorted(starts, hi - 1, side="right")) - 1, 0)
+        base = np.frombuffer(view, dtype=np.uint8).ctypes.data
+        jobs, edges = [], []
+        for i in range(first, last + 1):
+            s0, s1 = starts[i], starts[i] + lens[i]
+            if s0 >= lo and s1 <= hi:
+                jobs.append((i, base + (s0 - lo)))
+            elif i not in self._edge:
+                scratch = np.empty(lens[i], dtype=np.uint8)
+                self._edge[i] = scratch
+                jobs.append((i, scratch.ctypes.data))
+            if not (s0 >= lo and s1 <= hi):
+                edges.append(i)
+        if jobs:
+            n = len(jobs)
+            off = (ctypes.c_int64 * n)(*[ix["data_offset"] + ix["comp_start"][i] for i, _ in jobs])
+            clen = (ctypes.c_int64 * n)(*[ix["comp_len"][i] for i, _ in jobs])
+            rlen = (ctypes.c_int64 * n)(*[lens[i] for i, _ in jobs])
+            dst = (ctypes.c_void_p * n)(*[p for _, p in jobs])
+            rc = self._io.mdsf_io_inflate_pieces(self._fd, n, off, clen, dst, rlen, self._threads)
+            if rc:
+                raise EOFError("trajectory npz: piece %d is corrupt or disagrees with its index" % jobs[-rc - 1][0])
+        out = np.frombuffer(view, dtype=np.uint8)
+        for i in edges:
+            s0 = starts[i]
+            a, b = max(lo, s0), min(hi, s0 + lens[i])
+            out[a - lo:b - lo] = self._edge[i][a - s0:b - s0]
+        for i in [k for k in self._edge if starts[k] + lens[k] <= hi]:
+            del self._edge[i]
 
     def read_into(self, buf):
         if buf.dtype != self.dtype or buf.shape[1:] != self.shape[1:] or not buf.flags.c_contiguous:
@@ -99,6 +175,10 @@ class NpzFrameStream:
         if want <= 0:
             return 0
         view = memoryview(buf[:want].reshape(-1).view(np.uint8))
+        if self.parallel:
+            self._read_parallel(view)
+            self.position += want
+            return want
         got = 0
         while got < len(view):
             n = self._fh.readinto(view[got:])
@@ -110,6 +190,9 @@ class NpzFrameStream:
 
     def skip(self, nframes):
         nframes = min(int(nframes), self.shape[0] - self.position)
+        if self.parallel:                  # random access: nothing to inflate
+            self.position += max(nframes, 0)
+            return
         left = nframes * self._frame_bytes
         while left > 0:
             chunk = self._fh.read(min(left, 16 << 20))
@@ -119,6 +202,9 @@ class NpzFrameStream:
         self.position += max(nframes, 0)
 
     def close(self):
+        if self.parallel:
+            os.close(self._fd)
+            self._edge.clear()
         self._fh.close()
         self._zip.close()
 

@@ -12,7 +12,10 @@ compresses every member as independent chunks on a thread pool (zlib releases th
   final-block bit; only the last piece ends with ``Z_FINISH``.  The concatenation is one valid
   deflate stream (pieces never reference each other's history);
 * CRC-32 runs over the raw bytes on the calling thread while the workers compress;
-* zip64 records are written whenever a size or offset needs them (kgridplt is 4.2 GB at 512^3).
+* zip64 records are written whenever a size or offset needs them (kgridplt is 4.2 GB at 512^3);
+* the compressed size of every piece is recorded in a private zip extra field (``PIECE_INDEX_ID``) of the member's
+  local header.  Other zip readers skip unknown extra fields; ``read_piece_index`` / ``load_traj.NpzFrameStream``
+  use it to inflate the pieces of a member on all cores as well (trajectory ingest).
 
 Only the standard library and numpy are used; nothing here touches the GPU.
 """
@@ -27,6 +30,8 @@ import numpy as np
 CHUNK = 8 << 20          # raw bytes per independently compressed piece
 LEVEL = 6                # zlib default, what np.savez_compressed uses
 ZIP64_LIMIT = 0xFFFFFFFF
+PIECE_INDEX_ID = 0x534D  # "MS": private extra-field id holding the piece index of a member
+PIECE_INDEX_MAGIC = b"MDSFPI01"
 
 
 def _npy_header(arr):
@@ -59,6 +64,55 @@ def _pieces(header, data, chunk):
         yield data[off:off + chunk]
 
 
+def _index_field(first_raw, chunk, csizes):
+    """Extra-field record: id, length, magic, raw bytes of the first piece, raw bytes of the others, count, compressed sizes."""
+    body = PIECE_INDEX_MAGIC + struct.pack("<QQI", first_raw, chunk, len(csizes)) + struct.pack("<%dQ" % len(csizes), *csizes)
+    return struct.pack("<HH", PIECE_INDEX_ID, len(body)) + body
+
+
+def read_piece_index(path, member):
+    """Piece index of ``member`` (e.g. ``"coords.npy"``) of an npz written by ``savez_parallel``.
+
+    Returns None when the member has no index (np.savez_compressed output, stored members), else a dict with
+    ``data_offset`` (file offset of the member's first compressed byte), ``raw_size``, and the lists ``raw_start``,
+    ``raw_len``, ``comp_start``, ``comp_len`` per piece (raw positions count from the start of the .npy member)."""
+    import zipfile
+    with zipfile.ZipFile(path) as zf:
+        info = zf.getinfo(member)
+    if info.compress_type != zipfile.ZIP_DEFLATED:
+        return None
+    with open(path, "rb") as fh:
+        fh.seek(info.header_offset)
+        fixed = fh.read(30)
+        sig, _, _, _, _, _, _, _, _, nlen, xlen = struct.unpack("<IHHHHHIIIHH", fixed)
+        if sig != 0x04034B50:
+            return None
+        fh.seek(nlen, 1)
+        extra = fh.read(xlen)
+        data_offset = fh.tell()
+    pos = 0
+    while pos + 4 <= len(extra):
+        fid, flen = struct.unpack_from("<HH", extra, pos)
+        body = extra[pos + 4:pos + 4 + flen]
+        pos += 4 + flen
+        if fid != PIECE_INDEX_ID or not body.startswith(PIECE_INDEX_MAGIC):
+            continue
+        first_raw, chunk, n = struct.unpack_from("<QQI", body, len(PIECE_INDEX_MAGIC))
+        csizes = struct.unpack_from("<%dQ" % n, body, len(PIECE_INDEX_MAGIC) + 20)
+        raw_size = info.file_size
+        raw_start, raw_len, comp_start, comp_len = [], [], [], []
+        r, c = 0, 0
+        for i in range(n):
+            ln = min(first_raw if i == 0 else chunk, raw_size - r)
+            raw_start.append(r); raw_len.append(ln); comp_start.append(c); comp_len.append(csizes[i])
+            r += ln; c += csizes[i]
+        if r != raw_size or c != info.compress_size:
+            return None
+        return dict(data_offset=data_offset, raw_size=raw_size, raw_start=raw_start, raw_len=raw_len,
+                    comp_start=comp_start, comp_len=comp_len)
+    return None
+
+
 def savez_parallel(file, compressed=True, threads=None, chunk=CHUNK, level=LEVEL, force_zip64=False, **arrays):
     """``np.savez_compressed(file, **arrays)`` with the deflate work spread over ``threads`` cores
     (``compressed=False``: stored members, like ``np.savez``).  ``file`` gets ``.npz`` appended when missing,
@@ -86,19 +140,25 @@ def savez_parallel(file, compressed=True, threads=None, chunk=CHUNK, level=LEVEL
             raw_size = len(header) + len(data)
             zip64 = force_zip64 or raw_size >= ZIP64_LIMIT or fh.tell() >= ZIP64_LIMIT
             offset = fh.tell()
+            mchunk = chunk
+            while compressed and 64 + 8 * (raw_size // mchunk + 2) > 60000:     # the index must fit a zip extra field
+                mchunk *= 2
+            views = list(_pieces(header, data, mchunk))
+            indexed = compressed and len(views) > 1
+            csizes = [0] * len(views)
             # local header with the sizes still unknown: written again once the member is complete
-            extra = struct.pack("<HHQQ", 1, 16, 0, 0) if zip64 else b""
+            extra = (struct.pack("<HHQQ", 1, 16, 0, 0) if zip64 else b"") + (_index_field(len(views[0]), mchunk, csizes) if indexed else b"")
             fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 45 if zip64 else 20, 0x800, method, 0, 0x21, 0, 0, 0, len(name), len(extra)))
             fh.write(name)
             fh.write(extra)
             crc, csize = 0, 0
-            views = list(_pieces(header, data, chunk))
             if compressed:
                 jobs = pool.map(_deflate_piece, [(v, i == len(views) - 1, level) for i, v in enumerate(views)])
-                for v, blob in zip(views, jobs):
+                for i, (v, blob) in enumerate(zip(views, jobs)):
                     crc = zlib.crc32(v, crc)
                     fh.write(blob)
                     csize += len(blob)
+                    csizes[i] = len(blob)
             else:
                 for v in views:
                     crc = zlib.crc32(v, crc)
@@ -106,11 +166,13 @@ def savez_parallel(file, compressed=True, threads=None, chunk=CHUNK, level=LEVEL
                     csize += len(v)
             end = fh.tell()
             fh.seek(offset)
+            index = _index_field(len(views[0]), mchunk, csizes) if indexed else b""
             if zip64:
-                extra = struct.pack("<HHQQ", 1, 16, raw_size, csize)
+                extra = struct.pack("<HHQQ", 1, 16, raw_size, csize) + index
                 fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 45, 0x800, method, 0, 0x21, crc, ZIP64_LIMIT, ZIP64_LIMIT, len(name), len(extra)))
             else:
-                fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0x800, method, 0, 0x21, crc, csize, raw_size, len(name), 0))
+                extra = index
+                fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0x800, method, 0, 0x21, crc, csize, raw_size, len(name), len(extra)))
             fh.write(name)
             fh.write(extra)
             fh.seek(end)

@@ -188,3 +188,60 @@ def test_npz_frame_stream_reads_chunks_like_np_load(tmp_path):
             assert fs.read_into(buf) == 0
             with pytest.raises(ValueError):
                 fs.read_into(np.zeros((4, 11, 3), dtype=np.float64))
+
+
+def test_io_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mdsf_io.h")).read()
+    declared = sorted(set(re.findall(r"\b(mdsf_io_[a-z_0-9]+)\s*\(", header)))
+    import load_traj
+    lib = load_traj._io_lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(load_traj.IO_EXPORTS) == declared
+    assert lib.mdsf_io_abi_version() == 1
+
+
+def test_indexed_traj_npz_is_inflated_in_parallel_and_stays_a_numpy_container(tmp_path):
+    """save_traj_npz writes the reference's container (load_traj.py:110) as a chain of independently deflated pieces
+    plus a piece index in a private zip extra field; NpzFrameStream inflates those pieces on all cores through
+    libmdsf_io (straight into the chunk buffer) and falls back to sequential inflate for plain np.savez_compressed files."""
+    import zipfile
+    import load_traj
+    import npz_writer
+    rng = np.random.default_rng(5)
+    T, na = 29, 4001
+    coords = rng.uniform(0, 60, size=(T, na, 3)).astype(np.float32)
+    dims = np.full((T, 3), 60.0, dtype=np.float32)
+    names = np.array(["O", "H", "H", "C", "NA", "N", "C"] * (na // 7 + 1))[:na]
+    path = npz_writer.savez_parallel(str(tmp_path / "p_traj"), chunk=70001, dims=dims, coords=coords, name=names, mass=np.zeros(na), typ=names)
+    z = np.load(path)                                         # numpy and the reference read it as before
+    assert z.files == ["dims", "coords", "name", "mass", "typ"] and np.array_equal(z["coords"], coords) and list(z["typ"]) == list(names)
+    assert zipfile.ZipFile(path).testzip() is None            # CRCs and sizes of every member are right
+    ix = npz_writer.read_piece_index(path, "coords.npy")
+    assert ix is not None and len(ix["raw_len"]) == -(-(coords.nbytes + 128) // 70001) and sum(ix["raw_len"]) == ix["raw_size"]
+    assert npz_writer.read_piece_index(path, "dims.npy") is None          # single-piece members carry no index
+    for chunk_frames, threads in ((1, 1), (4, 3), (9, 0), (64, 0)):
+        with load_traj.NpzFrameStream(path, threads=threads) as fs:
+            assert fs.parallel and fs.shape == coords.shape
+            fs.skip(2)
+            got, buf = [], np.zeros((chunk_frames, na, 3), dtype=np.float32)
+            while True:
+                k = fs.read_into(buf)
+                if k == 0:
+                    break
+                got.append(buf[:k].copy())
+            assert np.array_equal(np.concatenate(got), coords[2:]), (chunk_frames, threads)
+    ref = str(tmp_path / "r_traj.npz")
+    np.savez_compressed(ref, dims=dims, coords=coords, name=names, mass=np.zeros(na), typ=names)
+    with load_traj.NpzFrameStream(ref) as fs:
+        assert not fs.parallel
+        buf = np.zeros((T, na, 3), dtype=np.float32)
+        assert fs.read_into(buf) == T and np.array_equal(buf, coords)
+    # a piece whose bytes disagree with the index is reported, not silently mis-decoded
+    blob = bytearray(open(path, "rb").read())
+    mid = ix["data_offset"] + ix["comp_start"][3] + 4
+    blob[mid:mid + 64] = b"\x00" * 64
+    bad = str(tmp_path / "bad_traj.npz")
+    open(bad, "wb").write(bytes(blob))
+    with load_traj.NpzFrameStream(bad) as fs, pytest.raises(EOFError):
+        fs.read_into(np.zeros((T, na, 3), dtype=np.float32))
