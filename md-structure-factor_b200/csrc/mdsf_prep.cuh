@@ -40,20 +40,26 @@ template <typename F>
 __device__ __forceinline__ void for_each_pair(const AtomRec& rec, int a, int f, const GridParams& gp, const TypeTable& tt, F&& fn) {
     const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
     const int ntiles = gp.ntx * gp.nty;
+    const int ltx = __ffs(gp.tx) - 1, lty = __ffs(gp.ty) - 1;     // tile sizes are powers of two; destinations are >= 0
     for (int sx = -1; sx <= 1; ++sx) {
         int xlo, xhi;
         stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
         if (xhi <= xlo) continue;
-        const int tx0 = (xlo - sx * gp.n[0]) / gp.tx, tx1 = (xhi - 1 - sx * gp.n[0]) / gp.tx;
+        const int tx0 = (xlo - sx * gp.n[0]) >> ltx, tx1 = (xhi - 1 - sx * gp.n[0]) >> ltx;
         for (int sy = -1; sy <= 1; ++sy) {
             int ylo, yhi;
             stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
             if (yhi <= ylo) continue;
-            const int ty0 = (ylo - sy * gp.n[1]) / gp.ty, ty1 = (yhi - 1 - sy * gp.n[1]) / gp.ty;
+            const int ty0 = (ylo - sy * gp.n[1]) >> lty, ty1 = (yhi - 1 - sy * gp.n[1]) >> lty;
             const unsigned payload = (unsigned)a | ((unsigned)(sx + 1) << MDSF_ATOM_BITS) |
                                      ((unsigned)(sy + 1) << (MDSF_ATOM_BITS + 2));
-            int shlo, shhi, kA, kB;
-            const unsigned sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
+            unsigned sm;
+            if (gp.nslab == 1) {
+                sm = Az > 0 ? 1u : 0u;          // one list per tile (tile mode): every image with cells belongs to it
+            } else {
+                int shlo, shhi, kA, kB;
+                sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
+            }
             for (int tX = tx0; tX <= tx1; ++tX)
                 for (int tY = ty0; tY <= ty1; ++tY) {
                     const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
@@ -152,23 +158,25 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
         const unsigned span = __reduce_max_sync(0xffffffffu, off + size);
         const bool staged = span <= MDSF_PREP_STAGE;       // false where a warp straddles two frames or holds heavy ions
         if (ok) {
-            const double t2 = tt.two_sig2[t], amp = tt.amp[t];
+            // one reciprocal per atom instead of a divide per table entry (the argument moves by <= 1 ulp: 1e-16 of a
+            // term; the golden-vector density tolerance is 1e-13 of the peak)
+            const double it2 = 1.0 / tt.two_sig2[t], amp = tt.amp[t];
             double* T = staged ? &s_tab[warp][off] : tables + rec.tbase;
             const double bx0 = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax), gp.dr[0]));
             const double by0 = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay), gp.dr[1]));
             for (int i = 0; i < 2 * Ax; ++i) {
                 const double b = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax + i), gp.dr[0]));
-                T[i] = exp(-(gp.cxx * b * b + 2.0 * gp.gxy * b * by0) / t2);
+                T[i] = exp(-(gp.cxx * b * b + 2.0 * gp.gxy * b * by0) * it2);
             }
             T += 2 * Ax;
             for (int j = 0; j < 2 * Ay; ++j) {
                 const double b = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay + j), gp.dr[1]));
-                T[j] = exp(-(gp.cyy * b * b - 2.0 * gp.gxy * ((double)j * gp.dr[1]) * bx0) / t2);
+                T[j] = exp(-(gp.cyy * b * b - 2.0 * gp.gxy * ((double)j * gp.dr[1]) * bx0) * it2);
             }
             T += 2 * Ay;
             for (int k = 0; k < 2 * Az; ++k) {
                 const double b = __dsub_rn(rec.r[2], __dmul_rn((double)(rec.ir[2] - Az + k), gp.dr[2]));
-                T[k] = amp * exp(-(gp.czz * b * b) / t2);
+                T[k] = amp * exp(-(gp.czz * b * b) * it2);
             }
         }
         __syncwarp();

@@ -22,11 +22,14 @@ if __name__ == "__main__":
     dims = np.repeat(wl["box"][None, :], len(coords), axis=0)
     d = tempfile.mkdtemp()
     t = time.perf_counter(); lt.save_traj_npz(os.path.join(d, "par_traj"), dims, coords, wl["typ"]); tw_par = time.perf_counter() - t
-    t = time.perf_counter(); np.savez_compressed(os.path.join(d, "ref_traj"), dims=dims, coords=coords, typ=wl["typ"]); tw_ref = time.perf_counter() - t
+    skip_ref = "--skip-ref" in sys.argv
+    tw_ref = float("nan")
+    if not skip_ref:
+        t = time.perf_counter(); np.savez_compressed(os.path.join(d, "ref_traj"), dims=dims, coords=coords, typ=wl["typ"]); tw_ref = time.perf_counter() - t
     print("write %d frames: indexed/parallel %.1f s, np.savez_compressed %.1f s (%d cores)" % (len(coords), tw_par, tw_ref, os.cpu_count()))
     dens.finish_sf = lambda sf, L, n, out: None
     dens.PRINT_DETAILS = False
-    for name in ("par_traj", "ref_traj", "par_traj"):
+    for name in (("par_traj", "par_traj") if skip_ref else ("par_traj", "ref_traj", "par_traj")):
         with lt.NpzFrameStream(os.path.join(d, name + ".npz")) as fs:
             t = time.perf_counter()
             dens.compute_sf_stream(fs, dims, wl["typ"], os.path.join(d, "out"), wl["rad"], wl["ucell"], wl["sres"])
