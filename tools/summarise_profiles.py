@@ -64,7 +64,7 @@ with open('profiles/r01_launches_c2.md', 'w') as f:
             'previous batch\'s y/x passes; its event span (%.2f ms) includes that waiting, its serialised ncu time is %.2f ms per step.\n\n'
             % (100 * st['splat_zfft'] / main3, 100 * ncu3['splat_zfft'] / sum(ncu3.values()), 100 * st['fft_y'] / main3, 100 * ncu3['fft_y'] / sum(ncu3.values()),
                100 * st['fft_x_accum'] / main3, 100 * ncu3['fft_x_accum'] / sum(ncu3.values()), st['prep_bin'],
-               (tot - sum(ncu3.values())) / 1e6 / 3))
+               (tot - sum(ncu3.values())) / 1e6 / max(1, sum(v[0] for n, v in agg.items() if 'splat_zfft' in n))))
     f.write('| kernel | launches | total us | share | grid | block |\n|---|---|---|---|---|---|\n')
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write('| %s | %d | %.1f | %.1f%% | %s | %s |\n' % (k, v[0], v[1] / 1e3, 100 * v[1] / tot, v[2], v[3]))
