@@ -60,7 +60,7 @@ with open('profiles/r01_launches_c2.md', 'w') as f:
     ncu3 = {k: sum(v[1] for n, v in agg.items() if k in n) for k in ('splat_zfft', 'fft_y', 'fft_x_accum')}
     f.write('Times are cold-cache and serialised under the profiler: compare SHARES with the CUDA-event stage times of the un-profiled\n'
             'bench (profiles/r01_bench_c2.json). Among the three compute-stream kernels: splat_zfft %.0f %% (ncu %.0f %%), fft_y %.0f %% (ncu %.0f %%), '
-            'fft_x_accum %.0f %% (ncu %.0f %%).\nprep+bin (prep_atoms, bin_pairs x2, scan) runs on its own stream underneath the '
+            'fft_x_accum %.0f %% (ncu %.0f %%).\nprep+bin (prep_atoms incl. list-length counting, scan, bin_pairs) runs on its own stream underneath the '
             'previous batch\'s y/x passes; its event span (%.2f ms) includes that waiting, its serialised ncu time is %.2f ms per step.\n\n'
             % (100 * st['splat_zfft'] / main3, 100 * ncu3['splat_zfft'] / sum(ncu3.values()), 100 * st['fft_y'] / main3, 100 * ncu3['fft_y'] / sum(ncu3.values()),
                100 * st['fft_x_accum'] / main3, 100 * ncu3['fft_x_accum'] / sum(ncu3.values()), st['prep_bin'],
