@@ -131,6 +131,11 @@ int64_t mdsf_frames_done(const mdsf_handle* h);
 const char* mdsf_fft_path(const mdsf_handle* h);
 const char* mdsf_splat_path(const mdsf_handle* h);   /* "owner" / "scatter" / "tile" (valid after mdsf_set_atoms) */
 int mdsf_batch_frames(const mdsf_handle* h);
+/* Coordinate pre-transform of the CLI (reference main_gromacs.py:204-207), applied by the first kernel to every
+ * frame pushed afterwards, before the rescale: y <- y / sin_theta; x <- x - y * cos_theta, evaluated in float64 and
+ * rounded to the coordinate dtype after each line exactly as numpy does for `T[..., 1] / np.sin(theta)`.
+ * With write_back the transformed (and rescaled, wrapped) coordinates are what comes back. */
+int mdsf_set_pretransform(mdsf_handle* h, int32_t enabled, double sin_theta, double cos_theta);
 /* Pipeline shape: returns 1 when the splat of batch b+1 overlaps the y/x passes of batch b (two pair-volume
  * sets), else 0; sms[0], sms[1] = SMs of the splat-side / pass-side green-context partition (0, 0 = unpartitioned). */
 int mdsf_pipeline_info(const mdsf_handle* h, int32_t* sms /* [2] */);

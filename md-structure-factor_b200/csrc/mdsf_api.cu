@@ -131,6 +131,8 @@ struct mdsf_handle {
     long long maxpairs_frame = 0;
     int chunk = 128;
     size_t splat_smem = 0;
+    int mono = 0;                     // K1 applies the monoclinic transform of main_gromacs.py:204-207 first
+    double mono_sin = 1.0, mono_cos = 0.0;
     bool direct_bin = false;          // tile mode: counting-sort binning with atomics instead of the stable radix sort
     int tw16_off = 0;                 // byte offset of the cp.async-prefetched stage-1 twiddle table in the splat's shared memory (0 = none)
     int sort_bits = 1;
@@ -900,7 +902,8 @@ template <typename C, typename P>
 static void launch_prep(mdsf_handle* h, cudaStream_t st, void* stage, const BatchScales& sc, int nf, long long wlo, long long whi) {
     const long long total = (long long)nf * h->natoms;
     prep_atoms_kernel<C, P><<<grid_for(total, 256, h->nsm), 256, 0, st>>>(
-        (C*)stage, h->d_type, h->d_recs, h->d_cnt, h->d_tables, h->gp, h->tt, sc, nf, wlo, whi, h->d_err, h->direct_bin ? h->d_counter : nullptr);
+        (C*)stage, h->d_type, h->d_recs, h->d_cnt, h->d_tables, h->gp, h->tt, sc, nf, wlo, whi, h->d_err, h->direct_bin ? h->d_counter : nullptr,
+        h->mono, h->mono_sin, h->mono_cos);
 }
 
 static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, long long wlo, long long whi, int write_back) {
@@ -1198,6 +1201,14 @@ extern "C" int64_t mdsf_frames_done(const mdsf_handle* h) { return h ? h->frames
 extern "C" const char* mdsf_fft_path(const mdsf_handle* h) { return (h && h->native_fft) ? "native" : "cufft"; }
 extern "C" const char* mdsf_splat_path(const mdsf_handle* h) { return (h && h->scatter) ? "scatter" : ((h && h->tile_atomic) ? "tile" : "owner"); }
 extern "C" int mdsf_batch_frames(const mdsf_handle* h) { return h ? h->F : 0; }
+extern "C" int mdsf_set_pretransform(mdsf_handle* h, int32_t enabled, double sin_theta, double cos_theta) {
+    if (!h) return fail(MDSF_EINVAL, "null handle");
+    if (enabled && !(sin_theta != 0.0)) return fail(MDSF_EINVAL, "sin(theta) must be non-zero");
+    h->mono = enabled ? 1 : 0;
+    h->mono_sin = sin_theta;
+    h->mono_cos = cos_theta;
+    return MDSF_OK;
+}
 extern "C" int mdsf_pipeline_info(const mdsf_handle* h, int32_t* sms) {
     if (sms) { sms[0] = h ? h->part_sms[0] : 0; sms[1] = h ? h->part_sms[1] : 0; }
     return h ? h->overlap : 0;

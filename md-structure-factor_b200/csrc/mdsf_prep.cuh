@@ -80,7 +80,8 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
                   double* __restrict__ tables,       // [nframes][tstride] per-atom Gaussian factor tables
                   GridParams gp, TypeTable tt, BatchScales sc, int nframes,
                   long long wrap_lo, long long wrap_hi, int* __restrict__ err_flag,
-                  unsigned* __restrict__ tile_counter /* direct binning: list lengths per (frame, tile) key, or nullptr */)
+                  unsigned* __restrict__ tile_counter /* direct binning: list lengths per (frame, tile) key, or nullptr */,
+                  int mono, double mono_sin, double mono_cos /* monoclinic pre-transform (main_gromacs.py:204-207) */)
 {
     // A lane's record (48 B) and factor tables (16 (Ax+Ay+Az) B) are contiguous with its neighbours' in global memory
     // but strided across the lanes of a store instruction; both are staged per warp in shared memory and written
@@ -103,10 +104,18 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
         bool bad = false;
         if (live) {
             C* src = coords + idx * 3;
+            C v[3] = {src[0], src[1], src[2]};
+            if (mono) {
+                // T[..., 1] = T[..., 1] / np.sin(theta); T[..., 0] = T[..., 0] - T[..., 1] * np.cos(theta)
+                // (main_gromacs.py:206-207): np.sin / np.cos return float64 scalars, so numpy evaluates both lines
+                // in float64 and rounds to the coords dtype on assignment; no fused multiply-add
+                v[1] = (C)((double)v[1] / mono_sin);
+                v[0] = (C)__dsub_rn((double)v[0], __dmul_rn((double)v[1], mono_cos));
+            }
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 // rc[it,:,i] *= a[it,i]   (dens.py:58)
-                C r = (C)mul_rn<P>((P)src[d], (P)sc.a[f][d]);
+                C r = (C)mul_rn<P>((P)v[d], (P)sc.a[f][d]);
                 if (a >= wrap_lo && a < wrap_hi) {
                     const P L = (P)gp.box[d];
                     // np.where(r < L, r, r - L) then np.where(r > 0, r, r + L)   (dens.py:211-212)

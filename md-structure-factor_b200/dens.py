@@ -38,6 +38,7 @@ FFT_MODE = "auto"         # "auto" | "native" | "cufft"
 SPLAT_MODE = "auto"       # "auto" | "owner" (fp64 owner-computes tiles) | "tile" / "scatter" (deterministic fixed-point accumulation)
 BATCH_FRAMES = 0          # frames per device batch (0 = automatic)
 SAVE_COMPRESSED = True    # np.savez_compressed like the reference; False writes an uncompressed npz
+GPU_MONOCLINIC = True     # compute_sf_stream: the monoclinic transform of main_gromacs.py:204-207 runs inside the first kernel, not in numpy
 PARALLEL_NPZ = True       # deflate the npz members on all host cores (same container, np.load reads it); False = numpy's writer
 LAST_RUN = {}             # filled by compute_sf: grid, batch size, FFT path, kernel launches
 
@@ -219,6 +220,8 @@ def compute_sf_stream(frames, L, typ, out_filename, rad, ucell, Sres, first_fram
         print("Calculating Structure factor for ", natoms, " atoms over ", nframes, " timesteps (streamed). \n", "Progress: ")
         print("GPU engine: batch of %d frames, %s splat, %s FFT, border %d cells" % (eng.batch_frames, eng.splat_path, eng.fft_path, nborder))
         chunk = int(chunk_frames or 2 * eng.batch_frames)
+        if monoclinic_theta is not None and GPU_MONOCLINIC:
+            eng.set_pretransform(monoclinic_theta)      # K1 does main_gromacs.py:206-207 (same float64 expressions, same bits)
         bufs = [_native.pinned_empty((chunk, natoms, 3), cdtype) for _ in range(2)]
         tickets = [None, None]
         wrap = _wrapped_atoms(nframes, natoms)
@@ -232,7 +235,7 @@ def compute_sf_stream(frames, L, typ, out_filename, rad, ucell, Sres, first_fram
             if k == 0:
                 raise EOFError("frame source ended after %d of %d frames" % (done, nframes))
             blk = bufs[b][:k]
-            if monoclinic_theta is not None:
+            if monoclinic_theta is not None and not GPU_MONOCLINIC:
                 blk[..., 1] = blk[..., 1] / np.sin(monoclinic_theta)
                 blk[..., 0] = blk[..., 0] - blk[..., 1] * np.cos(monoclinic_theta)
             eng.push_frames(blk, scale[done:done + k], wrap)

@@ -23,7 +23,7 @@ EXPORTS = [
     "mdsf_host_register", "mdsf_host_unregister", "mdsf_push_frames", "mdsf_push_density", "mdsf_sync",
     "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
     "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_splat_path",
-    "mdsf_batch_frames", "mdsf_pipeline_info",
+    "mdsf_batch_frames", "mdsf_pipeline_info", "mdsf_set_pretransform",
     "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_timer_start", "mdsf_timer_stop", "mdsf_last_error",
     "mdsf_input_mark", "mdsf_input_wait",
     "mdsf_abi_version",
@@ -83,6 +83,7 @@ def load():
         "mdsf_splat_path": (C.c_char_p, [vp]),
         "mdsf_batch_frames": (C.c_int, [vp]),
         "mdsf_pipeline_info": (C.c_int, [vp, C.POINTER(i32)]),
+        "mdsf_set_pretransform": (C.c_int, [vp, i32, C.c_double, C.c_double]),
         "mdsf_enable_timing": (C.c_int, [vp, i32]),
         "mdsf_stage_ms": (C.c_int, [vp, dp, C.POINTER(i64)]),
         "mdsf_input_mark": (C.c_int, [vp, C.POINTER(C.c_int64)]),
@@ -273,6 +274,15 @@ class Engine:
     @property
     def batch_frames(self):
         return int(self._lib.mdsf_batch_frames(self._h))
+
+    def set_pretransform(self, theta):
+        """Apply the CLI's monoclinic transform (reference main_gromacs.py:204-207) inside the first kernel to every frame
+        pushed from now on; ``theta`` in radians, ``None`` switches it off.  np.sin / np.cos give the float64 scalars
+        the reference divides / multiplies by."""
+        if theta is None:
+            _check(self._lib.mdsf_set_pretransform(self._h, 0, 1.0, 0.0))
+        else:
+            _check(self._lib.mdsf_set_pretransform(self._h, 1, float(np.sin(theta)), float(np.cos(theta))))
 
     @property
     def pipeline(self):

@@ -496,3 +496,32 @@ def test_pipeline_variants_are_bitwise_identical(mdsf, grid):
             assert info["overlap"] and info["sms"][0] >= 96 and info["sms"][1] > 0 and sum(info["sms"]) <= 148
         elif "MDSF_SM_SPLIT" in env:
             assert info["overlap"] and info["sms"] == (0, 0)
+
+
+@pytest.mark.parametrize("name", ["mono_f32", "gas_f64_ortho"])
+def test_monoclinic_pretransform_in_first_kernel_matches_numpy(mdsf, name):
+    """mdsf_set_pretransform: K1 applies `T[...,1] /= sin(theta); T[...,0] -= T[...,1]*cos(theta)` (reference
+    main_gromacs.py:206-207) with numpy's dtype flow -- written-back coordinates, cell indices and S(q) are bitwise those
+    of the same frames transformed on the host."""
+    c = load_case(name)
+    theta = 120.0 * np.pi / 180.0
+    host = c["coords"].copy()
+    host[..., 1] = host[..., 1] / np.sin(theta)
+    host[..., 0] = host[..., 0] - host[..., 1] * np.cos(theta)
+    dims = c["dims"]
+    arith = np.float32 if (host.dtype == np.float32 and dims.dtype == np.float32) else np.float64
+    L = np.average(dims, axis=0)
+    scale = (L / dims).astype(np.float64)
+    out = []
+    for pre, r in ((None, host.copy()), (theta, c["coords"].copy())):
+        eng, n, dr, nb = mdsf.dens.make_engine(L, c["typ"], c["rad"], c["ucell"], c["sres"], r.dtype, arith)
+        try:
+            eng.set_pretransform(pre)
+            eng.push_frames(r, scale, mdsf.dens._wrapped_atoms(r.shape[0], r.shape[1]), write_back=True)
+            eng.sync()
+            out.append((r, eng.debug_cell_indices(r.shape[0] - 1), eng.read_sf()))
+        finally:
+            eng.close()
+    assert np.array_equal(out[0][0], out[1][0])          # rescaled + wrapped coordinates written back
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
