@@ -102,6 +102,7 @@ struct mdsf_handle {
         AtomRec* recs = nullptr;
         unsigned *cnt = nullptr, *off = nullptr, *keys[2]{}, *vals[2]{}, *tile_start = nullptr;
         unsigned* counter = nullptr;      // direct binning: [nkeys+1] list lengths, then [nkeys+1] cursors
+        uint4* prec = nullptr;            // direct binning: 16-byte pair records in list order (splat_zfft_kernel, PREC)
         double* tables = nullptr;
         void* cub = nullptr;
         cudaEvent_t ev_binned = nullptr, ev_consumed = nullptr;
@@ -133,6 +134,7 @@ struct mdsf_handle {
     size_t splat_smem = 0;
     int mono = 0;                     // K1 applies the monoclinic transform of main_gromacs.py:204-207 first
     double mono_sin = 1.0, mono_cos = 0.0;
+    bool pair_records = true;         // direct binning writes 16-byte pair records (MDSF_PAIR_RECORDS=0: 4-byte payloads + atom records)
     bool direct_bin = false;          // tile mode: counting-sort binning with atomics instead of the stable radix sort
     int tw16_off = 0;                 // byte offset of the cp.async-prefetched stage-1 twiddle table in the splat's shared memory (0 = none)
     int sort_bits = 1;
@@ -538,14 +540,18 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         h->y_async = getenv("MDSF_Y_ASYNC") ? atoi(getenv("MDSF_Y_ASYNC")) : 0;
     }
     CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 20480));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     *out = h;
     return MDSF_OK;
 }
@@ -560,7 +566,7 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     for (void* b : bufs) if (b) cudaFree(b);
     for (int d = 0; d < 3; ++d) { if (h->ax[d].d_tw) cudaFree(h->ax[d].d_tw); if (h->ax[d].d_tw16) cudaFree(h->ax[d].d_tw16); if (h->ax[d].d_rev) cudaFree(h->ax[d].d_rev); }
     for (auto& ps : h->sets) {
-        void* pb[] = {ps.recs, ps.cnt, ps.off, ps.keys[0], ps.keys[1], ps.vals[0], ps.vals[1], ps.tile_start, ps.counter, ps.tables, ps.cub};
+        void* pb[] = {ps.recs, ps.cnt, ps.off, ps.keys[0], ps.keys[1], ps.vals[0], ps.vals[1], ps.tile_start, ps.counter, ps.prec, ps.tables, ps.cub};
         for (void* b : pb) if (b) cudaFree(b);
         if (ps.ev_binned) cudaEventDestroy(ps.ev_binned);
         if (ps.ev_consumed) cudaEventDestroy(ps.ev_consumed);
@@ -770,6 +776,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     CU(cudaMemcpy(h->d_toff, toff.data(), sizeof(unsigned) * natoms, cudaMemcpyHostToDevice));
     h->tt.toff = h->d_toff;
     h->nsets = (h->scatter || getenv("MDSF_ONE_STREAM")) ? 1 : 2;
+    h->pair_records = !getenv("MDSF_PAIR_RECORDS") || atoi(getenv("MDSF_PAIR_RECORDS")) != 0;
     h->direct_bin = h->tile_atomic && !h->scatter && (!getenv("MDSF_DIRECT_BIN") || atoi(getenv("MDSF_DIRECT_BIN")) != 0);
     {
         size_t b1 = 0, b2 = 0;
@@ -792,6 +799,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
             }
             CU(cudaMalloc(&ps.tile_start, sizeof(unsigned) * (nkeys + 2)));
             CU(cudaMalloc(&ps.counter, sizeof(unsigned) * 2 * (nkeys + 2)));
+            if (h->direct_bin && h->pair_records) CU(cudaMalloc(&ps.prec, sizeof(uint4) * std::max(1LL, cap)));
             CU(cudaMalloc(&ps.cub, h->cub_bytes));
         }
         CU(cudaEventCreateWithFlags(&ps.ev_binned, cudaEventDisableTiming));
@@ -1000,7 +1008,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     if (h->direct_bin) {
         // tile mode: order inside a list is irrelevant (integer adds commute) -> counting sort with atomics
         cub::DeviceScan::ExclusiveSum(h->d_cub, cb, ps.counter, h->d_tile_start, (long long)nkeys + 1, sp);
-        bin_pairs_kernel<true><<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(h->d_recs, h->d_cnt, ps.counter + nkeys + 1, h->d_tile_start, h->d_vals[1], gp, h->tt, nf);
+        bin_pairs_kernel<true><<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(h->d_recs, h->d_cnt, ps.counter + nkeys + 1, h->d_tile_start, h->d_vals[1], ps.prec, gp, h->tt, nf);
         h->launches += 1;
     } else {
     cub::DeviceScan::ExclusiveSum(h->d_cub, cb, h->d_cnt, h->d_off, total, sp);
@@ -1023,18 +1031,25 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
 
     // splat (+ fused z FFT on the native path)
     dim3 grid(gp.ntx * gp.nty, npairs);
-#define MDSF_SPLAT_LAUNCH(FUSE, ATOM, EZG)                                                                                \
-    splat_zfft_kernel<FUSE, ATOM, EZG><<<grid, 256, h->splat_smem, ss>>>(h->d_recs, h->d_vals[1], h->d_tile_start, h->d_vol, \
+    const bool use_prec = h->direct_bin && ps.prec != nullptr;
+    const unsigned* list = use_prec ? reinterpret_cast<const unsigned*>(ps.prec) : h->d_vals[1];
+#define MDSF_SPLAT_LAUNCH(FUSE, ATOM, EZG, PREC)                                                                          \
+    splat_zfft_kernel<FUSE, ATOM, EZG, PREC><<<grid, 256, h->splat_smem, ss>>>(h->d_recs, list, h->d_tile_start, h->d_vol, \
         h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err, h->ax[2].d_tw16, h->tw16_off)
-    switch ((h->native_fft ? 4 : 0) | (h->tile_atomic ? 2 : 0) | (h->ez_global ? 1 : 0)) {
-        case 0: MDSF_SPLAT_LAUNCH(false, false, false); break;
-        case 1: MDSF_SPLAT_LAUNCH(false, false, true); break;
-        case 2: MDSF_SPLAT_LAUNCH(false, true, false); break;
-        case 3: MDSF_SPLAT_LAUNCH(false, true, true); break;
-        case 4: MDSF_SPLAT_LAUNCH(true, false, false); break;
-        case 5: MDSF_SPLAT_LAUNCH(true, false, true); break;
-        case 6: MDSF_SPLAT_LAUNCH(true, true, false); break;
-        default: MDSF_SPLAT_LAUNCH(true, true, true); break;
+    switch ((use_prec ? 8 : 0) | (h->native_fft ? 4 : 0) | (h->tile_atomic ? 2 : 0) | (h->ez_global ? 1 : 0)) {
+        case 0: MDSF_SPLAT_LAUNCH(false, false, false, false); break;
+        case 1: MDSF_SPLAT_LAUNCH(false, false, true, false); break;
+        case 2: MDSF_SPLAT_LAUNCH(false, true, false, false); break;
+        case 3: MDSF_SPLAT_LAUNCH(false, true, true, false); break;
+        case 4: MDSF_SPLAT_LAUNCH(true, false, false, false); break;
+        case 5: MDSF_SPLAT_LAUNCH(true, false, true, false); break;
+        case 6: MDSF_SPLAT_LAUNCH(true, true, false, false); break;
+        case 7: MDSF_SPLAT_LAUNCH(true, true, true, false); break;
+        case 10: MDSF_SPLAT_LAUNCH(false, true, false, true); break;
+        case 11: MDSF_SPLAT_LAUNCH(false, true, true, true); break;
+        case 14: MDSF_SPLAT_LAUNCH(true, true, false, true); break;
+        case 15: MDSF_SPLAT_LAUNCH(true, true, true, true); break;
+        default: return fail(MDSF_ESTATE, "pair records without tile mode");
     }
     ++h->launches;
     CU(cudaGetLastError());

@@ -250,7 +250,8 @@ emit_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
 template <bool PLACE>
 __global__ void __launch_bounds__(256)
 bin_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ pair_count, unsigned* __restrict__ counter,
-                 const unsigned* __restrict__ start, unsigned* __restrict__ vals, GridParams gp, TypeTable tt, int nframes)
+                 const unsigned* __restrict__ start, unsigned* __restrict__ vals, uint4* __restrict__ prec,
+                 GridParams gp, TypeTable tt, int nframes)
 {
     const long long total = (long long)nframes * gp.natoms;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -260,8 +261,17 @@ bin_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ 
         const int a = (int)(idx - (long long)f * gp.natoms);
         const AtomRec rec = recs[idx];
         for_each_pair(rec, a, f, gp, tt, [&](unsigned key, unsigned payload) {
-            if (PLACE) vals[start[key] + atomicAdd(counter + key, 1u)] = payload;
-            else atomicAdd(counter + key, 1u);
+            if (PLACE) {
+                const unsigned pos = start[key] + atomicAdd(counter + key, 1u);
+                if (prec != nullptr) {       // 16-byte pair record (layout: splat_zfft_kernel, PREC)
+                    prec[pos] = make_uint4((unsigned)(rec.ir[0] + 1024) | ((unsigned)(rec.ir[1] + 1024) << 12) | ((payload >> MDSF_ATOM_BITS) << 24),
+                                           (unsigned)(rec.ir[2] + 1024) | ((unsigned)rec.type << 13), rec.tbase, (unsigned)a);
+                } else {
+                    vals[pos] = payload;
+                }
+            } else {
+                atomicAdd(counter + key, 1u);
+            }
         });
     }
 }

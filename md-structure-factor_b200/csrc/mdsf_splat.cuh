@@ -52,7 +52,12 @@ __device__ __forceinline__ void part_barrier(int part) {
 // terms with 64-bit FIXED-POINT integer atomics into the shared-memory tile (integer addition commutes, so
 // the result is still bitwise deterministic); the tile is converted to fp64 in place before the z FFT.
 // EZG = true compiles the path for stamps taller than `zstage` (EZ read from global memory in phase B).
-template <bool FUSE_ZFFT, bool ATOMIC, bool EZG>
+// PREC = true (tile mode with direct binning): the lists hold 16-byte PAIR RECORDS written by bin_pairs_kernel
+// (cell index, type, table offset, image) instead of 4-byte payloads that point at 48-byte atom records: one
+// dependent global round trip less per tile, a third of the bytes, contiguous instead of gathered.
+//   x: (ir_x + 1024) | (ir_y + 1024) << 12 | (sx + 1) << 24 | (sy + 1) << 26
+//   y: (ir_z + 1024) | type << 13          z: table offset          w: atom index
+template <bool FUSE_ZFFT, bool ATOMIC, bool EZG, bool PREC>
 __global__ void __launch_bounds__(256, MDSF_SPLAT_MINBLOCKS)
 splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ vals,
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
@@ -104,9 +109,15 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     unsigned pf_v = 0;
     AtomRec pf_rec;
     pf_rec.type = 0;
+    uint4 pf_p = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* __restrict__ prec = reinterpret_cast<const uint4*>(vals);
     if (lbeg < lend && pt < (int)min((unsigned)chunk, lend - lbeg)) {
-        pf_v = vals[lbeg + pt];
-        pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
+        if (PREC) {
+            pf_p = prec[lbeg + pt];
+        } else {
+            pf_v = vals[lbeg + pt];
+            pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
+        }
     }
     {
         double2* z2 = reinterpret_cast<double2*>(tile_re);
@@ -126,9 +137,21 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         // ---------------- A: one pair per thread
         unsigned colmask = 0;
         if (pt < npair) {
-            const unsigned v = pf_v;
-            const int sx = (int)((v >> MDSF_ATOM_BITS) & 3u) - 1, sy = (int)((v >> (MDSF_ATOM_BITS + 2)) & 3u) - 1;
-            const AtomRec rec = pf_rec;
+            int sx, sy;
+            struct { int ir[3]; int type; unsigned tbase; } rec;
+            unsigned atom;
+            if (PREC) {
+                const uint4 p = pf_p;
+                rec.ir[0] = (int)(p.x & 4095u) - 1024; rec.ir[1] = (int)((p.x >> 12) & 4095u) - 1024;
+                sx = (int)((p.x >> 24) & 3u) - 1; sy = (int)((p.x >> 26) & 3u) - 1;
+                rec.ir[2] = (int)(p.y & 8191u) - 1024; rec.type = (int)(p.y >> 13);
+                rec.tbase = p.z; atom = p.w;
+            } else {
+                const unsigned v = pf_v;
+                sx = (int)((v >> MDSF_ATOM_BITS) & 3u) - 1; sy = (int)((v >> (MDSF_ATOM_BITS + 2)) & 3u) - 1;
+                rec.ir[0] = pf_rec.ir[0]; rec.ir[1] = pf_rec.ir[1]; rec.ir[2] = pf_rec.ir[2];
+                rec.type = pf_rec.type; rec.tbase = pf_rec.tbase; atom = v & (MDSF_MAX_ATOMS - 1);
+            }
             const int Ax = tt.halfw[rec.type * 3], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
             int xlo, xhi, ylo, yhi;
             stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
@@ -180,7 +203,8 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                     }
                 }
             } else {
-                rxyz[pt * 3] = rec.r[0]; rxyz[pt * 3 + 1] = rec.r[1]; rxyz[pt * 3 + 2] = rec.r[2];
+                const double* rr = PREC ? recs[(long long)f * gp.natoms + (int)atom].r : pf_rec.r;     // general ucell: the coordinate itself
+                rxyz[pt * 3] = rr[0]; rxyz[pt * 3 + 1] = rr[1]; rxyz[pt * 3 + 2] = rr[2];
             }
         }
         int nvis = 0;
@@ -209,8 +233,12 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         }
         part_barrier(part);
         if (cb + chunk < lend && pt < (int)min((unsigned)chunk, lend - cb - chunk)) {      // prefetch the next chunk
-            pf_v = vals[cb + chunk + pt];
-            pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
+            if (PREC) {
+                pf_p = prec[cb + chunk + pt];
+            } else {
+                pf_v = vals[cb + chunk + pt];
+                pf_rec = recs[(long long)f * gp.natoms + (int)(pf_v & (MDSF_MAX_ATOMS - 1))];
+            }
         }
 
         // ---------------- B (tile mode): one thread per (pair, column), fixed-point integer atomics

@@ -458,7 +458,7 @@ def test_cli_trajectory_mode_gro_to_sf_npz(mdsf, tmp_path, monkeypatch):
 def _many_batches(mdsf, env, name="tiny", grid=None, nframes=23, batch=4):
     """S(q) of a multi-batch job under the engine knobs in `env` (read when the handle is created)."""
     workloads = __import__("workloads")
-    knobs = ("MDSF_SM_SPLIT", "MDSF_X_ASYNC", "MDSF_Y_ASYNC", "MDSF_DIRECT_BIN", "MDSF_TW_PREFETCH", "MDSF_PREP_PRIO")
+    knobs = ("MDSF_SM_SPLIT", "MDSF_X_ASYNC", "MDSF_Y_ASYNC", "MDSF_DIRECT_BIN", "MDSF_TW_PREFETCH", "MDSF_PREP_PRIO", "MDSF_PAIR_RECORDS")
     saved = {k: os.environ.pop(k, None) for k in knobs}
     os.environ.update(env)
     try:
@@ -483,13 +483,14 @@ def _many_batches(mdsf, env, name="tiny", grid=None, nframes=23, batch=4):
 
 @pytest.mark.parametrize("grid", [None, 64, 256])
 def test_pipeline_variants_are_bitwise_identical(mdsf, grid):
-    """The performance knobs change scheduling, not arithmetic: counting-sort vs radix-sort binning, the cp.async
+    """The performance knobs change scheduling, not arithmetic: counting-sort vs radix-sort binning, 16-byte pair
+    records vs payload + atom-record gathers, the cp.async
     x/y passes, the prefetched z twiddles, the overlapped pipeline and its green-context SM partition all give
     bitwise the S(q) of the plain serial pipeline over many (ragged) batches."""
     base, info = _many_batches(mdsf, {"MDSF_DIRECT_BIN": "0", "MDSF_X_ASYNC": "0", "MDSF_TW_PREFETCH": "0", "MDSF_PREP_PRIO": "0"}, grid=grid)
     assert not info["overlap"] and info["sms"] == (0, 0)
     assert np.all(np.isfinite(base)) and base.max() > 0
-    for env in ({}, {"MDSF_X_ASYNC": "1", "MDSF_Y_ASYNC": "1"}, {"MDSF_SM_SPLIT": "-1"}, {"MDSF_SM_SPLIT": "96", "MDSF_Y_ASYNC": "1"}):
+    for env in ({}, {"MDSF_PAIR_RECORDS": "0"}, {"MDSF_X_ASYNC": "1", "MDSF_Y_ASYNC": "1"}, {"MDSF_SM_SPLIT": "-1"}, {"MDSF_SM_SPLIT": "96", "MDSF_Y_ASYNC": "1"}):
         sf, info = _many_batches(mdsf, env, grid=grid)
         assert np.array_equal(sf, base), env
         if env.get("MDSF_SM_SPLIT") == "96":
