@@ -134,6 +134,7 @@ struct mdsf_handle {
     size_t splat_smem = 0;
     int mono = 0;                     // K1 applies the monoclinic transform of main_gromacs.py:204-207 first
     double mono_sin = 1.0, mono_cos = 0.0;
+    int pf_dist = 592;                // splat CTAs warm L2 for the CTA this many tiles later (two residency waves); MDSF_PF_DIST, 0 = off
     bool pair_records = true;         // direct binning writes 16-byte pair records (MDSF_PAIR_RECORDS=0: 4-byte payloads + atom records)
     bool direct_bin = false;          // tile mode: counting-sort binning with atomics instead of the stable radix sort
     int tw16_off = 0;                 // byte offset of the cp.async-prefetched stage-1 twiddle table in the splat's shared memory (0 = none)
@@ -776,6 +777,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     CU(cudaMemcpy(h->d_toff, toff.data(), sizeof(unsigned) * natoms, cudaMemcpyHostToDevice));
     h->tt.toff = h->d_toff;
     h->nsets = (h->scatter || getenv("MDSF_ONE_STREAM")) ? 1 : 2;
+    if (getenv("MDSF_PF_DIST")) h->pf_dist = std::max(0, atoi(getenv("MDSF_PF_DIST")));
     h->pair_records = !getenv("MDSF_PAIR_RECORDS") || atoi(getenv("MDSF_PAIR_RECORDS")) != 0;
     h->direct_bin = h->tile_atomic && !h->scatter && (!getenv("MDSF_DIRECT_BIN") || atoi(getenv("MDSF_DIRECT_BIN")) != 0);
     {
@@ -789,7 +791,7 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     for (int p = 0; p < h->nsets; ++p) {
         mdsf_handle::PrepSet& ps = h->sets[p];
         CU(cudaMalloc(&ps.recs, sizeof(AtomRec) * natoms * h->F));
-        CU(cudaMalloc(&ps.tables, sizeof(double) * std::max(1LL, tstride * h->F)));
+        CU(cudaMalloc(&ps.tables, sizeof(double) * (std::max(1LL, tstride * h->F) + 32)));     // + slack: the splat prefetches one line past a table's start
         CU(cudaMalloc(&ps.cnt, sizeof(unsigned) * natoms * h->F));
         CU(cudaMalloc(&ps.off, sizeof(unsigned) * natoms * h->F));
         if (!h->scatter) {
@@ -1035,7 +1037,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     const unsigned* list = use_prec ? reinterpret_cast<const unsigned*>(ps.prec) : h->d_vals[1];
 #define MDSF_SPLAT_LAUNCH(FUSE, ATOM, EZG, PREC)                                                                          \
     splat_zfft_kernel<FUSE, ATOM, EZG, PREC><<<grid, 256, h->splat_smem, ss>>>(h->d_recs, list, h->d_tile_start, h->d_vol, \
-        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err, h->ax[2].d_tw16, h->tw16_off)
+        h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err, h->ax[2].d_tw16, h->tw16_off, h->pf_dist)
     switch ((use_prec ? 8 : 0) | (h->native_fft ? 4 : 0) | (h->tile_atomic ? 2 : 0) | (h->ez_global ? 1 : 0)) {
         case 0: MDSF_SPLAT_LAUNCH(false, false, false, false); break;
         case 1: MDSF_SPLAT_LAUNCH(false, false, true, false); break;

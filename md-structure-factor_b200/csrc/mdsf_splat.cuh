@@ -63,7 +63,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
                   double2* __restrict__ dens_dump, GridParams gp, TypeTable tt, FftPlan zplan,
                   const double2* __restrict__ twz, const double* __restrict__ atom_tables, int chunk, int logS, int zfast,
-                  int zstage, int* __restrict__ err_flag, const double2* __restrict__ tw16, int tw16_off)
+                  int zstage, int* __restrict__ err_flag, const double2* __restrict__ tw16, int tw16_off, int pf_dist)
 {
     extern __shared__ double smem[];
     // Nz = 256 tile mode: stage-1 twiddles of the 16x16 z split arrive by cp.async while the splat runs
@@ -85,6 +85,18 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     const int mycol = pt % ncol, myslab = ATOMIC ? 0 : pt / ncol;
     const unsigned kbase = (unsigned)(f * ntiles + tile) * (unsigned)nslab;
     const unsigned lbeg = tile_start[kbase], lend = (gp.debug_skip & 16) ? lbeg : tile_start[kbase + nslab];
+    // L2 warm-up for the CTA that runs `pf_dist` tiles later (PREC lists): its list bounds are requested together with
+    // ours, its first pair records together with ours (the load itself pulls them into L2), and its atoms' factor tables
+    // are prefetched into L2 once those records have arrived -- the later CTA's dependent loads then hit L2, not HBM
+    unsigned fbeg = 0, fend = 0;
+    if (PREC && pf_dist > 0) {
+        const long long lin = (long long)q * ntiles + tile + pf_dist;
+        const int qf = (int)(lin / ntiles), tf = (int)(lin - (long long)qf * ntiles);
+        if (qf < (int)gridDim.y) {
+            const unsigned kf = (unsigned)((2 * qf + part) * ntiles + tf);
+            fbeg = tile_start[kf]; fend = tile_start[kf + 1];
+        }
+    }
     const unsigned sbeg = tile_start[kbase + myslab], send = tile_start[kbase + myslab + 1];
 
     // ---- shared memory carve-up
@@ -111,6 +123,8 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     pf_rec.type = 0;
     uint4 pf_p = make_uint4(0u, 0u, 0u, 0u);
     const uint4* __restrict__ prec = reinterpret_cast<const uint4*>(vals);
+    unsigned fut_tbase = 0xffffffffu;
+    if (PREC && pt < (int)min((unsigned)chunk, fend - fbeg)) fut_tbase = prec[fbeg + pt].z;
     if (lbeg < lend && pt < (int)min((unsigned)chunk, lend - lbeg)) {
         if (PREC) {
             pf_p = prec[lbeg + pt];
@@ -124,6 +138,11 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         for (int i = threadIdx.x; i < ncol * nzp; i += blockDim.x) z2[i] = make_double2(0.0, 0.0);
     }
     __syncthreads();
+    if (PREC && fut_tbase != 0xffffffffu) {
+        const double* T = atom_tables + fut_tbase;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(T));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(T + 15));
+    }
 
     const int lty = __ffs(gp.ty) - 1;                         // tx, ty are powers of two
     const int mycx = mycol >> lty, mycy = mycol & (gp.ty - 1);

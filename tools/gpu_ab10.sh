@@ -1,0 +1,14 @@
+#!/bin/sh
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+run() { echo "== $1"; shift; env "$@" timeout 300 python bench.py --steps ${STEPS:-20} --warmup 4 --no-cpu $EXTRA 2>gpurun_out/err.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); s=d['stage_ms_per_step']; print('frames/s %.0f e2e %.0f ms/step %.3f y %.3f x %.3f splat %.3f prep %.3f'%(d['value'],d['e2e']['value'],d['ms_per_step'],s['fft_y'],s['fft_x_accum'],s['splat_zfft'],s['prep_bin']))" || tail -5 gpurun_out/err.log; }
+run pf592 X=1
+run pf0 MDSF_PF_DIST=0
+run pf296 MDSF_PF_DIST=296
+run pf1184 MDSF_PF_DIST=1184
+run pf2368 MDSF_PF_DIST=2368
+EXTRA="--workload c1 --frames-per-step 64 --pool 64" run c1 X=1
+EXTRA="--workload c3 --frames-per-step 8 --pool 8" STEPS=4 run c3 X=1
