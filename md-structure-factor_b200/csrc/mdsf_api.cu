@@ -134,7 +134,7 @@ struct mdsf_handle {
     size_t splat_smem = 0;
     int mono = 0;                     // K1 applies the monoclinic transform of main_gromacs.py:204-207 first
     double mono_sin = 1.0, mono_cos = 0.0;
-    int pf_dist = 592;                // splat CTAs warm L2 for the CTA this many tiles later (two residency waves); MDSF_PF_DIST, 0 = off
+    int pf_dist = 0;                  // MDSF_PF_DIST = n: splat CTAs warm L2 for the CTA n tiles later; measured slower (c2 5.54 -> 5.77 ms), off
     bool pair_records = true;         // direct binning writes 16-byte pair records (MDSF_PAIR_RECORDS=0: 4-byte payloads + atom records)
     bool direct_bin = false;          // tile mode: counting-sort binning with atomics instead of the stable radix sort
     int tw16_off = 0;                 // byte offset of the cp.async-prefetched stage-1 twiddle table in the splat's shared memory (0 = none)
