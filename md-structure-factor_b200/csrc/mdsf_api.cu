@@ -541,18 +541,19 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         h->y_async = getenv("MDSF_Y_ASYNC") ? atoi(getenv("MDSF_Y_ASYNC")) : 0;
     }
     CU(cudaFuncSetAttribute(slab_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 20480));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(splat_zfft_kernel<false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     *out = h;
     return MDSF_OK;
 }
@@ -1035,8 +1036,9 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     dim3 grid(gp.ntx * gp.nty, npairs);
     const bool use_prec = h->direct_bin && ps.prec != nullptr;
     const unsigned* list = use_prec ? reinterpret_cast<const unsigned*>(ps.prec) : h->d_vals[1];
-#define MDSF_SPLAT_LAUNCH(FUSE, ATOM, EZG, PREC)                                                                          \
-    splat_zfft_kernel<FUSE, ATOM, EZG, PREC><<<grid, 256, h->splat_smem, ss>>>(h->d_recs, list, h->d_tile_start, h->d_vol, \
+#define MDSF_SPLAT_LAUNCH(FUSE, ATOM, EZG, PREC) MDSF_SPLAT_LAUNCH5(FUSE, ATOM, EZG, PREC, false)
+#define MDSF_SPLAT_LAUNCH5(FUSE, ATOM, EZG, PREC, T44)                                                                    \
+    splat_zfft_kernel<FUSE, ATOM, EZG, PREC, T44><<<grid, 256, h->splat_smem, ss>>>(h->d_recs, list, h->d_tile_start, h->d_vol, \
         h->d_dump, gp, h->tt, h->ax[2].plan, h->ax[2].d_tw, h->d_tables, h->chunk, h->logS, h->zfast, h->zstage, h->d_err, h->ax[2].d_tw16, h->tw16_off, h->pf_dist)
     switch ((use_prec ? 8 : 0) | (h->native_fft ? 4 : 0) | (h->tile_atomic ? 2 : 0) | (h->ez_global ? 1 : 0)) {
         case 0: MDSF_SPLAT_LAUNCH(false, false, false, false); break;
@@ -1049,7 +1051,10 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
         case 7: MDSF_SPLAT_LAUNCH(true, true, true, false); break;
         case 10: MDSF_SPLAT_LAUNCH(false, true, false, true); break;
         case 11: MDSF_SPLAT_LAUNCH(false, true, true, true); break;
-        case 14: MDSF_SPLAT_LAUNCH(true, true, false, true); break;
+        case 14:
+            if (gp.tx == 4 && gp.ty == 4 && h->logS == 4 && !getenv("MDSF_NO_T44")) MDSF_SPLAT_LAUNCH5(true, true, false, true, true);
+            else MDSF_SPLAT_LAUNCH(true, true, false, true);
+            break;
         case 15: MDSF_SPLAT_LAUNCH(true, true, true, true); break;
         default: return fail(MDSF_ESTATE, "pair records without tile mode");
     }

@@ -57,7 +57,9 @@ __device__ __forceinline__ void part_barrier(int part) {
 // dependent global round trip less per tile, a third of the bytes, contiguous instead of gathered.
 //   x: (ir_x + 1024) | (ir_y + 1024) << 12 | (sx + 1) << 24 | (sy + 1) << 26
 //   y: (ir_z + 1024) | type << 13          z: table offset          w: atom index
-template <bool FUSE_ZFFT, bool ATOMIC, bool EZG, bool PREC>
+// T44 = true compiles the common geometry in: 4x4-column tiles with 16-entry table slots (tx, ty, the slot stride and
+// every shift derived from them become constants; phase A's staging loop drops from ~28 to ~4 instructions per slot).
+template <bool FUSE_ZFFT, bool ATOMIC, bool EZG, bool PREC, bool T44>
 __global__ void __launch_bounds__(256, MDSF_SPLAT_MINBLOCKS)
 splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ vals,
                   const unsigned* __restrict__ tile_start, double2* __restrict__ vol,
@@ -69,11 +71,13 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     // Nz = 256 tile mode: stage-1 twiddles of the 16x16 z split arrive by cp.async while the splat runs
     double2* tw16s = reinterpret_cast<double2*>(reinterpret_cast<char*>(smem) + tw16_off);
     if (FUSE_ZFFT && ATOMIC && tw16_off > 0) cp_async16(tw16s + threadIdx.x, tw16 + threadIdx.x);
-    const int ncol = gp.tx * gp.ty;
+    const int TX = T44 ? 4 : gp.tx, TY = T44 ? 4 : gp.ty;
+    if (T44) logS = 4;
+    const int ncol = TX * TY;
     const int nzp = gp.nzp;
     const int ntiles = gp.ntx * gp.nty;
     const int tile = blockIdx.x, q = blockIdx.y;
-    const int X0 = (tile / gp.nty) * gp.tx, Y0 = (tile % gp.nty) * gp.ty;
+    const int X0 = (tile / gp.nty) * TX, Y0 = (tile % gp.nty) * TY;
     const int part = threadIdx.x >> 7, pt = threadIdx.x & 127, lane = threadIdx.x & 31, pw = pt >> 5;
     const int nz = gp.n[2];
     const int f = 2 * q + part;
@@ -144,8 +148,8 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         asm volatile("prefetch.global.L2 [%0];" ::"l"(T + 15));
     }
 
-    const int lty = __ffs(gp.ty) - 1;                         // tx, ty are powers of two
-    const int mycx = mycol >> lty, mycy = mycol & (gp.ty - 1);
+    const int lty = T44 ? 2 : __ffs(TY) - 1;                         // tx, ty are powers of two
+    const int mycx = mycol >> lty, mycy = mycol & (TY - 1);
     const int zlo = myslab * zs, zhi = min(zlo + zs, nz);
     const bool owner_valid = X0 + mycx < gp.n[0] && Y0 + mycy < gp.n[1] && zlo < zhi;
     double* col = mytile + (size_t)mycol * nzp;
@@ -176,8 +180,8 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
             stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
             // destination range of this image, clipped to the tile (tile-relative)
-            const int cx0 = max(xlo - sx * gp.n[0] - X0, 0), cx1 = min(xhi - sx * gp.n[0] - X0, gp.tx);
-            const int cy0 = max(ylo - sy * gp.n[1] - Y0, 0), cy1 = min(yhi - sy * gp.n[1] - Y0, gp.ty);
+            const int cx0 = max(xlo - sx * gp.n[0] - X0, 0), cx1 = min(xhi - sx * gp.n[0] - X0, TX);
+            const int cy0 = max(ylo - sy * gp.n[1] - Y0, 0), cy1 = min(yhi - sy * gp.n[1] - Y0, TY);
             const int w = max(cx1 - cx0, 0), h = max(cy1 - cy0, 0);
             const int i0 = X0 + cx0 + sx * gp.n[0] - (rec.ir[0] - Ax);       // stamp index of the first clipped column
             const int j0 = Y0 + cy0 + sy * gp.n[1] - (rec.ir[1] - Ay);
@@ -193,7 +197,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             info[pt] = pi;
             if (w * h > 0)
                 for (int cx = cx0; cx < cx0 + w; ++cx)
-                    colmask |= (((h >= 32) ? 0xffffffffu : ((1u << h) - 1u)) << (cx * gp.ty + cy0));
+                    colmask |= (((h >= 32) ? 0xffffffffu : ((1u << h) - 1u)) << (cx * TY + cy0));
             if (gp.separable) {
                 // slice of the atom's factor tables this tile needs: EX[i0..i0+w), EY[j0..j0+h), EZ[0..2Az)
                 if (!(gp.debug_skip & 4)) {
@@ -204,21 +208,21 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
 #pragma unroll
                         for (int sidx = 0; sidx < 16; ++sidx) {
                             int src = -1;
-                            if (sidx < gp.tx) { if (sidx < w) src = i0 + sidx; }
-                            else if (sidx < gp.tx + gp.ty) { if (sidx - gp.tx < h) src = 2 * Ax + j0 + (sidx - gp.tx); }
-                            else if (!ez_global && sidx - gp.tx - gp.ty < 2 * Az) src = 2 * (Ax + Ay) + (sidx - gp.tx - gp.ty);
+                            if (sidx < TX) { if (sidx < w) src = i0 + sidx; }
+                            else if (sidx < TX + TY) { if (sidx - TX < h) src = 2 * Ax + j0 + (sidx - TX); }
+                            else if (!ez_global && sidx - TX - TY < 2 * Az) src = 2 * (Ax + Ay) + (sidx - TX - TY);
                             vv[sidx] = (src >= 0 && sidx < S) ? T[src] : 0.0;
                         }
-                        if (ez_global) vv[gp.tx + gp.ty] = __longlong_as_double((long long)rec.tbase + 2 * (Ax + Ay));
+                        if (ez_global) vv[TX + TY] = __longlong_as_double((long long)rec.tbase + 2 * (Ax + Ay));
 #pragma unroll
                         for (int sidx = 0; sidx < 16; ++sidx) if (sidx < S) dst[sidx * chunk] = vv[sidx];
                     } else {
                         for (int sidx = 0; sidx < w; ++sidx) dst[sidx * chunk] = T[i0 + sidx];
-                        for (int sidx = 0; sidx < h; ++sidx) dst[(gp.tx + sidx) * chunk] = T[2 * Ax + j0 + sidx];
-                        if (ez_global) dst[(gp.tx + gp.ty) * chunk] = __longlong_as_double((long long)rec.tbase + 2 * (Ax + Ay));
+                        for (int sidx = 0; sidx < h; ++sidx) dst[(TX + sidx) * chunk] = T[2 * Ax + j0 + sidx];
+                        if (ez_global) dst[(TX + TY) * chunk] = __longlong_as_double((long long)rec.tbase + 2 * (Ax + Ay));
                         else
 #pragma unroll 4
-                            for (int sidx = 0; sidx < 2 * Az; ++sidx) dst[(gp.tx + gp.ty + sidx) * chunk] = T[2 * (Ax + Ay) + sidx];
+                            for (int sidx = 0; sidx < 2 * Az; ++sidx) dst[(TX + TY + sidx) * chunk] = T[2 * (Ax + Ay) + sidx];
                     }
                 }
             } else {
@@ -277,13 +281,13 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 unsigned long long* colp = itile + (size_t)((cx << lty) + cy) * nzp;
                 if (gp.separable) {
                     const double* T = tbl + lo;
-                    double exy = T[lx * chunk] * T[(gp.tx + ly) * chunk];
+                    double exy = T[lx * chunk] * T[(TX + ly) * chunk];
                     if (tt.ctab != nullptr) {
                         const int type = (pi.w >> 20) & 1023, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
                         exy *= tt.ctab[tt.ctab_off[type] + (i0 + lx) * 2 * tt.halfw[type * 3 + 1] + (j0 + ly)];
                     }
                     exy *= gp.fx_scale;
-                    const double* ez = T + (gp.tx + gp.ty) * chunk;
+                    const double* ez = T + (TX + TY) * chunk;
                     int ezs = chunk;                          // stride of the EZ entries (compile-time chunk stride when !EZG)
                     if (EZG && pi.w < 0) { ez = atom_tables + __double_as_longlong(ez[0]); ezs = 1; }
                     for (int k = 0; k < nzr; ++k) {
@@ -328,12 +332,12 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                     const int shlo = (pi.z & (1 << 30)) ? gp.nb : nz, shhi = (pi.z < 0) ? -gp.nb : -nz;
                     if (gp.separable) {
                         const double* T = tbl + i;
-                        double exy = T[lx * chunk] * T[(gp.tx + ly) * chunk];
+                        double exy = T[lx * chunk] * T[(TX + ly) * chunk];
                         if (tt.ctab != nullptr) {
                             const int type = (pi.w >> 20) & 1023, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
                             exy *= tt.ctab[tt.ctab_off[type] + (i0 + lx) * 2 * tt.halfw[type * 3 + 1] + (j0 + ly)];
                         }
-                        const double* ez = T + (gp.tx + gp.ty) * chunk;
+                        const double* ez = T + (TX + TY) * chunk;
                         int ezs = chunk;
                         if (EZG && pi.w < 0) { ez = atom_tables + __double_as_longlong(ez[0]); ezs = 1; }
                         {   // cell
@@ -408,7 +412,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     if (dens_dump != nullptr) {
         for (int i = threadIdx.x; i < ncol * nz; i += blockDim.x) {
             const int c = i / nz, z = i - c * nz;
-            const int x = X0 + (c >> lty), y = Y0 + (c & (gp.ty - 1));
+            const int x = X0 + (c >> lty), y = Y0 + (c & (TY - 1));
             if (x < gp.n[0] && y < gp.n[1]) {
                 const int a = c * nzp + z + (z >> gp.pad_shift);
                 dens_dump[(((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + z] = make_double2(tile_re[a], tile_im[a]);
@@ -467,7 +471,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         __syncthreads();
         for (int it = threadIdx.x; it < ncol * R; it += blockDim.x) {
             const int fcol = it / R, b = it - fcol * R;
-            const int x = X0 + (fcol >> lty), y = Y0 + (fcol & (gp.ty - 1));
+            const int x = X0 + (fcol >> lty), y = Y0 + (fcol & (TY - 1));
             if (x >= gp.n[0] || y >= gp.n[1]) continue;
             double2* dst = vol + (((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + b;
             if (R == 16) {
@@ -493,8 +497,8 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         // thread <-> z, loop over the tile's columns: 16-byte stores, one contiguous run per column
         for (int z = threadIdx.x; z < nz; z += blockDim.x) {
             const int a0 = z + (z >> gp.pad_shift);
-            const int ymax = min(gp.ty, gp.n[1] - Y0);
-            for (int cx = 0; cx < gp.tx; ++cx) {
+            const int ymax = min(TY, gp.n[1] - Y0);
+            for (int cx = 0; cx < TX; ++cx) {
                 const int x = X0 + cx;
                 if (x >= gp.n[0]) break;
                 double2* dst = vol + (((long long)q * gp.n[0] + x) * gp.n[1] + Y0) * nz + z;

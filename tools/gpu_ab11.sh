@@ -1,0 +1,10 @@
+#!/bin/sh
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+run() { echo "== $1"; shift; env "$@" timeout 300 python bench.py --steps ${STEPS:-20} --warmup 4 --no-cpu $EXTRA 2>gpurun_out/err.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); s=d['stage_ms_per_step']; print('frames/s %.0f e2e %.0f ms/step %.3f y %.3f x %.3f splat %.3f prep %.3f'%(d['value'],d['e2e']['value'],d['ms_per_step'],s['fft_y'],s['fft_x_accum'],s['splat_zfft'],s['prep_bin']))" || tail -5 gpurun_out/err.log; }
+run t44 X=1
+run generic MDSF_NO_T44=1
+run t44_again X=1
