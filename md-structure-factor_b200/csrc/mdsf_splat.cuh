@@ -72,15 +72,14 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
     double2* tw16s = reinterpret_cast<double2*>(reinterpret_cast<char*>(smem) + tw16_off);
     if (FUSE_ZFFT && ATOMIC && tw16_off > 0) cp_async16(tw16s + threadIdx.x, tw16 + threadIdx.x);
     const int TX = T44 ? 4 : gp.tx, TY = T44 ? 4 : gp.ty;
-    if (T44) { logS = 4; zfast = 16; }                        // T44 also fixes Nz = 256 = 16 x 16 (padded columns of 273)
-    const int PADS = T44 ? 4 : gp.pad_shift;
+    if (T44) logS = 4;
     const int ncol = TX * TY;
-    const int nzp = T44 ? 273 : gp.nzp;
+    const int nzp = gp.nzp;
     const int ntiles = gp.ntx * gp.nty;
     const int tile = blockIdx.x, q = blockIdx.y;
     const int X0 = (tile / gp.nty) * TX, Y0 = (tile % gp.nty) * TY;
     const int part = threadIdx.x >> 7, pt = threadIdx.x & 127, lane = threadIdx.x & 31, pw = pt >> 5;
-    const int nz = T44 ? 256 : gp.n[2];
+    const int nz = gp.n[2];
     const int f = 2 * q + part;
 
     // ---- ownership: owner o = slab * ncol + column; slab s covers z in [s*zs, (s+1)*zs).
@@ -274,9 +273,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 const PairInfo pi = info[lo];
                 const int hh = (pi.x >> 24) & 0xff;
                 const int local = v - voff[lo];
-                // T44: hh <= 4, local < 16 -> exact division by multiply-shift
-                const int lx = T44 ? (int)(((unsigned)local * (hh == 1 ? 65536u : (hh == 2 ? 32768u : (hh == 3 ? 21846u : 16384u)))) >> 16) : local / hh;
-                const int ly = local - lx * hh;
+                const int lx = local / hh, ly = local - lx * hh;
                 const int cx = (pi.x & 0xff) + lx, cy = ((pi.x >> 16) & 0xff) + ly;
                 if (X0 + cx >= gp.n[0] || Y0 + cy >= gp.n[1]) continue;
                 const int pz0 = pi.y, kA = pi.z & 1023, kB = (pi.z >> 10) & 1023, nzr = (pi.z >> 20) & 1023;
@@ -296,7 +293,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                     for (int k = 0; k < nzr; ++k) {
                         const int pz = pz0 + k;
                         const int cz = k < kA ? pz + shlo : (k < kB ? pz : pz + shhi);
-                        smem_add_u64(colp + cz + (cz >> PADS), (unsigned long long)__double2ll_rn(exy * ez[k * ezs]));
+                        smem_add_u64(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(exy * ez[k * ezs]));
                     }
                 } else {
                     const int type = (pi.w >> 20) & 1023, i0 = pi.w & 1023, j0 = (pi.w >> 10) & 1023;
@@ -313,7 +310,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                         const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
                         const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
                         const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
-                        smem_add_u64(colp + cz + (cz >> PADS), (unsigned long long)__double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2)));
+                        smem_add_u64(colp + cz + (cz >> gp.pad_shift), (unsigned long long)__double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2)));
                     }
                 }
             }
@@ -345,15 +342,15 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                         if (EZG && pi.w < 0) { ez = atom_tables + __double_as_longlong(ez[0]); ezs = 1; }
                         {   // cell
                             const int ka = max(kA, zlo - pz0), kb = min(kB, zhi - pz0);
-                            for (int k = ka; k < kb; ++k) { const int cz = pz0 + k; col[cz + (cz >> PADS)] += exy * ez[k * ezs]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = pz0 + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * ezs]; }
                         }
                         if (kA > 0) {   // low padding
                             const int sh = pz0 + shlo, ka = max(0, zlo - sh), kb = min(kA, zhi - sh);
-                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> PADS)] += exy * ez[k * ezs]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * ezs]; }
                         }
                         if (nzr > kB) { // high padding
                             const int sh = pz0 + shhi, ka = max(kB, zlo - sh), kb = min(nzr, zhi - sh);
-                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> PADS)] += exy * ez[k * ezs]; }
+                            for (int k = ka; k < kb; ++k) { const int cz = sh + k; col[cz + (cz >> gp.pad_shift)] += exy * ez[k * ezs]; }
                         }
                     } else {
                         // general ucell: one exp per cell, exactly the reference's expression
@@ -376,7 +373,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                                 const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
                                 const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
                                 const int cz = sh + k;
-                                col[cz + (cz >> PADS)] += amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2);
+                                col[cz + (cz >> gp.pad_shift)] += amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2);
                             }
                         }
                     }
@@ -417,7 +414,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             const int c = i / nz, z = i - c * nz;
             const int x = X0 + (c >> lty), y = Y0 + (c & (TY - 1));
             if (x < gp.n[0] && y < gp.n[1]) {
-                const int a = c * nzp + z + (z >> PADS);
+                const int a = c * nzp + z + (z >> gp.pad_shift);
                 dens_dump[(((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + z] = make_double2(tile_re[a], tile_im[a]);
             }
         }
@@ -438,7 +435,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int p = n2 + 16 * j;
-                    addr[j] = fcol * nzp + p + (p >> PADS);
+                    addr[j] = fcol * nzp + p + (p >> gp.pad_shift);
                     const long long qr = reinterpret_cast<long long*>(tile_re)[addr[j]], qi = reinterpret_cast<long long*>(tile_im)[addr[j]];
                     ovf |= (qr ^ (qr << 1)) | (qi ^ (qi << 1));
                     xr[j] = (double)qr * gp.fx_inv; xi[j] = (double)qi * gp.fx_inv;
@@ -468,7 +465,7 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 if (ovf < 0) atomicExch(err_flag, 2);
                 __syncthreads();
             }
-            fft_stage_dispatch<true, IO_SMEM, IO_SMEM>(R, tile_re, tile_im, twr, twi, nz, nz, ncol, nzp, 1, PADS, 0,
+            fft_stage_dispatch<true, IO_SMEM, IO_SMEM>(R, tile_re, tile_im, twr, twi, nz, nz, ncol, nzp, 1, gp.pad_shift, 0,
                                                        GlobalTile{nullptr, 0, 0}, nullptr, false);
         }
         __syncthreads();
@@ -480,14 +477,14 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
             if (R == 16) {
                 double xr[16], xi[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { const int p = b * 16 + j; const int a = fcol * nzp + p + (p >> PADS); xr[j] = tile_re[a]; xi[j] = tile_im[a]; }
+                for (int j = 0; j < 16; ++j) { const int p = b * 16 + j; const int a = fcol * nzp + p + (p >> gp.pad_shift); xr[j] = tile_re[a]; xi[j] = tile_im[a]; }
                 Dft<16>::run(xr, xi, twr, twi, nz);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) dst[16 * k] = make_double2(xr[k], xi[k]);
             } else {
                 double xr[8], xi[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const int p = b * 8 + j; const int a = fcol * nzp + p + (p >> PADS); xr[j] = tile_re[a]; xi[j] = tile_im[a]; }
+                for (int j = 0; j < 8; ++j) { const int p = b * 8 + j; const int a = fcol * nzp + p + (p >> gp.pad_shift); xr[j] = tile_re[a]; xi[j] = tile_im[a]; }
                 Dft<8>::run(xr, xi, twr, twi, nz);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) dst[8 * k] = make_double2(xr[k], xi[k]);
@@ -495,11 +492,11 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
         }
         return;
     }
-    if (FUSE_ZFFT && !(gp.debug_skip & 2)) fft_tile_z(tile_re, tile_im, twr, twi, zplan, ncol, nzp, PADS);
+    if (FUSE_ZFFT && !(gp.debug_skip & 2)) fft_tile_z(tile_re, tile_im, twr, twi, zplan, ncol, nzp, gp.pad_shift);
     if (!(gp.debug_skip & 8)) {
         // thread <-> z, loop over the tile's columns: 16-byte stores, one contiguous run per column
         for (int z = threadIdx.x; z < nz; z += blockDim.x) {
-            const int a0 = z + (z >> PADS);
+            const int a0 = z + (z >> gp.pad_shift);
             const int ymax = min(TY, gp.n[1] - Y0);
             for (int cx = 0; cx < TX; ++cx) {
                 const int x = X0 + cx;
