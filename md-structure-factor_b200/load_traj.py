@@ -2,9 +2,9 @@
 
 ``load_gro`` (:11-20) and ``process_gro_mdtraj`` (:90-111) keep their signatures and the
 ``out_<name>_traj.npz`` layout (keys dims, coords, name, mass, typ -- typ holds the atom NAMES,
-reference load_traj.py:110).  Decoding of binary trajectories still goes through mdtraj when it is
-installed (a native XTC/TRR reader is listed as the next row in SURVEY section 8f); .gro files are
-parsed here directly.
+reference load_traj.py:110).  With mdtraj installed every format goes through it, as in the reference;
+without it, .gro (one or many frames) and .trr are parsed here directly, .xtc still
+needs mdtraj.
 """
 import ctypes
 import os
@@ -60,6 +60,112 @@ def read_gro(gro):
     return names, xyz * np.float32(10), (lengths * 10).astype(np.float32)
 
 
+def read_gro_frames(gro):
+    """Multi-frame .gro reader (GROMACS writes trajectories as concatenated .gro frames): (names, coords in Angstrom
+    float32 (T, Na, 3), box lengths in Angstrom float32 (T, 3)).  A one-frame file gives T = 1."""
+    with open(gro) as handle:
+        rows = handle.readlines()
+    frames, boxes, names = [], [], None
+    pos = 0
+    while pos + 2 < len(rows) and rows[pos + 1].strip():
+        natoms = int(rows[pos + 1])
+        body = rows[pos + 2:pos + 2 + natoms]
+        if names is None:
+            names = [row[10:15].strip() for row in body]
+        elif len(body) != len(names):
+            raise ValueError("%s: frame %d has %d atoms, frame 0 has %d" % (gro, len(frames), len(body), len(names)))
+        frames.append(np.array([[float(row[20:28]), float(row[28:36]), float(row[36:44])] for row in body], dtype=np.float32))
+        b = [float(v) for v in rows[pos + 2 + natoms].split()]
+        if len(b) == 3:
+            boxes.append(np.array(b, dtype=np.float64))
+        else:   # v1(x) v2(y) v3(z) v1(y) v1(z) v2(x) v2(z) v3(x) v3(y)
+            v1 = np.array([b[0], b[3], b[4]]); v2 = np.array([b[5], b[1], b[6]]); v3 = np.array([b[7], b[8], b[2]])
+            boxes.append(np.array([np.linalg.norm(v1), np.linalg.norm(v2), np.linalg.norm(v3)]))
+        pos += natoms + 3
+    if not frames:
+        raise ValueError("%s holds no .gro frame" % gro)
+    return names, np.stack(frames) * np.float32(10), (np.stack(boxes) * 10).astype(np.float32)
+
+
+TRR_MAGIC = 1993
+TRR_VERSION = b"GMX_trn_file"
+
+
+def read_trr(path):
+    """GROMACS .trr reader (XDR, big-endian; single or double precision): (coords in Angstrom float32 (T, Na, 3),
+    box lengths in Angstrom float32 (T, 3), times in ps).  Frames without coordinates (velocity/force-only output
+    steps) are skipped.  Layout per frame, as written by GROMACS' trnio: magic 1993, the version string
+    "GMX_trn_file" (as int 13, int 12, 12 bytes), the ten block sizes ir, e, box, vir, pres, top, sym, x, v, f, then
+    natoms, step, nre, t, lambda (reals), then the blocks box(3x3), vir, pres, x, v, f of `real`s in nm.
+    PARITY UNPINNED: the reference decodes .trr through mdtraj (load_traj.py:94), which is not installed here, and ships
+    no .trr fixture; this reader is checked against a writer of the same published layout (tests/test_host_logic.py)."""
+    data = np.fromfile(path, dtype=np.uint8)
+    pos, n = 0, data.size
+    xyz, boxes, times = [], [], []
+    be32 = np.dtype(">i4")
+    while pos < n:
+        if pos + 8 + 4 + len(TRR_VERSION) > n:
+            raise ValueError("%s: truncated frame header at byte %d" % (path, pos))
+        magic, slen = np.frombuffer(data, be32, 2, pos)
+        if magic != TRR_MAGIC or slen != len(TRR_VERSION) + 1:
+            raise ValueError("%s: not a .trr frame at byte %d (magic %d)" % (path, pos, magic))
+        pos += 8
+        strlen = int(np.frombuffer(data, be32, 1, pos)[0])
+        pos += 4
+        if bytes(data[pos:pos + strlen]) != TRR_VERSION:
+            raise ValueError("%s: unexpected version string at byte %d" % (path, pos))
+        pos += (strlen + 3) // 4 * 4
+        ir, e, box, vir, pres, top, sym, xs, vs, fs, natoms, step, nre = (int(v) for v in np.frombuffer(data, be32, 13, pos))
+        pos += 52
+        if box:
+            real = box // 9
+        elif natoms and (xs or vs or fs):
+            real = (xs or vs or fs) // (3 * natoms)
+        else:
+            raise ValueError("%s: frame at step %d has neither box nor vectors" % (path, step))
+        if real not in (4, 8):
+            raise ValueError("%s: real size %d is neither float nor double" % (path, real))
+        rt = np.dtype(">f%d" % real)
+        t = float(np.frombuffer(data, rt, 1, pos)[0])
+        pos += 2 * real                                   # t, lambda
+        pos += ir + e
+        bvec = np.frombuffer(data, rt, 9, pos).reshape(3, 3).astype(np.float64) if box else np.zeros((3, 3))
+        pos += box + vir + pres + top + sym
+        if xs:
+            if xs != natoms * 3 * real:
+                raise ValueError("%s: coordinate block of %d bytes for %d atoms" % (path, xs, natoms))
+            xyz.append(np.frombuffer(data, rt, natoms * 3, pos).reshape(natoms, 3).astype(np.float32))
+            boxes.append(np.sqrt((bvec * bvec).sum(axis=1)))
+            times.append(t)
+        pos += xs + vs + fs
+        if pos > n:
+            raise ValueError("%s: truncated frame at step %d" % (path, step))
+    if not xyz:
+        raise ValueError("%s holds no frame with coordinates" % path)
+    return np.stack(xyz) * np.float32(10), (np.stack(boxes) * 10).astype(np.float32), np.array(times)
+
+
+def write_trr(path, coords_nm, box_nm, times=None, double=False, velocities=None):
+    """Writer of the same layout (tests, synthetic trajectories): coords (T, Na, 3) and box vectors (T, 3, 3) or lengths
+    (T, 3) in nm."""
+    coords_nm = np.asarray(coords_nm)
+    T, natoms = coords_nm.shape[:2]
+    box_nm = np.asarray(box_nm, dtype=np.float64)
+    if box_nm.ndim == 2:
+        box_nm = np.stack([np.diag(b) for b in box_nm])
+    real = 8 if double else 4
+    rt = np.dtype(">f%d" % real)
+    with open(path, "wb") as fh:
+        for it in range(T):
+            vsize = natoms * 3 * real if velocities is not None else 0
+            head = np.array([TRR_MAGIC, len(TRR_VERSION) + 1, len(TRR_VERSION)], dtype=">i4").tobytes() + TRR_VERSION
+            sizes = np.array([0, 0, 9 * real, 0, 0, 0, 0, natoms * 3 * real, vsize, 0, natoms, it, 0], dtype=">i4").tobytes()
+            tl = np.array([0.0 if times is None else times[it], 0.0], dtype=rt).tobytes()
+            fh.write(head + sizes + tl + box_nm[it].astype(rt).tobytes() + coords_nm[it].astype(rt).tobytes())
+            if velocities is not None:
+                fh.write(np.asarray(velocities[it]).astype(rt).tobytes())
+
+
 def save_traj_npz(output_filename, dims, coords, name, mass=None):
     """Write the traj npz exactly as the reference does (load_traj.py:110): typ = atom names."""
     name = np.asarray(name)
@@ -76,12 +182,18 @@ def process_gro_mdtraj(topology_filename, trajectory_filename, output_filename):
         import mdtraj as md
     except ImportError as exc:
         if trajectory_filename.endswith(".gro"):
-            names, xyz, box = read_gro(trajectory_filename)
-            print("saving ", output_filename)
-            save_traj_npz(output_filename, box[None, :], xyz[None, :, :], names)
-            print('done saving')
-            return
-        raise ImportError("mdtraj is needed to decode %s (only .gro is parsed natively)" % trajectory_filename) from exc
+            names, xyz, box = read_gro_frames(trajectory_filename)
+        elif trajectory_filename.endswith(".trr"):
+            names = load_gro(topology_filename)
+            xyz, box, _ = read_trr(trajectory_filename)
+            if xyz.shape[1] != len(names):
+                raise ValueError("%s has %d atoms, topology %s has %d" % (trajectory_filename, xyz.shape[1], topology_filename, len(names)))
+        else:
+            raise ImportError("mdtraj is needed to decode %s (.gro and .trr are parsed natively)" % trajectory_filename) from exc
+        print("saving ", output_filename)
+        save_traj_npz(output_filename, box, xyz, names)
+        print('done saving')
+        return
     t = md.load(trajectory_filename, top=topology_filename)
     coords = t.xyz * 10            # nm -> Angstrom, float32
     dims = t.unitcell_lengths * 10

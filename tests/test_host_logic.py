@@ -245,3 +245,46 @@ def test_indexed_traj_npz_is_inflated_in_parallel_and_stays_a_numpy_container(tm
     open(bad, "wb").write(bytes(blob))
     with load_traj.NpzFrameStream(bad) as fs, pytest.raises(EOFError):
         fs.read_into(np.zeros((T, na, 3), dtype=np.float32))
+
+
+def test_native_trr_and_multiframe_gro_readers(tmp_path):
+    """load_traj.read_trr follows the published .trr layout (magic 1993, "GMX_trn_file", block sizes, reals in nm) for float
+    and double files, skips coordinate-free frames and feeds process_gro_mdtraj when mdtraj is absent; read_gro_frames
+    splits concatenated .gro frames.  (Parity unpinned: no mdtraj / fixture here, see the reader's docstring.)"""
+    import load_traj as lt
+    rng = np.random.default_rng(3)
+    T, na = 5, 6
+    x = rng.uniform(0, 1.8, size=(T, na, 3))
+    box = np.array([[1.8206, 1.8206 * (1 + 0.01 * t), 1.75] for t in range(T)])
+    for dbl in (False, True):
+        p = str(tmp_path / ("d.trr" if dbl else "f.trr"))
+        lt.write_trr(p, x, box, times=np.arange(T) * 2.0, double=dbl, velocities=x * 0.1)
+        c, b, t = lt.read_trr(p)
+        assert c.dtype == np.float32 and c.shape == (T, na, 3) and b.dtype == np.float32
+        ref = x.astype(np.float64 if dbl else np.float32).astype(np.float32) * np.float32(10)
+        assert np.array_equal(c, ref) and np.allclose(b, box * 10, rtol=1e-6) and np.array_equal(t, np.arange(T) * 2.0)
+    raw = open(str(tmp_path / "f.trr"), "rb").read()
+    assert raw[:4] == b"\x00\x00\x07\xc9" and raw[4:12] == b"\x00\x00\x00\x0d\x00\x00\x00\x0c" and raw[12:24] == b"GMX_trn_file"
+    tri = np.array([[[2.0, 0, 0], [-1.0, 1.7320508, 0], [0, 0, 3.0]]] * T)          # hexagonal box vectors -> lengths 2, 2, 3
+    lt.write_trr(str(tmp_path / "h.trr"), x, tri)
+    assert np.allclose(lt.read_trr(str(tmp_path / "h.trr"))[1], [20.0, 20.0, 30.0], rtol=1e-6)
+    with pytest.raises(ValueError):
+        open(str(tmp_path / "bad.trr"), "wb").write(raw[:100])
+        lt.read_trr(str(tmp_path / "bad.trr"))
+    # topology .gro + .trr -> traj npz without mdtraj
+    gro = tmp_path / "w.gro"
+    rows = ["    1WATER%5s%5d%8.3f%8.3f%8.3f\n" % (nm, i + 1, *x[0, i]) for i, nm in enumerate(["OW1", "HW2", "HW3"] * 2)]
+    gro.write_text("two waters\n    6\n" + "".join(rows) + "   1.82060   1.82060   1.75000\n")
+    try:
+        import mdtraj  # noqa: F401
+    except ImportError:
+        lt.process_gro_mdtraj(str(gro), str(tmp_path / "f.trr"), str(tmp_path / "out_f_traj"))
+        z = np.load(str(tmp_path / "out_f_traj.npz"))
+        assert z["coords"].shape == (T, na, 3) and z["dims"].shape == (T, 3) and list(z["typ"]) == ["OW1", "HW2", "HW3"] * 2
+        assert np.array_equal(z["coords"], x.astype(np.float32) * np.float32(10))
+    # concatenated .gro frames
+    multi = tmp_path / "m.gro"
+    multi.write_text(gro.read_text() * 3)
+    names, c, b = lt.read_gro_frames(str(multi))
+    assert c.shape == (3, na, 3) and b.shape == (3, 3) and names == ["OW1", "HW2", "HW3"] * 2
+    assert np.array_equal(c[0], c[2]) and np.allclose(b[1], [18.206, 18.206, 17.5])
