@@ -1052,7 +1052,8 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
         case 10: MDSF_SPLAT_LAUNCH(false, true, false, true); break;
         case 11: MDSF_SPLAT_LAUNCH(false, true, true, true); break;
         case 14:
-            if (gp.tx == 4 && gp.ty == 4 && h->logS == 4 && !getenv("MDSF_NO_T44")) MDSF_SPLAT_LAUNCH5(true, true, false, true, true);
+            if (gp.tx == 4 && gp.ty == 4 && h->logS == 4 && !getenv("MDSF_NO_T44"))
+                MDSF_SPLAT_LAUNCH5(true, true, false, true, true);
             else MDSF_SPLAT_LAUNCH(true, true, false, true);
             break;
         case 15: MDSF_SPLAT_LAUNCH(true, true, true, true); break;

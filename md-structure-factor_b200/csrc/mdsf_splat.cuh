@@ -273,7 +273,9 @@ splat_zfft_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__
                 const PairInfo pi = info[lo];
                 const int hh = (pi.x >> 24) & 0xff;
                 const int local = v - voff[lo];
-                const int lx = local / hh, ly = local - lx * hh;
+                // T44: hh <= 4 and local < 16, so the division is an exact multiply-shift
+                const int lx = T44 ? (int)(((unsigned)local * (hh == 1 ? 65536u : (hh == 2 ? 32768u : (hh == 3 ? 21846u : 16384u)))) >> 16) : local / hh;
+                const int ly = local - lx * hh;
                 const int cx = (pi.x & 0xff) + lx, cy = ((pi.x >> 16) & 0xff) + ly;
                 if (X0 + cx >= gp.n[0] || Y0 + cy >= gp.n[1]) continue;
                 const int pz0 = pi.y, kA = pi.z & 1023, kB = (pi.z >> 10) & 1023, nzr = (pi.z >> 20) & 1023;

@@ -10,7 +10,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmdsf.so")
+LIB_PATH = os.environ.get("MDSF_LIB") or os.path.join(_HERE, "libmdsf.so")      # MDSF_LIB: A/B builds of the same ABI
 ABI_VERSION = 1
 
 F32, F64 = 0, 1
