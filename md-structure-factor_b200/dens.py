@@ -136,15 +136,21 @@ def _grid(L, Sres):
 def _k_lattices(shape, L):
     """kgrid / kgridplt coordinate lattices (reference dens.py:325-342)."""
     nx, ny, m = shape
+    # the reference fills kgrid slice by slice (dens.py:327-334); the per-index scalars below are its expressions, the
+    # assignment is one broadcast per channel (indices it never writes, e.g. the middle one of an odd axis, stay 0)
     kgrid = np.zeros((nx, ny, m, 4))
+    vx, vy, vz = np.zeros(nx), np.zeros(ny), np.zeros(m)
     for ix in range(int(nx / 2)):
-        kgrid[ix, :, :, 0] = ix * 2.0 * math.pi / L[0]
-        kgrid[nx - 1 - ix, :, :, 0] = -(ix + 0.5) * 2.0 * math.pi / L[0]
+        vx[ix] = ix * 2.0 * math.pi / L[0]
+        vx[nx - 1 - ix] = -(ix + 0.5) * 2.0 * math.pi / L[0]
     for iy in range(int(ny / 2)):
-        kgrid[:, iy, :, 1] = iy * 2.0 * math.pi / L[1]
-        kgrid[:, ny - 1 - iy, :, 1] = -(iy + 0.5) * 2.0 * math.pi / L[1]
+        vy[iy] = iy * 2.0 * math.pi / L[1]
+        vy[ny - 1 - iy] = -(iy + 0.5) * 2.0 * math.pi / L[1]
     for iz in range(m):
-        kgrid[:, :, iz, 2] = iz * 2.0 * math.pi / L[2]
+        vz[iz] = iz * 2.0 * math.pi / L[2]
+    kgrid[..., 0] = vx[:, None, None]
+    kgrid[..., 1] = vy[None, :, None]
+    kgrid[..., 2] = vz[None, None, :]
     kplt = np.zeros((nx - 2, ny - 2, m * 2 - 3, 4))
     for d in range(3):
         nd = kplt.shape[d]
