@@ -666,6 +666,124 @@ fft_y_async_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, in
     }
 }
 
+// ------------------------------------------------------------------ y / x pass, three radix stages (long axes)
+// N = R1*R2*R3 (512 = 8*8*8, 1024 = 8*8*16, 768 = 16*16*3): same decimation-in-frequency scheme and output order as
+// fft_stage (position space), written out with compile-time radices and strides.  Tile [N][W] in shared memory
+// (re / im planes); every thread owns the same butterflies for every pair of the batch, so the x pass keeps
+// sum_q |C_q|^2 of its stage-3 outputs in registers and touches P once (the generic kernel keeps a third [N][W]
+// plane in shared memory for that and dispatches radices at run time).
+//   XPASS = false: in place on the volume, grid = (z chunks, Nx, pairs)
+//   XPASS = true : grid = (z chunks, Ny), loops over the pairs, P += sum |C|^2
+template <int R1, int R2, int R3, int LOGW, int THR, int MINB, bool XPASS>
+__global__ void __launch_bounds__(THR, MINB)
+fft3_pass_kernel(double2* __restrict__ vol, double* __restrict__ P, const double2* __restrict__ tw,
+                 int nouter, int nz, int npairs)
+{
+    constexpr int N = R1 * R2 * R3, M1 = N / R1, M2 = M1 / R2;
+    extern __shared__ double smem[];
+    constexpr int W = 1 << LOGW, logw = LOGW;
+    double* sre = smem;
+    double* sim = sre + (size_t)N * W;
+    double* twr = sim + (size_t)N * W;
+    double* twi = twr + N;
+    load_twiddles(twr, twi, tw, N);
+    const int z0 = blockIdx.x * W;
+    // XPASS: rows are x (stride Ny*Nz), the CTA sits at y = blockIdx.y; else rows are y (stride Nz) at x = blockIdx.y
+    const long long row = XPASS ? (long long)nouter * nz : (long long)nz;
+    const long long pair_stride = XPASS ? (long long)N * row : (long long)nouter * N * nz;
+    const long long off = XPASS ? (long long)blockIdx.y * nz + z0 : ((long long)blockIdx.z * nouter + blockIdx.y) * N * (long long)nz + z0;
+    constexpr int NB1 = M1, NB2 = N / R2, NB3 = N / R3;      // butterflies per column and stage
+    constexpr int items1 = NB1 * W, items2 = NB2 * W, items3 = NB3 * W;
+    constexpr int MAXI3 = (items3 + THR - 1) / THR;           // stage-3 butterflies per thread
+    double acc[MAXI3][R3];
+    if (XPASS) {
+#pragma unroll
+        for (int i = 0; i < MAXI3; ++i)
+#pragma unroll
+            for (int k = 0; k < R3; ++k) acc[i][k] = 0.0;
+    }
+    const int nq = XPASS ? npairs : 1;
+    for (int q = 0; q < nq; ++q) {
+        double2* base = vol + off + (long long)q * pair_stride;
+        __syncthreads();                                       // twiddles loaded / previous pair's stage 3 done
+        // ---- stage 1: points n2 + M1*j straight from global memory
+        for (int it = threadIdx.x; it < items1; it += THR) {
+            const int f = it & (W - 1), n2 = it >> logw;
+            const bool ok = z0 + f < nz;
+            double xr[R1], xi[R1];
+#pragma unroll
+            for (int j = 0; j < R1; ++j) {
+                double2 v = make_double2(0.0, 0.0);
+                if (ok) v = base[(long long)(n2 + M1 * j) * row + f];
+                xr[j] = v.x; xi[j] = v.y;
+            }
+            Dft<R1>::run(xr, xi, twr, twi, N);
+#pragma unroll
+            for (int k = 1; k < R1; ++k) {
+                const double wr = twr[n2 * k], wi = twi[n2 * k];
+                const double yr = xr[k] * wr - xi[k] * wi;
+                xi[k] = xr[k] * wi + xi[k] * wr;
+                xr[k] = yr;
+            }
+#pragma unroll
+            for (int k = 0; k < R1; ++k) { const int a = ((n2 + M1 * k) << logw) + f; sre[a] = xr[k]; sim[a] = xi[k]; }
+        }
+        __syncthreads();
+        // ---- stage 2: block b of M1 points, points b*M1 + n2 + M2*j, twiddle w_N^(R1 n2 k)
+        for (int it = threadIdx.x; it < items2; it += THR) {
+            const int f = it & (W - 1), bf = it >> logw;
+            const int b = bf / M2, n2 = bf - b * M2;
+            const int p0 = b * M1 + n2;
+            double xr[R2], xi[R2];
+#pragma unroll
+            for (int j = 0; j < R2; ++j) { const int a = ((p0 + M2 * j) << logw) + f; xr[j] = sre[a]; xi[j] = sim[a]; }
+            Dft<R2>::run(xr, xi, twr, twi, N);
+#pragma unroll
+            for (int k = 1; k < R2; ++k) {
+                const double wr = twr[n2 * k * R1], wi = twi[n2 * k * R1];
+                const double yr = xr[k] * wr - xi[k] * wi;
+                xi[k] = xr[k] * wi + xi[k] * wr;
+                xr[k] = yr;
+            }
+#pragma unroll
+            for (int k = 0; k < R2; ++k) { const int a = ((p0 + M2 * k) << logw) + f; sre[a] = xr[k]; sim[a] = xi[k]; }
+        }
+        __syncthreads();
+        // ---- stage 3: R3 consecutive points of block bf; outputs stay at bf*R3 + k
+#pragma unroll
+        for (int i = 0; i < MAXI3; ++i) {
+            const int it = threadIdx.x + i * THR;
+            if (it < items3) {
+                const int f = it & (W - 1), bf = it >> logw;
+                double xr[R3], xi[R3];
+#pragma unroll
+                for (int j = 0; j < R3; ++j) { const int a = ((bf * R3 + j) << logw) + f; xr[j] = sre[a]; xi[j] = sim[a]; }
+                Dft<R3>::run(xr, xi, twr, twi, N);
+                if (XPASS) {
+#pragma unroll
+                    for (int k = 0; k < R3; ++k) acc[i][k] += xr[k] * xr[k] + xi[k] * xi[k];
+                } else if (z0 + f < nz) {
+#pragma unroll
+                    for (int k = 0; k < R3; ++k) base[(long long)(bf * R3 + k) * row + f] = make_double2(xr[k], xi[k]);
+                }
+            }
+        }
+    }
+    if (XPASS) {
+#pragma unroll
+        for (int i = 0; i < MAXI3; ++i) {
+            const int it = threadIdx.x + i * THR;
+            if (it < items3) {
+                const int f = it & (W - 1), bf = it >> logw;
+                if (z0 + f < nz) {
+#pragma unroll
+                    for (int k = 0; k < R3; ++k) P[(long long)(bf * R3 + k) * row + off + f] += acc[i][k];
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ library-FFT path helper
 // P += sum_q |vol_q|^2 after a cuFFT Z2Z (grids whose sizes have prime factors > 13)
 __global__ void accumulate_power_kernel(const double2* __restrict__ vol, double* __restrict__ P,
