@@ -44,6 +44,12 @@ static int fail(int code, const char* fmt, ...) {
         if (r_ != CUFFT_SUCCESS) return fail(MDSF_ECUDA, "%s failed: cufft error %d (%s:%d)", #call, (int)r_, __FILE__, __LINE__); \
     } while (0)
 
+#ifndef MDSF_FFT3_MINB_Y
+#define MDSF_FFT3_MINB_Y 2     // CTAs per SM of the three-stage y pass (measured: 2 -> 4.87 ms, 3 -> 4.95 ms on c3)
+#endif
+#ifndef MDSF_FFT3_MINB_X
+#define MDSF_FFT3_MINB_X 2     // ... of the x pass (register accumulators: 116 registers)
+#endif
 static const int kSlots = 2;
 static const int kMaxSmem = 227 * 1024;
 
@@ -536,8 +542,8 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaFuncSetAttribute(fft_x_accum_async_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_x_accum_async_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         h->x_async = getenv("MDSF_X_ASYNC") ? atoi(getenv("MDSF_X_ASYNC")) : 1;     // measured: c2 x pass 1.01 -> 0.92 ms
-        CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 8, 3, 256, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 8, 3, 256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_Y, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_X, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_y_async_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_y_async_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         h->y_async = getenv("MDSF_Y_ASYNC") ? atoi(getenv("MDSF_Y_ASYNC")) : 0;
@@ -852,7 +858,7 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             dim3 grid_a((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0]);
             const bool three8 = yp.nstages == 3 && yp.radix[0] == 8 && yp.radix[1] == 8 && yp.radix[2] == 8 && h->Wy == 8 && !getenv("MDSF_NO_FFT3");
             if (three8)
-                fft3_pass_kernel<8, 8, 8, 3, 256, 3, false><<<grid, 256, sm, h->s_comp>>>(h->d_vol, nullptr, h->ax[1].d_tw, gp.n[0], gp.n[2], npairs);
+                fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_Y, false><<<grid, 256, sm, h->s_comp>>>(h->d_vol, nullptr, h->ax[1].d_tw, gp.n[0], gp.n[2], npairs);
             else if (fast && h->y_async && yp.radix[0] == 16)
                 fft_y_async_kernel<16, 16><<<grid_a, h->thr_y, sya, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw, npairs);
             else if (fast && h->y_async)
@@ -881,7 +887,7 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             const size_t sma = smf + (size_t)xp.radix[0] * h->thr_x * 16;     // + cp.async staging slots
             const bool three8 = xp.nstages == 3 && xp.radix[0] == 8 && xp.radix[1] == 8 && xp.radix[2] == 8 && h->Wx == 8 && !getenv("MDSF_NO_FFT3");
             if (three8)
-                fft3_pass_kernel<8, 8, 8, 3, 256, 2, true><<<grid, 256, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], npairs);
+                fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_X, true><<<grid, 256, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], npairs);
             else if (fast && h->x_async && xp.radix[0] == 16)
                 fft_x_accum_async_kernel<16, 16><<<grid, h->thr_x, sma, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
             else if (fast && h->x_async)
