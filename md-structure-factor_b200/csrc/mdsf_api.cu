@@ -542,6 +542,8 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(cudaFuncSetAttribute(fft_x_accum_async_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_x_accum_async_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         h->x_async = getenv("MDSF_X_ASYNC") ? atoi(getenv("MDSF_X_ASYNC")) : 1;     // measured: c2 x pass 1.01 -> 0.92 ms
+        CU(cudaFuncSetAttribute(fft3_pass_kernel<16, 16, 3, 3, 256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft3_pass_kernel<16, 16, 3, 3, 256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_Y, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_X, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_y_async_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -856,9 +858,13 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
                               (yp.radix[0] == 16 || yp.radix[0] == 8) && !getenv("MDSF_NO_YFAST");
             const size_t sya = sm + (size_t)yp.radix[0] * h->thr_y * 16;
             dim3 grid_a((gp.n[2] + h->Wy - 1) / h->Wy, gp.n[0]);
-            const bool three8 = yp.nstages == 3 && yp.radix[0] == 8 && yp.radix[1] == 8 && yp.radix[2] == 8 && h->Wy == 8 && !getenv("MDSF_NO_FFT3");
+            const bool three = yp.nstages == 3 && h->Wy == 8 && !getenv("MDSF_NO_FFT3");
+            const bool three8 = three && yp.radix[0] == 8 && yp.radix[1] == 8 && yp.radix[2] == 8;          // 512
+            const bool three768 = three && yp.radix[0] == 16 && yp.radix[1] == 16 && yp.radix[2] == 3;     // 768
             if (three8)
                 fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_Y, false><<<grid, 256, sm, h->s_comp>>>(h->d_vol, nullptr, h->ax[1].d_tw, gp.n[0], gp.n[2], npairs);
+            else if (three768)
+                fft3_pass_kernel<16, 16, 3, 3, 256, 2, false><<<grid, 256, sm, h->s_comp>>>(h->d_vol, nullptr, h->ax[1].d_tw, gp.n[0], gp.n[2], npairs);
             else if (fast && h->y_async && yp.radix[0] == 16)
                 fft_y_async_kernel<16, 16><<<grid_a, h->thr_y, sya, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw, npairs);
             else if (fast && h->y_async)
@@ -885,9 +891,13 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
                               (xp.radix[0] == 16 || xp.radix[0] == 8) && !getenv("MDSF_NO_XFAST");
             const size_t smf = (size_t)2 * gp.n[0] * h->Wx * 8 + (size_t)2 * gp.n[0] * 8;
             const size_t sma = smf + (size_t)xp.radix[0] * h->thr_x * 16;     // + cp.async staging slots
-            const bool three8 = xp.nstages == 3 && xp.radix[0] == 8 && xp.radix[1] == 8 && xp.radix[2] == 8 && h->Wx == 8 && !getenv("MDSF_NO_FFT3");
+            const bool three = xp.nstages == 3 && h->Wx == 8 && !getenv("MDSF_NO_FFT3");
+            const bool three8 = three && xp.radix[0] == 8 && xp.radix[1] == 8 && xp.radix[2] == 8;
+            const bool three768 = three && xp.radix[0] == 16 && xp.radix[1] == 16 && xp.radix[2] == 3;
             if (three8)
                 fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_X, true><<<grid, 256, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], npairs);
+            else if (three768)
+                fft3_pass_kernel<16, 16, 3, 3, 256, 2, true><<<grid, 256, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], npairs);
             else if (fast && h->x_async && xp.radix[0] == 16)
                 fft_x_accum_async_kernel<16, 16><<<grid, h->thr_x, sma, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
             else if (fast && h->x_async)
