@@ -544,6 +544,8 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         h->x_async = getenv("MDSF_X_ASYNC") ? atoi(getenv("MDSF_X_ASYNC")) : 1;     // measured: c2 x pass 1.01 -> 0.92 ms
         CU(cudaFuncSetAttribute(fft3_pass_kernel<16, 16, 3, 3, 256, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft3_pass_kernel<16, 16, 3, 3, 256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 16, 3, 256, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 16, 3, 256, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_Y, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_X, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         CU(cudaFuncSetAttribute(fft_y_async_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -833,6 +835,14 @@ extern "C" int mdsf_host_unregister(void* p) { CU(cudaHostUnregister(p)); return
 
 // ------------------------------------------------------------------------------------------
 // FFT + accumulation of the pair volumes currently in d_vol (nf frames -> (nf+1)/2 pairs).
+// 1024-point axes (8*8*16) through the three-stage register kernels.  Measured on c5 (2 frames per step): y pass
+// 16.0 -> 15.2 ms, x pass 19.8 -> 25.2 ms (one 256-thread CTA per SM against the generic kernel's 512 threads), so
+// the y pass takes them by default and the x pass does not; MDSF_FFT3_1024_Y / MDSF_FFT3_1024_X = 0/1 for A/B runs.
+static bool fft3_1024_enabled(bool xpass) {
+    const char* e = getenv(xpass ? "MDSF_FFT3_1024_X" : "MDSF_FFT3_1024_Y");
+    return e ? atoi(e) != 0 : !xpass;
+}
+
 // `z_done`: the z pass already ran inside the fused splat kernel.
 static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEvent_t* tv = nullptr) {
     const GridParams& gp = h->gp;
@@ -861,10 +871,13 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             const bool three = yp.nstages == 3 && h->Wy == 8 && !getenv("MDSF_NO_FFT3");
             const bool three8 = three && yp.radix[0] == 8 && yp.radix[1] == 8 && yp.radix[2] == 8;          // 512
             const bool three768 = three && yp.radix[0] == 16 && yp.radix[1] == 16 && yp.radix[2] == 3;     // 768
+            const bool three1024 = three && yp.radix[0] == 8 && yp.radix[1] == 8 && yp.radix[2] == 16 && fft3_1024_enabled(false);
             if (three8)
                 fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_Y, false><<<grid, 256, sm, h->s_comp>>>(h->d_vol, nullptr, h->ax[1].d_tw, gp.n[0], gp.n[2], npairs);
             else if (three768)
                 fft3_pass_kernel<16, 16, 3, 3, 256, 2, false><<<grid, 256, sm, h->s_comp>>>(h->d_vol, nullptr, h->ax[1].d_tw, gp.n[0], gp.n[2], npairs);
+            else if (three1024)
+                fft3_pass_kernel<8, 8, 16, 3, 256, 1, false><<<grid, 256, sm, h->s_comp>>>(h->d_vol, nullptr, h->ax[1].d_tw, gp.n[0], gp.n[2], npairs);
             else if (fast && h->y_async && yp.radix[0] == 16)
                 fft_y_async_kernel<16, 16><<<grid_a, h->thr_y, sya, h->s_comp>>>(h->d_vol, h->ax[1].d_tw, gp.n[0], gp.n[2], logw, npairs);
             else if (fast && h->y_async)
@@ -894,10 +907,13 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, bool z_done, cudaEve
             const bool three = xp.nstages == 3 && h->Wx == 8 && !getenv("MDSF_NO_FFT3");
             const bool three8 = three && xp.radix[0] == 8 && xp.radix[1] == 8 && xp.radix[2] == 8;
             const bool three768 = three && xp.radix[0] == 16 && xp.radix[1] == 16 && xp.radix[2] == 3;
+            const bool three1024 = three && xp.radix[0] == 8 && xp.radix[1] == 8 && xp.radix[2] == 16 && fft3_1024_enabled(true);
             if (three8)
                 fft3_pass_kernel<8, 8, 8, 3, 256, MDSF_FFT3_MINB_X, true><<<grid, 256, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], npairs);
             else if (three768)
                 fft3_pass_kernel<16, 16, 3, 3, 256, 2, true><<<grid, 256, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], npairs);
+            else if (three1024)
+                fft3_pass_kernel<8, 8, 16, 3, 256, 1, true><<<grid, 256, smf, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], npairs);
             else if (fast && h->x_async && xp.radix[0] == 16)
                 fft_x_accum_async_kernel<16, 16><<<grid, h->thr_x, sma, h->s_comp>>>(h->d_vol, h->d_P, h->ax[0].d_tw, gp.n[1], gp.n[2], logw, npairs);
             else if (fast && h->x_async)

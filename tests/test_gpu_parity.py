@@ -171,7 +171,7 @@ def test_random_noise_mode_goes_through_gpu_fft(mdsf, tmp_path):
 
 
 @pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 64), (12, 20, 28), (22, 26, 30), (256, 8, 128), (34, 38, 46),
-                                   (512, 8, 16), (8, 512, 24), (768, 8, 16), (8, 768, 8)])      # 512 = 8*8*8, 768 = 16*16*3: three-stage register passes
+                                   (512, 8, 16), (8, 512, 24), (768, 8, 16), (8, 768, 8), (1024, 8, 8), (8, 1024, 8)])      # 512 = 8*8*8, 768 = 16*16*3, 1024 = 8*8*16: three-stage register passes
 def test_native_and_library_fft_agree_with_numpy(mdsf, shape):
     """Power spectrum of arbitrary real volumes: hand-written passes (radix 2..16, 3, 5, 7, 11, 13)
     and the cuFFT path (prime factors > 13) both against np.fft.rfftn."""
