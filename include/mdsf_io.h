@@ -19,6 +19,15 @@ extern "C" {
 int mdsf_io_inflate_pieces(int fd, int64_t n, const int64_t* file_off, const int64_t* comp_len,
                            void* const* dst, const int64_t* raw_len, int threads);
 
+/* Decode the coordinate blocks of `nframes` .xtc frames held in memory (`data`, `nbytes`: the whole file or a window
+ * of it).  coord_off[i] = byte offset of frame i's coordinate block (the atom-count word that follows the 3x3 box of
+ * the frame header: magic 1995, natoms, step, time, box).  Every frame must hold `natoms` atoms; out_nm receives
+ * [nframes][natoms][3] float32 in nm (xtc3 compressed integers / precision, or the plain floats of systems of <= 9
+ * atoms).  Frames are decoded on `threads` threads (<= 0: all cores).  Replaces the .xtc branch of mdtraj's md.load
+ * at reference load_traj.py:94.  Returns 0, or -(i+1) for the first frame that failed (truncated or corrupt). */
+int mdsf_io_xtc_decode_frames(const unsigned char* data, int64_t nbytes, int64_t nframes, const int64_t* coord_off,
+                              int natoms, float* out_nm, int threads);
+
 int mdsf_io_abi_version(void);
 
 #ifdef __cplusplus

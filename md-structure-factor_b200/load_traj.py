@@ -3,8 +3,8 @@
 ``load_gro`` (:11-20) and ``process_gro_mdtraj`` (:90-111) keep their signatures and the
 ``out_<name>_traj.npz`` layout (keys dims, coords, name, mass, typ -- typ holds the atom NAMES,
 reference load_traj.py:110).  With mdtraj installed every format goes through it, as in the reference;
-without it, .gro (one or many frames) and .trr are parsed here directly, .xtc still
-needs mdtraj.
+without it, .gro (one or many frames), .trr and .xtc are decoded here directly (the xtc3
+coordinate blocks by libmdsf_io on all host cores).
 """
 import ctypes
 import os
@@ -15,7 +15,7 @@ import npz_writer
 
 TRAJ_PIECE = 1 << 20      # raw bytes per independently deflated piece of a traj npz member (about one c2 frame)
 IO_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmdsf_io.so")
-IO_EXPORTS = ["mdsf_io_inflate_pieces", "mdsf_io_abi_version"]
+IO_EXPORTS = ["mdsf_io_inflate_pieces", "mdsf_io_xtc_decode_frames", "mdsf_io_abi_version"]
 _io = None
 
 
@@ -30,6 +30,9 @@ def _io_lib():
         lib.mdsf_io_inflate_pieces.restype = ctypes.c_int
         lib.mdsf_io_inflate_pieces.argtypes = [ctypes.c_int, ctypes.c_int64, p64, p64, ctypes.POINTER(ctypes.c_void_p), p64, ctypes.c_int]
         lib.mdsf_io_abi_version.restype = ctypes.c_int
+        lib.mdsf_io_xtc_decode_frames.restype = ctypes.c_int
+        lib.mdsf_io_xtc_decode_frames.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, p64, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_int]
         _io = lib
     return _io
 
@@ -166,6 +169,192 @@ def write_trr(path, coords_nm, box_nm, times=None, double=False, velocities=None
                 fh.write(np.asarray(velocities[it]).astype(rt).tobytes())
 
 
+XTC_MAGIC = 1995
+XTC_MAGICINTS = [0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406,
+                 512, 645, 812, 1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642,
+                 26007, 32768, 41285, 52015, 65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127,
+                 524287, 660561, 832255, 1048576, 1321122, 1664510, 2097152, 2642245, 3329021, 4194304, 5284491,
+                 6658042, 8388607, 10568983, 13316085, 16777216]
+XTC_FIRSTIDX = 9
+
+
+def read_xtc(path, threads=0):
+    """GROMACS .xtc reader: (coords in Angstrom float32 (T, Na, 3), box lengths in Angstrom float32 (T, 3), times ps).
+
+    Frame layout (XDR, big-endian): magic 1995, natoms, step, time f32, box 3x3 f32 (nm), then the coordinate block:
+    natoms again, and either natoms*3 plain floats (natoms <= 9) or precision f32, minint[3], maxint[3], smallidx,
+    byte count and the xtc3 bit stream padded to four bytes.  The headers are walked here; the coordinate blocks are
+    decoded by libmdsf_io (mdsf_io_xtc_decode_frames, include/mdsf_io.h), one frame per host thread.
+    PARITY UNPINNED: the reference decodes .xtc through mdtraj (load_traj.py:94), which is not installed here, and
+    ships no .xtc fixture; decoder and `write_xtc` are separate restatements of the published scheme checked against
+    each other (tests/test_host_logic.py)."""
+    data = np.fromfile(path, dtype=np.uint8)
+    n, pos = data.size, 0
+    be32, bf32 = np.dtype(">i4"), np.dtype(">f4")
+    offs, boxes, times = [], [], []
+    natoms = None
+    while pos < n:
+        if pos + 56 > n:
+            raise ValueError("%s: truncated frame header at byte %d" % (path, pos))
+        magic, na, step = (int(v) for v in np.frombuffer(data, be32, 3, pos))
+        if magic != XTC_MAGIC:
+            raise ValueError("%s: not an .xtc frame at byte %d (magic %d)" % (path, pos, magic))
+        if natoms is None:
+            natoms = na
+        elif na != natoms:
+            raise ValueError("%s: frame at step %d has %d atoms, the first one %d" % (path, step, na, natoms))
+        times.append(float(np.frombuffer(data, bf32, 1, pos + 12)[0]))
+        bvec = np.frombuffer(data, bf32, 9, pos + 16).reshape(3, 3).astype(np.float64)
+        boxes.append(np.sqrt((bvec * bvec).sum(axis=1)))
+        pos += 52
+        offs.append(pos)
+        if na <= 9:
+            pos += 4 + 12 * na
+        else:
+            if pos + 40 > n:
+                raise ValueError("%s: truncated coordinate header at step %d" % (path, step))
+            nbytes = int(np.frombuffer(data, be32, 1, pos + 36)[0])
+            if nbytes < 0:
+                raise ValueError("%s: negative byte count at step %d" % (path, step))
+            pos += 40 + (nbytes + 3) // 4 * 4
+        if pos > n:
+            raise ValueError("%s: truncated frame at step %d" % (path, step))
+    if not offs:
+        raise ValueError("%s holds no frame" % path)
+    out = np.empty((len(offs), natoms, 3), dtype=np.float32)
+    off = np.asarray(offs, dtype=np.int64)
+    rc = _io_lib().mdsf_io_xtc_decode_frames(data.ctypes.data, n, len(offs), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                             natoms, out.ctypes.data, threads)
+    if rc != 0:
+        raise ValueError("%s: corrupt coordinate block in frame %d" % (path, -rc - 1))
+    return out * np.float32(10), (np.stack(boxes) * 10).astype(np.float32), np.array(times)
+
+
+class _BitWriter:
+    def __init__(self):
+        self.acc, self.nacc, self.out = 0, 0, bytearray()
+
+    def bits(self, nbits, value):                 # most significant bit first
+        self.acc = (self.acc << nbits) | (int(value) & ((1 << nbits) - 1))
+        self.nacc += nbits
+        while self.nacc >= 8:
+            self.nacc -= 8
+            self.out.append((self.acc >> self.nacc) & 0xff)
+        self.acc &= (1 << self.nacc) - 1
+
+    def ints3(self, nbits, sizes, vals):          # ((a * s1) + b) * s2 + c, low byte first
+        v = (int(vals[0]) * sizes[1] + int(vals[1])) * sizes[2] + int(vals[2])
+        assert 0 <= v < (1 << nbits)
+        while nbits > 8:
+            self.bits(8, v & 0xff)
+            v >>= 8
+            nbits -= 8
+        self.bits(nbits, v)
+
+    def done(self):
+        if self.nacc:
+            self.out.append((self.acc << (8 - self.nacc)) & 0xff)
+        return bytes(self.out)
+
+
+def _xtc_pack(ints, precision):
+    """xtc3 coordinate block of one frame (ints (Na, 3) = round(x * precision), Na > 9): the encoder side of the
+    scheme read_xtc decodes -- bounding-box coded group leaders, runs of up to eight small-offset atoms with the
+    leader swapped behind the first of them, small range following the nearest-neighbour distances."""
+    M = XTC_MAGICINTS
+    size = len(ints)
+    c = [list(map(int, row)) for row in ints]
+    minint = [min(r[d] for r in c) for d in range(3)]
+    maxint = [max(r[d] for r in c) for d in range(3)]
+    mindiff = min(sum(abs(c[i][d] - c[i - 1][d]) for d in range(3)) for i in range(1, size))
+    sizeint = [maxint[d] - minint[d] + 1 for d in range(3)]
+    if max(sizeint) > 0xffffff:
+        bitsizeint, bitsize = [s.bit_length() for s in sizeint], 0
+    else:
+        bitsize = (sizeint[0] * sizeint[1] * sizeint[2]).bit_length()
+    smallidx = XTC_FIRSTIDX
+    while smallidx < len(M) - 1 and M[smallidx] < mindiff:
+        smallidx += 1
+    smallidx0 = smallidx
+    maxidx = min(len(M) - 1, smallidx + 8)
+    minidx = maxidx - 8
+    smaller = M[max(XTC_FIRSTIDX, smallidx - 1)] // 2
+    smallnum = M[smallidx] // 2
+    larger = M[maxidx] // 2
+    bw = _BitWriter()
+    i, prevrun, prev = 0, -1, [0, 0, 0]
+    while i < size:
+        is_small = False
+        if smallidx < maxidx and i >= 1 and all(abs(c[i][d] - prev[d]) < larger for d in range(3)):
+            is_smaller = 1
+        elif smallidx > minidx:
+            is_smaller = -1
+        else:
+            is_smaller = 0
+        if i + 1 < size and all(abs(c[i][d] - c[i + 1][d]) < smallnum for d in range(3)):
+            c[i], c[i + 1] = c[i + 1], c[i]        # water: the oxygen goes behind its first hydrogen
+            is_small = True
+        lead = [c[i][d] - minint[d] for d in range(3)]
+        if bitsize == 0:
+            for d in range(3):
+                bw.bits(bitsizeint[d], lead[d])
+        else:
+            bw.ints3(bitsize, sizeint, lead)
+        prev = c[i]
+        i += 1
+        run = []
+        if not is_small and is_smaller == -1:
+            is_smaller = 0
+        while is_small and len(run) < 8:
+            if is_smaller == -1 and sum((c[i][d] - prev[d]) ** 2 for d in range(3)) >= smaller * smaller:
+                is_smaller = 0
+            run.append([c[i][d] - prev[d] + smallnum for d in range(3)])
+            prev = c[i]
+            i += 1
+            is_small = i < size and all(abs(c[i][d] - prev[d]) < smallnum for d in range(3))
+        nrun = 3 * len(run)
+        if nrun != prevrun or is_smaller != 0:
+            prevrun = nrun
+            bw.bits(1, 1)
+            bw.bits(5, nrun + is_smaller + 1)
+        else:
+            bw.bits(1, 0)
+        for r in run:
+            bw.ints3(smallidx, [M[smallidx]] * 3, r)
+        if is_smaller != 0:
+            smallidx += is_smaller
+            if is_smaller < 0:
+                smallnum = smaller
+                smaller = M[smallidx - 1] // 2
+            else:
+                smaller = smallnum
+                smallnum = M[smallidx] // 2
+    payload = bw.done()
+    head = np.array([precision], dtype=">f4").tobytes() + np.array(minint + maxint + [smallidx0, len(payload)], dtype=">i4").tobytes()
+    return head + payload + b"\0" * (-len(payload) % 4)
+
+
+def write_xtc(path, coords_nm, box_nm, times=None, precision=1000.0):
+    """.xtc writer (tests, synthetic trajectories): coords (T, Na, 3) and box vectors (T, 3, 3) or lengths (T, 3) in nm."""
+    coords_nm = np.asarray(coords_nm, dtype=np.float32)
+    T, natoms = coords_nm.shape[:2]
+    box_nm = np.asarray(box_nm, dtype=np.float64)
+    if box_nm.ndim == 2:
+        box_nm = np.stack([np.diag(b) for b in box_nm])
+    with open(path, "wb") as fh:
+        for it in range(T):
+            fh.write(np.array([XTC_MAGIC, natoms, it], dtype=">i4").tobytes())
+            fh.write(np.array([0.0 if times is None else times[it]], dtype=">f4").tobytes())
+            fh.write(box_nm[it].astype(">f4").tobytes())
+            fh.write(np.array([natoms], dtype=">i4").tobytes())
+            if natoms <= 9:
+                fh.write(coords_nm[it].astype(">f4").tobytes())
+            else:
+                x = coords_nm[it].astype(np.float64) * np.float32(precision)
+                ints = np.where(x >= 0, np.floor(x + 0.5), np.ceil(x - 0.5)).astype(np.int64)
+                fh.write(_xtc_pack(ints, precision))
+
+
 def save_traj_npz(output_filename, dims, coords, name, mass=None):
     """Write the traj npz exactly as the reference does (load_traj.py:110): typ = atom names."""
     name = np.asarray(name)
@@ -188,8 +377,13 @@ def process_gro_mdtraj(topology_filename, trajectory_filename, output_filename):
             xyz, box, _ = read_trr(trajectory_filename)
             if xyz.shape[1] != len(names):
                 raise ValueError("%s has %d atoms, topology %s has %d" % (trajectory_filename, xyz.shape[1], topology_filename, len(names)))
+        elif trajectory_filename.endswith(".xtc"):
+            names = load_gro(topology_filename)
+            xyz, box, _ = read_xtc(trajectory_filename)
+            if xyz.shape[1] != len(names):
+                raise ValueError("%s has %d atoms, topology %s has %d" % (trajectory_filename, xyz.shape[1], topology_filename, len(names)))
         else:
-            raise ImportError("mdtraj is needed to decode %s (.gro and .trr are parsed natively)" % trajectory_filename) from exc
+            raise ImportError("mdtraj is needed to decode %s (.gro, .trr and .xtc are parsed natively)" % trajectory_filename) from exc
         print("saving ", output_filename)
         save_traj_npz(output_filename, box, xyz, names)
         print('done saving')

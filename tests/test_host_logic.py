@@ -198,7 +198,7 @@ def test_io_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(load_traj.IO_EXPORTS) == declared
-    assert lib.mdsf_io_abi_version() == 1
+    assert lib.mdsf_io_abi_version() == 2
 
 
 def test_indexed_traj_npz_is_inflated_in_parallel_and_stays_a_numpy_container(tmp_path):
@@ -288,3 +288,75 @@ def test_native_trr_and_multiframe_gro_readers(tmp_path):
     names, c, b = lt.read_gro_frames(str(multi))
     assert c.shape == (3, na, 3) and b.shape == (3, 3) and names == ["OW1", "HW2", "HW3"] * 2
     assert np.array_equal(c[0], c[2]) and np.allclose(b[1], [18.206, 18.206, 17.5])
+
+
+def _xtc_expected(x_nm, precision):
+    """what an xtc3 round trip does to float32 nm coordinates: round(x * precision) / precision in float32, then Angstrom"""
+    v = x_nm.astype(np.float64) * np.float32(precision)
+    q = np.where(v >= 0, np.floor(v + 0.5), np.ceil(v - 0.5)).astype(np.int32)
+    return q.astype(np.float32) * (np.float32(1) / np.float32(precision)) * np.float32(10)
+
+
+def test_native_xtc_reader_round_trips_every_coding_mode(tmp_path):
+    """load_traj.read_xtc (headers in Python, xtc3 blocks in libmdsf_io on host threads) against load_traj.write_xtc, a
+    separate restatement of the encoder: water (runs of small offsets with the leader swap), a random walk (long runs,
+    small-range adaptation both ways), a gas (no runs), a box wider than 24 bits of precision units (plain bit fields
+    instead of the mixed-radix triple), negative coordinates, <= 9 atoms (plain floats).  Bit-exact on the integers,
+    i.e. on the float32 output.  (Parity unpinned: no mdtraj / .xtc fixture here, see the reader's docstring.)"""
+    import load_traj as lt
+    rng = np.random.default_rng(11)
+    no = 300
+    O = rng.uniform(0, 3, size=(3, no, 3))
+    water = np.stack([O, O + rng.normal(0, 0.05, O.shape), O + rng.normal(0, 0.05, O.shape)], axis=2).reshape(3, no * 3, 3)
+    cases = {
+        "water": (water.astype(np.float32), 1000.0),
+        "walk": ((np.cumsum(rng.normal(0, 0.03, size=(2, 1500, 3)), axis=1) + 5).astype(np.float32), 1000.0),
+        "gas": (rng.uniform(-2, 12, size=(2, 700, 3)).astype(np.float32), 1000.0),
+        "wide": (rng.uniform(0, 30, size=(2, 40, 3)).astype(np.float32), 1e6),
+        "coarse": (rng.uniform(0, 4, size=(2, 64, 3)).astype(np.float32), 100.0),
+        "ten": (rng.uniform(0, 2, size=(4, 10, 3)).astype(np.float32), 1000.0),
+    }
+    for tag, (x, prec) in cases.items():
+        T = x.shape[0]
+        p = str(tmp_path / (tag + ".xtc"))
+        box = np.array([[3.0, 3.0 * (1 + 0.01 * t), 2.5] for t in range(T)])
+        lt.write_xtc(p, x, box, times=np.arange(T) * 0.5, precision=prec)
+        for threads in (1, 0):
+            c, b, t = lt.read_xtc(p, threads=threads)
+            assert c.dtype == np.float32 and c.shape == x.shape and b.dtype == np.float32, tag
+            assert np.array_equal(c, _xtc_expected(x, prec)), tag
+            assert np.allclose(b, box * 10, rtol=1e-6) and np.array_equal(t, np.arange(T) * 0.5), tag
+    # water at precision 1000 packs to 4-5 bytes per atom, as the scheme is known to (a plain-float frame takes 12)
+    assert 3.5 < os.path.getsize(str(tmp_path / "water.xtc")) / (3 * no * 3) < 5.5
+    # <= 9 atoms: plain floats, bit-exact
+    tiny = rng.uniform(0, 3, size=(2, 5, 3)).astype(np.float32)
+    lt.write_xtc(str(tmp_path / "tiny.xtc"), tiny, np.full((2, 3), 3.0))
+    assert np.array_equal(lt.read_xtc(str(tmp_path / "tiny.xtc"))[0], tiny * np.float32(10))
+    raw = open(str(tmp_path / "water.xtc"), "rb").read()
+    assert raw[:4] == b"\x00\x00\x07\xcb" and raw[4:8] == (3 * no).to_bytes(4, "big")
+    # truncated file, corrupt header fields and a payload cut short are errors, not garbage coordinates
+    for name, blob in (("cut.xtc", raw[:len(raw) // 2]), ("magic.xtc", b"\x00\x00\x07\xc9" + raw[4:])):
+        open(str(tmp_path / name), "wb").write(blob)
+        with pytest.raises(ValueError):
+            lt.read_xtc(str(tmp_path / name))
+    bad = bytearray(raw)
+    bad[52 + 32:52 + 36] = (200).to_bytes(4, "big")          # smallidx outside the table
+    open(str(tmp_path / "idx.xtc"), "wb").write(bytes(bad))
+    with pytest.raises(ValueError):
+        lt.read_xtc(str(tmp_path / "idx.xtc"))
+    # topology .gro + .xtc -> traj npz without mdtraj (reference load_traj.py:90-111)
+    x = cases["ten"][0]
+    gro = tmp_path / "ten.gro"
+    names = ["OW1", "HW2", "HW3", "OW1", "HW2", "HW3", "NA", "C1", "C2", "N"]
+    rows = ["    1MOL  %5s%5d%8.3f%8.3f%8.3f\n" % (nm, i + 1, *x[0, i]) for i, nm in enumerate(names)]
+    gro.write_text("ten atoms\n   10\n" + "".join(rows) + "   3.00000   3.00000   2.50000\n")
+    try:
+        import mdtraj  # noqa: F401
+    except ImportError:
+        lt.process_gro_mdtraj(str(gro), str(tmp_path / "ten.xtc"), str(tmp_path / "out_ten_traj"))
+        z = np.load(str(tmp_path / "out_ten_traj.npz"))
+        assert list(z["typ"]) == names and z["dims"].shape == (4, 3)
+        assert np.array_equal(z["coords"], _xtc_expected(x, 1000.0))
+        with pytest.raises(ValueError):          # atom count of the topology must match
+            gro.write_text("nine atoms\n    9\n" + "".join(rows[:9]) + "   3.00000   3.00000   2.50000\n")
+            lt.process_gro_mdtraj(str(gro), str(tmp_path / "ten.xtc"), str(tmp_path / "out_bad_traj"))
