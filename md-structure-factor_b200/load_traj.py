@@ -178,17 +178,9 @@ XTC_MAGICINTS = [0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 6
 XTC_FIRSTIDX = 9
 
 
-def read_xtc(path, threads=0):
-    """GROMACS .xtc reader: (coords in Angstrom float32 (T, Na, 3), box lengths in Angstrom float32 (T, 3), times ps).
-
-    Frame layout (XDR, big-endian): magic 1995, natoms, step, time f32, box 3x3 f32 (nm), then the coordinate block:
-    natoms again, and either natoms*3 plain floats (natoms <= 9) or precision f32, minint[3], maxint[3], smallidx,
-    byte count and the xtc3 bit stream padded to four bytes.  The headers are walked here; the coordinate blocks are
-    decoded by libmdsf_io (mdsf_io_xtc_decode_frames, include/mdsf_io.h), one frame per host thread.
-    PARITY UNPINNED: the reference decodes .xtc through mdtraj (load_traj.py:94), which is not installed here, and
-    ships no .xtc fixture; decoder and `write_xtc` are separate restatements of the published scheme checked against
-    each other (tests/test_host_logic.py)."""
-    data = np.fromfile(path, dtype=np.uint8)
+def _scan_xtc(data, path):
+    """Walk the frame headers of an .xtc image: (coordinate-block offsets int64 (T,), natoms, box lengths in Angstrom
+    float32 (T, 3), times)."""
     n, pos = data.size, 0
     be32, bf32 = np.dtype(">i4"), np.dtype(">f4")
     offs, boxes, times = [], [], []
@@ -221,13 +213,32 @@ def read_xtc(path, threads=0):
             raise ValueError("%s: truncated frame at step %d" % (path, step))
     if not offs:
         raise ValueError("%s holds no frame" % path)
-    out = np.empty((len(offs), natoms, 3), dtype=np.float32)
-    off = np.asarray(offs, dtype=np.int64)
-    rc = _io_lib().mdsf_io_xtc_decode_frames(data.ctypes.data, n, len(offs), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
-                                             natoms, out.ctypes.data, threads)
+    return np.asarray(offs, dtype=np.int64), natoms, (np.stack(boxes) * 10).astype(np.float32), np.array(times)
+
+
+def _decode_xtc(data, off, natoms, out, threads, path, first):
+    """xtc3 blocks at ``off`` -> ``out`` (k, natoms, 3) float32 nm, through libmdsf_io."""
+    rc = _io_lib().mdsf_io_xtc_decode_frames(data.ctypes.data, data.size, len(off), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                             natoms, out.ctypes.data, int(threads or 0))
     if rc != 0:
-        raise ValueError("%s: corrupt coordinate block in frame %d" % (path, -rc - 1))
-    return out * np.float32(10), (np.stack(boxes) * 10).astype(np.float32), np.array(times)
+        raise ValueError("%s: corrupt coordinate block in frame %d" % (path, first - rc - 1))
+
+
+def read_xtc(path, threads=0):
+    """GROMACS .xtc reader: (coords in Angstrom float32 (T, Na, 3), box lengths in Angstrom float32 (T, 3), times ps).
+
+    Frame layout (XDR, big-endian): magic 1995, natoms, step, time f32, box 3x3 f32 (nm), then the coordinate block:
+    natoms again, and either natoms*3 plain floats (natoms <= 9) or precision f32, minint[3], maxint[3], smallidx,
+    byte count and the xtc3 bit stream padded to four bytes.  The headers are walked here; the coordinate blocks are
+    decoded by libmdsf_io (mdsf_io_xtc_decode_frames, include/mdsf_io.h), one frame per host thread.
+    PARITY UNPINNED: the reference decodes .xtc through mdtraj (load_traj.py:94), which is not installed here, and
+    ships no .xtc fixture; decoder and `write_xtc` are separate restatements of the published scheme checked against
+    each other (tests/test_host_logic.py)."""
+    data = np.fromfile(path, dtype=np.uint8)
+    off, natoms, box, times = _scan_xtc(data, path)
+    out = np.empty((len(off), natoms, 3), dtype=np.float32)
+    _decode_xtc(data, off, natoms, out, threads, path, 0)
+    return out * np.float32(10), box, times
 
 
 class _BitWriter:
@@ -396,6 +407,48 @@ def process_gro_mdtraj(topology_filename, trajectory_filename, output_filename):
     print("saving ", output_filename)
     save_traj_npz(output_filename, dims, coords, name, mass)
     print('done saving')
+
+
+class XtcFrameStream:
+    """Frames of an .xtc file as a frame source for ``dens.compute_sf_stream`` (same interface as NpzFrameStream:
+    ``shape``, ``dtype``, ``read_into``, ``skip``), i.e. trajectory -> pinned chunk buffers without the intermediate
+    traj npz the reference writes and re-reads (load_traj.py:110, main_gromacs.py:200-202).  The frame headers are
+    walked once at open time, which also yields ``dims`` (T, 3) float32 Angstrom -- every box is needed before frame 0
+    (dens.py:52) -- and ``times``; ``read_into`` decodes the next frames' xtc3 blocks on all host cores (libmdsf_io)
+    straight into the caller's buffer and converts nm -> Angstrom in place (float32 * 10, the reference's
+    ``t.xyz * 10``, load_traj.py:98).  The file is memory-mapped, frames are random access."""
+
+    def __init__(self, path, threads=None):
+        self.path = path
+        self._data = np.memmap(path, dtype=np.uint8, mode="r")
+        self._off, natoms, self.dims, self.times = _scan_xtc(self._data, path)
+        self.shape, self.dtype = (len(self._off), natoms, 3), np.dtype(np.float32)
+        self._threads = int(threads or 0)
+        self.position = 0
+
+    def read_into(self, buf):
+        if buf.dtype != self.dtype or buf.shape[1:] != self.shape[1:] or not buf.flags.c_contiguous:
+            raise ValueError("chunk buffer must be C-contiguous float32 of shape (k, %d, 3)" % self.shape[1])
+        want = min(buf.shape[0], self.shape[0] - self.position)
+        if want <= 0:
+            return 0
+        off = np.ascontiguousarray(self._off[self.position:self.position + want])
+        _decode_xtc(self._data, off, self.shape[1], buf[:want], self._threads, self.path, self.position)
+        np.multiply(buf[:want], np.float32(10), out=buf[:want])
+        self.position += want
+        return want
+
+    def skip(self, nframes):
+        self.position += max(min(int(nframes), self.shape[0] - self.position), 0)
+
+    def close(self):
+        self._data = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class NpzFrameStream:

@@ -420,6 +420,31 @@ def test_streamed_trajectory_equals_in_memory_compute_sf(mdsf, tmp_path):
     assert rel <= 1e-9 and norm <= 1e-13, (rel, norm)
 
 
+def test_xtc_frame_source_equals_in_memory_compute_sf(mdsf, tmp_path):
+    """load_traj.XtcFrameStream (.xtc decoded by libmdsf_io straight into the pinned chunk buffers) as the frame source of
+    dens.compute_sf_stream writes the same sf npz as compute_sf on the coordinates read_xtc returns."""
+    import load_traj
+    c = load_case("mono_f32")
+    theta = 120.0 * np.pi / 180.0
+    box_nm = np.asarray(c["dims"], dtype=np.float64) / 10
+    path = str(tmp_path / "x.xtc")
+    load_traj.write_xtc(path, np.asarray(c["coords"], dtype=np.float32) / np.float32(10), box_nm)
+    T, dims, _ = load_traj.read_xtc(path)
+    T[..., 1] = T[..., 1] / np.sin(theta)
+    T[..., 0] = T[..., 0] - T[..., 1] * np.cos(theta)
+    dens = mdsf.dens
+    dens.compute_sf(T[1:3], dims[1:3], c["typ"], str(tmp_path / "mem"), c["rad"], c["ucell"], c["sres"])
+    a = np.load(str(tmp_path / "mem.npz"))
+    with load_traj.XtcFrameStream(path) as fs:
+        dens.compute_sf_stream(fs, fs.dims, c["typ"], str(tmp_path / "str"), c["rad"], c["ucell"], c["sres"],
+                               first_frame=1, end_frame=3, monoclinic_theta=theta, chunk_frames=2)
+    assert dens.LAST_RUN["streamed_chunks"] == 1 and dens.LAST_RUN["frames"] == 2
+    b = np.load(str(tmp_path / "str.npz"))
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+
+
 def test_cli_trajectory_mode_gro_to_sf_npz(mdsf, tmp_path, monkeypatch):
     """main_gromacs.py trajectory mode end to end (reference main_gromacs.py:188-212): topology/trajectory files ->
     out_<name>_traj.npz (load_traj.process_gro_mdtraj; .gro parsed natively) -> monoclinic transform -> streamed

@@ -326,6 +326,16 @@ def test_native_xtc_reader_round_trips_every_coding_mode(tmp_path):
             assert c.dtype == np.float32 and c.shape == x.shape and b.dtype == np.float32, tag
             assert np.array_equal(c, _xtc_expected(x, prec)), tag
             assert np.allclose(b, box * 10, rtol=1e-6) and np.array_equal(t, np.arange(T) * 0.5), tag
+    # the same files as a frame source for dens.compute_sf_stream: chunked reads, skip, dims up front, same bits
+    full, dims, _ = lt.read_xtc(str(tmp_path / "water.xtc"))
+    with lt.XtcFrameStream(str(tmp_path / "water.xtc")) as fs:
+        assert fs.shape == full.shape and fs.dtype == np.float32 and np.array_equal(fs.dims, dims) and fs.dims.dtype == np.float32
+        buf = np.zeros((2,) + full.shape[1:], dtype=np.float32)
+        fs.skip(1)
+        assert fs.read_into(buf) == 2 and np.array_equal(buf, full[1:3])
+        assert fs.read_into(buf) == 0
+        with pytest.raises(ValueError):
+            fs.read_into(np.zeros((2,) + full.shape[1:], dtype=np.float64))
     # water at precision 1000 packs to 4-5 bytes per atom, as the scheme is known to (a plain-float frame takes 12)
     assert 3.5 < os.path.getsize(str(tmp_path / "water.xtc")) / (3 * no * 3) < 5.5
     # <= 9 atoms: plain floats, bit-exact
