@@ -95,25 +95,49 @@ inline uint32_t be32(const unsigned char* p) { return ((uint32_t)p[0] << 24) | (
 inline float be_f32(const unsigned char* p) { const uint32_t u = be32(p); float f; memcpy(&f, &u, 4); return f; }
 
 struct BitReader {
-    const unsigned char* p; int64_t n, cnt = 0; unsigned lastbits = 0, lastbyte = 0; bool over = false;
-    unsigned next() { if (cnt < n) return p[cnt++]; over = true; return 0; }
-    unsigned bits(int nbits) {                            // most significant bit first
-        const unsigned mask = nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1);
-        unsigned num = 0;
-        while (nbits >= 8) {
-            lastbyte = (lastbyte << 8) | next();
-            num |= (lastbyte >> lastbits) << (nbits - 8);
-            nbits -= 8;
+    const unsigned char* p; int64_t n; int64_t pos = 0; bool over = false;     // pos in bits, most significant bit first
+    unsigned bits(int nbits) {                            // 1 <= nbits <= 32
+        const int64_t byte = pos >> 3;
+        const int sh = (int)(pos & 7);
+        pos += nbits;
+        uint64_t w;
+        if (byte + 8 <= n) {
+            memcpy(&w, p + byte, 8);
+            w = __builtin_bswap64(w);
+        } else {                                          // tail of the stream: bytes past the end read as zero
+            w = 0;
+            for (int k = 0; k < 8; ++k) w = (w << 8) | (byte + k < n ? p[byte + k] : 0u);
+            if (pos > n * 8) over = true;
         }
-        if (nbits > 0) {
-            if ((int)lastbits < nbits) { lastbits += 8; lastbyte = (lastbyte << 8) | next(); }
-            lastbits -= nbits;
-            num |= (lastbyte >> lastbits) & ((1u << nbits) - 1);
-        }
-        return num & mask;
+        return (unsigned)((w << sh) >> (64 - nbits));
     }
     // three integers packed as ((a * s1) + b) * s2 + c, the big number stored low byte first in `nbits` bits
     void ints3(int nbits, const unsigned* sizes, int* out) {
+        if (nbits <= 64) {
+            uint64_t v = 0;
+            int shift = 0;
+            while (nbits > 8) { v |= (uint64_t)bits(8) << shift; shift += 8; nbits -= 8; }
+            if (nbits > 0) v |= (uint64_t)bits(nbits) << shift;
+            if (v <= 0xffffffffu) {                       // the usual small-offset triple: 32-bit divides
+                const uint32_t w = (uint32_t)v, q2 = w / sizes[2], q1 = q2 / sizes[1];
+                out[2] = (int)(w - q2 * sizes[2]);
+                out[1] = (int)(q2 - q1 * sizes[1]);
+                out[0] = (int)q1;
+                return;
+            }
+            const uint64_t q2 = v / sizes[2];
+            out[2] = (int)(uint32_t)(v - q2 * sizes[2]);
+            if (q2 <= 0xffffffffu) {
+                const uint32_t w = (uint32_t)q2, q1 = w / sizes[1];
+                out[1] = (int)(w - q1 * sizes[1]);
+                out[0] = (int)q1;
+                return;
+            }
+            const uint64_t q1 = q2 / sizes[1];
+            out[1] = (int)(uint32_t)(q2 - q1 * sizes[1]);
+            out[0] = (int)(uint32_t)q1;
+            return;
+        }
         unsigned __int128 v = 0;
         int shift = 0;
         while (nbits > 8) { v |= (unsigned __int128)bits(8) << shift; shift += 8; nbits -= 8; }
