@@ -170,8 +170,9 @@ bool xtc_decode_block(const unsigned char* p, int64_t avail, int natoms, float* 
     unsigned sizeint[3], sizesmall[3];
     int bitsizeint[3] = {0, 0, 0}, bitsize;
     for (int d = 0; d < 3; ++d) {
-        if (maxint[d] < minint[d]) return false;
-        sizeint[d] = (unsigned)((int64_t)maxint[d] - minint[d] + 1);
+        const int64_t extent = (int64_t)maxint[d] - minint[d] + 1;
+        if (extent < 1 || extent > 0x7fffffff) return false;
+        sizeint[d] = (unsigned)extent;
     }
     if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffffu) {
         for (int d = 0; d < 3; ++d) bitsizeint[d] = bit_length(sizeint[d]);

@@ -191,6 +191,8 @@ def _scan_xtc(data, path):
         magic, na, step = (int(v) for v in np.frombuffer(data, be32, 3, pos))
         if magic != XTC_MAGIC:
             raise ValueError("%s: not an .xtc frame at byte %d (magic %d)" % (path, pos, magic))
+        if na <= 0:
+            raise ValueError("%s: frame at step %d declares %d atoms" % (path, step, na))
         if natoms is None:
             natoms = na
         elif na != natoms:
@@ -206,8 +208,8 @@ def _scan_xtc(data, path):
             if pos + 40 > n:
                 raise ValueError("%s: truncated coordinate header at step %d" % (path, step))
             nbytes = int(np.frombuffer(data, be32, 1, pos + 36)[0])
-            if nbytes < 0:
-                raise ValueError("%s: negative byte count at step %d" % (path, step))
+            if nbytes < 0 or na > 8 * nbytes:          # every atom takes more than one bit of the stream
+                raise ValueError("%s: byte count %d cannot hold %d atoms at step %d" % (path, nbytes, na, step))
             pos += 40 + (nbytes + 3) // 4 * 4
         if pos > n:
             raise ValueError("%s: truncated frame at step %d" % (path, step))

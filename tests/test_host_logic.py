@@ -354,6 +354,19 @@ def test_native_xtc_reader_round_trips_every_coding_mode(tmp_path):
     open(str(tmp_path / "idx.xtc"), "wb").write(bytes(bad))
     with pytest.raises(ValueError):
         lt.read_xtc(str(tmp_path / "idx.xtc"))
+    # random damage anywhere in the file: an error or some coordinates, never a crash or an out-of-bounds write
+    frng = np.random.default_rng(5)
+    for trial in range(150):
+        blob = bytearray(raw)
+        for _ in range(int(frng.integers(1, 4))):
+            at = int(frng.integers(0, 200)) if trial % 3 == 0 else int(frng.integers(0, len(blob)))
+            blob[at] = int(frng.integers(0, 256))
+        open(str(tmp_path / "fuzz.xtc"), "wb").write(bytes(blob))
+        try:
+            got = lt.read_xtc(str(tmp_path / "fuzz.xtc"), threads=1)[0]
+            assert got.shape[1:] == (3 * no, 3)
+        except ValueError:
+            pass
     # topology .gro + .xtc -> traj npz without mdtraj (reference load_traj.py:90-111)
     x = cases["ten"][0]
     gro = tmp_path / "ten.gro"
