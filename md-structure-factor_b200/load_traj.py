@@ -3,7 +3,7 @@
 ``load_gro`` (:11-20) and ``process_gro_mdtraj`` (:90-111) keep their signatures and the
 ``out_<name>_traj.npz`` layout (keys dims, coords, name, mass, typ -- typ holds the atom NAMES,
 reference load_traj.py:110).  With mdtraj installed every format goes through it, as in the reference;
-without it, .gro (one or many frames), .trr and .xtc are decoded here directly (the xtc3
+without it, .gro (one or many frames), .trr, .xtc and NAMD .psf/.dcd are decoded here directly (the xtc3
 coordinate blocks by libmdsf_io on all host cores).
 """
 import ctypes
@@ -167,6 +167,125 @@ def write_trr(path, coords_nm, box_nm, times=None, double=False, velocities=None
             fh.write(head + sizes + tl + box_nm[it].astype(rt).tobytes() + coords_nm[it].astype(rt).tobytes())
             if velocities is not None:
                 fh.write(np.asarray(velocities[it]).astype(rt).tobytes())
+
+
+def load_psf(psf):
+    """(atom names, masses) from the !NATOM section of a CHARMM/NAMD/X-PLOR .psf topology: one line per atom,
+    ``id segment resid resname NAME type charge mass ...`` (whitespace separated, standard or EXT widths).  The NAMD
+    route of the reference CLI (main_gromacs.py:95-96: foo.psf + foo.dcd) reads it through mdtraj."""
+    with open(psf) as handle:
+        rows = handle.readlines()
+    for i, row in enumerate(rows):
+        if "!NATOM" in row:
+            natoms = int(row.split()[0])
+            body = rows[i + 1:i + 1 + natoms]
+            if len(body) != natoms:
+                raise ValueError("%s: !NATOM announces %d atoms, %d lines follow" % (psf, natoms, len(body)))
+            cols = [r.split() for r in body]
+            if any(len(c) < 8 for c in cols):
+                raise ValueError("%s: atom line with fewer than 8 fields" % psf)
+            return [c[4] for c in cols], np.array([float(c[7]) for c in cols])
+    raise ValueError("%s holds no !NATOM section" % psf)
+
+
+def read_dcd(path):
+    """CHARMM/NAMD .dcd reader: (coords in Angstrom float32 (T, Na, 3), box lengths in Angstrom float32 (T, 3)).
+
+    Fortran unformatted records with 4-byte markers, either endianness: an 84-byte header ``CORD`` + 20 control words
+    (frames, first step, step stride, ..., fixed atoms [8], time step [9], unit-cell flag [10], 4-D flag [11], ...,
+    CHARMM version [19]), the title record, the atom count, then per frame an optional unit-cell record of six
+    doubles (A, gamma, B, beta, alpha, C: lengths at 0, 2, 5) and the X, Y, Z records of natoms float32 each (and a
+    fourth one when the 4-D flag is set).  The file is in Angstrom; mdtraj hands the reference nanometres in float32
+    and the reference multiplies by ten again (load_traj.py:97-98), so the same two float32 roundings are applied.
+    Files with fixed atoms (later frames hold the free atoms only) are not supported.
+    PARITY UNPINNED: no mdtraj and no .dcd fixture here; checked against `write_dcd` (tests/test_host_logic.py)."""
+    data = np.fromfile(path, dtype=np.uint8)
+    if data.size < 92:
+        raise ValueError("%s: too short for a .dcd header" % path)
+    for order in ("<", ">"):
+        if int(np.frombuffer(data, order + "i4", 1, 0)[0]) == 84:
+            break
+    else:
+        raise ValueError("%s: no 84-byte header record (64-bit record markers are not supported)" % path)
+    i4, f4, f8 = np.dtype(order + "i4"), np.dtype(order + "f4"), np.dtype(order + "f8")
+    if bytes(data[4:8]) != b"CORD":
+        raise ValueError("%s: header does not start with CORD" % path)
+    ctl = np.frombuffer(data, i4, 20, 8)
+    if int(ctl[8]) != 0:
+        raise NotImplementedError("%s: %d fixed atoms (partial frames) are not supported" % (path, int(ctl[8])))
+    has_cell, has_4d = int(ctl[10]) != 0, int(ctl[11]) != 0 and int(ctl[19]) != 0
+    pos = 92
+
+    def record(at):
+        if at + 4 > data.size:
+            raise ValueError("%s: truncated record at byte %d" % (path, at))
+        n = int(np.frombuffer(data, i4, 1, at)[0])
+        if n < 0 or at + 8 + n > data.size or int(np.frombuffer(data, i4, 1, at + 4 + n)[0]) != n:
+            raise ValueError("%s: broken record at byte %d" % (path, at))
+        return at + 4, n
+
+    at, n = record(pos)                                # title
+    pos = at + n + 4
+    at, n = record(pos)                                # atom count
+    if n != 4:
+        raise ValueError("%s: atom-count record of %d bytes" % (path, n))
+    natoms = int(np.frombuffer(data, i4, 1, at)[0])
+    pos = at + n + 4
+    xyz, boxes = [], []
+    while pos < data.size:
+        cell = np.zeros(3)
+        if has_cell:
+            at, n = record(pos)
+            if n != 48:
+                raise ValueError("%s: unit-cell record of %d bytes" % (path, n))
+            c = np.frombuffer(data, f8, 6, at)
+            cell = np.array([c[0], c[2], c[5]])
+            pos = at + n + 4
+        frame = np.empty((natoms, 3), dtype=np.float32)
+        for d in range(3 + (1 if has_4d else 0)):
+            at, n = record(pos)
+            if n != 4 * natoms:
+                raise ValueError("%s: coordinate record of %d bytes for %d atoms" % (path, n, natoms))
+            if d < 3:
+                frame[:, d] = np.frombuffer(data, f4, natoms, at)
+            pos = at + n + 4
+        xyz.append(frame)
+        boxes.append(cell)
+    if not xyz:
+        raise ValueError("%s holds no frame" % path)
+    nm, ten = np.float32(0.1), np.float32(10)
+    return (np.stack(xyz) * nm) * ten, (np.stack(boxes).astype(np.float32) * nm) * ten
+
+
+def write_dcd(path, coords_A, box_A=None, big_endian=False, namd_cosines=True):
+    """.dcd writer of the same layout (tests, synthetic trajectories): coords (T, Na, 3) and box lengths (T, 3) in Angstrom
+    (orthorhombic: the three angle slots hold cos 90 = 0 as NAMD writes them, or 90 degrees as CHARMM does)."""
+    coords_A = np.asarray(coords_A, dtype=np.float32)
+    T, natoms = coords_A.shape[:2]
+    o = ">" if big_endian else "<"
+
+    def rec(payload):
+        n = np.array([len(payload)], dtype=o + "i4").tobytes()
+        return n + payload + n
+
+    ctl = np.zeros(20, dtype=o + "i4")
+    ctl[0], ctl[1], ctl[2], ctl[3] = T, 0, 1, T
+    ctl[10] = 1 if box_A is not None else 0
+    ctl[19] = 24
+    ctl_bytes = bytearray(ctl.tobytes())
+    ctl_bytes[36:40] = np.array([1.0], dtype=o + "f4").tobytes()        # time step
+    title = b"written by mdsf-b200".ljust(80)
+    with open(path, "wb") as fh:
+        fh.write(rec(b"CORD" + bytes(ctl_bytes)))
+        fh.write(rec(np.array([1], dtype=o + "i4").tobytes() + title))
+        fh.write(rec(np.array([natoms], dtype=o + "i4").tobytes()))
+        ang = 0.0 if namd_cosines else 90.0
+        for it in range(T):
+            if box_A is not None:
+                a, b, c = (float(v) for v in box_A[it])
+                fh.write(rec(np.array([a, ang, b, ang, ang, c], dtype=o + "f8").tobytes()))
+            for d in range(3):
+                fh.write(rec(np.ascontiguousarray(coords_A[it, :, d]).astype(o + "f4").tobytes()))
 
 
 XTC_MAGIC = 1995
@@ -390,13 +509,25 @@ def process_gro_mdtraj(topology_filename, trajectory_filename, output_filename):
             xyz, box, _ = read_trr(trajectory_filename)
             if xyz.shape[1] != len(names):
                 raise ValueError("%s has %d atoms, topology %s has %d" % (trajectory_filename, xyz.shape[1], topology_filename, len(names)))
+        elif trajectory_filename.endswith(".dcd"):       # the CLI's NAMD route (main_gromacs.py:95-96): foo.psf + foo.dcd
+            if topology_filename.endswith(".psf"):
+                names, mass = load_psf(topology_filename)
+            else:
+                names, mass = load_gro(topology_filename), None
+            xyz, box = read_dcd(trajectory_filename)
+            if xyz.shape[1] != len(names):
+                raise ValueError("%s has %d atoms, topology %s has %d" % (trajectory_filename, xyz.shape[1], topology_filename, len(names)))
+            print("saving ", output_filename)
+            save_traj_npz(output_filename, box, xyz, names, mass)
+            print('done saving')
+            return
         elif trajectory_filename.endswith(".xtc"):
             names = load_gro(topology_filename)
             xyz, box, _ = read_xtc(trajectory_filename)
             if xyz.shape[1] != len(names):
                 raise ValueError("%s has %d atoms, topology %s has %d" % (trajectory_filename, xyz.shape[1], topology_filename, len(names)))
         else:
-            raise ImportError("mdtraj is needed to decode %s (.gro, .trr and .xtc are parsed natively)" % trajectory_filename) from exc
+            raise ImportError("mdtraj is needed to decode %s (.gro, .trr, .xtc and .dcd are parsed natively)" % trajectory_filename) from exc
         print("saving ", output_filename)
         save_traj_npz(output_filename, box, xyz, names)
         print('done saving')

@@ -383,3 +383,45 @@ def test_native_xtc_reader_round_trips_every_coding_mode(tmp_path):
         with pytest.raises(ValueError):          # atom count of the topology must match
             gro.write_text("nine atoms\n    9\n" + "".join(rows[:9]) + "   3.00000   3.00000   2.50000\n")
             lt.process_gro_mdtraj(str(gro), str(tmp_path / "ten.xtc"), str(tmp_path / "out_bad_traj"))
+
+
+def test_native_dcd_and_psf_readers(tmp_path):
+    """The CLI's NAMD route (reference main_gromacs.py:95-96: foo.psf + foo.dcd) without mdtraj: load_traj.read_dcd follows
+    the CHARMM/NAMD record layout in either byte order, with and without unit-cell records; load_psf takes the atom
+    names of the !NATOM section.  (Parity unpinned: no mdtraj / fixture here, see the reader's docstring.)"""
+    import load_traj as lt
+    rng = np.random.default_rng(8)
+    T, na = 4, 7
+    x = rng.uniform(-3, 40, size=(T, na, 3)).astype(np.float32)
+    box = np.array([[40.0, 41.0 + t, 39.5] for t in range(T)])
+    want = (x * np.float32(0.1)) * np.float32(10)            # Angstrom -> mdtraj's float32 nm -> the reference's * 10
+    assert np.abs(want - x).max() < 1e-5
+    for big in (False, True):
+        for cosines in (True, False):
+            p = str(tmp_path / "t.dcd")
+            lt.write_dcd(p, x, box, big_endian=big, namd_cosines=cosines)
+            c, b = lt.read_dcd(p)
+            assert c.dtype == np.float32 and b.dtype == np.float32 and np.array_equal(c, want)
+            assert np.allclose(b, box, rtol=1e-6)
+    lt.write_dcd(str(tmp_path / "nobox.dcd"), x)
+    c, b = lt.read_dcd(str(tmp_path / "nobox.dcd"))
+    assert np.array_equal(c, want) and not b.any()
+    raw = open(str(tmp_path / "t.dcd"), "rb").read()
+    for name, blob in (("cut.dcd", raw[:len(raw) - 9]), ("magic.dcd", raw[:4] + b"VELD" + raw[8:]), ("short.dcd", raw[:50])):
+        open(str(tmp_path / name), "wb").write(blob)
+        with pytest.raises(ValueError):
+            lt.read_dcd(str(tmp_path / name))
+    names = ["OH2", "H1", "H2", "SOD", "C1", "N", "O"]
+    psf = tmp_path / "t.psf"
+    psf.write_text("PSF\n\n       1 !NTITLE\n REMARKS test\n\n%8d !NATOM\n" % na +
+                   "".join("%8d W    %-4d TIP3 %-4s %-4s %10.6f %13.4f %11d\n" % (i + 1, i // 3 + 1, nm, "OT", -0.834, 15.9994 + i, 0)
+                           for i, nm in enumerate(names)) + "\n%8d !NBOND: bonds\n" % 0)
+    got, mass = lt.load_psf(str(psf))
+    assert got == names and np.allclose(mass, 15.9994 + np.arange(na))
+    try:
+        import mdtraj  # noqa: F401
+    except ImportError:
+        lt.process_gro_mdtraj(str(psf), str(tmp_path / "t.dcd"), str(tmp_path / "out_t_traj"))
+        z = np.load(str(tmp_path / "out_t_traj.npz"))
+        assert list(z["typ"]) == names and list(z["name"]) == names and np.allclose(z["mass"], mass)
+        assert np.array_equal(z["coords"], want) and np.allclose(z["dims"], box, rtol=1e-6) and z["dims"].dtype == np.float32
