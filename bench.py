@@ -47,7 +47,6 @@ def parse():
     ap.add_argument("--ref-budget", type=float, default=200.0, help="reference arm: stop timing after this many seconds")
     ap.add_argument("--fft", default="auto")
     ap.add_argument("--tile", default="0x0")
-    ap.add_argument("--splat", default="auto")
     return ap.parse_args()
 
 
@@ -206,7 +205,7 @@ def main():
     box = wl["box"]
     tile = tuple(int(v) for v in args.tile.split("x"))
     eng, n, dr, nb = dens.make_engine(box, wl["typ"], wl["rad"], wl["ucell"], wl["sres"], np.float32, np.float32,
-                                      device=local, batch_frames=F, fft_mode=args.fft, tile=tile, splat_mode=args.splat)
+                                      device=local, batch_frames=F, fft_mode=args.fft, tile=tile)
     assert tuple(int(v) for v in n) == tuple(wl["grid"]), (n, wl["grid"])
     # frame pool: pinned host memory (e2e leg) and a device-resident copy (value leg); rank r starts
     # at a different offset so ranks do not process identical frames
@@ -324,7 +323,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "grid": list(wl["grid"]), "atoms": natoms,
                        "frames_per_step": F, "pool_frames": pool_n, "fft": eng.fft_path, "splat": eng.splat_path, "Nborder": nb,
-                       "pipeline": eng.pipeline,
+                       "geometry": eng.geometry,
                        "l2": "per-step working set (%.0f MB of pair volumes + accumulator) exceeds the 126 MB L2; no explicit flush"
                              % ((F // 2) * np.prod(wl["grid"]) * 16 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": F * frame_bytes,

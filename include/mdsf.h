@@ -37,11 +37,6 @@ enum { MDSF_F32 = 0, MDSF_F64 = 1 };
 enum { MDSF_FOLD_REFERENCE = 0,   /* reproduce the corner rule of dens.py:107 (default) */
        MDSF_FOLD_PERIODIC = 1 };  /* mathematically periodic fold                       */
 enum { MDSF_FFT_AUTO = 0, MDSF_FFT_NATIVE = 1, MDSF_FFT_CUFFT = 2 };
-enum { MDSF_SPLAT_AUTO = 0,      /* scatter when stamps are small, owner otherwise                    */
-       MDSF_SPLAT_OWNER = 1,     /* owner-computes column tiles in shared memory, fp64 accumulation   */
-       MDSF_SPLAT_SCATTER = 2,   /* slab-pipelined 64-bit fixed-point integer reductions (L2-resident) */
-       MDSF_SPLAT_TILE = 3 };    /* column tiles in shared memory, one thread per (atom image, column),
-                                    64-bit fixed-point integer shared-memory atomics, fused z FFT       */
 
 typedef struct mdsf_handle mdsf_handle;
 
@@ -65,9 +60,9 @@ typedef struct mdsf_config {
     int32_t fold_mode;       /* MDSF_FOLD_*                                                   */
     int32_t fft_mode;        /* MDSF_FFT_*                                                    */
     int32_t batch_frames;    /* frames per device batch (even, >= 2); 0 = pick automatically  */
-    int32_t tile_x, tile_y;  /* splat tile in columns; 0 = pick automatically                 */
+    int32_t tile_x, tile_y;  /* splat tile in columns (2x2, 4x2, 4x4 or 8x4); 0 = pick automatically */
     int32_t keep_density;    /* keep per-frame densities of the last batch for the debug tap  */
-    int32_t splat_mode;      /* MDSF_SPLAT_*                                                  */
+    int32_t splat_mode;      /* must be 0 (round 1 had selectable splat variants; one remains) */
     int32_t reserved[6];
 } mdsf_config;
 
@@ -129,19 +124,20 @@ int mdsf_debug_density(mdsf_handle* h, int64_t frame, double* d1_out /* [Nx][Ny]
 int64_t mdsf_kernel_launches(const mdsf_handle* h);
 int64_t mdsf_frames_done(const mdsf_handle* h);
 const char* mdsf_fft_path(const mdsf_handle* h);
-const char* mdsf_splat_path(const mdsf_handle* h);   /* "owner" / "scatter" / "tile" (valid after mdsf_set_atoms) */
+const char* mdsf_splat_path(const mdsf_handle* h);   /* "register-ortho" / "register-mono" / "register-general" */
 int mdsf_batch_frames(const mdsf_handle* h);
 /* Coordinate pre-transform of the CLI (reference main_gromacs.py:204-207), applied by the first kernel to every
  * frame pushed afterwards, before the rescale: y <- y / sin_theta; x <- x - y * cos_theta, evaluated in float64 and
  * rounded to the coordinate dtype after each line exactly as numpy does for `T[..., 1] / np.sin(theta)`.
  * With write_back the transformed (and rescaled, wrapped) coordinates are what comes back. */
 int mdsf_set_pretransform(mdsf_handle* h, int32_t enabled, double sin_theta, double cos_theta);
-/* Pipeline shape: returns 1 when the splat of batch b+1 overlaps the y/x passes of batch b (two pair-volume
- * sets), else 0; sms[0], sms[1] = SMs of the splat-side / pass-side green-context partition (0, 0 = unpartitioned). */
-int mdsf_pipeline_info(const mdsf_handle* h, int32_t* sms /* [2] */);
+/* Launch geometry for bench.py / DESIGN.md: out[0..7] = splat tile columns in x, in y, z-slab width of one warp,
+ * slabs per column, volume layout chunk width (Nz = plain [x][y][z]), y-pass tile width, x-pass tile width,
+ * KiB of shared memory per splat CTA. */
+int mdsf_geometry(const mdsf_handle* h, int32_t* out8);
 /* Record CUDA events around every stage of subsequent batches; query the accumulated
  * per-stage device milliseconds: out[0..5] = copy, prep+bin, splat+zfft, y pass, x pass+accumulate
- * (library path: FFT, accumulate), compute-stream total */
+ * (library path: cuFFT, accumulate), compute-stream total */
 int mdsf_enable_timing(mdsf_handle* h, int32_t on);
 int mdsf_stage_ms(mdsf_handle* h, double* out6, int64_t* batches);
 /* CUDA-event stopwatch around everything queued between the two calls (start: copy stream,

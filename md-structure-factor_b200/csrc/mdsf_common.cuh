@@ -5,10 +5,10 @@
 #include <stdint.h>
 
 #define MDSF_MAX_BATCH 64          // frames per device batch (scale factors travel as kernel params)
-#define MDSF_MAX_TILE_COLS 32      // columns per splat tile (one bit each in a 32-bit hit mask)
-#define MDSF_ATOM_BITS 26          // atom index bits inside a pair payload
-#define MDSF_MAX_ATOMS (1 << MDSF_ATOM_BITS)
+#define MDSF_MAX_ATOMS (1 << 28)
 #define MDSF_MAX_RADIX_STAGES 12
+#define MDSF_MAX_STAMP 1023        // 2*A: stamp indices travel in 10-bit fields / int offsets
+#define MDSF_SPLAT_WARPS 16        // warps per splat CTA; warp w owns z slabs w, w+16, ...
 
 // Frame-invariant geometry, passed to kernels by value.
 struct GridParams {
@@ -16,21 +16,29 @@ struct GridParams {
     int nb;             // Nborder (dens.py:231)
     int fold_mode;      // 0 = reference corner rule (dens.py:107), 1 = periodic
     int separable;      // ucell couples z to nothing else -> exp splits into xy and z factors
-    int tx, ty;         // splat tile, in (x,y) columns; a tile spans all z
+    int lcol;           // splat tile = 2^lcol (x,y) columns over all z: TX = 2^((lcol+1)/2), TY = 2^(lcol/2)
     int ntx, nty;       // tiles per dimension
+    int nslab, zw;      // z slabs per column, slab width zw = 256 >> lcol cells (one warp: 2^lcol columns x 32>>lcol lanes x 8 cells)
     int natoms;
-    int debug_skip;     // profiling aid (MDSF_SPLAT_SKIP): 1 phase B, 2 z FFT, 4 table staging, 8 store, 16 whole list loop
-    int nslab, zs;      // a tile column is owned in nslab z slabs of zs cells (nslab * tx*ty = 128 owner threads)
     int nzp;            // padded z length of one column in shared memory
     int pad_shift;      // column position p is stored at p + (p >> pad_shift)
+    // volume layout: element (x, y, z) of a pair volume sits at ((z / lw * Nx + x) * Ny + y) * lw + z % lw.
+    // lw = Nz is the plain C order [x][y][z]; a smaller lw makes every (x, z-chunk) row block of the y pass one
+    // contiguous run and lets the y -> x hand-over of a chunk stay L2-resident.
+    int lw, nch;        // chunk width, chunks per column (nch * lw = Nz)
     double dr[3];       // dens.py:202
     double box[3];      // mean box (dens.py:52)
     double u[9];        // ucell row-major (dens.py:301)
     // separable case: |c|^2 = cxx bx^2 + cyy by^2 + 2 gxy bx by + czz bz^2
     double cxx, cyy, gxy, czz;
     long long tstride;  // doubles of per-atom factor tables per frame
-    double fx_scale, fx_inv;   // fixed-point scale 2^(52-e) and its inverse (tile-atomic / scatter modes)
+    double fx_scale, fx_inv;   // fixed-point scale 2^(52-e) and its inverse (amax < 2^e)
 };
+
+__host__ __device__ inline long long vol_index(const GridParams& gp, int x, int y, int z) {
+    const int ch = z / gp.lw, zw = z - ch * gp.lw;
+    return (((long long)ch * gp.n[0] + x) * gp.n[1] + y) * gp.lw + zw;
+}
 
 struct TypeTable {
     const double* amp;       // Nel / sigma^3
@@ -47,7 +55,7 @@ struct AtomRec {
     int ir[3];     // trunc(r/dr)  (dens.py:285)
     int type;
     unsigned tbase;   // offset of this atom's factor tables (frame block included), in doubles
-    unsigned pad_;
+    unsigned pad_;    // 1: K1 rejected the atom (stamp outside the padded grid / NaN)
 };
 
 struct BatchScales {
@@ -64,35 +72,37 @@ __host__ __device__ inline void stamp_segment(int ir, int A, int N, int s, int& 
     else             { plo = p0 > N ? p0 : N;  phi = p1; }
 }
 
-// number of tiles (width t) a stamp touches along one dimension, summed over its segments
-__host__ __device__ inline int stamp_tiles_1d(int ir, int A, int N, int t) {
+// Fold shift of the z segment `sz` of image (sx, sy): destination z = padded z + shift.  Faces and edges move by
+// -sz*Nz; in the 8 corner regions the reference picks the z block by the y side (dens.py:107), which turns the
+// shift into +-Nborder when the y side differs from the z side.
+__host__ __device__ inline int fold_shift_z(int sx, int sy, int sz, int nz, int nb, int fold_mode) {
+    if (sz == 0) return 0;
+    const bool corner = (sx != 0 && sy != 0 && fold_mode == 0);
+    if (sz < 0) return (corner && sy != -1) ? nb : nz;
+    return (corner && sy != 1) ? -nb : -nz;
+}
+
+// number of width-t bins the folded stamp [ir-A, ir+A) touches along one dimension, summed over its segments;
+// `sh_lo` / `sh_hi` are the shifts of the low / high padding segment (normally +N / -N)
+__host__ __device__ inline int stamp_bins_1d(int ir, int A, int N, int t, int sh_lo, int sh_hi) {
     int cnt = 0;
     for (int s = -1; s <= 1; ++s) {
         int plo, phi;
         stamp_segment(ir, A, N, s, plo, phi);
         if (phi > plo) {
-            int clo = plo - s * N, chi = phi - s * N;
-            cnt += (chi - 1) / t - clo / t + 1;
+            const int sh = s < 0 ? sh_lo : (s > 0 ? sh_hi : 0);
+            cnt += (phi - 1 + sh) / t - (plo + sh) / t + 1;
         }
     }
     return cnt;
 }
 
-// z slabs (bit s = slab s of zs cells) the image (sx,sy) of an atom touches after the fold.
-// The three z segments of the stamp (low padding / cell / high padding) move by shlo / 0 / shhi;
-// in the 8 corner regions the reference picks the z block by the y side (dens.py:107), which
-// turns the shift into +-Nborder when the y side differs from the z side.
-__host__ __device__ inline unsigned image_slabmask(int irz, int Az, int sx, int sy, int nz, int nb, int fold_mode,
-                                                   int zs, int& shlo, int& shhi, int& kA, int& kB) {
-    const int pz0 = irz - Az, nzr = 2 * Az;
-    kA = -pz0 < 0 ? 0 : (-pz0 > nzr ? nzr : -pz0);
-    kB = nz - pz0 < 0 ? 0 : (nz - pz0 > nzr ? nzr : nz - pz0);
-    const bool corner = (sx != 0 && sy != 0 && fold_mode == 0);
-    shlo = (corner && sy != -1) ? nb : nz;
-    shhi = (corner && sy != 1) ? -nb : -nz;
-    unsigned m = 0;
-    if (kA > 0)   for (int sl = (pz0 + shlo) / zs; sl <= (pz0 + kA - 1 + shlo) / zs; ++sl) m |= 1u << sl;
-    if (kB > kA)  for (int sl = (pz0 + kA) / zs; sl <= (pz0 + kB - 1) / zs; ++sl) m |= 1u << sl;
-    if (nzr > kB) for (int sl = (pz0 + kB + shhi) / zs; sl <= (pz0 + nzr - 1 + shhi) / zs; ++sl) m |= 1u << sl;
-    return m;
-}
+// One (atom image, tile, z slab) pair, pre-clipped by the binning kernel; what a splat warp consumes.
+//   separable ucell:  x = index of EZ[k] for slab-local z 0 (tables + x + zz, zz in [zoff, zend))
+//                     y = index of EX[i] for tile column x 0, z = index of EY[j] for tile column y 0
+//   general ucell:    x, y, z = padded-grid index of tile column x 0 / tile column y 0 / slab-local z 0
+//   w = cx0 | cx1 << 3 | cy0 << 7 | cy1 << 10 | zoff << 14 | zend << 21   (clip box, tile / slab relative, [lo, hi))
+// PairAux (monoclinic or general ucell only): x = index of the cross-term table entry of tile column (0,0) / atom index,
+//                                             y = row stride 2*Ay of that table / unused
+typedef uint4 PairRec;
+typedef uint2 PairAux;

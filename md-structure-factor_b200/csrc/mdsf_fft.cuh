@@ -244,14 +244,24 @@ __device__ __forceinline__ void fft_stage_dispatch(int R, double* sre, double* s
     }
 }
 
-// all stages of one axis over a tile resident in shared memory (z pass; caller syncs before)
+// all stages of one axis over a tile resident in shared memory (z pass inside the splat kernel; caller syncs before).
+// z plans use radices <= 8 only (2, 4, 8, 3, 5, 7): the splat kernel runs 1024 threads per SM, i.e. 64 registers per
+// thread, and a radix-8 butterfly (32 registers of data) is what fits without spills.
 __device__ __forceinline__ void fft_tile_z(double* sre, double* sim, const double* twr, const double* twi,
                                            const FftPlan& plan, int nfft, int fs, int pad)
 {
     GlobalTile none{nullptr, 0, 0};
     int L = plan.n;
     for (int s = 0; s < plan.nstages; ++s) {
-        fft_stage_dispatch<true, IO_SMEM, IO_SMEM>(plan.radix[s], sre, sim, twr, twi, plan.n, L, nfft, fs, 1, pad, 0, none, nullptr, false);
+        switch (plan.radix[s]) {
+            case 8: fft_stage<8, true, IO_SMEM, IO_SMEM>(sre, sim, twr, twi, plan.n, L, nfft, fs, 1, pad, 0, none, nullptr, false); break;
+            case 4: fft_stage<4, true, IO_SMEM, IO_SMEM>(sre, sim, twr, twi, plan.n, L, nfft, fs, 1, pad, 0, none, nullptr, false); break;
+            case 2: fft_stage<2, true, IO_SMEM, IO_SMEM>(sre, sim, twr, twi, plan.n, L, nfft, fs, 1, pad, 0, none, nullptr, false); break;
+            case 3: fft_stage<3, true, IO_SMEM, IO_SMEM>(sre, sim, twr, twi, plan.n, L, nfft, fs, 1, pad, 0, none, nullptr, false); break;
+            case 5: fft_stage<5, true, IO_SMEM, IO_SMEM>(sre, sim, twr, twi, plan.n, L, nfft, fs, 1, pad, 0, none, nullptr, false); break;
+            case 7: fft_stage<7, true, IO_SMEM, IO_SMEM>(sre, sim, twr, twi, plan.n, L, nfft, fs, 1, pad, 0, none, nullptr, false); break;
+            default: break;
+        }
         L /= plan.radix[s];
         __syncthreads();
     }
@@ -299,61 +309,34 @@ __device__ __forceinline__ void load_twiddles(double* twr, double* twi, const do
 #define MDSF_FAST_MINBLOCKS 5          // two-stage kernels: 5 CTAs/SM (102 registers) measured best on B200
 #endif
 
-// ------------------------------------------------------------------ z pass (stand-alone)
-// grid = (column groups, pairs).  A group is `ncol` consecutive (x,y) columns, contiguous in
-// memory.  Used by mdsf_push_density and by the un-fused debug path; the production path runs
-// the same stages inside splat_zfft_kernel without the load.
-__global__ void __launch_bounds__(256)
-fft_z_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw,
-             long long ncolumns, int ncol, int nzp, int pad, int zfast)
-{
-    extern __shared__ double smem[];
-    const int nz = plan.n;
-    double* sre = smem;
-    double* sim = sre + (size_t)ncol * nzp;
-    double* twr = sim + (size_t)ncol * nzp;
-    double* twi = twr + nz;
-    load_twiddles(twr, twi, tw, nz);
-    const long long col0 = (long long)blockIdx.x * ncol;
-    const int nc = (int)min((long long)ncol, ncolumns - col0);
-    double2* base = vol + ((long long)blockIdx.y * ncolumns + col0) * nz;
-    for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
-        const int c = i / nz, z = i - c * nz;
-        const double2 v = base[i];
-        const int a = c * nzp + z + (z >> pad);
-        sre[a] = v.x; sim[a] = v.y;
-    }
-    __syncthreads();
-    fft_tile_z(sre, sim, twr, twi, plan, nc, nzp, pad);
-    for (int i = threadIdx.x; i < nc * nz; i += blockDim.x) {
-        const int c = i / nz, z = i - c * nz;
-        // Nz = R*R engines keep z in natural frequency order: frequency z sits at position (z % R)*R + z / R
-        const int p = zfast ? (z % zfast) * zfast + z / zfast : z;
-        const int a = c * nzp + p + (p >> pad);
-        base[i] = make_double2(sre[a], sim[a]);
-    }
-}
+// Pass geometry.  A y-pass CTA sits at (z tile, x, pair), an x-pass CTA at (z tile, y) and walks the pairs; element
+// (row, f) of its [n][W] tile is base[row * rs + f] with base = vol + pair * ncell + outer * os + ztile * cs.
+//   plain layout [x][y][z]:        y pass os = Ny*Nz, rs = Nz;     x pass os = Nz, rs = Ny*Nz;   cs = W
+//   chunked layout [z/lw][x][y][lw]: y pass os = Ny*lw, rs = lw;   x pass os = lw, rs = Ny*lw;   cs = Nx*Ny*lw, W = lw
+struct PassGeom {
+    long long ncell, os, cs, rs;
+    int nz, W;          // valid columns of tile t: min(W, nz - t*W)
+};
 
 // ------------------------------------------------------------------ y pass, in place
 // grid = (z chunks, Nx, pairs); tile = [Ny][W] at fixed x; rows are W*16 contiguous bytes.
 // THR x MINB: 128 x 4 for short axes ([n][8] tiles <= 36 KB); 256 x 2 / 512 x 1 keep 128-byte rows on long axes.
 template <int THR, int MINB>
 __global__ void __launch_bounds__(THR, MINB)
-fft_y_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw,
-             int nx, int ny, int nz, int W, int logw)
+fft_y_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict__ tw, PassGeom pg, int logw)
 {
     extern __shared__ double smem[];
+    const int ny = plan.n, W = pg.W;
     double* sre = smem;
     double* sim = sre + (size_t)ny * W;
     double* twr = sim + (size_t)ny * W;
     double* twi = twr + ny;
     load_twiddles(twr, twi, tw, ny);
     __syncthreads();
-    const int z0 = blockIdx.x * W;
     GlobalTile g;
-    g.base = vol + (((long long)blockIdx.z * nx + blockIdx.y) * ny) * (long long)nz + z0;
-    g.row_stride = nz;
-    g.w = min(W, nz - z0);
+    g.base = vol + (long long)blockIdx.z * pg.ncell + (long long)blockIdx.y * pg.os + (long long)blockIdx.x * pg.cs;
+    g.row_stride = pg.rs;
+    g.w = min(W, pg.nz - (int)blockIdx.x * W);
     fft_tile_strided<false>(sre, sim, twr, twi, plan, W, logw, g, nullptr, false);
 }
 
@@ -364,25 +347,24 @@ fft_y_kernel(double2* __restrict__ vol, FftPlan plan, const double2* __restrict_
 template <int THR, int MINB>
 __global__ void __launch_bounds__(THR, MINB)
 fft_x_accum_kernel(double2* __restrict__ vol, double* __restrict__ P, FftPlan plan,
-                   const double2* __restrict__ tw, int nx, int ny, int nz, int W, int logw, int npairs)
+                   const double2* __restrict__ tw, PassGeom pg, int logw, int npairs)
 {
     extern __shared__ double smem[];
+    const int nx = plan.n, W = pg.W;
     double* sre = smem;
     double* sim = sre + (size_t)nx * W;
     double* acc = sim + (size_t)nx * W;
     double* twr = acc + (size_t)nx * W;
     double* twi = twr + nx;
     load_twiddles(twr, twi, tw, nx);
-    const int z0 = blockIdx.x * W;
-    const int y = blockIdx.y;
-    const long long xstride = (long long)ny * nz;
-    const long long off = (long long)y * nz + z0;
+    const long long xstride = pg.rs;
+    const long long off = (long long)blockIdx.y * pg.os + (long long)blockIdx.x * pg.cs;
     GlobalTile g;
     g.row_stride = xstride;
-    g.w = min(W, nz - z0);
+    g.w = min(W, pg.nz - (int)blockIdx.x * W);
     for (int q = 0; q < npairs; ++q) {
         __syncthreads();
-        g.base = vol + (long long)q * nx * xstride + off;
+        g.base = vol + (long long)q * pg.ncell + off;
         fft_tile_strided<true>(sre, sim, twr, twi, plan, W, logw, g, acc, q == 0);
     }
     __syncthreads();
@@ -396,7 +378,7 @@ fft_x_accum_kernel(double2* __restrict__ vol, double* __restrict__ P, FftPlan pl
 // grid = (z chunks, Nx, pairs), one butterfly per thread and stage; in place on the volume.
 template <int R1, int R2>
 __global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_FAST_MINBLOCKS)
-fft_y_fast_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, int nx, int nz, int logw)
+fft_y_fast_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, PassGeom pg, int logw)
 {
     constexpr int NY = R1 * R2;
     extern __shared__ double smem[];
@@ -406,10 +388,10 @@ fft_y_fast_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, int
     double* twr = sim + (size_t)NY * W;
     double* twi = twr + NY;
     load_twiddles(twr, twi, tw, NY);
-    const int z0 = blockIdx.x * W;
     const int f = threadIdx.x & (W - 1), bf = threadIdx.x >> logw;
-    const bool ok = z0 + f < nz;
-    double2* base = vol + (((long long)blockIdx.z * nx + blockIdx.y) * NY) * (long long)nz + z0 + f;
+    const bool ok = (int)blockIdx.x * W + f < pg.nz;
+    const long long nz = pg.rs;                    // row stride
+    double2* base = vol + (long long)blockIdx.z * pg.ncell + (long long)blockIdx.y * pg.os + (long long)blockIdx.x * pg.cs + f;
     {
         double xr[R1], xi[R1];
 #pragma unroll
@@ -443,74 +425,8 @@ fft_y_fast_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, int
     }
 }
 
-// ------------------------------------------------------------------ x pass, two-stage fast path (Nx = R1*R2)
-// Same data flow as fft_x_accum_kernel, written out for plans with exactly two stages whose butterfly count
-// per tile equals the block size (Nx/R1 * W == Nx/R2 * W == blockDim): every thread owns ONE butterfly per
-// stage, so the |C|^2 sums of its R2 outputs stay in registers across the pairs of the batch and P sees a
-// single read-modify-write straight from registers (no accumulator tile in shared memory).
-template <int R1, int R2>
-__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_FAST_MINBLOCKS)
-fft_x_accum_fast_kernel(double2* __restrict__ vol, double* __restrict__ P, const double2* __restrict__ tw,
-                        int ny, int nz, int logw, int npairs)
-{
-    constexpr int NX = R1 * R2;
-    extern __shared__ double smem[];
-    const int W = 1 << logw;
-    double* sre = smem;
-    double* sim = sre + (size_t)NX * W;
-    double* twr = sim + (size_t)NX * W;
-    double* twi = twr + NX;
-    load_twiddles(twr, twi, tw, NX);
-    const int z0 = blockIdx.x * W;
-    const int y = blockIdx.y;
-    const long long xstride = (long long)ny * nz;
-    const long long off = (long long)y * nz + z0;
-    const int f = threadIdx.x & (W - 1), bf = threadIdx.x >> logw;      // column, butterfly index (same for both stages)
-    const bool ok = z0 + f < nz;
-    double acc[R2];
-#pragma unroll
-    for (int k = 0; k < R2; ++k) acc[k] = 0.0;
-    __syncthreads();                               // twiddle table is in shared memory
-    for (int q = 0; q < npairs; ++q) {
-        const double2* base = vol + (long long)q * NX * xstride + off + f;
-        {   // stage 1: points n2 + R2*j (n2 = bf), straight from global memory
-            double xr[R1], xi[R1];
-#pragma unroll
-            for (int j = 0; j < R1; ++j) {
-                double2 v = make_double2(0.0, 0.0);
-                if (ok) v = base[(long long)(bf + R2 * j) * xstride];
-                xr[j] = v.x; xi[j] = v.y;
-            }
-            Dft<R1>::run(xr, xi, twr, twi, NX);
-#pragma unroll
-            for (int k = 1; k < R1; ++k) {
-                const double wr = twr[bf * k], wi = twi[bf * k];
-                const double yr = xr[k] * wr - xi[k] * wi;
-                xi[k] = xr[k] * wi + xi[k] * wr;
-                xr[k] = yr;
-            }
-            __syncthreads();                       // previous pair's stage 2 has finished reading the tile
-#pragma unroll
-            for (int k = 0; k < R1; ++k) { const int a = ((k * R2 + bf) << logw) + f; sre[a] = xr[k]; sim[a] = xi[k]; }
-        }
-        __syncthreads();
-        {   // stage 2: block b = bf holds points b*R2 + j; outputs stay at b*R2 + k (position space)
-            double xr[R2], xi[R2];
-#pragma unroll
-            for (int j = 0; j < R2; ++j) { const int a = ((bf * R2 + j) << logw) + f; xr[j] = sre[a]; xi[j] = sim[a]; }
-            Dft<R2>::run(xr, xi, twr, twi, NX);
-#pragma unroll
-            for (int k = 0; k < R2; ++k) acc[k] += xr[k] * xr[k] + xi[k] * xi[k];
-        }
-    }
-    if (ok) {
-#pragma unroll
-        for (int k = 0; k < R2; ++k) P[(long long)(bf * R2 + k) * xstride + off + f] += acc[k];
-    }
-}
-
 // ------------------------------------------------------------------ x pass, two-stage, cp.async-prefetched
-// Same arithmetic as fft_x_accum_fast_kernel.  The stage-1 inputs of pair q+1 are copied global -> shared
+// Two-stage x pass (Nx = R1*R2, one butterfly per thread and stage, sum_q |C_q|^2 of its R2 outputs in registers).  The stage-1 inputs of pair q+1 are copied global -> shared
 // memory with cp.async (16 bytes per copy, each thread copies exactly the R1 points it will consume, so no
 // barrier guards the staging buffer) while the thread runs the butterflies of pair q: every CTA always has
 // its next 32 KB in flight, which keeps the HBM queues full from few SMs (SM-partitioned pipeline) as well.
@@ -526,7 +442,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int R1, int R2>
 __global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_XASYNC_MINBLOCKS)
 fft_x_accum_async_kernel(const double2* __restrict__ vol, double* __restrict__ P, const double2* __restrict__ tw,
-                         int ny, int nz, int logw, int npairs)
+                         PassGeom pg, int logw, int npairs)
 {
     constexpr int NX = R1 * R2;
     extern __shared__ double smem[];
@@ -538,12 +454,10 @@ fft_x_accum_async_kernel(const double2* __restrict__ vol, double* __restrict__ P
     double2* stage = reinterpret_cast<double2*>(twi + NX);     // [R1][blockDim.x]: point j of thread t at stage[j*T + t]
     const int T = blockDim.x;
     load_twiddles(twr, twi, tw, NX);
-    const int z0 = blockIdx.x * W;
-    const int y = blockIdx.y;
-    const long long xstride = (long long)ny * nz;
-    const long long off = (long long)y * nz + z0;
+    const long long xstride = pg.rs;
+    const long long off = (long long)blockIdx.y * pg.os + (long long)blockIdx.x * pg.cs;
     const int f = threadIdx.x & (W - 1), bf = threadIdx.x >> logw;
-    const bool ok = z0 + f < nz;
+    const bool ok = (int)blockIdx.x * W + f < pg.nz;
     double acc[R2];
 #pragma unroll
     for (int k = 0; k < R2; ++k) acc[k] = 0.0;
@@ -565,7 +479,7 @@ fft_x_accum_async_kernel(const double2* __restrict__ vol, double* __restrict__ P
                 xr[j] = v.x; xi[j] = v.y;
             }
             if (ok && q + 1 < npairs) {            // the slots are free again: fetch the next pair behind this one's math
-                const double2* base = vol + (long long)(q + 1) * NX * xstride + off + f;
+                const double2* base = vol + (long long)(q + 1) * pg.ncell + off + f;
 #pragma unroll
                 for (int j = 0; j < R1; ++j) cp_async16(mine + j * T, base + (long long)(bf + R2 * j) * xstride);
             }
@@ -597,75 +511,6 @@ fft_x_accum_async_kernel(const double2* __restrict__ vol, double* __restrict__ P
     }
 }
 
-// ------------------------------------------------------------------ y pass, two-stage, cp.async-prefetched
-// grid = (z chunks, Nx); the CTA walks the pairs of the batch at fixed (x, z chunk) and fetches the tile of pair
-// q+1 behind the butterflies of pair q (see fft_x_accum_async_kernel).  In place on the volume.
-template <int R1, int R2>
-__global__ void __launch_bounds__(MDSF_PASS_THREADS, MDSF_XASYNC_MINBLOCKS)
-fft_y_async_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, int nx, int nz, int logw, int npairs)
-{
-    constexpr int NY = R1 * R2;
-    extern __shared__ double smem[];
-    const int W = 1 << logw;
-    double* sre = smem;
-    double* sim = sre + (size_t)NY * W;
-    double* twr = sim + (size_t)NY * W;
-    double* twi = twr + NY;
-    double2* stage = reinterpret_cast<double2*>(twi + NY);
-    const int T = blockDim.x;
-    load_twiddles(twr, twi, tw, NY);
-    const int z0 = blockIdx.x * W;
-    const int f = threadIdx.x & (W - 1), bf = threadIdx.x >> logw;
-    const bool ok = z0 + f < nz;
-    const long long pair_stride = (long long)nx * NY * nz;
-    double2* base0 = vol + ((long long)blockIdx.y * NY) * (long long)nz + z0 + f;
-    double2* mine = stage + threadIdx.x;
-    if (ok) {
-#pragma unroll
-        for (int j = 0; j < R1; ++j) cp_async16(mine + j * T, base0 + (long long)(bf + R2 * j) * nz);
-    }
-    __syncthreads();
-    for (int q = 0; q < npairs; ++q) {
-        double2* base = base0 + (long long)q * pair_stride;
-        {
-            double xr[R1], xi[R1];
-            cp_async_wait_all();
-#pragma unroll
-            for (int j = 0; j < R1; ++j) {
-                double2 v = make_double2(0.0, 0.0);
-                if (ok) v = mine[j * T];
-                xr[j] = v.x; xi[j] = v.y;
-            }
-            if (ok && q + 1 < npairs) {
-#pragma unroll
-                for (int j = 0; j < R1; ++j) cp_async16(mine + j * T, base + pair_stride + (long long)(bf + R2 * j) * nz);
-            }
-            Dft<R1>::run(xr, xi, twr, twi, NY);
-#pragma unroll
-            for (int k = 1; k < R1; ++k) {
-                const double wr = twr[bf * k], wi = twi[bf * k];
-                const double yr = xr[k] * wr - xi[k] * wi;
-                xi[k] = xr[k] * wi + xi[k] * wr;
-                xr[k] = yr;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < R1; ++k) { const int a = ((k * R2 + bf) << logw) + f; sre[a] = xr[k]; sim[a] = xi[k]; }
-        }
-        __syncthreads();
-        {
-            double xr[R2], xi[R2];
-#pragma unroll
-            for (int j = 0; j < R2; ++j) { const int a = ((bf * R2 + j) << logw) + f; xr[j] = sre[a]; xi[j] = sim[a]; }
-            Dft<R2>::run(xr, xi, twr, twi, NY);
-            if (ok) {
-#pragma unroll
-                for (int k = 0; k < R2; ++k) base[(long long)(bf * R2 + k) * nz] = make_double2(xr[k], xi[k]);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------ y / x pass, three radix stages (long axes)
 // N = R1*R2*R3 (512 = 8*8*8, 1024 = 8*8*16, 768 = 16*16*3): same decimation-in-frequency scheme and output order as
 // fft_stage (position space), written out with compile-time radices and strides.  Tile [N][W] in shared memory
@@ -677,7 +522,7 @@ fft_y_async_kernel(double2* __restrict__ vol, const double2* __restrict__ tw, in
 template <int R1, int R2, int R3, int LOGW, int THR, int MINB, bool XPASS>
 __global__ void __launch_bounds__(THR, MINB)
 fft3_pass_kernel(double2* __restrict__ vol, double* __restrict__ P, const double2* __restrict__ tw,
-                 int nouter, int nz, int npairs)
+                 PassGeom pg, int npairs)
 {
     constexpr int N = R1 * R2 * R3, M1 = N / R1, M2 = M1 / R2;
     extern __shared__ double smem[];
@@ -687,11 +532,11 @@ fft3_pass_kernel(double2* __restrict__ vol, double* __restrict__ P, const double
     double* twr = sim + (size_t)N * W;
     double* twi = twr + N;
     load_twiddles(twr, twi, tw, N);
-    const int z0 = blockIdx.x * W;
-    // XPASS: rows are x (stride Ny*Nz), the CTA sits at y = blockIdx.y; else rows are y (stride Nz) at x = blockIdx.y
-    const long long row = XPASS ? (long long)nouter * nz : (long long)nz;
-    const long long pair_stride = XPASS ? (long long)N * row : (long long)nouter * N * nz;
-    const long long off = XPASS ? (long long)blockIdx.y * nz + z0 : ((long long)blockIdx.z * nouter + blockIdx.y) * N * (long long)nz + z0;
+    const int z0 = blockIdx.x * W, nz = pg.nz;
+    // XPASS: rows are x, the CTA sits at y = blockIdx.y and walks the pairs; else rows are y at x = blockIdx.y of pair blockIdx.z
+    const long long row = pg.rs;
+    const long long pair_stride = pg.ncell;
+    const long long off = (long long)blockIdx.y * pg.os + (long long)blockIdx.x * pg.cs + (XPASS ? 0LL : (long long)blockIdx.z * pg.ncell);
     constexpr int NB1 = M1, NB2 = N / R2, NB3 = N / R3;      // butterflies per column and stage
     constexpr int items1 = NB1 * W, items2 = NB2 * W, items3 = NB3 * W;
     constexpr int MAXI3 = (items3 + THR - 1) / THR;           // stage-3 butterflies per thread
@@ -786,7 +631,7 @@ fft3_pass_kernel(double2* __restrict__ vol, double* __restrict__ P, const double
 
 // ------------------------------------------------------------------ library-FFT path helper
 // P += sum_q |vol_q|^2 after a cuFFT Z2Z (grids whose sizes have prime factors > 13)
-__global__ void accumulate_power_kernel(const double2* __restrict__ vol, double* __restrict__ P,
+static __global__ void accumulate_power_kernel(const double2* __restrict__ vol, double* __restrict__ P,
                                         long long ncell, int npairs)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncell;
@@ -803,10 +648,11 @@ __global__ void accumulate_power_kernel(const double2* __restrict__ vol, double*
 // ------------------------------------------------------------------ S(q) read-out
 // sf[kx][ky][kz] = (P[pos(k)] + P[pos(-k)]) / 2 for kz in [0, Nz/2]: the half spectrum that
 // dens.py:318 accumulates.  rev* map a frequency index to its position (identity for cuFFT).
-__global__ void export_sf_kernel(const double* __restrict__ P, double* __restrict__ sf,
+static __global__ void export_sf_kernel(const double* __restrict__ P, double* __restrict__ sf,
                                  const int* __restrict__ revx, const int* __restrict__ revy,
-                                 const int* __restrict__ revz, int nx, int ny, int nz)
+                                 const int* __restrict__ revz, GridParams gp)
 {
+    const int nx = gp.n[0], ny = gp.n[1], nz = gp.n[2];
     const int m = nz / 2 + 1;
     const long long total = (long long)nx * ny * m;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -814,28 +660,14 @@ __global__ void export_sf_kernel(const double* __restrict__ P, double* __restric
         const int kz = (int)(i % m);
         const long long t = i / m;
         const int ky = (int)(t % ny), kx = (int)(t / ny);
-        const long long a = ((long long)revx[kx] * ny + revy[ky]) * nz + revz[kz];
-        const long long b = ((long long)revx[(nx - kx) % nx] * ny + revy[(ny - ky) % ny]) * nz + revz[(nz - kz) % nz];
+        const long long a = vol_index(gp, revx[kx], revy[ky], revz[kz]);
+        const long long b = vol_index(gp, revx[(nx - kx) % nx], revy[(ny - ky) % ny], revz[(nz - kz) % nz]);
         sf[i] = 0.5 * (P[a] + P[b]);
     }
 }
 
-// pack real densities d1[frame][cell] into complex pair volumes (RANDOM_NOISE mode, dens.py:280)
-__global__ void pack_density_kernel(const double* __restrict__ d1, double2* __restrict__ vol,
-                                    long long ncell, int nframes)
-{
-    const int npairs = (nframes + 1) / 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncell * npairs;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long q = i / ncell, c = i - q * ncell;
-        const double re = d1[(2 * q) * ncell + c];
-        const double im = (2 * q + 1 < nframes) ? d1[(2 * q + 1) * ncell + c] : 0.0;
-        vol[i] = make_double2(re, im);
-    }
-}
-
 // un-pack a pair volume (before any FFT) into the real density of one frame (debug tap)
-__global__ void unpack_density_kernel(const double2* __restrict__ vol, double* __restrict__ d1,
+static __global__ void unpack_density_kernel(const double2* __restrict__ vol, double* __restrict__ d1,
                                       long long ncell, int part)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncell;

@@ -1,4 +1,4 @@
-// K1/K2: per-atom preparation and deterministic binning of (atom image, tile) pairs.
+// K1/K2: per-atom preparation and binning of (atom image, tile, z slab) pairs.
 #pragma once
 #include "mdsf_common.cuh"
 
@@ -13,74 +13,89 @@ template <typename P> __device__ __forceinline__ P add_rn(P a, P b);
 template <> __device__ __forceinline__ float  add_rn<float>(float a, float b)   { return __fadd_rn(a, b); }
 template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
 
-// (image, tile, slab) pairs of one atom: for every periodic image (sx,sy) of the stamp's xy
-// rectangle, every tile it overlaps, every z slab it touches.  emit_pairs_kernel walks the same loops.
-__device__ __forceinline__ unsigned count_pairs(const AtomRec& rec, const GridParams& gp, const TypeTable& tt) {
-    const int Ax = tt.halfw[rec.type * 3], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
-    unsigned total = 0;
-    for (int sx = -1; sx <= 1; ++sx) {
-        int xlo, xhi;
-        stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
-        if (xhi <= xlo) continue;
-        const int ntx = (xhi - 1 - sx * gp.n[0]) / gp.tx - (xlo - sx * gp.n[0]) / gp.tx + 1;
-        for (int sy = -1; sy <= 1; ++sy) {
-            int ylo, yhi;
-            stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
-            if (yhi <= ylo) continue;
-            const int nty = (yhi - 1 - sy * gp.n[1]) / gp.ty - (ylo - sy * gp.n[1]) / gp.ty + 1;
-            int shlo, shhi, kA, kB;
-            const unsigned sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
-            total += (unsigned)(ntx * nty * __popc(sm));
-        }
-    }
-    return total;
-}
-
+// Every (image, tile, slab) pair of one atom.  The stamp [ir-A, ir+A)^3 on the padded grid is cut into its
+// <= 27 fold images (side s = -1 / 0 / +1 per dimension: low padding / cell / high padding, dens.py:86-108);
+// each image is one box in destination space with ONE shift, so the splat never sees segments or the corner
+// rule again.  fn(key, rec, aux): key = (frame * ntiles + tile) * nslab + slab.
 template <typename F>
 __device__ __forceinline__ void for_each_pair(const AtomRec& rec, int a, int f, const GridParams& gp, const TypeTable& tt, F&& fn) {
     const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
+    if (Ax <= 0 || Ay <= 0 || Az <= 0) return;
+    const int ltx = (gp.lcol + 1) >> 1, lty = gp.lcol >> 1;
+    const int TX = 1 << ltx, TY = 1 << lty;
+    const int lzw = 8 - gp.lcol, ZW = 1 << lzw;                 // slab width 256 >> lcol
     const int ntiles = gp.ntx * gp.nty;
-    const int ltx = __ffs(gp.tx) - 1, lty = __ffs(gp.ty) - 1;     // tile sizes are powers of two; destinations are >= 0
+    const int ctbase = (tt.ctab != nullptr) ? tt.ctab_off[rec.type] : 0;
     for (int sx = -1; sx <= 1; ++sx) {
         int xlo, xhi;
         stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
         if (xhi <= xlo) continue;
-        const int tx0 = (xlo - sx * gp.n[0]) >> ltx, tx1 = (xhi - 1 - sx * gp.n[0]) >> ltx;
+        const int dx0 = xlo - sx * gp.n[0], dx1 = xhi - sx * gp.n[0];         // destination range
+        const int ix0 = xlo - (rec.ir[0] - Ax);                              // stamp index of dx0
         for (int sy = -1; sy <= 1; ++sy) {
             int ylo, yhi;
             stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
             if (yhi <= ylo) continue;
-            const int ty0 = (ylo - sy * gp.n[1]) >> lty, ty1 = (yhi - 1 - sy * gp.n[1]) >> lty;
-            const unsigned payload = (unsigned)a | ((unsigned)(sx + 1) << MDSF_ATOM_BITS) |
-                                     ((unsigned)(sy + 1) << (MDSF_ATOM_BITS + 2));
-            unsigned sm;
-            if (gp.nslab == 1) {
-                sm = Az > 0 ? 1u : 0u;          // one list per tile (tile mode): every image with cells belongs to it
-            } else {
-                int shlo, shhi, kA, kB;
-                sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
-            }
-            for (int tX = tx0; tX <= tx1; ++tX)
-                for (int tY = ty0; tY <= ty1; ++tY) {
-                    const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
-                    for (unsigned m = sm; m; m &= m - 1) fn(kbase + (unsigned)(__ffs(m) - 1), payload);
+            const int dy0 = ylo - sy * gp.n[1], dy1 = yhi - sy * gp.n[1];
+            const int jy0 = ylo - (rec.ir[1] - Ay);
+            for (int sz = -1; sz <= 1; ++sz) {
+                int zlo, zhi;
+                stamp_segment(rec.ir[2], Az, gp.n[2], sz, zlo, zhi);
+                if (zhi <= zlo) continue;
+                const int shz = fold_shift_z(sx, sy, sz, gp.n[2], gp.nb, gp.fold_mode);
+                const int dz0 = zlo + shz, dz1 = zhi + shz;
+                const int kz0 = zlo - (rec.ir[2] - Az);
+                for (int tX = dx0 >> ltx; tX <= (dx1 - 1) >> ltx; ++tX) {
+                    const int X0 = tX << ltx;
+                    const int cx0 = max(dx0 - X0, 0), cx1 = min(dx1 - X0, TX);
+                    const int i0 = ix0 + (X0 + cx0 - dx0);
+                    for (int tY = dy0 >> lty; tY <= (dy1 - 1) >> lty; ++tY) {
+                        const int Y0 = tY << lty;
+                        const int cy0 = max(dy0 - Y0, 0), cy1 = min(dy1 - Y0, TY);
+                        const int j0 = jy0 + (Y0 + cy0 - dy0);
+                        const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
+                        for (int s = dz0 >> lzw; s <= (dz1 - 1) >> lzw; ++s) {
+                            const int Z0 = s << lzw;
+                            const int zoff = max(dz0 - Z0, 0), zend = min(dz1 - Z0, ZW);
+                            const int k0 = kz0 + (Z0 + zoff - dz0);
+                            PairRec pr;
+                            PairAux pa;
+                            pr.w = (unsigned)(cx0 | (cx1 << 3) | (cy0 << 7) | (cy1 << 10) | (zoff << 14) | (zend << 21));
+                            if (gp.separable) {
+                                pr.x = (unsigned)((int)rec.tbase + 2 * (Ax + Ay) + k0 - zoff);
+                                pr.y = (unsigned)((int)rec.tbase + i0 - cx0);
+                                pr.z = (unsigned)((int)rec.tbase + 2 * Ax + j0 - cy0);
+                                pa.x = (unsigned)(ctbase + (i0 - cx0) * 2 * Ay + (j0 - cy0));
+                                pa.y = (unsigned)(2 * Ay);
+                            } else {
+                                pr.x = (unsigned)(Z0 - shz);                  // padded z of slab-local cell 0
+                                pr.y = (unsigned)(X0 + sx * gp.n[0]);         // padded x of tile column 0
+                                pr.z = (unsigned)(Y0 + sy * gp.n[1]);
+                                pa.x = (unsigned)a;
+                                pa.y = 0u;
+                            }
+                            fn(kbase + (unsigned)s, pr, pa);
+                        }
+                    }
                 }
+            }
         }
     }
 }
 
 #define MDSF_PREP_STAGE 512        // doubles of factor tables one warp stages in shared memory (c2: 32 atoms x 12)
 
+// K1.  Also counts the pairs of every list (atomicAdd on `counter[key]`): the scan of those counts gives the list
+// starts, bin_place_kernel then fills the lists.
 template <typename C, typename P>
 __global__ void __launch_bounds__(256)
 prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], rewritten in place
                   const int* __restrict__ type_id,   // [natoms]
                   AtomRec* __restrict__ recs,        // [nframes][natoms]
-                  unsigned* __restrict__ pair_count, // [nframes*natoms]
                   double* __restrict__ tables,       // [nframes][tstride] per-atom Gaussian factor tables
                   GridParams gp, TypeTable tt, BatchScales sc, int nframes,
                   long long wrap_lo, long long wrap_hi, int* __restrict__ err_flag,
-                  unsigned* __restrict__ tile_counter /* direct binning: list lengths per (frame, tile) key, or nullptr */,
+                  unsigned* __restrict__ counter     /* [nkeys] list lengths */,
                   int mono, double mono_sin, double mono_cos /* monoclinic pre-transform (main_gromacs.py:204-207) */)
 {
     // A lane's record (48 B) and factor tables (16 (Ax+Ay+Az) B) are contiguous with its neighbours' in global memory
@@ -135,6 +150,7 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
                 rec.ir[d] = ir;
             }
         }
+        rec.pad_ = bad ? 1u : 0u;                          // bin_place_kernel skips rejected atoms
         {   // records: 6 eight-byte words per lane -> 192 contiguous words per warp
             const double* w = reinterpret_cast<const double*>(&rec);
 #pragma unroll
@@ -146,19 +162,15 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
             for (int j = lane; j < nvalid; j += 32) dst[j] = s_rec[warp][j];
             __syncwarp();
         }
-        unsigned npairs = 0;
         if (live && bad) atomicExch(err_flag, 1);
         const bool ok = live && !bad;
-        if (ok) {
-            if (tile_counter != nullptr) for_each_pair(rec, a, f, gp, tt, [&](unsigned key, unsigned) { atomicAdd(tile_counter + key, 1u); ++npairs; });
-            else npairs = count_pairs(rec, gp, tt);
-        }
-        if (live) pair_count[idx] = npairs;
+        if (ok) for_each_pair(rec, a, f, gp, tt, [&](unsigned key, const PairRec&, const PairAux&) { atomicAdd(counter + key, 1u); });
         if (!gp.separable) continue;                       // warp-uniform
         // One-dimensional Gaussian factors of this atom's stamp (dens.py:299-308 factorised):
         //   exp(-|c|^2/(2s^2)) = EX[i] * EY[j] * C_type[i][j] * EZ[k]/amp, with
         //   EX[i] = exp(-(cxx bx_i^2 + 2 gxy bx_i by_0)/(2s^2)),  EY[j] = exp(-(cyy by_j^2 - 2 gxy (j dy) bx_0)/(2s^2)),
-        //   EZ[k] = Nel/s^3 exp(-czz bz_k^2/(2s^2)),  C[i][j] = exp(-2 gxy dx dy i j/(2s^2)) (per type, host-built).
+        //   EZ[k] = 2^(52-e) Nel/s^3 exp(-czz bz_k^2/(2s^2)),  C[i][j] = exp(-2 gxy dx dy i j/(2s^2)) (per type, host-built).
+        // EZ carries the fixed-point scale of the splat accumulators (a power of two: exact).
         // b = r - (i - B)*dr with the product rounded on its own, as numpy does (dens.py:252-256,299).
         const int Ax = tt.halfw[t * 3], Ay = tt.halfw[t * 3 + 1], Az = tt.halfw[t * 3 + 2];
         const unsigned size = ok ? (unsigned)(2 * (Ax + Ay + Az)) : 0u;
@@ -169,7 +181,7 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
         if (ok) {
             // one reciprocal per atom instead of a divide per table entry (the argument moves by <= 1 ulp: 1e-16 of a
             // term; the golden-vector density tolerance is 1e-13 of the peak)
-            const double it2 = 1.0 / tt.two_sig2[t], amp = tt.amp[t];
+            const double it2 = 1.0 / tt.two_sig2[t], amp = tt.amp[t] * gp.fx_scale;
             double* T = staged ? &s_tab[warp][off] : tables + rec.tbase;
             const double bx0 = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax), gp.dr[0]));
             const double by0 = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay), gp.dr[1]));
@@ -198,98 +210,30 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
     }
 }
 
-// ---- K2a: emit (key = (frame*ntiles + tile)*nslab + slab, payload = atom | sx | sy) at scanned offsets
+// ---- K2: fill the lists.  The splat accumulates in 64-bit fixed point (integer adds commute), so the order inside
+// a list is irrelevant and a counting sort with atomics is deterministic in its RESULT: start = exclusive scan of the
+// K1 counts, every pair claims a slot of its list from a per-key cursor.
+template <bool AUX>
 __global__ void __launch_bounds__(256)
-emit_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ pair_count,
-                  const unsigned* __restrict__ pair_off, unsigned* __restrict__ keys,
-                  unsigned* __restrict__ vals, GridParams gp, TypeTable tt, int nframes)
+bin_place_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ start, unsigned* __restrict__ cursor,
+                 PairRec* __restrict__ prec, PairAux* __restrict__ paux, GridParams gp, TypeTable tt, int nframes,
+                 unsigned nkeys, unsigned long long cap, int* __restrict__ err_flag)
 {
-    const long long total = (long long)nframes * gp.natoms;
-    const int ntiles = gp.ntx * gp.nty;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        if (pair_count[idx] == 0) continue;
-        const int f = (int)(idx / gp.natoms);
-        const int a = (int)(idx - (long long)f * gp.natoms);
-        const AtomRec rec = recs[idx];
-        const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
-        unsigned o = pair_off[idx];
-        for (int sx = -1; sx <= 1; ++sx) {
-            int xlo, xhi;
-            stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
-            if (xhi <= xlo) continue;
-            const int tx0 = (xlo - sx * gp.n[0]) / gp.tx, tx1 = (xhi - 1 - sx * gp.n[0]) / gp.tx;
-            for (int sy = -1; sy <= 1; ++sy) {
-                int ylo, yhi;
-                stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
-                if (yhi <= ylo) continue;
-                const int ty0 = (ylo - sy * gp.n[1]) / gp.ty, ty1 = (yhi - 1 - sy * gp.n[1]) / gp.ty;
-                const unsigned payload = (unsigned)a | ((unsigned)(sx + 1) << MDSF_ATOM_BITS) |
-                                         ((unsigned)(sy + 1) << (MDSF_ATOM_BITS + 2));
-                int shlo, shhi, kA, kB;
-                const unsigned sm = image_slabmask(rec.ir[2], Az, sx, sy, gp.n[2], gp.nb, gp.fold_mode, gp.zs, shlo, shhi, kA, kB);
-                for (int tX = tx0; tX <= tx1; ++tX)
-                    for (int tY = ty0; tY <= ty1; ++tY) {
-                        const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
-                        for (unsigned m = sm; m; m &= m - 1) {
-                            keys[o] = kbase + (unsigned)(__ffs(m) - 1);
-                            vals[o] = payload;
-                            ++o;
-                        }
-                    }
-            }
-        }
+    if ((unsigned long long)start[nkeys] > cap) {       // cannot happen unless the host bound is wrong: refuse to overrun
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(err_flag, 4);
+        return;
     }
-}
-
-// ---- K2 (tile splat mode): direct binning.  The fixed-point tile accumulation is order-independent, so the
-// lists need no stable sort: count the pairs of every (frame, tile) key with integer atomics, scan the counts
-// into list starts, and let every pair claim a slot of its list from a per-key cursor.  Replaces scan + fill +
-// emit + radix sort + list starts (0.43 ms -> 0.15 ms per 32 c2 frames, serialised ncu times).
-// PLACE = false: list lengths; PLACE = true: payloads into their lists (start = scanned lengths, cursor zeroed)
-template <bool PLACE>
-__global__ void __launch_bounds__(256)
-bin_pairs_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ pair_count, unsigned* __restrict__ counter,
-                 const unsigned* __restrict__ start, unsigned* __restrict__ vals, uint4* __restrict__ prec,
-                 GridParams gp, TypeTable tt, int nframes)
-{
     const long long total = (long long)nframes * gp.natoms;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        if (pair_count[idx] == 0) continue;
         const int f = (int)(idx / gp.natoms);
         const int a = (int)(idx - (long long)f * gp.natoms);
         const AtomRec rec = recs[idx];
-        for_each_pair(rec, a, f, gp, tt, [&](unsigned key, unsigned payload) {
-            if (PLACE) {
-                const unsigned pos = start[key] + atomicAdd(counter + key, 1u);
-                if (prec != nullptr) {       // 16-byte pair record (layout: splat_zfft_kernel, PREC)
-                    prec[pos] = make_uint4((unsigned)(rec.ir[0] + 1024) | ((unsigned)(rec.ir[1] + 1024) << 12) | ((payload >> MDSF_ATOM_BITS) << 24),
-                                           (unsigned)(rec.ir[2] + 1024) | ((unsigned)rec.type << 13), rec.tbase, (unsigned)a);
-                } else {
-                    vals[pos] = payload;
-                }
-            } else {
-                atomicAdd(counter + key, 1u);
-            }
+        if (rec.pad_) continue;                           // atoms K1 rejected have no counted pairs
+        for_each_pair(rec, a, f, gp, tt, [&](unsigned key, const PairRec& pr, const PairAux& pa) {
+            const unsigned pos = start[key] + atomicAdd(cursor + key, 1u);
+            prec[pos] = pr;
+            if (AUX) paux[pos] = pa;
         });
-    }
-}
-
-__global__ void fill_u32_kernel(unsigned* __restrict__ p, unsigned v, long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) p[i] = v;
-}
-
-// ---- K2c: list boundaries in the sorted key array: start[k] = first index with key >= k -----
-__global__ void __launch_bounds__(256)
-tile_starts_kernel(const unsigned* __restrict__ keys, long long n, unsigned nkeys,
-                   unsigned* __restrict__ start /* [nkeys+1] */)
-{
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i <= n;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long kprev = (i == 0) ? -1 : (long long)min(keys[i - 1], nkeys);
-        const long long kcur = (i == n) ? (long long)nkeys : (long long)min(keys[i], nkeys);
-        for (long long k = kprev + 1; k <= kcur; ++k) start[k] = (unsigned)i;
     }
 }

@@ -35,7 +35,6 @@ FOLD_MODE = "reference"   # "reference": reproduce the corner rule of reference 
 WRITE_BACK_COORDS = True  # the reference rescales/wraps ``r`` in place; keep that side effect
 DEVICE = 0                # CUDA device ordinal used by compute_sf
 FFT_MODE = "auto"         # "auto" | "native" | "cufft"
-SPLAT_MODE = "auto"       # "auto" | "owner" (fp64 owner-computes tiles) | "tile" / "scatter" (deterministic fixed-point accumulation)
 BATCH_FRAMES = 0          # frames per device batch (0 = automatic)
 SAVE_COMPRESSED = True    # np.savez_compressed like the reference; False writes an uncompressed npz
 GPU_MONOCLINIC = True     # compute_sf_stream: the monoclinic transform of main_gromacs.py:204-207 runs inside the first kernel, not in numpy
@@ -162,7 +161,7 @@ def _k_lattices(shape, L):
 
 
 def make_engine(L_mean, typ, rad, ucell, Sres, coord_dtype, arith_dtype, keep_density=False, device=None,
-                batch_frames=None, fft_mode=None, tile=(0, 0), fold_mode=None, splat_mode=None):
+                batch_frames=None, fft_mode=None, tile=(0, 0), fold_mode=None):
     """Build the GPU engine for one call: everything that is frame-invariant (dens.py:181-231).
 
     Returns (engine, N, dr).  Raises KeyError for labels missing from ``rad`` like the reference."""
@@ -176,8 +175,7 @@ def make_engine(L_mean, typ, rad, ucell, Sres, coord_dtype, arith_dtype, keep_de
     halfw = np.array([bdict[l].astype(int) for l in labels])                    # dens.py:287
     fold = {"reference": _native.FOLD_REFERENCE, "periodic": _native.FOLD_PERIODIC}[fold_mode or FOLD_MODE]
     fft = {"auto": _native.FFT_AUTO, "native": _native.FFT_NATIVE, "cufft": _native.FFT_CUFFT}[fft_mode or FFT_MODE]
-    splat = {"auto": _native.SPLAT_AUTO, "owner": _native.SPLAT_OWNER, "scatter": _native.SPLAT_SCATTER, "tile": _native.SPLAT_TILE}[splat_mode or SPLAT_MODE]
-    eng = _native.Engine(n, nborder, dr, L_mean, ucell, amp, two_sig2, halfw, coord_dtype, arith_dtype, splat_mode=splat,
+    eng = _native.Engine(n, nborder, dr, L_mean, ucell, amp, two_sig2, halfw, coord_dtype, arith_dtype,
                          fold_mode=fold, fft_mode=fft, batch_frames=BATCH_FRAMES if batch_frames is None else batch_frames,
                          tile=tile, keep_density=keep_density, device=DEVICE if device is None else device)
     eng.set_atoms(type_ids)

@@ -16,14 +16,13 @@ ABI_VERSION = 1
 F32, F64 = 0, 1
 FOLD_REFERENCE, FOLD_PERIODIC = 0, 1
 FFT_AUTO, FFT_NATIVE, FFT_CUFFT = 0, 1, 2
-SPLAT_AUTO, SPLAT_OWNER, SPLAT_SCATTER, SPLAT_TILE = 0, 1, 2, 3
 
 EXPORTS = [
     "mdsf_create", "mdsf_destroy", "mdsf_set_atoms", "mdsf_host_alloc", "mdsf_host_free",
     "mdsf_host_register", "mdsf_host_unregister", "mdsf_push_frames", "mdsf_push_density", "mdsf_sync",
     "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
     "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_splat_path",
-    "mdsf_batch_frames", "mdsf_pipeline_info", "mdsf_set_pretransform",
+    "mdsf_batch_frames", "mdsf_geometry", "mdsf_set_pretransform",
     "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_timer_start", "mdsf_timer_stop", "mdsf_last_error",
     "mdsf_input_mark", "mdsf_input_wait",
     "mdsf_abi_version",
@@ -82,7 +81,7 @@ def load():
         "mdsf_fft_path": (C.c_char_p, [vp]),
         "mdsf_splat_path": (C.c_char_p, [vp]),
         "mdsf_batch_frames": (C.c_int, [vp]),
-        "mdsf_pipeline_info": (C.c_int, [vp, C.POINTER(i32)]),
+        "mdsf_geometry": (C.c_int, [vp, C.POINTER(i32)]),
         "mdsf_set_pretransform": (C.c_int, [vp, i32, C.c_double, C.c_double]),
         "mdsf_enable_timing": (C.c_int, [vp, i32]),
         "mdsf_stage_ms": (C.c_int, [vp, dp, C.POINTER(i64)]),
@@ -129,7 +128,7 @@ class Engine:
 
     def __init__(self, n, nborder, dr, box, ucell, amp, two_sig2, halfw, coord_dtype, arith_dtype,
                  fold_mode=FOLD_REFERENCE, fft_mode=FFT_AUTO, batch_frames=0, tile=(0, 0), keep_density=False,
-                 device=0, splat_mode=SPLAT_AUTO):
+                 device=0):
         self._lib = load()
         self._h = C.c_void_p()
         self.n = tuple(int(v) for v in n)
@@ -142,6 +141,7 @@ class Engine:
         cfg = Config()
         cfg.abi_version = ABI_VERSION
         cfg.device = int(device)
+        self.device = int(device)
         cfg.n[:] = self.n
         cfg.nborder = int(nborder)
         cfg.dr[:] = [float(v) for v in dr]
@@ -158,7 +158,7 @@ class Engine:
         cfg.batch_frames = int(batch_frames)
         cfg.tile_x, cfg.tile_y = int(tile[0]), int(tile[1])
         cfg.keep_density = 1 if keep_density else 0
-        cfg.splat_mode = int(splat_mode)
+        cfg.splat_mode = 0
         _check(self._lib.mdsf_create(C.byref(cfg), C.byref(self._h)))
         self.natoms = 0
         self._finalizer = weakref.finalize(self, self._lib.mdsf_destroy, C.c_void_p(self._h.value))
@@ -285,11 +285,12 @@ class Engine:
             _check(self._lib.mdsf_set_pretransform(self._h, 1, float(np.sin(theta)), float(np.cos(theta))))
 
     @property
-    def pipeline(self):
-        """{"overlap": bool, "sms": (splat-side SMs, pass-side SMs)}; (0, 0) = no SM partition."""
-        sms = (C.c_int32 * 2)()
-        ov = self._lib.mdsf_pipeline_info(self._h, sms)
-        return {"overlap": bool(ov), "sms": (int(sms[0]), int(sms[1]))}
+    def geometry(self):
+        """Launch geometry: splat tile, z-slab width, volume layout chunk width, pass tile widths, splat smem (KiB)."""
+        g = (C.c_int32 * 8)()
+        _check(self._lib.mdsf_geometry(self._h, g))
+        return {"tile": (int(g[0]), int(g[1])), "slab": int(g[2]), "nslab": int(g[3]), "layout_w": int(g[4]),
+                "wy": int(g[5]), "wx": int(g[6]), "splat_smem_kib": int(g[7])}
 
     def enable_timing(self, on=True):
         _check(self._lib.mdsf_enable_timing(self._h, 1 if on else 0))

@@ -18,13 +18,29 @@ def frame_shard(nframes, rank, world):
     return start, start + base + (1 if rank < extra else 0)
 
 
+def default_device():
+    """GPU of this rank when the caller names none: LOCAL_RANK (torchrun), else torch's current device."""
+    import os
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except ImportError:
+        pass
+    return dens.DEVICE
+
+
 def reduce_partial_sf(engine, group=None, dst=0):
     """Sum the per-rank partial sf onto ``dst``; returns the numpy array there, None elsewhere."""
     import torch
     import torch.distributed as dist
     shape = (engine.n[0], engine.n[1], engine.n[2] // 2 + 1)
     if dist.get_backend(group) == "nccl":
-        dev = torch.device("cuda", torch.cuda.current_device())
+        # the reduce buffer lives on the ENGINE's GPU: export_sf_kernel writes it, NCCL reads it
+        dev = torch.device("cuda", int(getattr(engine, "device", torch.cuda.current_device())))
+        torch.cuda.set_device(dev)
         buf = torch.empty(shape, dtype=torch.float64, device=dev)
         engine.sync()
         engine.export_sf_device(buf.data_ptr())
@@ -55,6 +71,8 @@ def compute_sf_sharded(r, L, typ, out_filename, rad, ucell, Sres, group=None, en
     Lmean = np.average(dims, axis=0)
     scale = (Lmean / dims).astype(np.float64)
     factory = engine_factory or dens.make_engine
+    if device is None and engine_factory is None:
+        device = default_device()
     eng, n, dr, nborder = factory(Lmean, typ, rad, ucell, Sres, mine.dtype, arith, device=device)
     try:
         lo, hi = dens._wrapped_atoms(nframes, mine.shape[1])
