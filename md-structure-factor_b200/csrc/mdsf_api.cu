@@ -44,7 +44,7 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 static const int kSlots = 2;
-static const int kMaxSmem = 227 * 1024;
+static const int kMaxSmem = 227 * 1024 - 256;
 enum { SPLAT_ORTHO_ = 0, SPLAT_MONO_ = 1, SPLAT_GENERAL_ = 2, SPLAT_DENSITY_ = 3 };     // = the enum of mdsf_splat.cuh
 
 struct AxisPlan {
@@ -58,10 +58,9 @@ struct AxisPlan {
 // splat/FFT kernels of batch b (stream s_comp)
 struct PrepSet {
     AtomRec* recs = nullptr;
-    double* tables = nullptr;
+    double *tables = nullptr, *tables_alloc = nullptr;
     unsigned *count = nullptr, *start = nullptr, *cursor = nullptr;     // [nkeys+1] each
-    PairRec* prec = nullptr;
-    PairAux* paux = nullptr;
+    uint4* prec = nullptr;            // [2 * pair_cap]: 32-byte records {PairRec, PairAux + padding}
     void* cub = nullptr;
     cudaEvent_t ev_binned = nullptr, ev_consumed = nullptr;
     bool used = false;
@@ -79,6 +78,8 @@ struct mdsf_handle {
     long long ncell = 0;
     int splat_mode = 0;               // SPLAT_ORTHO / MONO / GENERAL
     size_t splat_smem = 0;
+    double2* d_tws = nullptr;         // per-stage z twiddle tables of the compile-time z path (nullptr: generic stages)
+    int tws_n = 0, tws_off = 0;
     // streams / events
     cudaStream_t s_copy = nullptr, s_prep = nullptr, s_comp = nullptr, s_back = nullptr;
     cudaEvent_t ev_h2d[kSlots]{}, ev_free[kSlots]{}, ev_prep[kSlots]{}, ev_back[kSlots]{};
@@ -108,6 +109,7 @@ struct mdsf_handle {
     int cufft_batch = 0;
     long long natoms = 0;
     long long maxpairs_frame = 0;
+    int KX = 1, KY = 1;               // most x / y tiles one atom's stamp touches: bin_place_kernel runs KX*KY threads per atom
     unsigned long long pair_cap = 0;
     int mono = 0;                     // K1 applies the monoclinic transform of main_gromacs.py:204-207 first
     double mono_sin = 1.0, mono_cos = 0.0;
@@ -184,6 +186,22 @@ static int grid_for(long long n, int threads, int nsm) {
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
+}
+
+// Slab geometry of the splat for `sub` lists per warp (1: one slab of 256 >> lcol cells per warp, 2: two half-width
+// slabs side by side), its shared memory, and whether the z twiddle tables get their own region (prefetched while the
+// splat runs) -- they do when two CTAs still fit an SM.
+static void configure_splat(mdsf_handle* h, int sub) {
+    GridParams& gp = h->gp;
+    gp.sub = sub;
+    gp.zw = (256 >> gp.lcol) / sub;
+    gp.nslab = (gp.n[2] + gp.zw - 1) / gp.zw;
+    h->splat_smem = mdsf_splat_smem(gp.lcol, sub, gp.nzp, gp.n[2]);
+    h->tws_off = 0;
+    if (h->d_tws) {
+        const size_t base = (h->splat_smem + 15) / 16 * 16, need = base + sizeof(double2) * (size_t)h->tws_n;
+        if (2 * (need + 1024) <= (size_t)kMaxSmem + 1024) { h->tws_off = (int)base; h->splat_smem = need; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -271,18 +289,38 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         gp.lcol = l;
     } else {
         gp.lcol = 5;
-        while (gp.lcol > 2 && mdsf_splat_smem(gp.lcol, gp.nzp, gp.n[2]) > 112 * 1024) --gp.lcol;
+        while (gp.lcol > 2 && mdsf_splat_smem(gp.lcol, 1, gp.nzp, gp.n[2]) > 112 * 1024) --gp.lcol;
     }
-    if (mdsf_splat_smem(gp.lcol, gp.nzp, gp.n[2]) > (size_t)kMaxSmem)
+    if (mdsf_splat_smem(gp.lcol, 1, gp.nzp, gp.n[2]) > (size_t)kMaxSmem)
         return fail(MDSF_EINVAL, "grid too long in z (%d) for the column-tile splat", gp.n[2]);
-    h->splat_smem = mdsf_splat_smem(gp.lcol, gp.nzp, gp.n[2]);
     {
         const int TX = 1 << ((gp.lcol + 1) / 2), TY = 1 << (gp.lcol / 2);
-        gp.zw = 256 >> gp.lcol;
-        gp.nslab = (gp.n[2] + gp.zw - 1) / gp.zw;
         gp.ntx = (gp.n[0] + TX - 1) / TX;
         gp.nty = (gp.n[1] + TY - 1) / TY;
     }
+    // ---- compile-time z stages: per-stage twiddle tables [k-1][n2] = w^(n2 k N/L)
+    if (h->native_fft && mdsf_zspec_applies(gp.lcol, gp.n[2], gp.pad_shift)) {
+        const FftPlan& zp = h->ax[2].plan;
+        const int N = gp.n[2];
+        std::vector<double2> tws;
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        int L = N;
+        for (int st = 0; st < zp.nstages; ++st) {
+            const int R = zp.radix[st], M = L / R;
+            if (M > 1)
+                for (int k = 1; k < R; ++k)
+                    for (int n2 = 0; n2 < M; ++n2) {
+                        const int j = (int)(((long long)n2 * k * (N / L)) % N);
+                        const long double a = two_pi * (long double)j / (long double)N;
+                        tws.push_back(make_double2((double)cosl(a), (double)(-sinl(a))));
+                    }
+            L = M;
+        }
+        h->tws_n = (int)tws.size();
+        CU(cudaMalloc(&h->d_tws, sizeof(double2) * tws.size()));
+        CU(cudaMemcpy(h->d_tws, tws.data(), sizeof(double2) * tws.size(), cudaMemcpyHostToDevice));
+    }
+    configure_splat(h, 1);
 
     // ---- volume layout: plain [x][y][z], or z-chunked [z/lw][x][y][lw] (MDSF_LAYOUT_W = 4 / 8; native FFT only)
     gp.lw = gp.n[2];
@@ -332,8 +370,13 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     h->tt.ctab = nullptr; h->tt.ctab_off = nullptr; h->tt.toff = nullptr;
     if (h->splat_mode == SPLAT_MONO_) {
         // cross-term table of every type: C[i][j] = exp(-2 gxy dx dy i j / (2 sigma^2))
+        // columns outside a stamp index the tables out of a type's range (their EX / EY factor is an exact zero, so the
+        // value only has to be finite): pads of ones in front and behind cover the largest excursion, 8 rows + 8 entries
         std::vector<int> off(nt);
-        std::vector<double> ctab;
+        int amax2 = 2;
+        for (int t = 0; t < nt; ++t) amax2 = std::max(amax2, 2 * cfg->halfw[t * 3 + 1]);
+        const size_t cpad = (size_t)8 * amax2 + 8;
+        std::vector<double> ctab(cpad, 1.0);
         for (int t = 0; t < nt; ++t) {
             off[t] = (int)ctab.size();
             const int ax2 = 2 * cfg->halfw[t * 3], ay2 = 2 * cfg->halfw[t * 3 + 1];
@@ -341,7 +384,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
                 for (int j = 0; j < ay2; ++j)
                     ctab.push_back(std::exp(-(2.0 * gp.gxy * gp.dr[0] * gp.dr[1] * (double)i * (double)j) / cfg->two_sig2[t]));
         }
-        if (ctab.empty()) ctab.push_back(1.0);
+        ctab.insert(ctab.end(), cpad, 1.0);
         if (ctab.size() >= (1u << 30)) return fail(MDSF_EINVAL, "cross-term tables too large");
         CU(cudaMalloc(&h->d_ctab, sizeof(double) * ctab.size()));
         CU(cudaMalloc(&h->d_ctab_off, sizeof(int) * nt));
@@ -421,12 +464,12 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->cufft_plan) cufftDestroy(h->cufft_plan);
-    void* bufs[] = {h->d_ctab, h->d_ctab_off, h->d_toff, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1],
+    void* bufs[] = {h->d_tws, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1],
                     h->d_vol, h->d_dump, h->d_P, h->d_sf, h->d_err};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int d = 0; d < 3; ++d) { if (h->ax[d].d_tw) cudaFree(h->ax[d].d_tw); if (h->ax[d].d_rev) cudaFree(h->ax[d].d_rev); }
     for (auto& ps : h->sets) {
-        void* pb[] = {ps.recs, ps.tables, ps.count, ps.start, ps.cursor, ps.prec, ps.paux, ps.cub};
+        void* pb[] = {ps.recs, ps.tables_alloc, ps.count, ps.start, ps.cursor, ps.prec, ps.cub};
         for (void* b : pb) if (b) cudaFree(b);
         if (ps.ev_binned) cudaEventDestroy(ps.ev_binned);
         if (ps.ev_consumed) cudaEventDestroy(ps.ev_consumed);
@@ -458,12 +501,25 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     if (natoms < 1 || natoms >= MDSF_MAX_ATOMS) return fail(MDSF_EINVAL, "natoms=%lld outside [1, %d)", (long long)natoms, MDSF_MAX_ATOMS);
     if (h->d_type) return fail(MDSF_ESTATE, "atoms already set on this handle");
     CU(cudaSetDevice(h->device));
-    const GridParams& g0 = h->gp;
     const int nt = h->cfg.ntypes;
+    {
+        // two lists per warp when the stamps are short against a full-warp slab (most of its cells would add zeros)
+        double zsum = 0;
+        for (int64_t a = 0; a < natoms; ++a) {
+            if (type_id[a] < 0 || type_id[a] >= nt) return fail(MDSF_EINVAL, "type_id[%lld]=%d out of range", (long long)a, type_id[a]);
+            zsum += 2.0 * h->halfw_host[type_id[a] * 3 + 2];
+        }
+        int sub = (zsum / (double)natoms <= 0.5 * (256 >> h->gp.lcol)) ? 2 : 1;
+        sub = env_int("MDSF_SUB", sub);
+        if (sub != 1 && sub != 2) return fail(MDSF_EINVAL, "MDSF_SUB must be 1 or 2");
+        configure_splat(h, sub);
+    }
+    const GridParams& g0 = h->gp;
     const int TX = 1 << ((g0.lcol + 1) / 2), TY = 1 << (g0.lcol / 2);
     // worst-case (image, tile, slab) pairs per atom of each type: exact maximum over every admissible cell index,
     // per dimension (z: both fold shifts of a padding segment, -+Nz and the corner rule's +-Nborder)
     std::vector<long long> bound(nt);
+    h->KX = h->KY = 1;
     for (int t = 0; t < nt; ++t) {
         long long m[3] = {1, 1, 1};
         for (int d = 0; d < 3; ++d) {
@@ -477,6 +533,8 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
             }
         }
         bound[t] = m[0] * m[1] * m[2];
+        h->KX = std::max(h->KX, (int)m[0]);
+        h->KY = std::max(h->KY, (int)m[1]);
     }
     long long maxpairs = 0;
     std::vector<unsigned> toff(natoms);
@@ -486,11 +544,11 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
         maxpairs += bound[type_id[a]];
         toff[a] = (unsigned)tstride;
         const int* hw = &h->halfw_host[type_id[a] * 3];
-        tstride += 2 * (hw[0] + hw[1] + hw[2]);
+        tstride += table_doubles(g0.lcol, hw[0], hw[1], hw[2]);
     }
     // pair lists and factor tables scale with the batch: shrink it until both fit 32-bit offsets and ~24 GB
     while (h->F > 2 && (tstride * h->F >= (1LL << 31) - 64 || maxpairs * h->F >= (1LL << 32) - 2 ||
-                        (double)maxpairs * h->F * 24.0 > 12.0e9) && h->cfg.batch_frames <= 0)
+                        (double)maxpairs * h->F * 32.0 > 12.0e9) && h->cfg.batch_frames <= 0)
         h->F -= 2;
     if (tstride * h->F >= (1LL << 31) - 64) return fail(MDSF_EINVAL, "factor tables overflow 31-bit offsets; lower batch_frames");
     h->gp.tstride = tstride;
@@ -517,12 +575,15 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     for (int p = 0; p < 2; ++p) {
         PrepSet& ps = h->sets[p];
         CU(cudaMalloc(&ps.recs, sizeof(AtomRec) * natoms * h->F));
-        CU(cudaMalloc(&ps.tables, sizeof(double) * (std::max(1LL, tstride * h->F) + 32)));
+        // 64 doubles of slack on both sides: zero-filled cp.async copies of EZ entries outside a record's window still
+        // carry an address up to one slab width before / behind the atom's block
+        CU(cudaMalloc(&ps.tables_alloc, sizeof(double) * (std::max(1LL, tstride * h->F) + 128)));
+        CU(cudaMemset(ps.tables_alloc, 0, sizeof(double) * (std::max(1LL, tstride * h->F) + 128)));
+        ps.tables = ps.tables_alloc + 64;
         CU(cudaMalloc(&ps.count, sizeof(unsigned) * (nkeys + 2)));
         CU(cudaMalloc(&ps.start, sizeof(unsigned) * (nkeys + 2)));
         CU(cudaMalloc(&ps.cursor, sizeof(unsigned) * (nkeys + 2)));
-        CU(cudaMalloc(&ps.prec, sizeof(PairRec) * h->pair_cap));
-        if (h->splat_mode != SPLAT_ORTHO_) CU(cudaMalloc(&ps.paux, sizeof(PairAux) * h->pair_cap));
+        CU(cudaMalloc(&ps.prec, 2 * sizeof(uint4) * h->pair_cap));
         CU(cudaMalloc(&ps.cub, h->cub_bytes));
         CU(cudaEventCreateWithFlags(&ps.ev_binned, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ps.ev_consumed, cudaEventDisableTiming));
@@ -633,10 +694,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     size_t cb = h->cub_bytes;
     cub::DeviceScan::ExclusiveSum(ps.cub, cb, ps.count, ps.start, (long long)nkeys + 1, sp);
     const long long total = (long long)nf * h->natoms;
-    if (h->splat_mode != SPLAT_ORTHO_)
-        bin_place_kernel<true><<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.start, ps.cursor, ps.prec, ps.paux, gp, h->tt, nf, nkeys, h->pair_cap, h->d_err);
-    else
-        bin_place_kernel<false><<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.start, ps.cursor, ps.prec, ps.paux, gp, h->tt, nf, nkeys, h->pair_cap, h->d_err);
+    bin_place_kernel<<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.start, ps.cursor, ps.prec, gp, h->tt, nf, nkeys, h->pair_cap, h->d_err);
     h->launches += 2;
     CU(cudaGetLastError());
     if (tv) CU(cudaEventRecord(tv[2], sp));
@@ -647,9 +705,10 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     // K3: splat (+ fused z FFT on the native path)
     const int npairs = (nf + 1) / 2;
     SplatArgs sa{};
-    sa.prec = ps.prec; sa.paux = ps.paux; sa.start = ps.start; sa.recs = ps.recs; sa.tables = ps.tables;
+    sa.prec = ps.prec; sa.start = ps.start; sa.recs = ps.recs; sa.tables = ps.tables;
     sa.src_density = nullptr; sa.nframes = nf; sa.vol = h->d_vol; sa.dens_dump = h->d_dump; sa.gp = gp; sa.tt = h->tt;
     sa.zplan = h->ax[2].plan; sa.twz = h->ax[2].d_tw; sa.err_flag = h->d_err;
+    sa.tws = h->d_tws; sa.tws_n = h->tws_n; sa.tws_off = h->tws_off;
     CU(mdsf_launch_splat(gp.lcol, h->splat_mode, h->native_fft, dim3(gp.ntx * gp.nty, npairs), h->splat_smem, h->s_comp, sa));
     ++h->launches;
     CU(cudaEventRecord(ps.ev_consumed, h->s_comp));
@@ -697,6 +756,7 @@ extern "C" int mdsf_push_density(mdsf_handle* h, const double* d1, int64_t nfram
         SplatArgs sa{};
         sa.src_density = d_tmp; sa.nframes = nf; sa.vol = h->d_vol; sa.dens_dump = h->d_dump; sa.gp = gp; sa.tt = h->tt;
         sa.zplan = h->ax[2].plan; sa.twz = h->ax[2].d_tw; sa.err_flag = h->d_err;
+        sa.tws = h->d_tws; sa.tws_n = h->tws_n; sa.tws_off = h->tws_off;
         cudaError_t ce = mdsf_launch_splat(gp.lcol, SPLAT_DENSITY_, h->native_fft, dim3(gp.ntx * gp.nty, npairs), h->splat_smem, h->s_comp, sa);
         if (ce != cudaSuccess) { cudaFree(d_tmp); return fail(MDSF_ECUDA, "density tile kernel launch failed: %s", cudaGetErrorString(ce)); }
         ++h->launches;

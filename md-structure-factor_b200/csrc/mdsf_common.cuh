@@ -8,7 +8,9 @@
 #define MDSF_MAX_ATOMS (1 << 28)
 #define MDSF_MAX_RADIX_STAGES 12
 #define MDSF_MAX_STAMP 1023        // 2*A: stamp indices travel in 10-bit fields / int offsets
-#define MDSF_SPLAT_WARPS 16        // warps per splat CTA; warp w owns z slabs w, w+16, ...
+#ifndef MDSF_SPLAT_WARPS
+#define MDSF_SPLAT_WARPS 12        // warps per splat CTA: 2 CTAs x 384 threads leave 80 registers per thread (16 warps: 64 registers, the inner loop re-materialised its lane constants; measured c3 splat 10.97 -> 9.92 ms)
+#endif
 
 // Frame-invariant geometry, passed to kernels by value.
 struct GridParams {
@@ -18,7 +20,8 @@ struct GridParams {
     int separable;      // ucell couples z to nothing else -> exp splits into xy and z factors
     int lcol;           // splat tile = 2^lcol (x,y) columns over all z: TX = 2^((lcol+1)/2), TY = 2^(lcol/2)
     int ntx, nty;       // tiles per dimension
-    int nslab, zw;      // z slabs per column, slab width zw = 256 >> lcol cells (one warp: 2^lcol columns x 32>>lcol lanes x 8 cells)
+    int nslab, zw;      // z slabs per column, slab width zw = (256 >> lcol) / sub cells: one list per slab and tile
+    int sub;            // lists a splat warp walks side by side (1 or 2 half-warp groups)
     int natoms;
     int nzp;            // padded z length of one column in shared memory
     int pad_shift;      // column position p is stored at p + (p >> pad_shift)
@@ -97,11 +100,13 @@ __host__ __device__ inline int stamp_bins_1d(int ir, int A, int N, int t, int sh
     return cnt;
 }
 
-// One (atom image, tile, z slab) pair, pre-clipped by the binning kernel; what a splat warp consumes.
-//   separable ucell:  x = index of EZ[k] for slab-local z 0 (tables + x + zz, zz in [zoff, zend))
-//                     y = index of EX[i] for tile column x 0, z = index of EY[j] for tile column y 0
-//   general ucell:    x, y, z = padded-grid index of tile column x 0 / tile column y 0 / slab-local z 0
-//   w = cx0 | cx1 << 3 | cy0 << 7 | cy1 << 10 | zoff << 14 | zend << 21   (clip box, tile / slab relative, [lo, hi))
+// One (atom image, tile, z slab) pair, prepared by the binning kernel; what a splat warp consumes.
+//   separable ucell:  x = index of EZ[k] for slab-local z 0 (tables[x + zz], zz in [zoff, zoff + zlen))
+//                     y = index of EX[i] for tile column x 0, z = index of EY[j] for tile column y 0 (columns outside
+//                     the stamp read the zero pads of the table block, see table_doubles in mdsf_prep.cuh)
+//                     w = zoff | zlen << 7
+//   general ucell:    x, y, z = padded-grid index of slab-local z 0 / tile column x 0 / tile column y 0
+//                     w = cx0 | cx1 << 3 | cy0 << 7 | cy1 << 10 | zoff << 14 | zend << 21   (clip box, [lo, hi))
 // PairAux (monoclinic or general ucell only): x = index of the cross-term table entry of tile column (0,0) / atom index,
 //                                             y = row stride 2*Ay of that table / unused
 typedef uint4 PairRec;

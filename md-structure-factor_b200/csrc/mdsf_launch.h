@@ -6,14 +6,16 @@
 #include "mdsf_fft.cuh"
 
 struct SplatArgs {
-    const PairRec* prec; const PairAux* paux; const unsigned* start; const AtomRec* recs; const double* tables;
+    const uint4* prec /* 32-byte records */; const unsigned* start; const AtomRec* recs; const double* tables;
     const double* src_density; int nframes;
     double2* vol; double2* dens_dump; GridParams gp; TypeTable tt; FftPlan zplan; const double2* twz; int* err_flag;
+    const double2* tws; int tws_n; int tws_off;      // per-stage z twiddle tables (compile-time z path): device pointer, entries, smem byte offset (0: late load)
 };
 // mode: SPLAT_ORTHO / SPLAT_MONO / SPLAT_GENERAL / SPLAT_DENSITY (mdsf_splat.cuh); grid = (tiles, pairs)
 cudaError_t mdsf_launch_splat(int lcol, int mode, bool fuse, dim3 grid, size_t smem, cudaStream_t st, const SplatArgs& a);
 cudaError_t mdsf_splat_configure(void);                   // opt in to the large dynamic shared memory sizes
-size_t mdsf_splat_smem(int lcol, int nzp, int nz);        // dynamic shared memory of one splat CTA
+size_t mdsf_splat_smem(int lcol, int sub, int nzp, int nz);        // dynamic shared memory of one splat CTA (without a twiddle region)
+bool mdsf_zspec_applies(int lcol, int nz, int pad_shift); // compile-time z stages available for this geometry
 
 struct PassArgs {
     double2* vol; double* P; const FftPlan* plan; const double2* tw; PassGeom pg; int npairs; int nouter;   // nouter: Nx (y pass) / Ny (x pass)

@@ -13,80 +13,106 @@ template <typename P> __device__ __forceinline__ P add_rn(P a, P b);
 template <> __device__ __forceinline__ float  add_rn<float>(float a, float b)   { return __fadd_rn(a, b); }
 template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
 
-// Every (image, tile, slab) pair of one atom.  The stamp [ir-A, ir+A)^3 on the padded grid is cut into its
-// <= 27 fold images (side s = -1 / 0 / +1 per dimension: low padding / cell / high padding, dens.py:86-108);
-// each image is one box in destination space with ONE shift, so the splat never sees segments or the corner
-// rule again.  fn(key, rec, aux): key = (frame * ntiles + tile) * nslab + slab.
+// Per-atom factor tables (one block per atom and frame, K1 writes them):
+//   [TX-1 zeros][EX: 2Ax][TX-1 zeros] [TY-1 zeros][EY: 2Ay][TY-1 zeros] [EZ: 2Az]
+// The zero pads let a splat warp read EX / EY for EVERY column of its tile without a clip test: columns outside the
+// atom's stamp fall into a pad and contribute exactly zero.
+__host__ __device__ inline int table_doubles(int lcol, int Ax, int Ay, int Az) {
+    const int TX = 1 << ((lcol + 1) >> 1), TY = 1 << (lcol >> 1);
+    return 2 * (Ax + Ay + Az) + 2 * (TX - 1) + 2 * (TY - 1);
+}
+
+// The k-th tile (width 2^lt) the folded stamp [ir-A, ir+A) touches along one dimension, counted over its fold images
+// in the order side = -1, 0, +1 (low padding / cell / high padding, dens.py:86-108).  Returns false when the stamp
+// touches fewer tiles.  d0, d1: destination range of that image; ist: stamp index of d0.
+__device__ __forceinline__ bool axis_slot(int ir, int A, int N, int lt, int k, int& side, int& tile, int& d0, int& d1, int& ist) {
+#pragma unroll
+    for (int s = -1; s <= 1; ++s) {
+        int plo, phi;
+        stamp_segment(ir, A, N, s, plo, phi);
+        if (phi > plo) {
+            const int a0 = plo - s * N, a1 = phi - s * N;
+            const int t0 = a0 >> lt, nt = ((a1 - 1) >> lt) - t0 + 1;
+            if (k < nt) { side = s; tile = t0 + k; d0 = a0; d1 = a1; ist = plo - (ir - A); return true; }
+            k -= nt;
+        }
+    }
+    return false;
+}
+
+// Every (image, tile, slab) pair of one atom inside ONE (x tile, y tile) column of tiles.  The stamp on the padded grid
+// is cut into its <= 27 fold images; each image is one box in destination space with ONE shift, so the splat never
+// sees segments or the corner rule again.  fn(key, rec, aux): key = (frame * ntiles + tile) * nslab + slab.
+template <typename F>
+__device__ __forceinline__ void pairs_of_tile(const AtomRec& rec, int a, int f, const GridParams& gp, const TypeTable& tt,
+                                              int Ax, int Ay, int Az, int sx, int tX, int dx0, int dx1, int ix0,
+                                              int sy, int tY, int dy0, int dy1, int jy0, F&& fn) {
+    const int ltx = (gp.lcol + 1) >> 1, lty = gp.lcol >> 1;
+    const int TX = 1 << ltx, TY = 1 << lty;
+    const int ZW = gp.zw, lzw = 31 - __clz(ZW);                  // slab width (a power of two)
+    const int X0 = tX << ltx, Y0 = tY << lty;
+    const int cx0 = max(dx0 - X0, 0), cy0 = max(dy0 - Y0, 0);
+    const int i0 = ix0 + (X0 + cx0 - dx0), j0 = jy0 + (Y0 + cy0 - dy0);
+    const unsigned kbase = (unsigned)(f * gp.ntx * gp.nty + tX * gp.nty + tY) * (unsigned)gp.nslab;
+    const int ex0 = (int)rec.tbase + (TX - 1);                                   // index of EX[0]
+    const int ey0 = (int)rec.tbase + 2 * (TX - 1) + 2 * Ax + (TY - 1);           // index of EY[0]
+    const int ez0 = (int)rec.tbase + 2 * (TX - 1) + 2 * Ax + 2 * (TY - 1) + 2 * Ay;
+    const int ctbase = (tt.ctab != nullptr) ? tt.ctab_off[rec.type] : 0;
+    for (int sz = -1; sz <= 1; ++sz) {
+        int zlo, zhi;
+        stamp_segment(rec.ir[2], Az, gp.n[2], sz, zlo, zhi);
+        if (zhi <= zlo) continue;
+        const int shz = fold_shift_z(sx, sy, sz, gp.n[2], gp.nb, gp.fold_mode);
+        const int dz0 = zlo + shz, dz1 = zhi + shz;
+        const int kz0 = zlo - (rec.ir[2] - Az);
+        for (int s = dz0 >> lzw; s <= (dz1 - 1) >> lzw; ++s) {
+            const int Z0 = s << lzw;
+            const int zoff = max(dz0 - Z0, 0), zend = min(dz1 - Z0, ZW);
+            const int k0 = kz0 + (Z0 + zoff - dz0);
+            PairRec pr;
+            PairAux pa;
+            if (gp.separable) {
+                pr.x = (unsigned)(ez0 + k0 - zoff);
+                pr.y = (unsigned)(ex0 + i0 - cx0);
+                pr.z = (unsigned)(ey0 + j0 - cy0);
+                pr.w = (unsigned)(zoff | ((zend - zoff) << 7));
+                pa.x = (unsigned)(ctbase + (i0 - cx0) * 2 * Ay + (j0 - cy0));
+                pa.y = (unsigned)(2 * Ay);
+            } else {
+                const int cx1 = min(dx1 - X0, TX), cy1 = min(dy1 - Y0, TY);
+                pr.x = (unsigned)(Z0 - shz);                  // padded z of slab-local cell 0
+                pr.y = (unsigned)(X0 + sx * gp.n[0]);         // padded x of tile column 0
+                pr.z = (unsigned)(Y0 + sy * gp.n[1]);
+                pr.w = (unsigned)(cx0 | (cx1 << 3) | (cy0 << 7) | (cy1 << 10) | (zoff << 14) | (zend << 21));
+                pa.x = (unsigned)a;
+                pa.y = 0u;
+            }
+            fn(kbase + (unsigned)s, pr, pa);
+        }
+    }
+}
+
+// all pairs of one atom: walk its (x tile, y tile) slots
 template <typename F>
 __device__ __forceinline__ void for_each_pair(const AtomRec& rec, int a, int f, const GridParams& gp, const TypeTable& tt, F&& fn) {
     const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
     if (Ax <= 0 || Ay <= 0 || Az <= 0) return;
     const int ltx = (gp.lcol + 1) >> 1, lty = gp.lcol >> 1;
-    const int TX = 1 << ltx, TY = 1 << lty;
-    const int lzw = 8 - gp.lcol, ZW = 1 << lzw;                 // slab width 256 >> lcol
-    const int ntiles = gp.ntx * gp.nty;
-    const int ctbase = (tt.ctab != nullptr) ? tt.ctab_off[rec.type] : 0;
-    for (int sx = -1; sx <= 1; ++sx) {
-        int xlo, xhi;
-        stamp_segment(rec.ir[0], Ax, gp.n[0], sx, xlo, xhi);
-        if (xhi <= xlo) continue;
-        const int dx0 = xlo - sx * gp.n[0], dx1 = xhi - sx * gp.n[0];         // destination range
-        const int ix0 = xlo - (rec.ir[0] - Ax);                              // stamp index of dx0
-        for (int sy = -1; sy <= 1; ++sy) {
-            int ylo, yhi;
-            stamp_segment(rec.ir[1], Ay, gp.n[1], sy, ylo, yhi);
-            if (yhi <= ylo) continue;
-            const int dy0 = ylo - sy * gp.n[1], dy1 = yhi - sy * gp.n[1];
-            const int jy0 = ylo - (rec.ir[1] - Ay);
-            for (int sz = -1; sz <= 1; ++sz) {
-                int zlo, zhi;
-                stamp_segment(rec.ir[2], Az, gp.n[2], sz, zlo, zhi);
-                if (zhi <= zlo) continue;
-                const int shz = fold_shift_z(sx, sy, sz, gp.n[2], gp.nb, gp.fold_mode);
-                const int dz0 = zlo + shz, dz1 = zhi + shz;
-                const int kz0 = zlo - (rec.ir[2] - Az);
-                for (int tX = dx0 >> ltx; tX <= (dx1 - 1) >> ltx; ++tX) {
-                    const int X0 = tX << ltx;
-                    const int cx0 = max(dx0 - X0, 0), cx1 = min(dx1 - X0, TX);
-                    const int i0 = ix0 + (X0 + cx0 - dx0);
-                    for (int tY = dy0 >> lty; tY <= (dy1 - 1) >> lty; ++tY) {
-                        const int Y0 = tY << lty;
-                        const int cy0 = max(dy0 - Y0, 0), cy1 = min(dy1 - Y0, TY);
-                        const int j0 = jy0 + (Y0 + cy0 - dy0);
-                        const unsigned kbase = (unsigned)(f * ntiles + tX * gp.nty + tY) * (unsigned)gp.nslab;
-                        for (int s = dz0 >> lzw; s <= (dz1 - 1) >> lzw; ++s) {
-                            const int Z0 = s << lzw;
-                            const int zoff = max(dz0 - Z0, 0), zend = min(dz1 - Z0, ZW);
-                            const int k0 = kz0 + (Z0 + zoff - dz0);
-                            PairRec pr;
-                            PairAux pa;
-                            pr.w = (unsigned)(cx0 | (cx1 << 3) | (cy0 << 7) | (cy1 << 10) | (zoff << 14) | (zend << 21));
-                            if (gp.separable) {
-                                pr.x = (unsigned)((int)rec.tbase + 2 * (Ax + Ay) + k0 - zoff);
-                                pr.y = (unsigned)((int)rec.tbase + i0 - cx0);
-                                pr.z = (unsigned)((int)rec.tbase + 2 * Ax + j0 - cy0);
-                                pa.x = (unsigned)(ctbase + (i0 - cx0) * 2 * Ay + (j0 - cy0));
-                                pa.y = (unsigned)(2 * Ay);
-                            } else {
-                                pr.x = (unsigned)(Z0 - shz);                  // padded z of slab-local cell 0
-                                pr.y = (unsigned)(X0 + sx * gp.n[0]);         // padded x of tile column 0
-                                pr.z = (unsigned)(Y0 + sy * gp.n[1]);
-                                pa.x = (unsigned)a;
-                                pa.y = 0u;
-                            }
-                            fn(kbase + (unsigned)s, pr, pa);
-                        }
-                    }
-                }
-            }
+    for (int kx = 0;; ++kx) {
+        int sx, tX, dx0, dx1, ix0;
+        if (!axis_slot(rec.ir[0], Ax, gp.n[0], ltx, kx, sx, tX, dx0, dx1, ix0)) break;
+        for (int ky = 0;; ++ky) {
+            int sy, tY, dy0, dy1, jy0;
+            if (!axis_slot(rec.ir[1], Ay, gp.n[1], lty, ky, sy, tY, dy0, dy1, jy0)) break;
+            pairs_of_tile(rec, a, f, gp, tt, Ax, Ay, Az, sx, tX, dx0, dx1, ix0, sy, tY, dy0, dy1, jy0, fn);
         }
     }
 }
 
 #define MDSF_PREP_STAGE 512        // doubles of factor tables one warp stages in shared memory (c2: 32 atoms x 12)
 
-// K1.  Also counts the pairs of every list (atomicAdd on `counter[key]`): the scan of those counts gives the list
-// starts, bin_place_kernel then fills the lists.
+// K1: records and factor tables.  Also counts the pairs of every list (atomicAdd on `counter[key]`, no return value):
+// the scan of those counts gives the list starts, bin_place_kernel then fills the lists.
 template <typename C, typename P>
 __global__ void __launch_bounds__(256)
 prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], rewritten in place
@@ -173,7 +199,8 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
         // EZ carries the fixed-point scale of the splat accumulators (a power of two: exact).
         // b = r - (i - B)*dr with the product rounded on its own, as numpy does (dens.py:252-256,299).
         const int Ax = tt.halfw[t * 3], Ay = tt.halfw[t * 3 + 1], Az = tt.halfw[t * 3 + 2];
-        const unsigned size = ok ? (unsigned)(2 * (Ax + Ay + Az)) : 0u;
+        const int padx = (1 << ((gp.lcol + 1) >> 1)) - 1, pady = (1 << (gp.lcol >> 1)) - 1;
+        const unsigned size = ok ? (unsigned)table_doubles(gp.lcol, Ax, Ay, Az) : 0u;
         const unsigned base = __reduce_min_sync(0xffffffffu, ok ? rec.tbase : 0xffffffffu);
         const unsigned off = ok ? rec.tbase - base : 0u;
         const unsigned span = __reduce_max_sync(0xffffffffu, off + size);
@@ -185,16 +212,22 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
             double* T = staged ? &s_tab[warp][off] : tables + rec.tbase;
             const double bx0 = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax), gp.dr[0]));
             const double by0 = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay), gp.dr[1]));
+            for (int i = 0; i < padx; ++i) T[i] = 0.0;
+            T += padx;
             for (int i = 0; i < 2 * Ax; ++i) {
                 const double b = __dsub_rn(rec.r[0], __dmul_rn((double)(rec.ir[0] - Ax + i), gp.dr[0]));
                 T[i] = exp(-(gp.cxx * b * b + 2.0 * gp.gxy * b * by0) * it2);
             }
             T += 2 * Ax;
+            for (int i = 0; i < padx + pady; ++i) T[i] = 0.0;
+            T += padx + pady;
             for (int j = 0; j < 2 * Ay; ++j) {
                 const double b = __dsub_rn(rec.r[1], __dmul_rn((double)(rec.ir[1] - Ay + j), gp.dr[1]));
                 T[j] = exp(-(gp.cyy * b * b - 2.0 * gp.gxy * ((double)j * gp.dr[1]) * bx0) * it2);
             }
             T += 2 * Ay;
+            for (int i = 0; i < pady; ++i) T[i] = 0.0;
+            T += pady;
             for (int k = 0; k < 2 * Az; ++k) {
                 const double b = __dsub_rn(rec.r[2], __dmul_rn((double)(rec.ir[2] - Az + k), gp.dr[2]));
                 T[k] = amp * exp(-(gp.czz * b * b) * it2);
@@ -212,11 +245,13 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
 
 // ---- K2: fill the lists.  The splat accumulates in 64-bit fixed point (integer adds commute), so the order inside
 // a list is irrelevant and a counting sort with atomics is deterministic in its RESULT: start = exclusive scan of the
-// K1 counts, every pair claims a slot of its list from a per-key cursor.
-template <bool AUX>
-__global__ void __launch_bounds__(256)
+// K1 counts, every pair claims a slot of its list from a per-key cursor.  One record is one aligned 32-byte sector
+// (PairRec + PairAux + padding): the lists are written at random positions, and a full-sector store needs no fill read
+// from DRAM (16 + 8-byte stores into two arrays moved 6.6 GB for 50 M pairs: the kernel was bound by random DRAM
+// sectors, not by the atomics).
+__global__ void __launch_bounds__(256, 6)
 bin_place_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ start, unsigned* __restrict__ cursor,
-                 PairRec* __restrict__ prec, PairAux* __restrict__ paux, GridParams gp, TypeTable tt, int nframes,
+                 uint4* __restrict__ prec2 /* [2 * pairs] */, GridParams gp, TypeTable tt, int nframes,
                  unsigned nkeys, unsigned long long cap, int* __restrict__ err_flag)
 {
     if ((unsigned long long)start[nkeys] > cap) {       // cannot happen unless the host bound is wrong: refuse to overrun
@@ -232,8 +267,8 @@ bin_place_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ 
         if (rec.pad_) continue;                           // atoms K1 rejected have no counted pairs
         for_each_pair(rec, a, f, gp, tt, [&](unsigned key, const PairRec& pr, const PairAux& pa) {
             const unsigned pos = start[key] + atomicAdd(cursor + key, 1u);
-            prec[pos] = pr;
-            if (AUX) paux[pos] = pa;
+            prec2[2 * (size_t)pos] = pr;
+            prec2[2 * (size_t)pos + 1] = make_uint4(pa.x, pa.y, 0u, 0u);
         });
     }
 }

@@ -2,17 +2,21 @@
 //
 // Replaces the per-atom Python loop dens.py:283-308 and the 26-region fold dens.py:86-108.
 // A CTA owns 2^LCOL (x,y) columns over all z for ONE pair of frames (frame 2q -> real part, frame 2q+1 ->
-// imaginary part).  A warp owns one z slab of the tile at a time: lane = (column, z lane), 8 consecutive cells per
-// lane, held in REGISTERS as 64-bit fixed-point sums (LSB = 2^-52 of the largest Nel/sigma^3).  The warp walks its
-// own (tile, slab) list of pre-clipped pair records (K2): per record the slab's window of the atom's EZ table and
-// the tile's slices of its EX / EY (/ cross-term) tables arrive in a small per-warp staging ring by cp.async, NS-1
-// records ahead; entries outside the clip box are zero-filled, so the accumulation is branch-free:
-//     acc[k] += int(EX[cx] * EY[cy] * C[c] * EZ[zl*8 + k])          one DFMA (magic-number rounding) + one 64-bit add
+// imaginary part).  A warp owns one z slab of the tile at a time: lane = (tile row y, z lane) holds the TX columns of
+// its row x KZ = 8/TX consecutive cells in REGISTERS as 64-bit fixed-point sums (LSB = 2^-52 of the largest
+// Nel/sigma^3); per record it needs EX[0..TX) (the same for every lane: broadcast loads), one EY, its row of the
+// cross-term table and KZ entries of EZ -- a third of the shared-memory wavefronts of a (column, 8 cells) lane.  The warp walks its
+// own (tile, slab) list of pair records (K2): per record the slab's window of the atom's EZ table and the tile's
+// slices of its EX / EY (/ cross-term) tables arrive in a small per-warp staging ring by cp.async, NS-1 records
+// ahead.  EZ entries outside the record's z window are zero-filled by the copy, EX / EY entries of columns outside
+// the stamp come from the zero pads of the table block, so the accumulation is branch-free:
+//     acc[i][k] += int(EX[i] * EY[cy] * C[cy][i] * EZ[zl*KZ + k])   one DFMA (magic-number rounding) + one 64-bit add
 // Integer addition commutes, so the density is bitwise reproducible whatever order K2's atomics filled the lists
 // in -- no float atomics, no shared-memory atomics, no CTA barriers inside the splat.  The fold (incl. the corner
 // rule of dens.py:107) was resolved by K2: every record is one box in destination space.
 // Afterwards the slab sums are converted to fp64 into the shared-memory tile, which is transformed along z in
-// place (native FFT path) and stored: the density never touches HBM.
+// place (native FFT path; compile-time radix stages for Nz = 64 / 256 / 512 / 768 / 1024) and stored: the density
+// never touches HBM.
 #pragma once
 #include "mdsf_common.cuh"
 #include "mdsf_fft.cuh"
@@ -26,33 +30,123 @@ enum { SPLAT_ORTHO = 0,      // separable ucell, no in-plane cross term
        SPLAT_GENERAL = 2,    // arbitrary 3x3 ucell: one exp per cell, exactly the reference's expression
        SPLAT_DENSITY = 3 };  // no atoms: real densities d1[frame][x][y][z] are the source (RANDOM_NOISE mode, dens.py:279-280)
 
-template <int LCOL> struct SplatGeom {
+// SUB = lists a warp walks side by side: 1 (the whole warp owns one slab) or 2 (each half-warp owns a slab of half
+// the width: small stamps touch few cells of a slab, two records per instruction stream halve the issue and
+// shared-memory cost per record at the price of ~15% more records)
+template <int LCOL, int SUB> struct SplatGeom {
     static constexpr int NCOL = 1 << LCOL, LTY = LCOL / 2, TX = 1 << ((LCOL + 1) / 2), TY = 1 << LTY;
-    static constexpr int ZL = 32 >> LCOL, ZW = ZL * 8;              // z lanes per warp, slab width
+    static constexpr int LTX = (LCOL + 1) / 2;
+    static constexpr int G = 32 / SUB;                              // lanes of one group
+    static constexpr int KZ = 8 / TX, ZLN = G / TY, ZW = ZLN * KZ;  // cells per lane in z, z lanes per group, slab width
     static constexpr int NS = (LCOL == 2) ? 2 : 3;                  // staging slots per warp
-    static constexpr int SLOT = (ZW + TX + TY + NCOL + 1) & ~1;     // doubles: [EZ: ZW][EX: TX][EY: TY][C: NCOL]
-    static constexpr int WARP_BYTES = 32 * 16 + 32 * 8 + NS * SLOT * 8;
+    static constexpr int SLOTG = (ZW + TX + TY + NCOL + 1) & ~1;    // doubles per group: [EZ: ZW][EX: TX][EY: TY][C: TY][TX]
+    static constexpr int SLOT = SUB * SLOTG;
+    static constexpr int RB = 32 / (SUB * SUB);                     // records per group and batch (32 / 8)
+    static constexpr int WARP_BYTES = SUB * RB * 16 + SUB * RB * 8 + NS * SLOT * 8;
 };
 
-__device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gsrc, bool valid) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(unsigned smem_dst, const void* gsrc, bool valid) {
     const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int LCOL, int MODE>
+// exact int64 -> fp64 (|v| < 2^62) from two 32-bit conversions and one FMA (the 64-bit conversion is a long sequence)
+__device__ __forceinline__ double fx_to_double(long long v) {
+    return __fma_rn(__int2double_rn((int)(v >> 32)), 4294967296.0, __uint2double_rn((unsigned)v));
+}
+
+// ------------------------------------------------------------------ z FFT of the tile, compile-time radices
+// In-place decimation-in-frequency stages over [NCOL][nzp] re / im planes (position p of a column at p + (p >> PAD)):
+// same scheme and output order as fft_stage, with every stride and index split a constant.  The inter-stage
+// twiddles come from per-stage tables tws[TOFF + (k-1)*M + n2] = w_N^(n2 k N/L) (host-built, zstage_table_size): lanes
+// walk n2, so the reads are conflict-free (the strided reads of the full table were half of all bank conflicts).
+template <int NCOL, int N, int R, int L, int PAD, int TOFF>
+__device__ __forceinline__ void zstage(double* __restrict__ sre, double* __restrict__ sim, const double2* __restrict__ tws, int nzp)
+{
+    constexpr int M = L / R, NBF = N / R;
+    constexpr int ITEMS = NCOL * NBF;
+    for (int it = threadIdx.x; it < ITEMS; it += MDSF_SPLAT_THREADS) {
+        const int f = it / NBF, bf = it % NBF;              // constants: shifts / masks for powers of two
+        const int b = bf / M, n2 = bf % M;
+        const int base = b * L + n2;
+        double xr[R], xi[R];
+        int a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int p = base + j * M;
+            a[j] = f * nzp + p + (p >> PAD);
+            xr[j] = sre[a[j]]; xi[j] = sim[a[j]];
+        }
+        Dft<R>::run(xr, xi, nullptr, nullptr, N);
+        if (M > 1) {
+#pragma unroll
+            for (int k = 1; k < R; ++k) {
+                const double2 w = tws[TOFF + (k - 1) * M + n2];
+                const double yr = xr[k] * w.x - xi[k] * w.y;
+                xi[k] = xr[k] * w.y + xi[k] * w.x;
+                xr[k] = yr;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) { sre[a[k]] = xr[k]; sim[a[k]] = xi[k]; }
+    }
+    __syncthreads();
+}
+
+// radix lists as produced by factorize() for the z axis (radices <= 8); table offsets = running sum of (R-1)*M
+template <int NCOL, int PAD> __device__ __forceinline__ void zfft_64(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 64, 8, 64, PAD, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 64, 8, 8, PAD, 56>(sre, sim, tws, nzp);
+}
+template <int NCOL, int PAD> __device__ __forceinline__ void zfft_256(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 256, 4, 256, PAD, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 256, 8, 64, PAD, 192>(sre, sim, tws, nzp);
+    zstage<NCOL, 256, 8, 8, PAD, 248>(sre, sim, tws, nzp);
+}
+template <int NCOL, int PAD> __device__ __forceinline__ void zfft_512(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 512, 8, 512, PAD, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 512, 8, 64, PAD, 448>(sre, sim, tws, nzp);
+    zstage<NCOL, 512, 8, 8, PAD, 504>(sre, sim, tws, nzp);
+}
+template <int NCOL, int PAD> __device__ __forceinline__ void zfft_1024(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 1024, 4, 1024, PAD, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 1024, 4, 256, PAD, 768>(sre, sim, tws, nzp);
+    zstage<NCOL, 1024, 8, 64, PAD, 960>(sre, sim, tws, nzp);
+    zstage<NCOL, 1024, 8, 8, PAD, 1016>(sre, sim, tws, nzp);
+}
+template <int NCOL> __device__ __forceinline__ void zfft_768(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 768, 4, 768, 31, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 768, 8, 192, 31, 576>(sre, sim, tws, nzp);
+    zstage<NCOL, 768, 8, 24, 31, 744>(sre, sim, tws, nzp);
+    zstage<NCOL, 768, 3, 3, 31, 765>(sre, sim, tws, nzp);
+}
+// does the compile-time path cover this (tile, z length, padding)?  (host and device agree through this function)
+__host__ __device__ inline bool zspec_applies(int lcol, int nz, int pad_shift) {
+    return (lcol == 5 && nz == 64 && pad_shift == 3) || (lcol == 4 && nz == 256 && pad_shift == 3) ||
+           (lcol == 3 && nz == 512 && pad_shift == 3) || (lcol == 2 && nz == 1024 && pad_shift == 3) ||
+           (lcol == 2 && nz == 768 && pad_shift == 31);
+}
+
+template <int LCOL, int MODE, int SUB>
 __global__ void __launch_bounds__(MDSF_SPLAT_THREADS, 2)
-splat_zfft_kernel(const PairRec* __restrict__ prec, const PairAux* __restrict__ paux, const unsigned* __restrict__ start,
+splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, const unsigned* __restrict__ start,
                   const AtomRec* __restrict__ recs, const double* __restrict__ tables,
                   const double* __restrict__ src_density, int nframes,
                   double2* __restrict__ vol, double2* __restrict__ dens_dump, GridParams gp, TypeTable tt, FftPlan zplan,
-                  const double2* __restrict__ twz, int* __restrict__ err_flag, int FUSE /* z FFT fused (native path) */)
+                  const double2* __restrict__ twz, int* __restrict__ err_flag, int FUSE /* z FFT fused (native path) */,
+                  const double2* __restrict__ tws_g /* per-stage twiddle tables (compile-time z path) */, int tws_n, int tws_off
+                  /* > 0: byte offset of their own shared-memory region, filled by cp.async while the splat runs */)
 {
-    using G = SplatGeom<LCOL>;
-    constexpr int NCOL = G::NCOL, TX = G::TX, TY = G::TY, LTY = G::LTY, ZW = G::ZW, NS = G::NS, SLOT = G::SLOT;
+    using G = SplatGeom<LCOL, SUB>;
+    constexpr int NCOL = G::NCOL, TX = G::TX, TY = G::TY, LTY = G::LTY, LTX = G::LTX, ZW = G::ZW, NS = G::NS, SLOT = G::SLOT;
+    constexpr int KZ = G::KZ, ZLN = G::ZLN, GL = G::G, SLOTG = G::SLOTG, RB = G::RB;
     extern __shared__ double smem[];
+    __shared__ int s_next;                                    // next (slab group, part) item: warps claim them dynamically
     const int nzp = gp.nzp, nz = gp.n[2];
     double* tile_re = smem;                                   // [NCOL][nzp]  frame 2q
     double* tile_im = tile_re + (size_t)NCOL * nzp;           // [NCOL][nzp]  frame 2q+1
@@ -60,146 +154,214 @@ splat_zfft_kernel(const PairRec* __restrict__ prec, const PairAux* __restrict__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, q = blockIdx.y;
     const int X0 = (tile / gp.nty) * TX, Y0 = (tile % gp.nty) * TY;
-    const int c = lane & (NCOL - 1), zl = lane >> LCOL;       // my column of the tile, my z lane of the slab
-    const int cx = c >> LTY, cy = c & (TY - 1);
+    const int grp = lane / GL, gl = lane % GL;                // my group (list) of the warp, my lane inside it
+    const int zl = gl & (ZLN - 1), cy = gl / ZLN;             // my z lane of the slab, my row of the tile (columns c = i*TY + cy)
     const int ntiles = gp.ntx * gp.nty;
-    const bool col_ok = X0 + cx < gp.n[0] && Y0 + cy < gp.n[1];
 
-    PairRec* rbuf = reinterpret_cast<PairRec*>(area + (size_t)warp * G::WARP_BYTES);
-    PairAux* abuf = reinterpret_cast<PairAux*>(reinterpret_cast<char*>(rbuf) + 32 * 16);
-    double* slots = reinterpret_cast<double*>(reinterpret_cast<char*>(rbuf) + 32 * 16 + 32 * 8);
+    PairRec* rbuf = reinterpret_cast<PairRec*>(area + (size_t)warp * G::WARP_BYTES);          // [SUB][RB]
+    PairAux* abuf = reinterpret_cast<PairAux*>(reinterpret_cast<char*>(rbuf) + SUB * RB * 16);
+    double* slots = reinterpret_cast<double*>(reinterpret_cast<char*>(rbuf) + SUB * RB * 24);  // [NS][SUB][SLOTG]
+    const unsigned slots_s = (unsigned)__cvta_generic_to_shared(slots);
     bool ovf = false;
+    const bool zspec = FUSE && tws_g != nullptr;
+    double2* tws_s = reinterpret_cast<double2*>(reinterpret_cast<char*>(smem) + tws_off);
+    if (threadIdx.x == 0) s_next = MDSF_SPLAT_WARPS;
+    if (zspec && tws_off > 0) {                               // the twiddles arrive behind the splat
+        for (int i = threadIdx.x; i < tws_n; i += MDSF_SPLAT_THREADS) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(tws_s + i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(tws_g + i) : "memory");
+        }
+        cp_async_commit();
+    }
+    __syncthreads();
 
-    for (int s = warp; s < gp.nslab; s += MDSF_SPLAT_WARPS) {
-        const int zbase = s * ZW + zl * 8;                    // my 8 cells: z = zbase + k
-#pragma unroll 1
-        for (int part = 0; part < 2; ++part) {
+    // staging roles of this lane: entry e = gl + GL * round of its group's slot [EZ: ZW][EX: TX][EY: TY][C: TY][TX].
+    // small entry (e >= ZW): source index = base(kind) + soff + smul * (2 Ay);  kind 1: EX, 2: EY, 3: C
+    constexpr int E = ZW + TX + TY + (MODE == SPLAT_MONO ? NCOL : 0);
+    constexpr int ROUNDS = (E + GL - 1) / GL;
+    int skind[ROUNDS], soff[ROUNDS], smul[ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int e = gl + GL * rd - ZW;
+        skind[rd] = 0; soff[rd] = 0; smul[rd] = 0;
+        if (e >= 0 && e < TX) { skind[rd] = 1; soff[rd] = e; }
+        else if (e >= TX && e < TX + TY) { skind[rd] = 2; soff[rd] = e - TX; }
+        else if (MODE == SPLAT_MONO && e >= TX + TY && e < TX + TY + NCOL) { skind[rd] = 3; soff[rd] = (e - TX - TY) >> LTX; smul[rd] = (e - TX - TY) & (TX - 1); }
+    }
+
+    // work items: (group of SUB consecutive slabs, part); the first MDSF_SPLAT_WARPS go out statically, the rest are
+    // claimed from a shared counter (list lengths vary: the barrier before the FFT waited 15% of the time for the longest)
+    const int nsg = (gp.nslab + SUB - 1) / SUB, nitems = 2 * nsg;
+    for (int item = warp; item < nitems;) {
+        const int sg = item >> 1, part = item & 1;
+        const int s = sg * SUB + grp;                         // my group's slab
+        const bool slab_ok = s < gp.nslab;
+        const int zbase = s * ZW + zl * KZ;                   // my cells: x = X0 + i, y = Y0 + cy, z = zbase + k
+        {
             const int f = 2 * q + part;
-            double* col = (part ? tile_im : tile_re) + (size_t)c * nzp;
+            double* row = (part ? tile_im : tile_re) + (size_t)cy * nzp;        // column (i, cy) at row + i*TY*nzp
             if (MODE == SPLAT_DENSITY) {
-                const bool live = f < nframes && col_ok;
-                const double* src = src_density + (((long long)f * gp.n[0] + (X0 + cx)) * gp.n[1] + (Y0 + cy)) * nz;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int z = zbase + k;
-                    if (z < nz) col[z + (z >> gp.pad_shift)] = live ? src[z] : 0.0;
+                for (int i = 0; i < TX; ++i) {
+                    const bool live = f < nframes && X0 + i < gp.n[0] && Y0 + cy < gp.n[1];
+                    const double* src = src_density + (((long long)f * gp.n[0] + (X0 + i)) * gp.n[1] + (Y0 + cy)) * nz;
+#pragma unroll
+                    for (int k = 0; k < KZ; ++k) {
+                        const int z = zbase + k;
+                        if (slab_ok && z < nz) row[(size_t)i * TY * nzp + z + (z >> gp.pad_shift)] = live ? src[z] : 0.0;
+                    }
                 }
-                continue;
-            }
-            long long acc[8];
+            } else {
+            long long acc[TX][KZ];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = 0;
-            const unsigned key = (unsigned)(f * ntiles + tile) * (unsigned)gp.nslab + (unsigned)s;
-            const unsigned lbeg = start[key], lend = start[key + 1];
-            const int n = (int)(lend - lbeg);
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int k = 0; k < KZ; ++k) acc[i][k] = 0;
+            const unsigned key = (unsigned)(f * ntiles + tile) * (unsigned)gp.nslab + (unsigned)(slab_ok ? s : 0);
+            const unsigned lbeg = start[key];
+            const int n = slab_ok ? (int)(start[key + 1] - lbeg) : 0;           // my group's list
+            int nmax = n;                                                       // the longest list of the warp
+            if (SUB > 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
             PairRec nxt = make_uint4(0u, 0u, 0u, 0u);
             PairAux nxa = make_uint2(0u, 0u);
-            if (lane < n) { nxt = prec[lbeg + lane]; if (MODE != SPLAT_ORTHO) nxa = paux[lbeg + lane]; }
-            for (int b = 0; b < n; b += 32) {
-                const int m = min(32, n - b);
+            if (gl < RB && gl < n) { nxt = prec[2 * (size_t)(lbeg + gl)]; if (MODE != SPLAT_ORTHO) { const uint4 t = prec[2 * (size_t)(lbeg + gl) + 1]; nxa = make_uint2(t.x, t.y); } }
+            for (int b = 0; b < nmax; b += RB) {
+                const int m = min(RB, n - b);                  // my group's records in this batch (<= 0: none)
+                const int mmax = min(RB, nmax - b);
                 __syncwarp();                                  // the previous batch is consumed
-                rbuf[lane] = nxt;
-                if (MODE != SPLAT_ORTHO) abuf[lane] = nxa;
+                if (gl < RB) { rbuf[grp * RB + gl] = nxt; if (MODE != SPLAT_ORTHO) abuf[grp * RB + gl] = nxa; }
                 __syncwarp();
-                if (b + 32 + lane < n) { nxt = prec[lbeg + b + 32 + lane]; if (MODE != SPLAT_ORTHO) nxa = paux[lbeg + b + 32 + lane]; }
+                if (gl < RB && b + RB + gl < n) { nxt = prec[2 * (size_t)(lbeg + b + RB + gl)]; if (MODE != SPLAT_ORTHO) { const uint4 t = prec[2 * (size_t)(lbeg + b + RB + gl) + 1]; nxa = make_uint2(t.x, t.y); } }
                 if (MODE == SPLAT_GENERAL) {
                     // one exp per cell: amp * exp(-|b . ucell|^2 / (2 sigma^2))  (dens.py:299-308)
-                    for (int i = 0; i < m; ++i) {
-                        const PairRec r = rbuf[i];
+                    for (int r_i = 0; r_i < m; ++r_i) {
+                        const PairRec r = rbuf[grp * RB + r_i];
                         const unsigned g = r.w;
                         const int cx0 = g & 7, cx1 = (g >> 3) & 15, cy0 = (g >> 7) & 7, cy1 = (g >> 10) & 15;
                         const int zoff = (g >> 14) & 127, zend = (g >> 21) & 127;
-                        if (cx < cx0 || cx >= cx1 || cy < cy0 || cy >= cy1) continue;
-                        const AtomRec* ar = recs + (long long)f * gp.natoms + abuf[i].x;
+                        if (cy < cy0 || cy >= cy1) continue;
+                        const AtomRec* ar = recs + (long long)f * gp.natoms + abuf[grp * RB + r_i].x;
                         const double rx = ar->r[0], ry = ar->r[1], rz = ar->r[2];
                         const int type = ar->type;
-                        const double bx = __dsub_rn(rx, __dmul_rn((double)((int)r.y + cx), gp.dr[0]));
                         const double by = __dsub_rn(ry, __dmul_rn((double)((int)r.z + cy), gp.dr[1]));
                         const double t2 = tt.two_sig2[type], amp = tt.amp[type];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int zz = zl * 8 + k;
-                            if (zz < zoff || zz >= zend) continue;
-                            const double bzv = __dsub_rn(rz, __dmul_rn((double)((int)r.x + zz), gp.dr[2]));
-                            const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
-                            const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
-                            const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
-                            acc[k] += __double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2) * gp.fx_scale);
+                        for (int i = 0; i < TX; ++i) {
+                            if (i < cx0 || i >= cx1) continue;
+                            const double bx = __dsub_rn(rx, __dmul_rn((double)((int)r.y + i), gp.dr[0]));
+#pragma unroll
+                            for (int k = 0; k < KZ; ++k) {
+                                const int zz = zl * KZ + k;
+                                if (zz < zoff || zz >= zend) continue;
+                                const double bzv = __dsub_rn(rz, __dmul_rn((double)((int)r.x + zz), gp.dr[2]));
+                                const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
+                                const double c1 = gp.u[1] * bx + gp.u[4] * by + gp.u[7] * bzv;
+                                const double c2 = gp.u[2] * bx + gp.u[5] * by + gp.u[8] * bzv;
+                                acc[i][k] += __double2ll_rn(amp * exp(-(c0 * c0 + c1 * c1 + c2 * c2) / t2) * gp.fx_scale);
+                            }
                         }
                     }
                     continue;
                 }
-                // ---- separable ucell: cp.async staging ring, NS-1 records ahead
-                constexpr int E = ZW + TX + TY + (MODE == SPLAT_MONO ? NCOL : 0);
-                constexpr int ROUNDS = (E + 31) / 32;
+                // ---- separable ucell: cp.async staging ring, NS-1 records ahead.  A group whose list is exhausted
+                // stages nothing and accumulates the zeros of a slot it cleared once (below).
                 auto produce = [&](int i, int slot) {
-                    const PairRec r = rbuf[i];
-                    const unsigned g = r.w;
-                    const int cx0 = g & 7, cx1 = (g >> 3) & 15, cy0 = (g >> 7) & 7, cy1 = (g >> 10) & 15;
-                    const int zoff = (g >> 14) & 127, zend = (g >> 21) & 127;
-                    double* dst = slots + slot * SLOT;
+                    if (i >= m) return;
+                    const PairRec r = rbuf[grp * RB + i];
+                    const unsigned dst = slots_s + (unsigned)((slot * SUB + grp) * SLOTG + gl) * 8u;
 #pragma unroll
                     for (int rd = 0; rd < ROUNDS; ++rd) {
-                        const int e = lane + 32 * rd;
-                        if (e >= E) break;
-                        bool valid;
-                        const double* src;
-                        if (e < ZW) { valid = e >= zoff && e < zend; src = tables + ((int)r.x + e); }
-                        else if (e < ZW + TX) { const int xe = e - ZW; valid = xe >= cx0 && xe < cx1; src = tables + ((int)r.y + xe); }
-                        else if (e < ZW + TX + TY) { const int ye = e - ZW - TX; valid = ye >= cy0 && ye < cy1; src = tables + ((int)r.z + ye); }
-                        else {
-                            const int ce = e - ZW - TX - TY, xe = ce >> LTY, ye = ce & (TY - 1);
-                            valid = xe >= cx0 && xe < cx1 && ye >= cy0 && ye < cy1;
-                            const PairAux a = abuf[i];
-                            src = tt.ctab + ((int)a.x + xe * (int)a.y + ye);
+                        if ((rd + 1) * GL <= ZW) {             // every lane stages an EZ entry
+                            const unsigned e = (unsigned)(gl + GL * rd);
+                            cp_async8_zfill(dst + rd * GL * 8u, tables + ((int)r.x + (int)e), e - (r.w & 127u) < (r.w >> 7));
+                        } else {
+                            const int e = gl + GL * rd;
+                            if (e < ZW) {
+                                cp_async8_zfill(dst + rd * GL * 8u, tables + ((int)r.x + e), (unsigned)e - (r.w & 127u) < (r.w >> 7));
+                            } else if (skind[rd] != 0) {
+                                const double* src;
+                                if (MODE == SPLAT_MONO && skind[rd] == 3) {
+                                    const PairAux a = abuf[grp * RB + i];
+                                    src = tt.ctab + ((int)a.x + smul[rd] * (int)a.y + soff[rd]);
+                                } else {
+                                    src = tables + ((int)(skind[rd] == 1 ? r.y : r.z) + soff[rd]);
+                                }
+                                cp_async8(dst + rd * GL * 8u, src);
+                            }
                         }
-                        if (!valid) src = tables;
-                        cp_async8_zfill(dst + e, src, valid);
                     }
                 };
                 int ps = 0, cs = 0;
 #pragma unroll
                 for (int i = 0; i < NS - 1; ++i) {
-                    if (i < m) produce(i, ps);
+                    produce(i, ps);
                     cp_async_commit();
                     ps = (ps + 1 == NS) ? 0 : ps + 1;
                 }
-                for (int i = 0; i < m; ++i) {
-                    if (i + NS - 1 < m) produce(i + NS - 1, ps);
+                for (int r_i = 0; r_i < mmax; ++r_i) {
+                    produce(r_i + NS - 1, ps);
                     cp_async_commit();
                     ps = (ps + 1 == NS) ? 0 : ps + 1;
                     cp_async_wait<NS - 1>();
                     __syncwarp();
-                    const double* sl = slots + cs * SLOT;
-                    double exy = sl[ZW + cx] * sl[ZW + TX + cy];
-                    if (MODE == SPLAT_MONO) exy *= sl[ZW + TX + TY + c];
-                    const double2* ez2 = reinterpret_cast<const double2*>(sl + zl * 8);
+                    if (SUB == 1 || r_i < m) {
+                    const double* sl = slots + (cs * SUB + grp) * SLOTG;
+                    const double ey = sl[ZW + TX + cy];
+                    double exy[TX], ez[KZ];
+                    const double2* ex2 = reinterpret_cast<const double2*>(sl + ZW);                        // EX: the same address in every lane of the group
+                    const double2* cc2 = reinterpret_cast<const double2*>(sl + ZW + TX + TY + cy * TX);    // my row of the cross-term table
 #pragma unroll
-                    for (int k2 = 0; k2 < 4; ++k2) {
-                        const double2 e = ez2[k2];
-                        acc[2 * k2]     += __double_as_longlong(__fma_rn(exy, e.x, MDSF_MAGIC)) - MDSF_MAGIC_BITS;
-                        acc[2 * k2 + 1] += __double_as_longlong(__fma_rn(exy, e.y, MDSF_MAGIC)) - MDSF_MAGIC_BITS;
+                    for (int i = 0; i < TX; i += 2) {
+                        const double2 e = ex2[i >> 1];
+                        exy[i] = e.x * ey; exy[i + 1] = e.y * ey;
+                        if (MODE == SPLAT_MONO) { const double2 cv = cc2[i >> 1]; exy[i] *= cv.x; exy[i + 1] *= cv.y; }
+                    }
+                    if (KZ == 1) {
+                        ez[0] = sl[zl];
+                    } else {
+                        const double2* ez2 = reinterpret_cast<const double2*>(sl + zl * KZ);
+#pragma unroll
+                        for (int k = 0; k < KZ; k += 2) { const double2 e = ez2[k >> 1]; ez[k] = e.x; ez[k + (KZ > 1 ? 1 : 0)] = e.y; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < TX; ++i)
+#pragma unroll
+                        for (int k = 0; k < KZ; ++k)
+                            acc[i][k] += __double_as_longlong(__fma_rn(exy[i], ez[k], MDSF_MAGIC)) - MDSF_MAGIC_BITS;
                     }
                     cs = (cs + 1 == NS) ? 0 : cs + 1;
                     __syncwarp();                              // slot cs-1 may be refilled
                 }
             }
             // fixed point -> fp64 (overflow: a cell held > 2048 peak amplitudes)
+            long long any = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int z = zbase + k;
-                ovf |= (acc[k] < 0) | (acc[k] >= (1LL << 62));
-                if (z < nz) col[z + (z >> gp.pad_shift)] = (double)acc[k] * gp.fx_inv;
+            for (int i = 0; i < TX; ++i)
+#pragma unroll
+                for (int k = 0; k < KZ; ++k) {
+                    const int z = zbase + k;
+                    any |= acc[i][k];
+                    if (slab_ok && z < nz) row[(size_t)i * TY * nzp + z + (z >> gp.pad_shift)] = fx_to_double(acc[i][k]) * gp.fx_inv;
+                }
+            ovf |= (any >> 62) != 0;                           // terms are >= 0: bit 62 or 63 set in any sum
             }
         }
+        int nxt_item = 0;
+        if (lane == 0) nxt_item = atomicAdd(&s_next, 1);
+        item = __shfl_sync(0xffffffffu, nxt_item, 0);
     }
     if (ovf) atomicExch(err_flag, 2);
     cp_async_wait<0>();
     __syncthreads();
 
-    double* twr = reinterpret_cast<double*>(area);            // z twiddles reuse the staging area
+    double* twr = reinterpret_cast<double*>(area);            // generic path / late load: twiddles reuse the staging area
     double* twi = twr + nz;
-    if (FUSE) load_twiddles(twr, twi, twz, nz);
+    if (zspec && tws_off == 0) {
+        tws_s = reinterpret_cast<double2*>(area);
+        for (int i = threadIdx.x; i < tws_n; i += MDSF_SPLAT_THREADS) tws_s[i] = tws_g[i];
+    } else if (FUSE && !zspec) {
+        load_twiddles(twr, twi, twz, nz);
+    }
     if (dens_dump != nullptr) {                               // parity tap: plain [q][x][y][z] pairs, before any FFT
         for (int i = threadIdx.x; i < NCOL * nz; i += blockDim.x) {
             const int cc = i / nz, z = i - cc * nz;
@@ -215,34 +377,40 @@ splat_zfft_kernel(const PairRec* __restrict__ prec, const PairAux* __restrict__ 
     const long long ncell = (long long)gp.n[0] * gp.n[1] * nz;
     const long long cs_ = (long long)gp.n[0] * gp.n[1] * gp.lw;      // chunk stride
     double2* volq = vol + (long long)q * ncell;
-    if (FUSE) fft_tile_z(tile_re, tile_im, twr, twi, zplan, NCOL, nzp, gp.pad_shift);      // ends with a barrier
-    // store: runs of TY * lw contiguous cells (chunked layout) / whole columns (plain layout)
-    if (gp.lw == nz) {
-        for (int cc = 0; cc < NCOL; ++cc) {
-            const int x = X0 + (cc >> LTY), y = Y0 + (cc & (TY - 1));
-            if (x >= gp.n[0] || y >= gp.n[1]) continue;
-            double2* dst = volq + ((long long)x * gp.n[1] + y) * nz;
-            const double* sre = tile_re + (size_t)cc * nzp;
-            const double* sim = tile_im + (size_t)cc * nzp;
-            for (int z = threadIdx.x; z < nz; z += blockDim.x) {
-                const int a = z + (z >> gp.pad_shift);
-                dst[z] = make_double2(sre[a], sim[a]);
+    if (FUSE) {
+        // the tile size a grid selects fixes its z length class: compile-time stages for the power-of-two lengths
+        // (and 768) the BASELINE configs use, the generic run-time stages for everything else
+        if (!zspec) fft_tile_z(tile_re, tile_im, twr, twi, zplan, NCOL, nzp, gp.pad_shift);      // ends with a barrier
+        else if (LCOL == 5) zfft_64<NCOL, 3>(tile_re, tile_im, tws_s, nzp);
+        else if (LCOL == 4) zfft_256<NCOL, 3>(tile_re, tile_im, tws_s, nzp);
+        else if (LCOL == 3) zfft_512<NCOL, 3>(tile_re, tile_im, tws_s, nzp);
+        else if (nz == 1024) zfft_1024<NCOL, 3>(tile_re, tile_im, tws_s, nzp);
+        else zfft_768<NCOL>(tile_re, tile_im, tws_s, nzp);
+    }
+    // store: every tile row x is one run of TY * Nz contiguous cells (plain layout), or Nz / lw runs of TY * lw cells
+    // (chunked layout): 16-byte stores, consecutive threads -> consecutive addresses
+    const int per_x = TY * nz;
+    const bool pw2 = (nz & (nz - 1)) == 0;
+    const int lnz = __ffs(nz) - 1, llw = __ffs(gp.lw) - 1;
+    for (int xx = 0; xx < TX; ++xx) {
+        const int x = X0 + xx;
+        if (x >= gp.n[0]) break;
+        double2* dstx = volq + (long long)x * gp.n[1] * gp.lw;
+        for (int j = threadIdx.x; j < per_x; j += MDSF_SPLAT_THREADS) {
+            int yy, z;
+            long long o;
+            if (gp.lw == nz) {                                 // plain: j = yy * Nz + z
+                if (pw2) { yy = j >> lnz; z = j & (nz - 1); } else { yy = j / nz; z = j - yy * nz; }
+                o = (long long)(Y0 + yy) * nz + z;
+            } else {                                           // chunked: j = (ch * TY + yy) * lw + zw
+                const int ch = j >> (LTY + llw), zw = j & (gp.lw - 1);
+                yy = (j >> llw) & (TY - 1);
+                z = (ch << llw) + zw;
+                o = (long long)ch * cs_ + (long long)(Y0 + yy) * gp.lw + zw;
             }
-        }
-    } else {
-        const int llw = __ffs(gp.lw) - 1;
-        const int per_x = TY * nz;                             // elements of one tile row x: [ch][cy][zw]
-        for (int xx = 0; xx < TX; ++xx) {
-            const int x = X0 + xx;
-            if (x >= gp.n[0]) break;
-            for (int j = threadIdx.x; j < per_x; j += blockDim.x) {
-                const int ch = j >> (LTY + llw), yy = (j >> llw) & (TY - 1), zw = j & (gp.lw - 1);
-                const int y = Y0 + yy;
-                if (y >= gp.n[1]) continue;
-                const int z = (ch << llw) + zw;
-                const int a = ((xx << LTY) + yy) * nzp + z + (z >> gp.pad_shift);
-                volq[(long long)ch * cs_ + ((long long)x * gp.n[1] + y) * gp.lw + zw] = make_double2(tile_re[a], tile_im[a]);
-            }
+            if (Y0 + yy >= gp.n[1]) continue;
+            const int a = ((xx << LTY) + yy) * nzp + z + (z >> gp.pad_shift);
+            dstx[o] = make_double2(tile_re[a], tile_im[a]);
         }
     }
 }

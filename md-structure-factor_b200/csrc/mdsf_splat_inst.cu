@@ -2,22 +2,28 @@
 #include "mdsf_launch.h"
 #include "mdsf_splat.cuh"
 
-static const int kMaxSmemSplat = 227 * 1024;
+static const int kMaxSmemSplat = 227 * 1024 - 256;     // the kernel also holds a few bytes of static shared memory
 
-template <int LCOL> static size_t warp_bytes() { return (size_t)SplatGeom<LCOL>::WARP_BYTES; }
+template <int LCOL> static size_t warp_bytes(int sub) { return sub == 2 ? (size_t)SplatGeom<LCOL, 2>::WARP_BYTES : (size_t)SplatGeom<LCOL, 1>::WARP_BYTES; }
 
-size_t mdsf_splat_smem(int lcol, int nzp, int nz) {
-    size_t wb = lcol == 2 ? warp_bytes<2>() : (lcol == 3 ? warp_bytes<3>() : (lcol == 4 ? warp_bytes<4>() : warp_bytes<5>()));
+size_t mdsf_splat_smem(int lcol, int sub, int nzp, int nz) {
+    size_t wb = lcol == 2 ? warp_bytes<2>(sub) : (lcol == 3 ? warp_bytes<3>(sub) : (lcol == 4 ? warp_bytes<4>(sub) : warp_bytes<5>(sub)));
     size_t area = wb * MDSF_SPLAT_WARPS;
     const size_t tw = (size_t)2 * (nz > 256 ? nz : 256) * sizeof(double);     // z twiddles reuse the staging area
     if (area < tw) area = tw;
     return (size_t)2 * ((size_t)1 << lcol) * nzp * sizeof(double) + area;
 }
 
+bool mdsf_zspec_applies(int lcol, int nz, int pad_shift) { return zspec_applies(lcol, nz, pad_shift); }
+
 template <int LCOL, int MODE>
 static cudaError_t launch1(bool fuse, dim3 grid, size_t smem, cudaStream_t st, const SplatArgs& a) {
-    splat_zfft_kernel<LCOL, MODE><<<grid, MDSF_SPLAT_THREADS, smem, st>>>(a.prec, a.paux, a.start, a.recs, a.tables, a.src_density, a.nframes,
-        a.vol, a.dens_dump, a.gp, a.tt, a.zplan, a.twz, a.err_flag, fuse ? 1 : 0);
+    if (a.gp.sub == 2)
+        splat_zfft_kernel<LCOL, MODE, 2><<<grid, MDSF_SPLAT_THREADS, smem, st>>>(a.prec, a.start, a.recs, a.tables, a.src_density, a.nframes,
+            a.vol, a.dens_dump, a.gp, a.tt, a.zplan, a.twz, a.err_flag, fuse ? 1 : 0, a.tws, a.tws_n, a.tws_off);
+    else
+        splat_zfft_kernel<LCOL, MODE, 1><<<grid, MDSF_SPLAT_THREADS, smem, st>>>(a.prec, a.start, a.recs, a.tables, a.src_density, a.nframes,
+            a.vol, a.dens_dump, a.gp, a.tt, a.zplan, a.twz, a.err_flag, fuse ? 1 : 0, a.tws, a.tws_n, a.tws_off);
     return cudaGetLastError();
 }
 
@@ -43,7 +49,9 @@ cudaError_t mdsf_launch_splat(int lcol, int mode, bool fuse, dim3 grid, size_t s
 }
 
 template <int LCOL, int MODE> static cudaError_t cfg1() {
-    return cudaFuncSetAttribute(splat_zfft_kernel<LCOL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemSplat);
+    cudaError_t e = cudaFuncSetAttribute(splat_zfft_kernel<LCOL, MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemSplat);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(splat_zfft_kernel<LCOL, MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemSplat);
 }
 template <int LCOL> static cudaError_t cfg_mode() {
     cudaError_t e;

@@ -640,19 +640,19 @@ def test_full_grids_subsampled_atoms_against_oracle(mdsf, workload, natoms):
 
 def test_c5_grid_long_z_density_against_numpy(mdsf):
     """1024^3 is too large for a full oracle run inside the test budget; its tile geometry (2x2 columns, 64-cell slabs,
-    1024-point z columns = 2*8*8*8) is checked on a 16 x 16 x 1024 box with NA stamps, and the 1024-point y / x passes on
+    1024-point z columns = 2*8*8*8) is checked on a 40 x 40 x 1024 box with NA stamps, and the 1024-point y / x passes on
     the FFT shape list above."""
     rng = np.random.default_rng(5)
-    box = np.array([16.0, 16.0, 1024.0], dtype=np.float32)
-    natoms = 300
+    box = np.array([40.0, 40.0, 1024.0], dtype=np.float32)
+    natoms = 600
     coords = (rng.uniform(0.0, 1.0, size=(2, natoms, 3)) * box).astype(np.float32)
-    coords[0, 0] = (0.3, 15.9, 1023.8)
-    coords[0, 1] = (15.8, 0.2, 0.1)
+    coords[0, 0] = (0.3, 39.9, 1023.8)
+    coords[0, 1] = (39.8, 0.2, 0.1)
     typ = np.array(["NA", "C", "H", "O"] * (natoms // 4))
     w = __import__("workloads")
     c = dict(coords=coords, dims=np.repeat(box[None, :], 2, axis=0), typ=typ, rad=w.RAD, ucell=np.eye(3), sres=1.0)
     got = run_engine(mdsf, c, "auto", batch=2)
-    assert tuple(int(v) for v in got["N"]) == (16, 16, 1024) and got["fft"] == "native"
+    assert tuple(int(v) for v in got["N"]) == (40, 40, 1024) and got["fft"] == "native"
     _oracle_case(c, got)
 
 

@@ -58,64 +58,71 @@ def emulate_frame(frame, typ, rad, widths, n, dr, nb, ucell, lcol, fold_mode=0):
         amp = nel / sig ** 3
         bx0 = r[0] - (ir[0] - Ax) * dr[0]
         by0 = r[1] - (ir[1] - Ay) * dr[1]
-        T = []
+        padx, pady = TX - 1, TY - 1
+        T = [0.0] * padx
         for i in range(2 * Ax):
             b = r[0] - (ir[0] - Ax + i) * dr[0]
             T.append(math.exp(-(cxx * b * b + 2.0 * gxy * b * by0) * it2))
+        T += [0.0] * (padx + pady)
         for j in range(2 * Ay):
             b = r[1] - (ir[1] - Ay + j) * dr[1]
             T.append(math.exp(-(cyy * b * b - 2.0 * gxy * (j * dr[1]) * bx0) * it2))
+        T += [0.0] * pady
         for k in range(2 * Az):
             b = r[2] - (ir[2] - Az + k) * dr[2]
             T.append(amp * math.exp(-(czz * b * b) * it2))
         T = np.array(T)
-        ctab = np.array([[math.exp(-(2.0 * gxy * dr[0] * dr[1] * i * j) * it2) for j in range(2 * Ay)] for i in range(2 * Ax)]).reshape(-1)
+        cpad = 8 * 2 * Ay + 8
+        ctab = np.concatenate([np.ones(cpad), np.array([[math.exp(-(2.0 * gxy * dr[0] * dr[1] * i * j) * it2) for j in range(2 * Ay)]
+                                                         for i in range(2 * Ax)]).reshape(-1), np.ones(cpad)])
         tbase = 0
+        ex0 = tbase + padx
+        ey0 = tbase + 2 * padx + 2 * Ax + pady
+        ez0 = tbase + 2 * padx + 2 * Ax + 2 * pady + 2 * Ay
         for sx in (-1, 0, 1):
             xlo, xhi = stamp_segment(ir[0], Ax, nx, sx)
             if xhi <= xlo:
                 continue
             dx0, dx1 = xlo - sx * nx, xhi - sx * nx
             ix0 = xlo - (ir[0] - Ax)
-            for sy in (-1, 0, 1):
-                ylo, yhi = stamp_segment(ir[1], Ay, ny, sy)
-                if yhi <= ylo:
-                    continue
-                dy0, dy1 = ylo - sy * ny, yhi - sy * ny
-                jy0 = ylo - (ir[1] - Ay)
-                for sz in (-1, 0, 1):
-                    zlo, zhi = stamp_segment(ir[2], Az, nz, sz)
-                    if zhi <= zlo:
+            for tX in range(dx0 >> ltx, ((dx1 - 1) >> ltx) + 1):
+                X0 = tX << ltx
+                cx0 = max(dx0 - X0, 0)
+                i0 = ix0 + (X0 + cx0 - dx0)
+                for sy in (-1, 0, 1):
+                    ylo, yhi = stamp_segment(ir[1], Ay, ny, sy)
+                    if yhi <= ylo:
                         continue
-                    shz = fold_shift_z(sx, sy, sz, nz, nb, fold_mode)
-                    dz0, dz1 = zlo + shz, zhi + shz
-                    kz0 = zlo - (ir[2] - Az)
-                    assert 0 <= dx0 < dx1 <= nx and 0 <= dy0 < dy1 <= ny and 0 <= dz0 < dz1 <= nz
-                    for tX in range(dx0 >> ltx, ((dx1 - 1) >> ltx) + 1):
-                        X0 = tX << ltx
-                        cx0, cx1 = max(dx0 - X0, 0), min(dx1 - X0, TX)
-                        i0 = ix0 + (X0 + cx0 - dx0)
-                        for tY in range(dy0 >> lty, ((dy1 - 1) >> lty) + 1):
-                            Y0 = tY << lty
-                            cy0, cy1 = max(dy0 - Y0, 0), min(dy1 - Y0, TY)
-                            j0 = jy0 + (Y0 + cy0 - dy0)
+                    dy0, dy1 = ylo - sy * ny, yhi - sy * ny
+                    jy0 = ylo - (ir[1] - Ay)
+                    for tY in range(dy0 >> lty, ((dy1 - 1) >> lty) + 1):
+                        Y0 = tY << lty
+                        cy0 = max(dy0 - Y0, 0)
+                        j0 = jy0 + (Y0 + cy0 - dy0)
+                        for sz in (-1, 0, 1):
+                            zlo, zhi = stamp_segment(ir[2], Az, nz, sz)
+                            if zhi <= zlo:
+                                continue
+                            shz = fold_shift_z(sx, sy, sz, nz, nb, fold_mode)
+                            dz0, dz1 = zlo + shz, zhi + shz
+                            kz0 = zlo - (ir[2] - Az)
                             for s in range(dz0 >> lzw, ((dz1 - 1) >> lzw) + 1):
                                 Z0 = s << lzw
                                 zoff, zend = max(dz0 - Z0, 0), min(dz1 - Z0, ZW)
                                 k0 = kz0 + (Z0 + zoff - dz0)
-                                ez_idx = tbase + 2 * (Ax + Ay) + k0 - zoff
-                                ex_idx = tbase + i0 - cx0
-                                ey_idx = tbase + 2 * Ax + j0 - cy0
-                                ct_idx = (i0 - cx0) * 2 * Ay + (j0 - cy0)
-                                assert 0 <= cx0 < cx1 <= 8 and 0 <= cy0 < cy1 <= 8 and 0 <= zoff < zend <= 64
+                                ez_idx = ez0 + k0 - zoff
+                                ex_idx = ex0 + i0 - cx0
+                                ey_idx = ey0 + j0 - cy0
+                                ct_idx = cpad + (i0 - cx0) * 2 * Ay + (j0 - cy0)
                                 npairs += 1
-                                # ---- what the splat warp does with this record
-                                ex = np.array([T[ex_idx + cx] for cx in range(cx0, cx1)])
-                                ey = np.array([T[ey_idx + cy] for cy in range(cy0, cy1)])
-                                cc = np.array([[ctab[ct_idx + cx * 2 * Ay + cy] for cy in range(cy0, cy1)] for cx in range(cx0, cx1)])
+                                # ---- what the splat warp does with this record: EVERY tile column, no clip test
+                                ex = np.array([T[ex_idx + cx] for cx in range(TX)])
+                                ey = np.array([T[ey_idx + cy] for cy in range(TY)])
+                                cc = np.array([[ctab[ct_idx + cx * 2 * Ay + cy] for cy in range(TY)] for cx in range(TX)])
                                 ez = np.array([T[ez_idx + zz] for zz in range(zoff, zend)])
                                 exy = ex[:, None] * ey[None, :] * cc
-                                d[X0 + cx0:X0 + cx1, Y0 + cy0:Y0 + cy1, Z0 + zoff:Z0 + zend] += exy[:, :, None] * ez[None, None, :]
+                                x1, y1 = min(X0 + TX, nx), min(Y0 + TY, ny)        # columns outside the grid are never stored
+                                d[X0:x1, Y0:y1, Z0 + zoff:Z0 + zend] += (exy[:, :, None] * ez[None, None, :])[:x1 - X0, :y1 - Y0]
     return d, npairs
 
 

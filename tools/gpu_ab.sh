@@ -1,0 +1,23 @@
+#!/bin/sh
+# A/B of engine builds (MDSF_LIB) / knobs on the bench workloads: prints frames/s and stage times
+mkdir -p gpurun_out
+run() {  # name env...
+  name=$1; shift
+  for wl in c2 c3; do
+    env "$@" timeout 300 python bench.py --workload $wl --steps 4 --warmup 2 --no-cpu --frames-per-step $( [ $wl = c2 ] && echo 64 || echo 8 ) --pool 16 > gpurun_out/ab_${name}_$wl.json 2> gpurun_out/ab_${name}_$wl.err
+    python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/ab_${name}_$wl.json').read().strip().splitlines()[-1])
+    print('$name $wl', round(d['value'],1), 'frames/s', {k: round(v,2) for k,v in d['stage_ms_per_step'].items()})
+except Exception as e:
+    print('$name $wl FAILED', e)
+PY
+  done
+}
+run w16 X=1
+run w12 MDSF_LIB=$PWD/md-structure-factor_b200/libmdsf_w12.so
+run w8 MDSF_LIB=$PWD/md-structure-factor_b200/libmdsf_w8.so
+run w16_sub1 MDSF_SUB=1
+run w12_sub1 MDSF_LIB=$PWD/md-structure-factor_b200/libmdsf_w12.so MDSF_SUB=1
+run w8_sub1 MDSF_LIB=$PWD/md-structure-factor_b200/libmdsf_w8.so MDSF_SUB=1
