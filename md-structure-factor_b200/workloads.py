@@ -82,6 +82,12 @@ def get(name):
         typ, base, box = uniform_box(334080, 511.9, LLC_COMPOSITION, 3000)
         return dict(typ=typ, base=base, box=box, ucell=ucell_for(120.0), sres=1.0, grid=(512, 512, 512), jitter=0.3,
                     seed0=3000, rad=RAD, desc="LLC-composition box, 334080 atoms, 512^3 grid, theta=120")
+    if name == "c3d":  # c3's atoms at the number density of a condensed phase (0.1 atoms / A^3, what an LLC membrane or water has):
+        # the 512^3 grid then resolves 0.29 A, stamps are 26^3 (H) ... 36^3 (C) ... 118^3 (NA) cells and the splat dominates
+        L = (334080 / 0.1) ** (1.0 / 3.0)
+        typ, base, box = uniform_box(334080, L, LLC_COMPOSITION, 3100)
+        return dict(typ=typ, base=base, box=box, ucell=ucell_for(120.0), sres=float(box[0]) / 512 * (1 + 1e-6), grid=(512, 512, 512),
+                    jitter=0.3, seed0=3100, rad=RAD, desc="LLC-composition box at 0.1 atoms/A^3, 334080 atoms, 512^3 grid (dr = 0.29 A), theta=120")
     if name == "c4":
         typ, base, box = uniform_box(1000000, 767.9, BOX_COMPOSITION, 4000)
         return dict(typ=typ, base=base, box=box, ucell=np.eye(3), sres=1.0, grid=(768, 768, 768), jitter=0.3,

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 run() {  # name env...
   name=$1; shift
-  for wl in c2 c3; do
+  for wl in ${WLS:-c2 c3}; do
     env "$@" timeout 300 python bench.py --workload $wl --steps 4 --warmup 2 --no-cpu --frames-per-step $( [ $wl = c2 ] && echo 64 || echo 8 ) --pool 16 > gpurun_out/ab_${name}_$wl.json 2> gpurun_out/ab_${name}_$wl.err
     python - <<PY
 import json
@@ -15,9 +15,6 @@ except Exception as e:
 PY
   done
 }
-run w16 X=1
-run w12 MDSF_LIB=$PWD/md-structure-factor_b200/libmdsf_w12.so
-run w8 MDSF_LIB=$PWD/md-structure-factor_b200/libmdsf_w8.so
-run w16_sub1 MDSF_SUB=1
-run w12_sub1 MDSF_LIB=$PWD/md-structure-factor_b200/libmdsf_w12.so MDSF_SUB=1
-run w8_sub1 MDSF_LIB=$PWD/md-structure-factor_b200/libmdsf_w8.so MDSF_SUB=1
+run base X=1
+run lw8 MDSF_LAYOUT_W=8
+run lw4 MDSF_LAYOUT_W=4

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
-"""Turn gpurun_out/{prof_r01_c2.ncu-rep, launches.csv, bench_default.json} into the committed summaries
-under profiles/ (run here, no GPU needed)."""
-import collections, csv, json, shutil, subprocess
+"""Turn gpurun_out/{prof_r02_<wl>.ncu-rep, launches_<wl>.csv} into the committed summaries under profiles/
+(run here, no GPU needed):  profiles/r02_ncu_<wl>_kernels.md, r02_traffic_<wl>.json, r02_launches_<wl>.csv / .md.
+usage: summarise_profiles.py <workload> <frames_per_launch>"""
+import collections, csv, json, shutil, subprocess, sys
+wl, F = sys.argv[1], int(sys.argv[2])
 PEAK = json.load(open('MEASURED_PEAKS.json'))['hbm_gbs'] / 1e3      # TB/s, driver-written for this pod
-raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_r01_c2.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
+rows = list(csv.reader(open("gpurun_out/prof_r02_%s_raw.csv" % wl)))     # `ncu -i prof.ncu-rep --page raw --csv`, exported on the GPU box
 h, units = rows[0], rows[1]
 def num(s):
     try: return float(s.replace(',', ''))
@@ -14,61 +15,55 @@ want = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'sm__warps_active.avg.per_cycle_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
-        'smsp__thread_inst_executed_per_inst_executed.ratio', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__inst_executed_op_shared_atom.sum', 'lts__t_sector_hit_rate.pct']
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'lts__t_sector_hit_rate.pct']
 stalls = [n for n in h if 'issue_stalled' in n and n.endswith('.ratio')]
-bench = json.loads(open('gpurun_out/bench_default.json').readline())
-F = bench['config']['frames_per_step']
-out, summ = [], {}
+short = {'prep_atoms': 'prep_bin', 'bin_place': 'prep_bin', 'DeviceScan': 'prep_bin', 'splat_zfft': 'splat_zfft', 'fft3_pass_kernel<8, 8, 8, 3, 256, 2, 0>': 'fft_y',
+         'fft3_pass_kernel<8, 8, 8, 3, 256, 2, 1>': 'fft_x_accum', 'fft_y': 'fft_y', 'fft_x': 'fft_x_accum', 'yx_pass': 'fft_yx'}
+out, traffic = ['# ncu --set full, %s, one launch per kernel (%d frames per launch); peak = %.2f TB/s measured' % (wl, F, PEAK), ''], collections.OrderedDict()
+seen = set()
 for r in rows[2:]:
-    k = r[h.index('Kernel Name')].split('(')[0]
-    out.append('## ' + k)
+    k = r[h.index('Kernel Name')]
+    base = k.split('(')[0]
+    if base in seen: continue
+    seen.add(base)
+    out.append('## ' + base)
     d = {}
     for w in want:
         if w in h:
-            out.append('- %s = %s %s' % (w, r[h.index(w)], units[h.index(w)])); d[w] = num(r[h.index(w)]); d[w + '_unit'] = units[h.index(w)]
+            out.append('- %s = %s %s' % (w, r[h.index(w)], units[h.index(w)])); d[w] = num(r[h.index(w)])
     st = sorted([(n, num(r[h.index(n)])) for n in stalls], key=lambda x: -x[1])
-    out.append('- top stalls (warps per issue): ' + ', '.join('%s %.2f' % (n.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''), v) for n, v in st[:5]))
-    summ[k] = d
-def tobytes(v, u): return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
-tr, lines = {}, []
-for k, d in summ.items():
-    b = tobytes(d['dram__bytes_read.sum'], d['dram__bytes_read.sum_unit']) + tobytes(d['dram__bytes_write.sum'], d['dram__bytes_write.sum_unit'])
-    ms = d['gpu__time_duration.sum'] * {'ms': 1, 'us': 1e-3, 's': 1e3}.get(d['gpu__time_duration.sum_unit'], 1)
-    tr[k] = {'dram_bytes_per_launch': b, 'frames_per_launch': F}
-    lines.append('| %s | %.2f | %.3f | %.2f | %.0f %% |' % (k, b / 1e9, ms, b / 1e9 / ms, 100 * b / 1e9 / ms / PEAK))
-head = ('# Round 1 - ncu --set full, c2 (256^3, 105456 atoms), %d frames per launch, %s splat mode\n\n'
-        'Command: `ncu --set full --clock-control none --import-source on -k regex:"splat_zfft|fft_y|fft_x" -s 3 -c 3 python bench.py --steps 2 --warmup 1 --no-cpu`\n'
-        '(the .ncu-rep itself is not committed: 40 MB).\n\n| kernel | DRAM GB / launch | ms (under ncu) | TB/s | of measured %.2f TB/s |\n|---|---|---|---|---|\n' % (F, bench['config']['splat'], PEAK)
-        + '\n'.join(lines) + '\n\nThe y and x passes are HBM-bound; the fused splat + z pass writes the pair volumes once and is bound by instruction\n'
-        'issue / dependent-load latency of its per-tile phases, not by HBM.\n\n')
-open('profiles/r01_ncu_c2_kernels.md', 'w').write(head + '\n'.join(out) + '\n')
-json.dump({'workload': 'c2', 'source': 'profiles/r01_ncu_c2_kernels.md', 'kernels': tr}, open('profiles/r01_traffic_c2.json', 'w'), indent=1)
-rows = list(csv.reader(open('gpurun_out/launches.csv')))
-hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
-h = rows[hdr]; ki = h.index('Kernel Name'); vi = h.index('Metric Value'); gi = h.index('Grid Size'); bi = h.index('Block Size')
-agg = collections.OrderedDict()
-for r in rows[hdr + 1:]:
-    if len(r) <= vi: continue
-    d = agg.setdefault(r[ki].split('(')[0][:70], [0, 0.0, r[gi], r[bi]]); d[0] += 1; d[1] += float(r[vi].replace(',', ''))
-tot = sum(v[1] for v in agg.values())
-st = bench['stage_ms_per_step']
-with open('profiles/r01_launches_c2.md', 'w') as f:
-    f.write('# Round 1 - ncu launch list, c2 (256^3, 105456 atoms), %d frames per step, %s splat mode\n\n' % (F, bench['config']['splat']))
-    f.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv python bench.py --steps 3 --warmup 2 --no-cpu`.\n')
-    main3 = sum(st[k] for k in ('splat_zfft', 'fft_y', 'fft_x_accum'))
-    ncu3 = {k: sum(v[1] for n, v in agg.items() if k in n) for k in ('splat_zfft', 'fft_y', 'fft_x_accum')}
-    f.write('Times are cold-cache and serialised under the profiler: compare SHARES with the CUDA-event stage times of the un-profiled\n'
-            'bench (profiles/r01_bench_c2.json). Among the three compute-stream kernels: splat_zfft %.0f %% (ncu %.0f %%), fft_y %.0f %% (ncu %.0f %%), '
-            'fft_x_accum %.0f %% (ncu %.0f %%).\nprep+bin (prep_atoms incl. list-length counting, scan, bin_pairs) runs on its own stream underneath the '
-            'previous batch\'s y/x passes; its event span (%.2f ms) includes that waiting, its serialised ncu time is %.2f ms per step.\n\n'
-            % (100 * st['splat_zfft'] / main3, 100 * ncu3['splat_zfft'] / sum(ncu3.values()), 100 * st['fft_y'] / main3, 100 * ncu3['fft_y'] / sum(ncu3.values()),
-               100 * st['fft_x_accum'] / main3, 100 * ncu3['fft_x_accum'] / sum(ncu3.values()), st['prep_bin'],
-               (tot - sum(ncu3.values())) / 1e6 / max(1, sum(v[0] for n, v in agg.items() if 'splat_zfft' in n))))
-    f.write('| kernel | launches | total us | share | grid | block |\n|---|---|---|---|---|---|\n')
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        f.write('| %s | %d | %.1f | %.1f%% | %s | %s |\n' % (k, v[0], v[1] / 1e3, 100 * v[1] / tot, v[2], v[3]))
-shutil.copy('gpurun_out/launches.csv', 'profiles/r01_launches_c2.csv')
-shutil.copy('gpurun_out/bench_default.json', 'profiles/r01_bench_c2.json')
-print(head)
-print(open('profiles/r01_launches_c2.md').read()[:1400])
+    out.append('- top stalls (warps per issue): ' + ', '.join('%s %.2f' % (n.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''), v) for n, v in st[:6]))
+    def tobytes(name):
+        v, u = d.get(name, 0.0), units[h.index(name)] if name in h else ''
+        return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12}.get(u, 1.0)
+    by = tobytes('dram__bytes_read.sum') + tobytes('dram__bytes_write.sum')
+    ms = d.get('gpu__time_duration.sum', 0.0) * {'ms': 1.0, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}.get(units[h.index('gpu__time_duration.sum')], 1.0)
+    out.append('- DRAM traffic %.3f GB in %.3f ms = %.2f TB/s = %.1f%% of the measured peak' % (by / 1e9, ms, by / 1e9 / max(ms, 1e-9), 100 * by / 1e9 / max(ms, 1e-9) / PEAK))
+    out.append('')
+    stage = next((v for kk, v in short.items() if kk in k), base)
+    t = traffic.setdefault(stage, {'dram_bytes_per_launch': 0.0, 'frames_per_launch': F, 'kernels': []})
+    t['dram_bytes_per_launch'] += by
+    t['kernels'].append(base)
+open('profiles/r02_ncu_%s_kernels.md' % wl, 'w').write('\n'.join(out) + '\n')
+json.dump({'workload': wl, 'source': 'ncu --set full --clock-control none, gpurun_out/prof_r02_%s_raw.csv (ncu --page raw --csv of the capture)' % wl, 'kernels': traffic}, open('profiles/r02_traffic_%s.json' % wl, 'w'), indent=1)
+# launch list
+src = 'gpurun_out/launches_%s.csv' % wl
+lr = list(csv.reader(open(src)))
+for i, r in enumerate(lr):
+    if r and r[0] == 'ID': hdr = r; start = i + 1; break
+ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
+tot = collections.OrderedDict()
+with open('profiles/r02_launches_%s.csv' % wl, 'w') as fh:
+    fh.write('id,kernel,ns\n')
+    for r in lr[start:]:
+        if len(r) > vi:
+            name = r[ki].split('(')[0]
+            fh.write('%s,"%s",%s\n' % (r[0], name, r[vi]))
+            tot[name] = tot.get(name, 0.0) + num(r[vi])
+s = sum(tot.values())
+with open('profiles/r02_launches_%s.md' % wl, 'w') as fh:
+    fh.write('# ncu launch list (gpu__time_duration.sum, cold-cache, serialised), %s: share of the step per kernel\n\n' % wl)
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+        fh.write('- %5.1f%%  %8.3f ms  %s\n' % (100 * v / s, v / 1e6, k))
+print(open('profiles/r02_launches_%s.md' % wl).read())
