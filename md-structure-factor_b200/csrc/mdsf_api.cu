@@ -20,6 +20,7 @@
 #include "mdsf_fft.cuh"
 #include "mdsf_launch.h"
 #include "mdsf_prep.cuh"
+#include "mdsf_yx.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
@@ -59,7 +60,7 @@ struct AxisPlan {
 struct PrepSet {
     AtomRec* recs = nullptr;
     double *tables = nullptr, *tables_alloc = nullptr;
-    unsigned *count = nullptr, *start = nullptr, *cursor = nullptr;     // [nkeys+1] each
+    unsigned *count = nullptr, *start = nullptr;     // [nkeys+1] each: list lengths (K1), list starts -> list ends (K2)
     uint4* prec = nullptr;            // [2 * pair_cap]: 32-byte records {PairRec, PairAux + padding}
     void* cub = nullptr;
     cudaEvent_t ev_binned = nullptr, ev_consumed = nullptr;
@@ -111,8 +112,15 @@ struct mdsf_handle {
     long long maxpairs_frame = 0;
     int KX = 1, KY = 1;               // most x / y tiles one atom's stamp touches: bin_place_kernel runs KX*KY threads per atom
     unsigned long long pair_cap = 0;
+    bool prep_early = false;          // prep+bin of batch b+1 may start while the splat of batch b still runs
     int mono = 0;                     // K1 applies the monoclinic transform of main_gromacs.py:204-207 first
     double mono_sin = 1.0, mono_cos = 0.0;
+    // fused y -> x pass (mdsf_yx.cuh)
+    bool fused_yx = false;
+    double2 *d_scratch = nullptr, *d_twsy = nullptr, *d_twsx = nullptr;
+    unsigned* d_yxctl = nullptr;
+    size_t yxctl_words = 0;
+    int yx_grid = 0;
     // y/x pass geometry
     PassGeom pgy{}, pgx{};
     int ntile_y = 1, ntile_x = 1;
@@ -188,6 +196,29 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+// per-stage twiddle tables [n2] = w_N^(n2 N/L) of a plan (stages with M = L/R > 1), concatenated in stage order
+static int stage_tables(const FftPlan& plan, double2** d_out, int* count) {
+    const int N = plan.n;
+    std::vector<double2> tws;
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    int L = N;
+    for (int st = 0; st < plan.nstages; ++st) {
+        const int R = plan.radix[st], M = L / R;
+        if (M > 1)
+            for (int n2 = 0; n2 < M; ++n2) {          // the kernels form the powers w^2 .. w^(R-1) themselves
+                const int j = (int)(((long long)n2 * (N / L)) % N);
+                const long double a = two_pi * (long double)j / (long double)N;
+                tws.push_back(make_double2((double)cosl(a), (double)(-sinl(a))));
+            }
+        L = M;
+    }
+    if (tws.empty()) tws.push_back(make_double2(1.0, 0.0));
+    if (count) *count = (int)tws.size();
+    CU(cudaMalloc(d_out, sizeof(double2) * tws.size()));
+    CU(cudaMemcpy(*d_out, tws.data(), sizeof(double2) * tws.size(), cudaMemcpyHostToDevice));
+    return MDSF_OK;
+}
+
 // Slab geometry of the splat for `sub` lists per warp (1: one slab of 256 >> lcol cells per warp, 2: two half-width
 // slabs side by side), its shared memory, and whether the z twiddle tables get their own region (prefetched while the
 // splat runs) -- they do when two CTAs still fit an SM.
@@ -253,16 +284,24 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     gp.gxy = gp.u[0] * gp.u[3] + gp.u[1] * gp.u[4];
     gp.czz = gp.u[8] * gp.u[8];
     h->ncell = (long long)gp.n[0] * gp.n[1] * gp.n[2];
+    h->prep_early = env_int("MDSF_PREP_EARLY", 0) != 0;
     h->splat_mode = !gp.separable ? SPLAT_GENERAL_ : (gp.gxy != 0.0 ? SPLAT_MONO_ : SPLAT_ORTHO_);
 
-    // ---- FFT plans
+    // ---- FFT plans.  Grids the fused y -> x kernel covers use radices <= 8 on every axis (its stage lists), a z-chunked
+    // volume layout of width 4 and the L2-resident hand-over; everything else runs separate y and x passes.
     const bool want_native = cfg->fft_mode != MDSF_FFT_CUFFT;
+    // measured on B200: 512^2 planes 17.7 vs 20.0 ms per 8 c3 frames (and a third of the HBM traffic); 256^2 planes lose
+    // (13.3 vs 5.8 ms per 64 c2 frames: 16 KB tiles, the per-tile hand-shakes dominate) -> on by default from 512 up
+    const int fused_dflt = (gp.n[0] >= 512 && gp.n[1] >= 512) ? 1 : 0;
+    h->fused_yx = want_native && mdsf_yx_supported(gp.n[1], gp.n[0]) && gp.n[2] % MDSF_YX_W == 0 && gp.n[2] <= 2048 &&
+                  env_int("MDSF_FUSED_YX", fused_dflt) != 0 && env_int("MDSF_LAYOUT_W", 0) == 0;
     for (int d = 0; d < 3; ++d) {
-        int rc = build_axis(h->ax[d], gp.n[d], want_native, d == 2);
+        int rc = build_axis(h->ax[d], gp.n[d], want_native, d == 2 || h->fused_yx);
         if (rc) return rc;
     }
     h->native_fft = h->ax[0].native && h->ax[1].native && h->ax[2].native;
     if (gp.n[2] > 2048 || gp.n[1] > 2048 || gp.n[0] > 2048) h->native_fft = false;
+    if (!h->native_fft) h->fused_yx = false;
     if (!h->native_fft) {
         if (cfg->fft_mode == MDSF_FFT_NATIVE)
             return fail(MDSF_EINVAL, "grid %dx%dx%d has a prime factor > 13 (> 7 in z) or an axis longer than 2048; native FFT unavailable", gp.n[0], gp.n[1], gp.n[2]);
@@ -289,7 +328,14 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         gp.lcol = l;
     } else {
         gp.lcol = 5;
-        while (gp.lcol > 2 && mdsf_splat_smem(gp.lcol, 1, gp.nzp, gp.n[2]) > 112 * 1024) --gp.lcol;
+        const size_t tile_budget = (size_t)env_int("MDSF_TILE_KB", 112) * 1024;      // 112 KB: two CTAs per SM
+        while (gp.lcol > 2 && mdsf_splat_smem(gp.lcol, 1, gp.nzp, gp.n[2]) > tile_budget) --gp.lcol;
+    }
+    gp.zswz = 0;
+    if (h->native_fft && mdsf_zswizzle_wanted(gp.lcol, gp.n[2])) {      // swizzled columns need no padding
+        gp.zswz = 1;
+        gp.pad_shift = 31;
+        gp.nzp = gp.n[2] + 8;
     }
     if (mdsf_splat_smem(gp.lcol, 1, gp.nzp, gp.n[2]) > (size_t)kMaxSmem)
         return fail(MDSF_EINVAL, "grid too long in z (%d) for the column-tile splat", gp.n[2]);
@@ -298,32 +344,15 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         gp.ntx = (gp.n[0] + TX - 1) / TX;
         gp.nty = (gp.n[1] + TY - 1) / TY;
     }
-    // ---- compile-time z stages: per-stage twiddle tables [k-1][n2] = w^(n2 k N/L)
-    if (h->native_fft && mdsf_zspec_applies(gp.lcol, gp.n[2], gp.pad_shift)) {
-        const FftPlan& zp = h->ax[2].plan;
-        const int N = gp.n[2];
-        std::vector<double2> tws;
-        const long double two_pi = 6.283185307179586476925286766559005768L;
-        int L = N;
-        for (int st = 0; st < zp.nstages; ++st) {
-            const int R = zp.radix[st], M = L / R;
-            if (M > 1)
-                for (int k = 1; k < R; ++k)
-                    for (int n2 = 0; n2 < M; ++n2) {
-                        const int j = (int)(((long long)n2 * k * (N / L)) % N);
-                        const long double a = two_pi * (long double)j / (long double)N;
-                        tws.push_back(make_double2((double)cosl(a), (double)(-sinl(a))));
-                    }
-            L = M;
-        }
-        h->tws_n = (int)tws.size();
-        CU(cudaMalloc(&h->d_tws, sizeof(double2) * tws.size()));
-        CU(cudaMemcpy(h->d_tws, tws.data(), sizeof(double2) * tws.size(), cudaMemcpyHostToDevice));
+    // ---- compile-time z stages: per-stage twiddle tables [n2] = w^(n2 N/L)
+    if (h->native_fft && mdsf_zspec_applies(gp.lcol, gp.n[2], gp.pad_shift, gp.zswz)) {
+        int rc = stage_tables(h->ax[2].plan, &h->d_tws, &h->tws_n);
+        if (rc) return rc;
     }
     configure_splat(h, 1);
 
     // ---- volume layout: plain [x][y][z], or z-chunked [z/lw][x][y][lw] (MDSF_LAYOUT_W = 4 / 8; native FFT only)
-    gp.lw = gp.n[2];
+    gp.lw = h->fused_yx ? MDSF_YX_W : gp.n[2];
     {
         const int want = env_int("MDSF_LAYOUT_W", 0);
         if (want > 0 && h->native_fft) {
@@ -455,6 +484,19 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(mdsf_pass_configure());
     }
     CU(mdsf_splat_configure());
+    if (h->fused_yx) {
+        int rc = stage_tables(h->ax[1].plan, &h->d_twsy, nullptr);
+        if (rc) return rc;
+        rc = stage_tables(h->ax[0].plan, &h->d_twsx, nullptr);
+        if (rc) return rc;
+        const long long slab = (long long)gp.n[0] * gp.n[1] * MDSF_YX_W;
+        CU(cudaMalloc(&h->d_scratch, sizeof(double2) * slab * MDSF_YX_RING));
+        h->yxctl_words = 1 + (size_t)2 * gp.nch * npairs + (size_t)gp.nch * gp.n[1];
+        CU(cudaMalloc(&h->d_yxctl, sizeof(unsigned) * h->yxctl_words));
+        const int per_sm = mdsf_yx_blocks_per_sm(gp.n[1], gp.n[0]);
+        if (per_sm < 1) return fail(MDSF_ECUDA, "fused y/x kernel does not fit an SM");
+        h->yx_grid = per_sm * h->nsm;
+    }
     *out = h;
     return MDSF_OK;
 }
@@ -464,12 +506,12 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->cufft_plan) cufftDestroy(h->cufft_plan);
-    void* bufs[] = {h->d_tws, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1],
+    void* bufs[] = {h->d_scratch, h->d_twsy, h->d_twsx, h->d_yxctl, h->d_tws, h->d_ctab, h->d_ctab_off, h->d_toff, h->d_amp, h->d_two, h->d_halfw, h->d_type, h->d_stage[0], h->d_stage[1],
                     h->d_vol, h->d_dump, h->d_P, h->d_sf, h->d_err};
     for (void* b : bufs) if (b) cudaFree(b);
     for (int d = 0; d < 3; ++d) { if (h->ax[d].d_tw) cudaFree(h->ax[d].d_tw); if (h->ax[d].d_rev) cudaFree(h->ax[d].d_rev); }
     for (auto& ps : h->sets) {
-        void* pb[] = {ps.recs, ps.tables_alloc, ps.count, ps.start, ps.cursor, ps.prec, ps.cub};
+        void* pb[] = {ps.recs, ps.tables_alloc, ps.count, ps.start, ps.prec, ps.cub};
         for (void* b : pb) if (b) cudaFree(b);
         if (ps.ev_binned) cudaEventDestroy(ps.ev_binned);
         if (ps.ev_consumed) cudaEventDestroy(ps.ev_consumed);
@@ -582,7 +624,6 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
         ps.tables = ps.tables_alloc + 64;
         CU(cudaMalloc(&ps.count, sizeof(unsigned) * (nkeys + 2)));
         CU(cudaMalloc(&ps.start, sizeof(unsigned) * (nkeys + 2)));
-        CU(cudaMalloc(&ps.cursor, sizeof(unsigned) * (nkeys + 2)));
         CU(cudaMalloc(&ps.prec, 2 * sizeof(uint4) * h->pair_cap));
         CU(cudaMalloc(&ps.cub, h->cub_bytes));
         CU(cudaEventCreateWithFlags(&ps.ev_binned, cudaEventDisableTiming));
@@ -608,7 +649,15 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, cudaEvent_t* tv = nu
     const GridParams& gp = h->gp;
     const int npairs = (nf + 1) / 2;
     if (tv) CU(cudaEventRecord(tv[3], h->s_comp));
-    if (h->native_fft) {
+    if (h->native_fft && h->fused_yx) {
+        CU(cudaMemsetAsync(h->d_yxctl, 0, sizeof(unsigned) * h->yxctl_words, h->s_comp));
+        YXParams yp{};
+        yp.vol = h->d_vol; yp.scratch = h->d_scratch; yp.P = h->d_P; yp.twy = h->d_twsy; yp.twx = h->d_twsx;
+        yp.nch = gp.nch; yp.npairs = npairs; yp.ctl = h->d_yxctl; yp.err = h->d_err;
+        CU(mdsf_launch_yx(gp.n[1], gp.n[0], yp, h->yx_grid, h->s_comp));
+        ++h->launches;
+        if (tv) CU(cudaEventRecord(tv[4], h->s_comp));
+    } else if (h->native_fft) {
         cudaError_t ce = cudaSuccess;
         PassArgs a{};
         a.vol = h->d_vol; a.P = h->d_P; a.npairs = npairs; a.scratch = nullptr;
@@ -667,7 +716,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     if (ps.used) CU(cudaStreamWaitEvent(sp, ps.ev_consumed, 0));      // the splat of batch b-2 has read this set
     // start after the splat of batch b-1: prep+bin then overlap its HBM-bound y/x passes instead of fighting the
     // issue-bound splat kernel for the SMs
-    if (other.used) CU(cudaStreamWaitEvent(sp, other.ev_consumed, 0));
+    if (other.used && !h->prep_early) CU(cudaStreamWaitEvent(sp, other.ev_consumed, 0));
     if (tv) CU(cudaEventRecord(tv[1], sp));
 
     BatchScales sc;
@@ -675,7 +724,6 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     // an odd batch gets a phantom last frame with empty lists (imaginary part of the last pair)
     const unsigned nkeys = (unsigned)((nf + (nf & 1)) * gp.ntx * gp.nty * gp.nslab);
     CU(cudaMemsetAsync(ps.count, 0, sizeof(unsigned) * (nkeys + 1), sp));
-    CU(cudaMemsetAsync(ps.cursor, 0, sizeof(unsigned) * (nkeys + 1), sp));
     const bool c32 = h->cfg.coord_dtype == MDSF_F32, p32 = h->cfg.arith_dtype == MDSF_F32;
     if (c32 && p32) launch_prep<float, float>(h, sp, h->d_stage[slot], ps, sc, nf, wlo, whi);
     else if (c32) launch_prep<float, double>(h, sp, h->d_stage[slot], ps, sc, nf, wlo, whi);
@@ -690,11 +738,12 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     }
     CU(cudaEventRecord(h->ev_back[slot], h->s_back));
 
-    // K2: list starts = exclusive scan of the K1 counts; placement claims slots with a per-list cursor
+    // K2: list starts = exclusive scan of the K1 counts (in place); placement claims slots from that same array, which
+    // leaves the list ENDS in it: list k = [k ? end[k-1] : 0, end[k])
     size_t cb = h->cub_bytes;
     cub::DeviceScan::ExclusiveSum(ps.cub, cb, ps.count, ps.start, (long long)nkeys + 1, sp);
     const long long total = (long long)nf * h->natoms;
-    bin_place_kernel<<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.start, ps.cursor, ps.prec, gp, h->tt, nf, nkeys, h->pair_cap, h->d_err);
+    bin_place_kernel<<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.start, ps.prec, gp, h->tt, nf, nkeys, h->pair_cap, h->d_err);
     h->launches += 2;
     CU(cudaGetLastError());
     if (tv) CU(cudaEventRecord(tv[2], sp));
@@ -784,6 +833,7 @@ extern "C" int mdsf_sync(mdsf_handle* h) {
         *h->h_err = 0;
         cudaMemset(h->d_err, 0, sizeof(int));
         if (code == 4) return fail(MDSF_ECUDA, "internal: pair lists exceed their computed capacity");
+        if (code == 5) return fail(MDSF_ECUDA, "internal: a dependency of the fused y/x pass never arrived (bounded wait expired)");
         if (code == 2) return fail(MDSF_ERANGE, "fixed-point density accumulator overflow (> 2048 peak amplitudes in one cell)");
         return fail(MDSF_ERANGE, "an atom's Gaussian stamp leaves the padded grid (coordinate more than one box outside the cell, NaN, or half width > Nborder); the reference fails with a numpy shape error here");
     }

@@ -24,7 +24,8 @@ struct GridParams {
     int sub;            // lists a splat warp walks side by side (1 or 2 half-warp groups)
     int natoms;
     int nzp;            // padded z length of one column in shared memory
-    int pad_shift;      // column position p is stored at p + (p >> pad_shift)
+    int pad_shift;      // column position p is stored at p + (p >> pad_shift) ...
+    int zswz;           // ... or, for the power-of-two z lengths of the compile-time z path, at p ^ swizzle(p) (mdsf_splat.cuh zpos)
     // volume layout: element (x, y, z) of a pair volume sits at ((z / lw * Nx + x) * Ny + y) * lw + z % lw.
     // lw = Nz is the plain C order [x][y][z]; a smaller lw makes every (x, z-chunk) row block of the y pass one
     // contiguous run and lets the y -> x hand-over of a chunk stay L2-resident.

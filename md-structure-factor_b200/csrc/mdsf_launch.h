@@ -15,7 +15,8 @@ struct SplatArgs {
 cudaError_t mdsf_launch_splat(int lcol, int mode, bool fuse, dim3 grid, size_t smem, cudaStream_t st, const SplatArgs& a);
 cudaError_t mdsf_splat_configure(void);                   // opt in to the large dynamic shared memory sizes
 size_t mdsf_splat_smem(int lcol, int sub, int nzp, int nz);        // dynamic shared memory of one splat CTA (without a twiddle region)
-bool mdsf_zspec_applies(int lcol, int nz, int pad_shift); // compile-time z stages available for this geometry
+bool mdsf_zspec_applies(int lcol, int nz, int pad_shift, int swz); // compile-time z stages available for this geometry
+bool mdsf_zswizzle_wanted(int lcol, int nz);              // ... with XOR-swizzled columns (no padding)
 
 struct PassArgs {
     double2* vol; double* P; const FftPlan* plan; const double2* tw; PassGeom pg; int npairs; int nouter;   // nouter: Nx (y pass) / Ny (x pass)
@@ -26,3 +27,9 @@ cudaError_t mdsf_pass_configure(void);
 // returns the number of launches issued (>= 1) or -1 with the CUDA error in *err
 int mdsf_launch_pass_y(const PassArgs& a, cudaStream_t st, cudaError_t* err);
 int mdsf_launch_pass_x(const PassArgs& a, cudaStream_t st, cudaError_t* err);
+
+// fused y -> x pass (mdsf_yx.cuh): one persistent kernel per batch, hand-over through L2
+struct YXParams;
+bool mdsf_yx_supported(int ny, int nx);
+int mdsf_yx_blocks_per_sm(int ny, int nx);
+cudaError_t mdsf_launch_yx(int ny, int nx, const YXParams& p, int grid, cudaStream_t st);

@@ -1,5 +1,6 @@
 // Instantiations + dispatch of the y / x FFT passes (see mdsf_fft.cuh).
 #include "mdsf_launch.h"
+#include "mdsf_yx.cuh"
 
 static const int kMaxSmemPass = 227 * 1024;
 
@@ -97,4 +98,33 @@ int mdsf_launch_pass_x(const PassArgs& a, cudaStream_t st, cudaError_t* err) {
     }
     *err = cudaGetLastError();
     return *err == cudaSuccess ? 1 : -1;
+}
+
+// ---- fused y -> x pass (mdsf_yx.cuh)
+static const int kYxSmem = 2 * (512 + 64) * MDSF_YX_W * 16;      // two padded [512][4] tile buffers
+
+template <int NY, int NX> static cudaError_t yx_go(const YXParams& p, int grid, cudaStream_t st) {
+    yx_pass_kernel<NY, NX><<<grid, MDSF_YX_CTA, kYxSmem, st>>>(p);
+    return cudaGetLastError();
+}
+template <int NY, int NX> static int yx_occ() {
+    int per_sm = 0;
+    if (cudaFuncSetAttribute(yx_pass_kernel<NY, NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kYxSmem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yx_pass_kernel<NY, NX>, MDSF_YX_CTA, kYxSmem) != cudaSuccess) return 0;
+    return per_sm;
+}
+bool mdsf_yx_supported(int ny, int nx) { return (ny == 256 || ny == 512) && (nx == 256 || nx == 512); }
+int mdsf_yx_blocks_per_sm(int ny, int nx) {
+    if (ny == 512 && nx == 512) return yx_occ<512, 512>();
+    if (ny == 256 && nx == 256) return yx_occ<256, 256>();
+    if (ny == 512 && nx == 256) return yx_occ<512, 256>();
+    if (ny == 256 && nx == 512) return yx_occ<256, 512>();
+    return 0;
+}
+cudaError_t mdsf_launch_yx(int ny, int nx, const YXParams& p, int grid, cudaStream_t st) {
+    if (ny == 512 && nx == 512) return yx_go<512, 512>(p, grid, st);
+    if (ny == 256 && nx == 256) return yx_go<256, 256>(p, grid, st);
+    if (ny == 512 && nx == 256) return yx_go<512, 256>(p, grid, st);
+    if (ny == 256 && nx == 512) return yx_go<256, 512>(p, grid, st);
+    return cudaErrorInvalidValue;
 }

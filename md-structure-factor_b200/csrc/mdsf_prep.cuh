@@ -244,17 +244,21 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
 }
 
 // ---- K2: fill the lists.  The splat accumulates in 64-bit fixed point (integer adds commute), so the order inside
-// a list is irrelevant and a counting sort with atomics is deterministic in its RESULT: start = exclusive scan of the
-// K1 counts, every pair claims a slot of its list from a per-key cursor.  One record is one aligned 32-byte sector
-// (PairRec + PairAux + padding): the lists are written at random positions, and a full-sector store needs no fill read
-// from DRAM (16 + 8-byte stores into two arrays moved 6.6 GB for 50 M pairs: the kernel was bound by random DRAM
-// sectors, not by the atomics).
+// a list is irrelevant and a counting sort with atomics is deterministic in its RESULT: the exclusive scan of the K1
+// counts gives the list starts, and every pair claims its slot with ONE atomic on that same array
+// (pos = atomicAdd(&cur[key], 1)): afterwards cur[key] is the END of list `key`, i.e. the start of list key+1, which is
+// all the splat needs (lists are contiguous; list 0 starts at 0).  One record is one aligned 32-byte sector (PairRec +
+// PairAux + padding): the lists are written at random positions, and a full-sector store needs no fill read from DRAM
+// (16 + 8-byte stores into two arrays plus a separate start / cursor pair moved 130 B of random DRAM sectors per pair:
+// the kernel was bound by those, not by the atomics).  Records and atom records stream (evict-first) so that the
+// per-list array stays L2-resident.
 __global__ void __launch_bounds__(256, 6)
-bin_place_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ start, unsigned* __restrict__ cursor,
+bin_place_kernel(const AtomRec* __restrict__ recs, unsigned* __restrict__ cur /* in: list starts; out: list ends */,
                  uint4* __restrict__ prec2 /* [2 * pairs] */, GridParams gp, TypeTable tt, int nframes,
                  unsigned nkeys, unsigned long long cap, int* __restrict__ err_flag)
 {
-    if ((unsigned long long)start[nkeys] > cap) {       // cannot happen unless the host bound is wrong: refuse to overrun
+    if ((unsigned long long)cur[nkeys] > cap) {         // total pairs (no list has index nkeys, so nobody moves this entry); cannot
+                                                        // exceed the capacity unless the host bound is wrong: refuse to overrun
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(err_flag, 4);
         return;
     }
@@ -263,12 +267,17 @@ bin_place_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ 
          idx += (long long)gridDim.x * blockDim.x) {
         const int f = (int)(idx / gp.natoms);
         const int a = (int)(idx - (long long)f * gp.natoms);
-        const AtomRec rec = recs[idx];
+        AtomRec rec;
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(recs + idx);
+            uint4* dst = reinterpret_cast<uint4*>(&rec);
+            dst[0] = __ldcs(src); dst[1] = __ldcs(src + 1); dst[2] = __ldcs(src + 2);
+        }
         if (rec.pad_) continue;                           // atoms K1 rejected have no counted pairs
         for_each_pair(rec, a, f, gp, tt, [&](unsigned key, const PairRec& pr, const PairAux& pa) {
-            const unsigned pos = start[key] + atomicAdd(cursor + key, 1u);
-            prec2[2 * (size_t)pos] = pr;
-            prec2[2 * (size_t)pos + 1] = make_uint4(pa.x, pa.y, 0u, 0u);
+            const unsigned pos = atomicAdd(cur + key, 1u);
+            __stcs(prec2 + 2 * (size_t)pos, pr);
+            __stcs(prec2 + 2 * (size_t)pos + 1, make_uint4(pa.x, pa.y, 0u, 0u));
         });
     }
 }

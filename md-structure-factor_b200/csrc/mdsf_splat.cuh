@@ -61,11 +61,21 @@ __device__ __forceinline__ double fx_to_double(long long v) {
 }
 
 // ------------------------------------------------------------------ z FFT of the tile, compile-time radices
-// In-place decimation-in-frequency stages over [NCOL][nzp] re / im planes (position p of a column at p + (p >> PAD)):
-// same scheme and output order as fft_stage, with every stride and index split a constant.  The inter-stage
-// twiddles come from per-stage tables tws[TOFF + (k-1)*M + n2] = w_N^(n2 k N/L) (host-built, zstage_table_size): lanes
-// walk n2, so the reads are conflict-free (the strided reads of the full table were half of all bank conflicts).
-template <int NCOL, int N, int R, int L, int PAD, int TOFF>
+// Position of cell z inside a shared-memory column.  Power-of-two z lengths use an XOR swizzle of the bank bits
+// (bits 0-2 ^= bits 4-6, bit 3 ^= bit 6): the 16 lanes of a half-warp then hit 16 different 8-byte banks in every
+// stage -- 16 consecutive cells (first stages), two runs of 8 cells 64 apart (the stride-8 stage) and 16 cells 8 apart
+// (last stage).  The padded form p + (p >> pad) of the generic path costs the first stages a third of their
+// wavefronts (a run of 16 cells straddles a pad and folds onto 15 banks).
+__device__ __forceinline__ int zpos(int z, int swz, int pad) {
+    return swz ? (z ^ (((z >> 4) & 7) | (((z >> 6) & 1) << 3))) : z + (z >> pad);
+}
+
+// In-place decimation-in-frequency stages over [NCOL][nzp] re / im planes: same scheme and output order as
+// fft_stage, with every stride and index split a constant.  Only w = w_N^(n2 N/L) is read per butterfly (per-stage table
+// tws[TOFF + n2], host-built, conflict-free for consecutive n2); its powers w^2 .. w^(R-1) come from complex
+// multiplications: the fp64 pipe idles at 15% here while the load/store pipe is the bottleneck, and seven strided
+// twiddle loads per radix-8 butterfly were a third of a stage's shared-memory wavefronts.
+template <int NCOL, int N, int R, int L, int SWZ, int PAD, int TOFF>
 __device__ __forceinline__ void zstage(double* __restrict__ sre, double* __restrict__ sim, const double2* __restrict__ tws, int nzp)
 {
     constexpr int M = L / R, NBF = N / R;
@@ -78,17 +88,24 @@ __device__ __forceinline__ void zstage(double* __restrict__ sre, double* __restr
         int a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const int p = base + j * M;
-            a[j] = f * nzp + p + (p >> PAD);
+            a[j] = f * nzp + zpos(base + j * M, SWZ, PAD);
             xr[j] = sre[a[j]]; xi[j] = sim[a[j]];
         }
         Dft<R>::run(xr, xi, nullptr, nullptr, N);
         if (M > 1) {
+            const double2 w1 = tws[TOFF + n2];
+            double wr[R], wi[R];
+            wr[1] = w1.x; wi[1] = w1.y;
+#pragma unroll
+            for (int k = 2; k < R; ++k) {                    // w^k = w^(k/2) * w^(k - k/2): depth log2(k)
+                const int ka = k >> 1, kb = k - ka;
+                wr[k] = wr[ka] * wr[kb] - wi[ka] * wi[kb];
+                wi[k] = wr[ka] * wi[kb] + wi[ka] * wr[kb];
+            }
 #pragma unroll
             for (int k = 1; k < R; ++k) {
-                const double2 w = tws[TOFF + (k - 1) * M + n2];
-                const double yr = xr[k] * w.x - xi[k] * w.y;
-                xi[k] = xr[k] * w.y + xi[k] * w.x;
+                const double yr = xr[k] * wr[k] - xi[k] * wi[k];
+                xi[k] = xr[k] * wi[k] + xi[k] * wr[k];
                 xr[k] = yr;
             }
         }
@@ -98,42 +115,49 @@ __device__ __forceinline__ void zstage(double* __restrict__ sre, double* __restr
     __syncthreads();
 }
 
-// radix lists as produced by factorize() for the z axis (radices <= 8); table offsets = running sum of (R-1)*M
-template <int NCOL, int PAD> __device__ __forceinline__ void zfft_64(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 64, 8, 64, PAD, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 64, 8, 8, PAD, 56>(sre, sim, tws, nzp);
+// radix lists as produced by factorize() for the z axis (radices <= 8); table offsets = running sum of M over the stages
+template <int NCOL> __device__ __forceinline__ void zfft_64(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 64, 8, 64, 0, 3, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 64, 8, 8, 0, 3, 8>(sre, sim, tws, nzp);
 }
-template <int NCOL, int PAD> __device__ __forceinline__ void zfft_256(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 256, 4, 256, PAD, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 256, 8, 64, PAD, 192>(sre, sim, tws, nzp);
-    zstage<NCOL, 256, 8, 8, PAD, 248>(sre, sim, tws, nzp);
+template <int NCOL> __device__ __forceinline__ void zfft_256(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 256, 4, 256, 1, 31, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 256, 8, 64, 1, 31, 64>(sre, sim, tws, nzp);
+    zstage<NCOL, 256, 8, 8, 1, 31, 72>(sre, sim, tws, nzp);
 }
-template <int NCOL, int PAD> __device__ __forceinline__ void zfft_512(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 512, 8, 512, PAD, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 512, 8, 64, PAD, 448>(sre, sim, tws, nzp);
-    zstage<NCOL, 512, 8, 8, PAD, 504>(sre, sim, tws, nzp);
+template <int NCOL> __device__ __forceinline__ void zfft_512(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 512, 8, 512, 1, 31, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 512, 8, 64, 1, 31, 64>(sre, sim, tws, nzp);
+    zstage<NCOL, 512, 8, 8, 1, 31, 72>(sre, sim, tws, nzp);
 }
-template <int NCOL, int PAD> __device__ __forceinline__ void zfft_1024(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 1024, 4, 1024, PAD, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 1024, 4, 256, PAD, 768>(sre, sim, tws, nzp);
-    zstage<NCOL, 1024, 8, 64, PAD, 960>(sre, sim, tws, nzp);
-    zstage<NCOL, 1024, 8, 8, PAD, 1016>(sre, sim, tws, nzp);
+template <int NCOL> __device__ __forceinline__ void zfft_1024(double* sre, double* sim, const double2* tws, int nzp) {
+    zstage<NCOL, 1024, 4, 1024, 1, 31, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 1024, 4, 256, 1, 31, 256>(sre, sim, tws, nzp);
+    zstage<NCOL, 1024, 8, 64, 1, 31, 320>(sre, sim, tws, nzp);
+    zstage<NCOL, 1024, 8, 8, 1, 31, 328>(sre, sim, tws, nzp);
 }
 template <int NCOL> __device__ __forceinline__ void zfft_768(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 768, 4, 768, 31, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 768, 8, 192, 31, 576>(sre, sim, tws, nzp);
-    zstage<NCOL, 768, 8, 24, 31, 744>(sre, sim, tws, nzp);
-    zstage<NCOL, 768, 3, 3, 31, 765>(sre, sim, tws, nzp);
+    zstage<NCOL, 768, 4, 768, 0, 31, 0>(sre, sim, tws, nzp);
+    zstage<NCOL, 768, 8, 192, 0, 31, 192>(sre, sim, tws, nzp);
+    zstage<NCOL, 768, 8, 24, 0, 31, 216>(sre, sim, tws, nzp);
+    zstage<NCOL, 768, 3, 3, 0, 31, 219>(sre, sim, tws, nzp);
 }
-// does the compile-time path cover this (tile, z length, padding)?  (host and device agree through this function)
-__host__ __device__ inline bool zspec_applies(int lcol, int nz, int pad_shift) {
-    return (lcol == 5 && nz == 64 && pad_shift == 3) || (lcol == 4 && nz == 256 && pad_shift == 3) ||
-           (lcol == 3 && nz == 512 && pad_shift == 3) || (lcol == 2 && nz == 1024 && pad_shift == 3) ||
-           (lcol == 2 && nz == 768 && pad_shift == 31);
+// does the compile-time path cover this (tile, z length, column layout)?  (host and device agree through this function)
+__host__ __device__ inline bool zspec_applies(int lcol, int nz, int pad_shift, int swz) {
+    (void)lcol;
+    return (nz == 64 && pad_shift == 3 && !swz) || ((nz == 256 || nz == 512 || nz == 1024) && swz) || (nz == 768 && pad_shift == 31 && !swz);
+}
+// z lengths whose columns use the XOR swizzle (chosen by the host before the tile is sized)
+__host__ __device__ inline bool zswizzle_wanted(int lcol, int nz) {
+    (void)lcol;
+    return nz == 256 || nz == 512 || nz == 1024;
 }
 
+#ifndef MDSF_SPLAT_MINB
+#define MDSF_SPLAT_MINB 2
+#endif
 template <int LCOL, int MODE, int SUB>
-__global__ void __launch_bounds__(MDSF_SPLAT_THREADS, 2)
+__global__ void __launch_bounds__(MDSF_SPLAT_THREADS, MDSF_SPLAT_MINB)
 splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, const unsigned* __restrict__ start,
                   const AtomRec* __restrict__ recs, const double* __restrict__ tables,
                   const double* __restrict__ src_density, int nframes,
@@ -196,7 +220,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
         const int sg = item >> 1, part = item & 1;
         const int s = sg * SUB + grp;                         // my group's slab
         const bool slab_ok = s < gp.nslab;
-        const int zbase = s * ZW + zl * KZ;                   // my cells: x = X0 + i, y = Y0 + cy, z = zbase + k
+        const int zbase = s * ZW + zl;                        // my cells: x = X0 + i, y = Y0 + cy, z = zbase + ZLN * k (lanes walk z: conflict-free stores)
         {
             const int f = 2 * q + part;
             double* row = (part ? tile_im : tile_re) + (size_t)cy * nzp;        // column (i, cy) at row + i*TY*nzp
@@ -207,8 +231,8 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
                     const double* src = src_density + (((long long)f * gp.n[0] + (X0 + i)) * gp.n[1] + (Y0 + cy)) * nz;
 #pragma unroll
                     for (int k = 0; k < KZ; ++k) {
-                        const int z = zbase + k;
-                        if (slab_ok && z < nz) row[(size_t)i * TY * nzp + z + (z >> gp.pad_shift)] = live ? src[z] : 0.0;
+                        const int z = zbase + ZLN * k;
+                        if (slab_ok && z < nz) row[(size_t)i * TY * nzp + zpos(z, gp.zswz, gp.pad_shift)] = live ? src[z] : 0.0;
                     }
                 }
             } else {
@@ -218,8 +242,8 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
 #pragma unroll
                 for (int k = 0; k < KZ; ++k) acc[i][k] = 0;
             const unsigned key = (unsigned)(f * ntiles + tile) * (unsigned)gp.nslab + (unsigned)(slab_ok ? s : 0);
-            const unsigned lbeg = start[key];
-            const int n = slab_ok ? (int)(start[key + 1] - lbeg) : 0;           // my group's list
+            const unsigned lbeg = key ? start[key - 1] : 0u;                    // K2 leaves the list ENDS in `start`
+            const int n = slab_ok ? (int)(start[key] - lbeg) : 0;               // my group's list
             int nmax = n;                                                       // the longest list of the warp
             if (SUB > 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
             PairRec nxt = make_uint4(0u, 0u, 0u, 0u);
@@ -251,7 +275,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
                             const double bx = __dsub_rn(rx, __dmul_rn((double)((int)r.y + i), gp.dr[0]));
 #pragma unroll
                             for (int k = 0; k < KZ; ++k) {
-                                const int zz = zl * KZ + k;
+                                const int zz = zl + ZLN * k;
                                 if (zz < zoff || zz >= zend) continue;
                                 const double bzv = __dsub_rn(rz, __dmul_rn((double)((int)r.x + zz), gp.dr[2]));
                                 const double c0 = gp.u[0] * bx + gp.u[3] * by + gp.u[6] * bzv;
@@ -316,13 +340,8 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
                         exy[i] = e.x * ey; exy[i + 1] = e.y * ey;
                         if (MODE == SPLAT_MONO) { const double2 cv = cc2[i >> 1]; exy[i] *= cv.x; exy[i + 1] *= cv.y; }
                     }
-                    if (KZ == 1) {
-                        ez[0] = sl[zl];
-                    } else {
-                        const double2* ez2 = reinterpret_cast<const double2*>(sl + zl * KZ);
 #pragma unroll
-                        for (int k = 0; k < KZ; k += 2) { const double2 e = ez2[k >> 1]; ez[k] = e.x; ez[k + (KZ > 1 ? 1 : 0)] = e.y; }
-                    }
+                    for (int k = 0; k < KZ; ++k) ez[k] = sl[zl + ZLN * k];
 #pragma unroll
                     for (int i = 0; i < TX; ++i)
 #pragma unroll
@@ -336,13 +355,16 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
             // fixed point -> fp64 (overflow: a cell held > 2048 peak amplitudes)
             long long any = 0;
 #pragma unroll
-            for (int i = 0; i < TX; ++i)
+            for (int k = 0; k < KZ; ++k) {
+                const int z = zbase + ZLN * k;
+                const bool live = slab_ok && z < nz;
+                double* cell = row + zpos(z, gp.zswz, gp.pad_shift);
 #pragma unroll
-                for (int k = 0; k < KZ; ++k) {
-                    const int z = zbase + k;
+                for (int i = 0; i < TX; ++i) {
                     any |= acc[i][k];
-                    if (slab_ok && z < nz) row[(size_t)i * TY * nzp + z + (z >> gp.pad_shift)] = fx_to_double(acc[i][k]) * gp.fx_inv;
+                    if (live) cell[i * TY * nzp] = fx_to_double(acc[i][k]) * gp.fx_inv;
                 }
+            }
             ovf |= (any >> 62) != 0;                           // terms are >= 0: bit 62 or 63 set in any sum
             }
         }
@@ -367,7 +389,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
             const int cc = i / nz, z = i - cc * nz;
             const int x = X0 + (cc >> LTY), y = Y0 + (cc & (TY - 1));
             if (x < gp.n[0] && y < gp.n[1]) {
-                const int a = cc * nzp + z + (z >> gp.pad_shift);
+                const int a = cc * nzp + zpos(z, gp.zswz, gp.pad_shift);
                 dens_dump[(((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + z] = make_double2(tile_re[a], tile_im[a]);
             }
         }
@@ -381,36 +403,37 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
         // the tile size a grid selects fixes its z length class: compile-time stages for the power-of-two lengths
         // (and 768) the BASELINE configs use, the generic run-time stages for everything else
         if (!zspec) fft_tile_z(tile_re, tile_im, twr, twi, zplan, NCOL, nzp, gp.pad_shift);      // ends with a barrier
-        else if (LCOL == 5) zfft_64<NCOL, 3>(tile_re, tile_im, tws_s, nzp);
-        else if (LCOL == 4) zfft_256<NCOL, 3>(tile_re, tile_im, tws_s, nzp);
-        else if (LCOL == 3) zfft_512<NCOL, 3>(tile_re, tile_im, tws_s, nzp);
-        else if (nz == 1024) zfft_1024<NCOL, 3>(tile_re, tile_im, tws_s, nzp);
+        else if (nz == 64) zfft_64<NCOL>(tile_re, tile_im, tws_s, nzp);
+        else if (nz == 256) zfft_256<NCOL>(tile_re, tile_im, tws_s, nzp);
+        else if (nz == 512) zfft_512<NCOL>(tile_re, tile_im, tws_s, nzp);
+        else if (nz == 1024) zfft_1024<NCOL>(tile_re, tile_im, tws_s, nzp);
         else zfft_768<NCOL>(tile_re, tile_im, tws_s, nzp);
     }
     // store: every tile row x is one run of TY * Nz contiguous cells (plain layout), or Nz / lw runs of TY * lw cells
-    // (chunked layout): 16-byte stores, consecutive threads -> consecutive addresses
-    const int per_x = TY * nz;
+    // (chunked layout): 16-byte stores, consecutive threads -> consecutive addresses.  One flat index over the tile,
+    // 32-bit arithmetic inside the tile row.
     const bool pw2 = (nz & (nz - 1)) == 0;
     const int lnz = __ffs(nz) - 1, llw = __ffs(gp.lw) - 1;
-    for (int xx = 0; xx < TX; ++xx) {
-        const int x = X0 + xx;
-        if (x >= gp.n[0]) break;
-        double2* dstx = volq + (long long)x * gp.n[1] * gp.lw;
-        for (int j = threadIdx.x; j < per_x; j += MDSF_SPLAT_THREADS) {
-            int yy, z;
-            long long o;
-            if (gp.lw == nz) {                                 // plain: j = yy * Nz + z
-                if (pw2) { yy = j >> lnz; z = j & (nz - 1); } else { yy = j / nz; z = j - yy * nz; }
-                o = (long long)(Y0 + yy) * nz + z;
-            } else {                                           // chunked: j = (ch * TY + yy) * lw + zw
-                const int ch = j >> (LTY + llw), zw = j & (gp.lw - 1);
-                yy = (j >> llw) & (TY - 1);
-                z = (ch << llw) + zw;
-                o = (long long)ch * cs_ + (long long)(Y0 + yy) * gp.lw + zw;
-            }
-            if (Y0 + yy >= gp.n[1]) continue;
-            const int a = ((xx << LTY) + yy) * nzp + z + (z >> gp.pad_shift);
-            dstx[o] = make_double2(tile_re[a], tile_im[a]);
+    const int per_x = TY * nz, xvalid = min(TX, gp.n[0] - X0), yvalid = min(TY, gp.n[1] - Y0);
+    const bool chunked = gp.lw != nz;
+    const int rowlen = gp.n[1] * gp.lw;
+    double2* dst0 = volq + (long long)X0 * rowlen + (long long)Y0 * gp.lw;
+    for (int i = threadIdx.x; i < xvalid * per_x; i += MDSF_SPLAT_THREADS) {
+        int xx, j;
+        if (pw2) { xx = i >> (lnz + LTY); j = i & (per_x - 1); } else { xx = i / per_x; j = i - xx * per_x; }
+        int yy, z;
+        long long o;
+        if (!chunked) {                                        // plain: j = yy * Nz + z
+            if (pw2) { yy = j >> lnz; z = j & (nz - 1); } else { yy = j / nz; z = j - yy * nz; }
+            o = (long long)xx * rowlen + j;
+        } else {                                               // chunked: j = (ch * TY + yy) * lw + zw
+            const int ch = j >> (LTY + llw), zw = j & (gp.lw - 1);
+            yy = (j >> llw) & (TY - 1);
+            z = (ch << llw) + zw;
+            o = (long long)ch * cs_ + (long long)(xx * rowlen + yy * gp.lw + zw);
         }
+        if (yy >= yvalid) continue;
+        const int a = ((xx << LTY) + yy) * nzp + zpos(z, gp.zswz, gp.pad_shift);
+        dst0[o] = make_double2(tile_re[a], tile_im[a]);
     }
 }

@@ -82,6 +82,10 @@ def get(name):
         typ, base, box = uniform_box(334080, 511.9, LLC_COMPOSITION, 3000)
         return dict(typ=typ, base=base, box=box, ucell=ucell_for(120.0), sres=1.0, grid=(512, 512, 512), jitter=0.3,
                     seed0=3000, rad=RAD, desc="LLC-composition box, 334080 atoms, 512^3 grid, theta=120")
+    if name == "c3s":  # development aid: c3's grid with a tenth of its atoms (isolates the grid passes from the atom work)
+        typ, base, box = uniform_box(33408, 511.9, LLC_COMPOSITION, 3000)
+        return dict(typ=typ, base=base, box=box, ucell=ucell_for(120.0), sres=1.0, grid=(512, 512, 512), jitter=0.3,
+                    seed0=3000, rad=RAD, desc="c3 grid, 33408 atoms")
     if name == "c3d":  # c3's atoms at the number density of a condensed phase (0.1 atoms / A^3, what an LLC membrane or water has):
         # the 512^3 grid then resolves 0.29 A, stamps are 26^3 (H) ... 36^3 (C) ... 118^3 (NA) cells and the splat dominates
         L = (334080 / 0.1) ** (1.0 / 3.0)
