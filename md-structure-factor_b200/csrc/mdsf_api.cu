@@ -61,6 +61,7 @@ struct PrepSet {
     AtomRec* recs = nullptr;
     double *tables = nullptr, *tables_alloc = nullptr;
     unsigned *count = nullptr, *start = nullptr;     // [nkeys+1] each: list lengths (K1), list starts -> list ends (K2)
+    unsigned *xcnt = nullptr, *perm = nullptr;       // [F*ntx+1] atoms per x bucket -> bucket starts; [F*natoms] walk order of K2
     uint4* prec = nullptr;            // [2 * pair_cap]: 32-byte records {PairRec, PairAux + padding}
     void* cub = nullptr;
     cudaEvent_t ev_binned = nullptr, ev_consumed = nullptr;
@@ -112,6 +113,7 @@ struct mdsf_handle {
     long long maxpairs_frame = 0;
     int KX = 1, KY = 1;               // most x / y tiles one atom's stamp touches: bin_place_kernel runs KX*KY threads per atom
     unsigned long long pair_cap = 0;
+    bool order_atoms = false;         // K2 walks the atoms of a frame by the x tile of their home cell (L2-local list writes)
     bool prep_early = false;          // prep+bin of batch b+1 may start while the splat of batch b still runs
     int mono = 0;                     // K1 applies the monoclinic transform of main_gromacs.py:204-207 first
     double mono_sin = 1.0, mono_cos = 0.0;
@@ -511,7 +513,7 @@ extern "C" int mdsf_destroy(mdsf_handle* h) {
     for (void* b : bufs) if (b) cudaFree(b);
     for (int d = 0; d < 3; ++d) { if (h->ax[d].d_tw) cudaFree(h->ax[d].d_tw); if (h->ax[d].d_rev) cudaFree(h->ax[d].d_rev); }
     for (auto& ps : h->sets) {
-        void* pb[] = {ps.recs, ps.tables_alloc, ps.count, ps.start, ps.prec, ps.cub};
+        void* pb[] = {ps.recs, ps.tables_alloc, ps.count, ps.start, ps.xcnt, ps.perm, ps.prec, ps.cub};
         for (void* b : pb) if (b) cudaFree(b);
         if (ps.ev_binned) cudaEventDestroy(ps.ev_binned);
         if (ps.ev_consumed) cudaEventDestroy(ps.ev_consumed);
@@ -603,6 +605,9 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
     const long long nkeys = (long long)h->F * g0.ntx * g0.nty * g0.nslab;
     if (nkeys >= (1LL << 31)) return fail(MDSF_EINVAL, "too many (tile, slab) lists per batch; lower batch_frames");
 
+    // K2 walks the atoms in x-bucket order (order_atoms_kernel) when the lists of one frame are too large to sit in L2
+    // while file-order atoms fill them (c3: ~220 MB per frame; c2's 27 MB do not need it)
+    h->order_atoms = env_int("MDSF_ORDER_ATOMS", (double)maxpairs * 32.0 > 96.0e6 ? 1 : 0) != 0 && (long long)natoms * h->F < (1LL << 32);
     CU(cudaMalloc(&h->d_type, sizeof(int) * natoms));
     CU(cudaMemcpy(h->d_type, type_id, sizeof(int) * natoms, cudaMemcpyHostToDevice));
     for (int s = 0; s < kSlots; ++s) CU(cudaMalloc(&h->d_stage[s], h->csize * 3 * natoms * h->F));
@@ -625,6 +630,10 @@ extern "C" int mdsf_set_atoms(mdsf_handle* h, int64_t natoms, const int32_t* typ
         CU(cudaMalloc(&ps.count, sizeof(unsigned) * (nkeys + 2)));
         CU(cudaMalloc(&ps.start, sizeof(unsigned) * (nkeys + 2)));
         CU(cudaMalloc(&ps.prec, 2 * sizeof(uint4) * h->pair_cap));
+        if (h->order_atoms) {
+            CU(cudaMalloc(&ps.xcnt, sizeof(unsigned) * ((size_t)h->F * g0.ntx + 2)));
+            CU(cudaMalloc(&ps.perm, sizeof(unsigned) * (size_t)natoms * h->F));
+        }
         CU(cudaMalloc(&ps.cub, h->cub_bytes));
         CU(cudaEventCreateWithFlags(&ps.ev_binned, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ps.ev_consumed, cudaEventDisableTiming));
@@ -686,7 +695,7 @@ template <typename C, typename P>
 static void launch_prep(mdsf_handle* h, cudaStream_t st, void* stage, PrepSet& ps, const BatchScales& sc, int nf, long long wlo, long long whi) {
     const long long total = (long long)nf * h->natoms;
     prep_atoms_kernel<C, P><<<grid_for(total, 256, h->nsm), 256, 0, st>>>(
-        (C*)stage, h->d_type, ps.recs, ps.tables, h->gp, h->tt, sc, nf, wlo, whi, h->d_err, ps.count,
+        (C*)stage, h->d_type, ps.recs, ps.tables, h->gp, h->tt, sc, nf, wlo, whi, h->d_err, ps.xcnt,
         h->mono, h->mono_sin, h->mono_cos);
 }
 
@@ -724,6 +733,7 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     // an odd batch gets a phantom last frame with empty lists (imaginary part of the last pair)
     const unsigned nkeys = (unsigned)((nf + (nf & 1)) * gp.ntx * gp.nty * gp.nslab);
     CU(cudaMemsetAsync(ps.count, 0, sizeof(unsigned) * (nkeys + 1), sp));
+    if (ps.xcnt) CU(cudaMemsetAsync(ps.xcnt, 0, sizeof(unsigned) * ((size_t)nf * gp.ntx + 1), sp));
     const bool c32 = h->cfg.coord_dtype == MDSF_F32, p32 = h->cfg.arith_dtype == MDSF_F32;
     if (c32 && p32) launch_prep<float, float>(h, sp, h->d_stage[slot], ps, sc, nf, wlo, whi);
     else if (c32) launch_prep<float, double>(h, sp, h->d_stage[slot], ps, sc, nf, wlo, whi);
@@ -741,9 +751,16 @@ static int run_batch(mdsf_handle* h, char* src, int nf, const double* scale, lon
     // K2: list starts = exclusive scan of the K1 counts (in place); placement claims slots from that same array, which
     // leaves the list ENDS in it: list k = [k ? end[k-1] : 0, end[k])
     size_t cb = h->cub_bytes;
-    cub::DeviceScan::ExclusiveSum(ps.cub, cb, ps.count, ps.start, (long long)nkeys + 1, sp);
     const long long total = (long long)nf * h->natoms;
-    bin_place_kernel<<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.start, ps.prec, gp, h->tt, nf, nkeys, h->pair_cap, h->d_err);
+    if (ps.xcnt) {      // K2a: bucket starts (in place), then the walk order
+        cub::DeviceScan::ExclusiveSum(ps.cub, cb, ps.xcnt, ps.xcnt, (long long)nf * gp.ntx + 1, sp);
+        order_atoms_kernel<<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.xcnt, ps.perm, gp, nf);
+        h->launches += 2;
+    }
+    bin_count_kernel<<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.perm, ps.count, gp, h->tt, nf);
+    ++h->launches;
+    cub::DeviceScan::ExclusiveSum(ps.cub, cb, ps.count, ps.start, (long long)nkeys + 1, sp);
+    bin_place_kernel<<<grid_for(total, 256, h->nsm), 256, 0, sp>>>(ps.recs, ps.perm, ps.start, ps.prec, gp, h->tt, nf, nkeys, h->pair_cap, h->d_err);
     h->launches += 2;
     CU(cudaGetLastError());
     if (tv) CU(cudaEventRecord(tv[2], sp));

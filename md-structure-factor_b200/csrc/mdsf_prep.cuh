@@ -92,27 +92,83 @@ __device__ __forceinline__ void pairs_of_tile(const AtomRec& rec, int a, int f, 
     }
 }
 
-// all pairs of one atom: walk its (x tile, y tile) slots
+// number of (image, tile) slots axis_slot() enumerates along one dimension
+__device__ __forceinline__ int axis_count(int ir, int A, int N, int lt) {
+    int cnt = 0;
+#pragma unroll
+    for (int s = -1; s <= 1; ++s) {
+        int plo, phi;
+        stamp_segment(ir, A, N, s, plo, phi);
+        if (phi > plo) cnt += ((phi - 1 - s * N) >> lt) - ((plo - s * N) >> lt) + 1;
+    }
+    return cnt;
+}
+
+// All pairs of 32 consecutive atoms of the walk order, spread evenly over the lanes of one warp.  One thread per atom
+// left most lanes idle: a sodium ion (34^3 cells at c3) has ~500 pairs, a hydrogen ~10, and every fifth warp holds an
+// ion.  Work unit = one (x tile, y tile) slot of one atom (its z slabs are a short loop); units are numbered through
+// an inclusive scan of the per-atom slot counts and lane l takes units l, l + 32, ...; the owner of a unit is found by
+// a 5-step search over the scanned counts (shuffles), its record sits in shared memory.
 template <typename F>
-__device__ __forceinline__ void for_each_pair(const AtomRec& rec, int a, int f, const GridParams& gp, const TypeTable& tt, F&& fn) {
-    const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
-    if (Ax <= 0 || Ay <= 0 || Az <= 0) return;
+__device__ __forceinline__ void walk_pairs_warp(const AtomRec* __restrict__ recs, const unsigned* __restrict__ perm,
+                                                long long slot0, long long total, const GridParams& gp, const TypeTable& tt,
+                                                AtomRec* __restrict__ s_rec /* [32] */, unsigned* __restrict__ s_idx /* [32] */, F&& fn) {
+    const int lane = threadIdx.x & 31;
     const int ltx = (gp.lcol + 1) >> 1, lty = gp.lcol >> 1;
-    for (int kx = 0;; ++kx) {
-        int sx, tX, dx0, dx1, ix0;
-        if (!axis_slot(rec.ir[0], Ax, gp.n[0], ltx, kx, sx, tX, dx0, dx1, ix0)) break;
-        for (int ky = 0;; ++ky) {
-            int sy, tY, dy0, dy1, jy0;
-            if (!axis_slot(rec.ir[1], Ay, gp.n[1], lty, ky, sy, tY, dy0, dy1, jy0)) break;
-            pairs_of_tile(rec, a, f, gp, tt, Ax, Ay, Az, sx, tX, dx0, dx1, ix0, sy, tY, dy0, dy1, jy0, fn);
+    int nys = 1, nu = 0;
+    __syncwarp();
+    if (slot0 + lane < total) {
+        const long long idx = perm != nullptr ? (long long)perm[slot0 + lane] : slot0 + lane;
+        const uint4* src = reinterpret_cast<const uint4*>(recs + idx);
+        uint4* dst = reinterpret_cast<uint4*>(s_rec + lane);
+        dst[0] = __ldcs(src); dst[1] = __ldcs(src + 1); dst[2] = __ldcs(src + 2);
+        s_idx[lane] = (unsigned)idx;
+        const AtomRec& rec = s_rec[lane];
+        const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
+        if (!rec.pad_ && Ax > 0 && Ay > 0 && Az > 0) {       // atoms K1 rejected have no pairs
+            nys = axis_count(rec.ir[1], Ay, gp.n[1], lty);
+            nu = axis_count(rec.ir[0], Ax, gp.n[0], ltx) * nys;
         }
     }
+    int incl = nu;                                             // inclusive scan of the unit counts
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    for (int u0 = 0; u0 < tot; u0 += 32) {
+        const int u = u0 + lane;
+        int o = 0;                                             // owner: first lane with incl > u
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, o + d - 1);
+            if (v <= u) o += d;
+        }
+        const int excl_o = __shfl_sync(0xffffffffu, incl - nu, o & 31);
+        const int nys_o = __shfl_sync(0xffffffffu, nys, o & 31);
+        if (u >= tot) continue;
+        const AtomRec rec = s_rec[o];
+        const long long idx = (long long)s_idx[o];
+        const int f = (int)(idx / gp.natoms), a = (int)(idx - (long long)f * gp.natoms);
+        const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
+        const int local = u - excl_o, kx = local / nys_o, ky = local - kx * nys_o;
+        int sx, tX, dx0, dx1, ix0, sy, tY, dy0, dy1, jy0;
+        axis_slot(rec.ir[0], Ax, gp.n[0], ltx, kx, sx, tX, dx0, dx1, ix0);
+        axis_slot(rec.ir[1], Ay, gp.n[1], lty, ky, sy, tY, dy0, dy1, jy0);
+        pairs_of_tile(rec, a, f, gp, tt, Ax, Ay, Az, sx, tX, dx0, dx1, ix0, sy, tY, dy0, dy1, jy0, fn);
+    }
+}
+
+// x bucket of an atom's home cell (= its x tile, clamped): K2 walks the atoms bucket by bucket
+__device__ __forceinline__ int x_bucket(int ir0, const GridParams& gp) {
+    return min(max(ir0, 0) >> ((gp.lcol + 1) >> 1), gp.ntx - 1);
 }
 
 #define MDSF_PREP_STAGE 512        // doubles of factor tables one warp stages in shared memory (c2: 32 atoms x 12)
 
-// K1: records and factor tables.  Also counts the pairs of every list (atomicAdd on `counter[key]`, no return value):
-// the scan of those counts gives the list starts, bin_place_kernel then fills the lists.
+// K1: records and factor tables (and the number of atoms per x bucket for the walk order of K2).
 template <typename C, typename P>
 __global__ void __launch_bounds__(256)
 prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], rewritten in place
@@ -121,7 +177,7 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
                   double* __restrict__ tables,       // [nframes][tstride] per-atom Gaussian factor tables
                   GridParams gp, TypeTable tt, BatchScales sc, int nframes,
                   long long wrap_lo, long long wrap_hi, int* __restrict__ err_flag,
-                  unsigned* __restrict__ counter     /* [nkeys] list lengths */,
+                  unsigned* __restrict__ xcnt        /* [nframes][ntx] atoms per x bucket of their home cell (nullptr: K2 keeps the atom order) */,
                   int mono, double mono_sin, double mono_cos /* monoclinic pre-transform (main_gromacs.py:204-207) */)
 {
     // A lane's record (48 B) and factor tables (16 (Ax+Ay+Az) B) are contiguous with its neighbours' in global memory
@@ -189,8 +245,8 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
             __syncwarp();
         }
         if (live && bad) atomicExch(err_flag, 1);
+        if (live && xcnt != nullptr) atomicAdd(xcnt + f * gp.ntx + x_bucket(rec.ir[0], gp), 1u);
         const bool ok = live && !bad;
-        if (ok) for_each_pair(rec, a, f, gp, tt, [&](unsigned key, const PairRec&, const PairAux&) { atomicAdd(counter + key, 1u); });
         if (!gp.separable) continue;                       // warp-uniform
         // One-dimensional Gaussian factors of this atom's stamp (dens.py:299-308 factorised):
         //   exp(-|c|^2/(2s^2)) = EX[i] * EY[j] * C_type[i][j] * EZ[k]/amp, with
@@ -252,32 +308,60 @@ prep_atoms_kernel(C* __restrict__ coords,            // [nframes][natoms][3], re
 // (16 + 8-byte stores into two arrays plus a separate start / cursor pair moved 130 B of random DRAM sectors per pair:
 // the kernel was bound by those, not by the atomics).  Records and atom records stream (evict-first) so that the
 // per-list array stays L2-resident.
-__global__ void __launch_bounds__(256, 6)
-bin_place_kernel(const AtomRec* __restrict__ recs, unsigned* __restrict__ cur /* in: list starts; out: list ends */,
+// ---- K2a: walk order of K2.  The lists of one frame are ~200 MB of 32-byte records at c3; atoms in file order hit
+// them at random, every record store then costs DRAM a 64-byte read-modify-write (ncu: 117 B of traffic per 32-byte
+// record).  Atoms ordered by the x tile of their home cell write into a window of a few tile rows -- some MB that
+// stay in L2 until whole lines are complete.  Counting sort: xcnt holds the bucket starts (exclusive scan of the K1
+// counts) and is advanced by one atomic per atom; the order inside a bucket is irrelevant (see below).
+__global__ void __launch_bounds__(256)
+order_atoms_kernel(const AtomRec* __restrict__ recs, unsigned* __restrict__ xcnt, unsigned* __restrict__ perm,
+                   GridParams gp, int nframes)
+{
+    const long long total = (long long)nframes * gp.natoms;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(idx / gp.natoms);
+        const int ir0 = recs[idx].ir[0];
+        perm[atomicAdd(xcnt + f * gp.ntx + x_bucket(ir0, gp), 1u)] = (unsigned)idx;
+    }
+}
+
+// K2b: list lengths (RED on count[key]); their exclusive scan gives the list starts
+__global__ void __launch_bounds__(256)
+bin_count_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ perm, unsigned* __restrict__ count,
+                 GridParams gp, TypeTable tt, int nframes)
+{
+    __shared__ __align__(16) AtomRec s_rec[8][32];
+    __shared__ unsigned s_idx[8][32];
+    const int warp = threadIdx.x >> 5;
+    const long long total = (long long)nframes * gp.natoms;
+    for (long long slot0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) & ~31LL; slot0 < total;
+         slot0 += (long long)gridDim.x * blockDim.x)
+        walk_pairs_warp(recs, perm, slot0, total, gp, tt, s_rec[warp], s_idx[warp],
+                        [&](unsigned key, const PairRec&, const PairAux&) { atomicAdd(count + key, 1u); });
+}
+
+__global__ void __launch_bounds__(256)
+bin_place_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ perm /* walk order (nullptr: atom order) */,
+                 unsigned* __restrict__ cur /* in: list starts; out: list ends */,
                  uint4* __restrict__ prec2 /* [2 * pairs] */, GridParams gp, TypeTable tt, int nframes,
                  unsigned nkeys, unsigned long long cap, int* __restrict__ err_flag)
 {
+    __shared__ __align__(16) AtomRec s_rec[8][32];
+    __shared__ unsigned s_idx[8][32];
     if ((unsigned long long)cur[nkeys] > cap) {         // total pairs (no list has index nkeys, so nobody moves this entry); cannot
                                                         // exceed the capacity unless the host bound is wrong: refuse to overrun
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(err_flag, 4);
         return;
     }
+    const int warp = threadIdx.x >> 5;
     const long long total = (long long)nframes * gp.natoms;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int f = (int)(idx / gp.natoms);
-        const int a = (int)(idx - (long long)f * gp.natoms);
-        AtomRec rec;
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(recs + idx);
-            uint4* dst = reinterpret_cast<uint4*>(&rec);
-            dst[0] = __ldcs(src); dst[1] = __ldcs(src + 1); dst[2] = __ldcs(src + 2);
-        }
-        if (rec.pad_) continue;                           // atoms K1 rejected have no counted pairs
-        for_each_pair(rec, a, f, gp, tt, [&](unsigned key, const PairRec& pr, const PairAux& pa) {
-            const unsigned pos = atomicAdd(cur + key, 1u);
-            __stcs(prec2 + 2 * (size_t)pos, pr);
-            __stcs(prec2 + 2 * (size_t)pos + 1, make_uint4(pa.x, pa.y, 0u, 0u));
-        });
-    }
+    for (long long slot0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) & ~31LL; slot0 < total;
+         slot0 += (long long)gridDim.x * blockDim.x)
+        walk_pairs_warp(recs, perm, slot0, total, gp, tt, s_rec[warp], s_idx[warp],
+                        [&](unsigned key, const PairRec& pr, const PairAux& pa) {
+                            const unsigned pos = atomicAdd(cur + key, 1u);
+                            __stcs(prec2 + 2 * (size_t)pos, pr);
+                            __stcs(prec2 + 2 * (size_t)pos + 1, make_uint4(pa.x, pa.y, 0u, 0u));
+                        });
 }
