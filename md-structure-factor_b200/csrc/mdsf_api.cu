@@ -21,6 +21,7 @@
 #include "mdsf_launch.h"
 #include "mdsf_prep.cuh"
 #include "mdsf_yx.cuh"
+#include "mdsf_tma_pass.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const char* fmt, ...) {
@@ -45,7 +46,7 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 static const int kSlots = 2;
-static const int kMaxSmem = 227 * 1024 - 256;
+static const int kMaxSmem = 227 * 1024 - 1536;      // dynamic shared memory budget: the splat kernels hold up to ~1.1 KB of static shared memory
 enum { SPLAT_ORTHO_ = 0, SPLAT_MONO_ = 1, SPLAT_GENERAL_ = 2, SPLAT_DENSITY_ = 3 };     // = the enum of mdsf_splat.cuh
 
 struct AxisPlan {
@@ -117,6 +118,7 @@ struct mdsf_handle {
     bool prep_early = false;          // prep+bin of batch b+1 may start while the splat of batch b still runs
     int mono = 0;                     // K1 applies the monoclinic transform of main_gromacs.py:204-207 first
     double mono_sin = 1.0, mono_cos = 0.0;
+    bool tma_y = false, tma_x = false; // TMA-fed persistent pass kernels (512-point axes, lw = 8 layout; mdsf_tma_pass.cuh)
     // fused y -> x pass (mdsf_yx.cuh)
     bool fused_yx = false;
     double2 *d_scratch = nullptr, *d_twsy = nullptr, *d_twsx = nullptr;
@@ -226,10 +228,16 @@ static int stage_tables(const FftPlan& plan, double2** d_out, int* count) {
 // splat runs) -- they do when two CTAs still fit an SM.
 static void configure_splat(mdsf_handle* h, int sub) {
     GridParams& gp = h->gp;
+    // z-lane kernel (separable ucell): one full-warp slab per list, lanes walk z (mdsf_splat.cuh); MDSF_ZLANE=0 keeps the
+    // (row, z lane) x TX-column kernel with `sub` half-warp lists per warp
+    // (measured, splat per step: c1 8.24 -> 4.97 ms, c3 19.7 -> 19.7 ms, c4 43.4 -> 42.5 ms; 4x4-column tiles lose:
+    // c2 7.19 -> 7.98 ms, so they keep the half-warp lists)
+    gp.zlane = (gp.separable && env_int("MDSF_ZLANE", gp.lcol == 4 ? 0 : 1) != 0) ? 1 : 0;
+    if (gp.zlane) sub = 1;
     gp.sub = sub;
     gp.zw = (256 >> gp.lcol) / sub;
     gp.nslab = (gp.n[2] + gp.zw - 1) / gp.zw;
-    h->splat_smem = mdsf_splat_smem(gp.lcol, sub, gp.nzp, gp.n[2]);
+    h->splat_smem = mdsf_splat_smem(gp.lcol, sub, gp.nzp, gp.n[2], gp.zlane);
     h->tws_off = 0;
     if (h->d_tws) {
         const size_t base = (h->splat_smem + 15) / 16 * 16, need = base + sizeof(double2) * (size_t)h->tws_n;
@@ -292,18 +300,30 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     // ---- FFT plans.  Grids the fused y -> x kernel covers use radices <= 8 on every axis (its stage lists), a z-chunked
     // volume layout of width 4 and the L2-resident hand-over; everything else runs separate y and x passes.
     const bool want_native = cfg->fft_mode != MDSF_FFT_CUFFT;
-    // measured on B200: 512^2 planes 17.7 vs 20.0 ms per 8 c3 frames (and a third of the HBM traffic); 256^2 planes lose
-    // (13.3 vs 5.8 ms per 64 c2 frames: 16 KB tiles, the per-tile hand-shakes dominate) -> on by default from 512 up
-    const int fused_dflt = (gp.n[0] >= 512 && gp.n[1] >= 512) ? 1 : 0;
+    // the fused kernel (opt-in, MDSF_FUSED_YX=1): a third of the HBM traffic of separate passes, but its per-tile
+    // hand-shakes leave it latency-bound (c3: 15.1 ms per 16 frames against 13.4 ms for the register-staged passes and
+    // 10 ms for the TMA-fed ones)
     h->fused_yx = want_native && mdsf_yx_supported(gp.n[1], gp.n[0]) && gp.n[2] % MDSF_YX_W == 0 && gp.n[2] <= 2048 &&
-                  env_int("MDSF_FUSED_YX", fused_dflt) != 0 && env_int("MDSF_LAYOUT_W", 0) == 0;
+                  env_int("MDSF_FUSED_YX", 0) != 0 && env_int("MDSF_LAYOUT_W", 0) == 0;
+    // TMA-fed persistent passes: 512-point y and / or x axis, z-chunked layout of width 8
+    // (MDSF_TMA_PASS: bit 0 = y pass, bit 1 = x pass)
+    const int tma_want = env_int("MDSF_TMA_PASS", 3);
+    const bool tma_ok = want_native && !h->fused_yx && gp.n[2] % 8 == 0 &&
+                        (env_int("MDSF_LAYOUT_W", 0) == 0 || env_int("MDSF_LAYOUT_W", 0) == 8);
+    h->tma_y = tma_ok && (tma_want & 1) && gp.n[1] == MDSF_TP_N;
+    h->tma_x = tma_ok && (tma_want & 2) && gp.n[0] == MDSF_TP_N;
     for (int d = 0; d < 3; ++d) {
         int rc = build_axis(h->ax[d], gp.n[d], want_native, d == 2 || h->fused_yx);
         if (rc) return rc;
     }
     h->native_fft = h->ax[0].native && h->ax[1].native && h->ax[2].native;
     if (gp.n[2] > 2048 || gp.n[1] > 2048 || gp.n[0] > 2048) h->native_fft = false;
-    if (!h->native_fft) h->fused_yx = false;
+    if (!h->native_fft) h->fused_yx = h->tma_y = h->tma_x = false;
+    {   // the TMA-fed kernels hard-wire the stage list 8 * 8 * 8 (and its digit-reversed output order)
+        auto is888 = [](const FftPlan& p) { return p.nstages == 3 && p.radix[0] == 8 && p.radix[1] == 8 && p.radix[2] == 8; };
+        if (!is888(h->ax[1].plan)) h->tma_y = false;
+        if (!is888(h->ax[0].plan)) h->tma_x = false;
+    }
     if (!h->native_fft) {
         if (cfg->fft_mode == MDSF_FFT_NATIVE)
             return fail(MDSF_EINVAL, "grid %dx%dx%d has a prime factor > 13 (> 7 in z) or an axis longer than 2048; native FFT unavailable", gp.n[0], gp.n[1], gp.n[2]);
@@ -354,7 +374,10 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
     configure_splat(h, 1);
 
     // ---- volume layout: plain [x][y][z], or z-chunked [z/lw][x][y][lw] (MDSF_LAYOUT_W = 4 / 8; native FFT only)
-    gp.lw = h->fused_yx ? MDSF_YX_W : gp.n[2];
+    gp.lw = h->fused_yx ? MDSF_YX_W : ((h->tma_y || h->tma_x) ? 8 : gp.n[2]);
+    // (large planes: x rows of the plain layout are Ny*Nz*16 bytes apart -- 4 MB at 512^3, one TLB entry per row; the
+    // chunked layout of width 8 keeps 128-byte rows and cuts that stride to Ny*128 bytes: c3 x pass 5.62 -> 5.35 ms, c4 +4 %)
+    if (!h->fused_yx && h->native_fft && gp.n[2] % 8 == 0 && (long long)gp.n[0] * gp.n[1] >= 512LL * 512) gp.lw = 8;
     {
         const int want = env_int("MDSF_LAYOUT_W", 0);
         if (want > 0 && h->native_fft) {
@@ -486,11 +509,17 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         CU(mdsf_pass_configure());
     }
     CU(mdsf_splat_configure());
-    if (h->fused_yx) {
+    if (h->tma_y || h->tma_x) {
+        if (gp.lw != 8) h->tma_y = h->tma_x = false;
+        else CU(mdsf_tma_pass_configure());
+    }
+    if (h->fused_yx || h->tma_y || h->tma_x) {
         int rc = stage_tables(h->ax[1].plan, &h->d_twsy, nullptr);
         if (rc) return rc;
         rc = stage_tables(h->ax[0].plan, &h->d_twsx, nullptr);
         if (rc) return rc;
+    }
+    if (h->fused_yx) {
         const long long slab = (long long)gp.n[0] * gp.n[1] * MDSF_YX_W;
         CU(cudaMalloc(&h->d_scratch, sizeof(double2) * slab * MDSF_YX_RING));
         h->yxctl_words = 1 + (size_t)2 * gp.nch * npairs + (size_t)gp.nch * gp.n[1];
@@ -670,13 +699,29 @@ static int transform_and_accumulate(mdsf_handle* h, int nf, cudaEvent_t* tv = nu
         cudaError_t ce = cudaSuccess;
         PassArgs a{};
         a.vol = h->d_vol; a.P = h->d_P; a.npairs = npairs; a.scratch = nullptr;
-        a.plan = &h->ax[1].plan; a.tw = h->ax[1].d_tw; a.pg = h->pgy; a.nouter = gp.n[0]; a.ntile = h->ntile_y;
-        int nl = mdsf_launch_pass_y(a, h->s_comp, &ce);
+        TPParams tp{};
+        tp.vol = h->d_vol; tp.P = h->d_P; tp.nx = gp.n[0]; tp.ny = gp.n[1]; tp.nch = gp.nch; tp.npairs = npairs;
+        int nl = 1;
+        if (h->tma_y) {
+            tp.tws = h->d_twsy;
+            ce = mdsf_launch_tma_pass(false, tp, h->nsm, h->s_comp);
+            if (ce != cudaSuccess) nl = -1;
+        } else {
+            a.plan = &h->ax[1].plan; a.tw = h->ax[1].d_tw; a.pg = h->pgy; a.nouter = gp.n[0]; a.ntile = h->ntile_y;
+            nl = mdsf_launch_pass_y(a, h->s_comp, &ce);
+        }
         if (nl < 0) return fail(MDSF_ECUDA, "y pass launch failed: %s", cudaGetErrorString(ce));
         h->launches += nl;
         if (tv) CU(cudaEventRecord(tv[4], h->s_comp));
-        a.plan = &h->ax[0].plan; a.tw = h->ax[0].d_tw; a.pg = h->pgx; a.nouter = gp.n[1]; a.ntile = h->ntile_x;
-        nl = mdsf_launch_pass_x(a, h->s_comp, &ce);
+        nl = 1;
+        if (h->tma_x) {
+            tp.tws = h->d_twsx;
+            ce = mdsf_launch_tma_pass(true, tp, h->nsm, h->s_comp);
+            if (ce != cudaSuccess) nl = -1;
+        } else {
+            a.plan = &h->ax[0].plan; a.tw = h->ax[0].d_tw; a.pg = h->pgx; a.nouter = gp.n[1]; a.ntile = h->ntile_x;
+            nl = mdsf_launch_pass_x(a, h->s_comp, &ce);
+        }
         if (nl < 0) return fail(MDSF_ECUDA, "x pass launch failed: %s", cudaGetErrorString(ce));
         h->launches += nl;
     } else {

@@ -22,6 +22,7 @@ struct GridParams {
     int ntx, nty;       // tiles per dimension
     int nslab, zw;      // z slabs per column, slab width zw = (256 >> lcol) / sub cells: one list per slab and tile
     int sub;            // lists a splat warp walks side by side (1 or 2 half-warp groups)
+    int zlane;          // 1: z-lane splat variant (sub = 1: lanes walk z, a lane holds up to 8 columns; mdsf_splat.cuh)
     int natoms;
     int nzp;            // padded z length of one column in shared memory
     int pad_shift;      // column position p is stored at p + (p >> pad_shift) ...

@@ -14,7 +14,7 @@ struct SplatArgs {
 // mode: SPLAT_ORTHO / SPLAT_MONO / SPLAT_GENERAL / SPLAT_DENSITY (mdsf_splat.cuh); grid = (tiles, pairs)
 cudaError_t mdsf_launch_splat(int lcol, int mode, bool fuse, dim3 grid, size_t smem, cudaStream_t st, const SplatArgs& a);
 cudaError_t mdsf_splat_configure(void);                   // opt in to the large dynamic shared memory sizes
-size_t mdsf_splat_smem(int lcol, int sub, int nzp, int nz);        // dynamic shared memory of one splat CTA (without a twiddle region)
+size_t mdsf_splat_smem(int lcol, int sub, int nzp, int nz, int zlane = 0);        // dynamic shared memory of one splat CTA (without a twiddle region)
 bool mdsf_zspec_applies(int lcol, int nz, int pad_shift, int swz); // compile-time z stages available for this geometry
 bool mdsf_zswizzle_wanted(int lcol, int nz);              // ... with XOR-swizzled columns (no padding)
 
@@ -33,3 +33,8 @@ struct YXParams;
 bool mdsf_yx_supported(int ny, int nx);
 int mdsf_yx_blocks_per_sm(int ny, int nx);
 cudaError_t mdsf_launch_yx(int ny, int nx, const YXParams& p, int grid, cudaStream_t st);
+
+// TMA-fed persistent y / x passes of 512-point axes on the lw = 8 chunked layout (mdsf_tma_pass.cuh)
+struct TPParams;
+cudaError_t mdsf_tma_pass_configure(void);
+cudaError_t mdsf_launch_tma_pass(bool xpass, const TPParams& p, int grid, cudaStream_t st);

@@ -1,6 +1,7 @@
 // Instantiations + dispatch of the y / x FFT passes (see mdsf_fft.cuh).
 #include "mdsf_launch.h"
 #include "mdsf_yx.cuh"
+#include "mdsf_tma_pass.cuh"
 
 static const int kMaxSmemPass = 227 * 1024;
 
@@ -127,4 +128,16 @@ cudaError_t mdsf_launch_yx(int ny, int nx, const YXParams& p, int grid, cudaStre
     if (ny == 512 && nx == 256) return yx_go<512, 256>(p, grid, st);
     if (ny == 256 && nx == 512) return yx_go<256, 512>(p, grid, st);
     return cudaErrorInvalidValue;
+}
+
+// ---- TMA-fed persistent passes for 512-point axes (mdsf_tma_pass.cuh)
+cudaError_t mdsf_tma_pass_configure(void) {
+    cudaError_t e = cudaFuncSetAttribute(tma_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDSF_TP_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tma_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDSF_TP_SMEM);
+}
+cudaError_t mdsf_launch_tma_pass(bool xpass, const TPParams& p, int grid, cudaStream_t st) {
+    if (xpass) tma_pass_kernel<true><<<grid, MDSF_TP_CTA, MDSF_TP_SMEM, st>>>(p);
+    else tma_pass_kernel<false><<<grid, MDSF_TP_CTA, MDSF_TP_SMEM, st>>>(p);
+    return cudaGetLastError();
 }

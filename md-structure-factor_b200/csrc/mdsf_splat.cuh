@@ -45,6 +45,25 @@ template <int LCOL, int SUB> struct SplatGeom {
     static constexpr int WARP_BYTES = SUB * RB * 16 + SUB * RB * 8 + NS * SLOT * 8;
 };
 
+// Z-lane variant (ZL): the whole warp owns one slab; a lane holds NCL = min(NCOL, 8) columns x KZ = 8 / NCL cells, lanes
+// walk z (CG = NCOL / NCL column groups x ZLN = 32 / CG z lanes; slab width ZLN * KZ = 256 >> LCOL, the SUB = 1 slab).
+// Per record a lane then needs its KZ entries of EZ -- loaded straight from the table block into registers, zero outside
+// the record's z window, two records ahead -- and the NCL products EX*EY*C of its columns, which are the same for every
+// z lane: the products of a whole batch of records are formed up front, one (record, column) pair per lane, and read
+// back from shared memory as broadcast 16-byte loads.  The list bounds of all slabs of the CTA sit in shared memory,
+// and a warp claims its next item and requests that item's first records before it works on the current one, so the
+// only global round trip left on an item's critical path is the one of the factor tables.
+#ifndef MDSF_ZL_RB
+#define MDSF_ZL_RB 8
+#endif
+template <int LCOL> struct ZLaneGeom {
+    static constexpr int NCOL = 1 << LCOL, NCL = NCOL < 8 ? NCOL : 8, CG = NCOL / NCL, ZLN = 32 / CG, KZ = 8 / NCL;
+    static constexpr int RB = (256 / NCOL) < MDSF_ZL_RB ? (256 / NCOL) : MDSF_ZL_RB;   // records per batch
+    static constexpr int RPI = 32 / NCOL;                                    // records whose products one warp instruction forms
+    static constexpr int WARP_BYTES = RB * 16 + RB * 8 + RB * NCOL * 8;      // [RB] PairRec, [RB] PairAux, [RB][NCOL] products
+};
+#define MDSF_ZL_MAXSLAB 128      // list bounds of a CTA's slabs are staged in shared memory up to this many slabs
+
 __device__ __forceinline__ void cp_async8(unsigned smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
@@ -156,7 +175,7 @@ __host__ __device__ inline bool zswizzle_wanted(int lcol, int nz) {
 #ifndef MDSF_SPLAT_MINB
 #define MDSF_SPLAT_MINB 2
 #endif
-template <int LCOL, int MODE, int SUB>
+template <int LCOL, int MODE, int SUB, bool ZL = false>
 __global__ void __launch_bounds__(MDSF_SPLAT_THREADS, MDSF_SPLAT_MINB)
 splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, const unsigned* __restrict__ start,
                   const AtomRec* __restrict__ recs, const double* __restrict__ tables,
@@ -182,9 +201,10 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
     const int zl = gl & (ZLN - 1), cy = gl / ZLN;             // my z lane of the slab, my row of the tile (columns c = i*TY + cy)
     const int ntiles = gp.ntx * gp.nty;
 
-    PairRec* rbuf = reinterpret_cast<PairRec*>(area + (size_t)warp * G::WARP_BYTES);          // [SUB][RB]
-    PairAux* abuf = reinterpret_cast<PairAux*>(reinterpret_cast<char*>(rbuf) + SUB * RB * 16);
-    double* slots = reinterpret_cast<double*>(reinterpret_cast<char*>(rbuf) + SUB * RB * 24);  // [NS][SUB][SLOTG]
+    constexpr int WB = ZL ? ZLaneGeom<LCOL>::WARP_BYTES : G::WARP_BYTES, NREC = ZL ? ZLaneGeom<LCOL>::RB : SUB * RB;
+    PairRec* rbuf = reinterpret_cast<PairRec*>(area + (size_t)warp * WB);                       // [SUB][RB] / [32]
+    PairAux* abuf = reinterpret_cast<PairAux*>(reinterpret_cast<char*>(rbuf) + NREC * 16);
+    double* slots = reinterpret_cast<double*>(reinterpret_cast<char*>(rbuf) + NREC * 24);      // [NS][SUB][SLOTG] / [2][NCOL]
     const unsigned slots_s = (unsigned)__cvta_generic_to_shared(slots);
     bool ovf = false;
     const bool zspec = FUSE && tws_g != nullptr;
@@ -213,6 +233,136 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
         else if (MODE == SPLAT_MONO && e >= TX + TY && e < TX + TY + NCOL) { skind[rd] = 3; soff[rd] = (e - TX - TY) >> LTX; smul[rd] = (e - TX - TY) & (TX - 1); }
     }
 
+    if constexpr (ZL && (MODE == SPLAT_ORTHO || MODE == SPLAT_MONO)) {
+        using Z = ZLaneGeom<LCOL>;
+        constexpr int NCL = Z::NCL, ZLNZ = Z::ZLN, KZZ = Z::KZ, RBZ = Z::RB, RPI = Z::RPI;
+        __shared__ unsigned s_bnd[2][MDSF_ZL_MAXSLAB + 1];                  // list begin of slab j of frame 2q / 2q+1 ([nslab]: end)
+        const bool bnd_s = gp.nslab <= MDSF_ZL_MAXSLAB;
+        const unsigned key0 = (unsigned)(2 * q * ntiles + tile) * (unsigned)gp.nslab, key1 = key0 + (unsigned)ntiles * (unsigned)gp.nslab;
+        if (bnd_s) {
+            for (int t = threadIdx.x; t < 2 * (gp.nslab + 1); t += MDSF_SPLAT_THREADS) {
+                const int pt = t / (gp.nslab + 1), j = t - pt * (gp.nslab + 1);
+                const unsigned key = (pt ? key1 : key0) + (unsigned)j;
+                s_bnd[pt][j] = key ? start[key - 1] : 0u;
+            }
+            __syncthreads();
+        }
+        const int cg = lane / ZLNZ, zlz = lane % ZLNZ;                       // my column group, my z lane
+        const int pc = lane & (NCOL - 1), prs = lane / NCOL;                 // product role: column, record of the instruction
+        const int pi = pc >> LTY, pcy = pc & (TY - 1);                       // column pc = pi * TY + pcy
+        double* pbuf = slots;                                                // [RBZ][NCOL]
+        const int nitems = 2 * gp.nslab;
+        auto bounds = [&](int it, unsigned& lb, int& cnt) {
+            lb = 0u; cnt = 0;
+            if (it >= nitems) return;
+            const int sl = it >> 1, pt = it & 1;
+            if (bnd_s) { lb = s_bnd[pt][sl]; cnt = (int)(s_bnd[pt][sl + 1] - lb); }
+            else { const unsigned key = (pt ? key1 : key0) + (unsigned)sl; lb = key ? start[key - 1] : 0u; cnt = (int)(start[key] - lb); }
+        };
+        PairRec nxt = make_uint4(0u, 0u, 0u, 0u);
+        PairAux nxa = make_uint2(0u, 0u);
+        auto fetch = [&](unsigned lb, int cnt, int b) {                      // record b + lane of a list -> nxt / nxa
+            if (lane < RBZ && b + lane < cnt) {
+                nxt = prec[2 * (size_t)(lb + b + lane)];
+                if (MODE != SPLAT_ORTHO) { const uint4 t = prec[2 * (size_t)(lb + b + lane) + 1]; nxa = make_uint2(t.x, t.y); }
+            }
+        };
+        int item = warp, n = 0;
+        unsigned lbeg = 0u;
+        bounds(item, lbeg, n);
+        fetch(lbeg, n, 0);
+        while (item < nitems) {
+            int item2 = 0;
+            if (lane == 0) item2 = atomicAdd(&s_next, 1);
+            item2 = __shfl_sync(0xffffffffu, item2, 0);
+            unsigned lbeg2;
+            int n2;
+            bounds(item2, lbeg2, n2);
+            const int s = item >> 1, part = item & 1;
+            long long acc[NCL][KZZ];
+#pragma unroll
+            for (int c = 0; c < NCL; ++c)
+#pragma unroll
+                for (int k = 0; k < KZZ; ++k) acc[c][k] = 0;
+            int b = 0;
+            do {
+                const int m = min(RBZ, n - b);
+                __syncwarp();                                              // the previous batch is consumed
+                if (lane < m) { rbuf[lane] = nxt; if (MODE != SPLAT_ORTHO) abuf[lane] = nxa; }
+                __syncwarp();
+                if (b + RBZ < n) fetch(lbeg, n, b + RBZ); else fetch(lbeg2, n2, 0);
+                if (m > 0) {
+                    auto ldez = [&](int k, double (&ez)[KZZ]) {
+#pragma unroll
+                        for (int kk = 0; kk < KZZ; ++kk) ez[kk] = 0.0;
+                        if (k < m) {
+                            const PairRec r = rbuf[k];
+                            const unsigned zoff = r.w & 127u, zlen = r.w >> 7;
+#pragma unroll
+                            for (int kk = 0; kk < KZZ; ++kk) {
+                                const unsigned zz = (unsigned)(zlz + ZLNZ * kk);
+                                if (zz - zoff < zlen) ez[kk] = __ldg(tables + ((int)r.x + (int)zz));
+                            }
+                        }
+                    };
+                    double ezA[KZZ], ezB[KZZ];
+                    ldez(0, ezA);
+                    ldez(1, ezB);
+                    // products EX[i] * EY[j] (* C[i][j]) of every (record, column) of the batch, two instructions' worth in flight
+                    for (int k0 = prs; k0 < m + prs; k0 += 2 * RPI) {       // (warp-uniform trip count)
+                        const int k1 = k0 + RPI;
+                        const bool v0 = k0 < m, v1 = k1 < m;
+                        double x0 = 0.0, y0 = 0.0, c0 = 1.0, x1 = 0.0, y1 = 0.0, c1 = 1.0;
+                        if (v0) {
+                            const PairRec r = rbuf[k0];
+                            x0 = __ldg(tables + ((int)r.y + pi)); y0 = __ldg(tables + ((int)r.z + pcy));
+                            if (MODE == SPLAT_MONO) { const PairAux a = abuf[k0]; c0 = __ldg(tt.ctab + ((int)a.x + pi * (int)a.y + pcy)); }
+                        }
+                        if (v1) {
+                            const PairRec r = rbuf[k1];
+                            x1 = __ldg(tables + ((int)r.y + pi)); y1 = __ldg(tables + ((int)r.z + pcy));
+                            if (MODE == SPLAT_MONO) { const PairAux a = abuf[k1]; c1 = __ldg(tt.ctab + ((int)a.x + pi * (int)a.y + pcy)); }
+                        }
+                        if (v0) { double e = x0 * y0; if (MODE == SPLAT_MONO) e *= c0; pbuf[k0 * NCOL + pc] = e; }
+                        if (v1) { double e = x1 * y1; if (MODE == SPLAT_MONO) e *= c1; pbuf[k1 * NCOL + pc] = e; }
+                    }
+                    __syncwarp();
+                    auto accumulate = [&](int k, const double (&ez)[KZZ]) {
+                        const double2* e2 = reinterpret_cast<const double2*>(pbuf + k * NCOL + cg * NCL);
+#pragma unroll
+                        for (int c = 0; c < NCL; c += 2) {
+                            const double2 e = e2[c >> 1];
+#pragma unroll
+                            for (int kk = 0; kk < KZZ; ++kk) {
+                                acc[c][kk] += __double_as_longlong(__fma_rn(e.x, ez[kk], MDSF_MAGIC)) - MDSF_MAGIC_BITS;
+                                acc[c + 1][kk] += __double_as_longlong(__fma_rn(e.y, ez[kk], MDSF_MAGIC)) - MDSF_MAGIC_BITS;
+                            }
+                        }
+                    };
+                    for (int k = 0; k < m; k += 2) {
+                        accumulate(k, ezA);
+                        ldez(k + 2, ezA);
+                        if (k + 1 < m) { accumulate(k + 1, ezB); ldez(k + 3, ezB); }
+                    }
+                }
+                b += RBZ;
+            } while (b < n);
+            // fixed point -> fp64 (overflow: a cell held > 2048 peak amplitudes)
+            long long any = 0;
+#pragma unroll
+            for (int kk = 0; kk < KZZ; ++kk) {
+                const int z = s * ZW + zlz + ZLNZ * kk;
+                double* cell = (part ? tile_im : tile_re) + (size_t)(cg * NCL) * nzp + zpos(z, gp.zswz, gp.pad_shift);
+#pragma unroll
+                for (int c = 0; c < NCL; ++c) {
+                    any |= acc[c][kk];
+                    if (z < nz) cell[(size_t)c * nzp] = fx_to_double(acc[c][kk]) * gp.fx_inv;
+                }
+            }
+            ovf |= (any >> 62) != 0;
+            item = item2; lbeg = lbeg2; n = n2;
+        }
+    } else {
     // work items: (group of SUB consecutive slabs, part); the first MDSF_SPLAT_WARPS go out statically, the rest are
     // claimed from a shared counter (list lengths vary: the barrier before the FFT waited 15% of the time for the longest)
     const int nsg = (gp.nslab + SUB - 1) / SUB, nitems = 2 * nsg;
@@ -371,6 +521,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
         int nxt_item = 0;
         if (lane == 0) nxt_item = atomicAdd(&s_next, 1);
         item = __shfl_sync(0xffffffffu, nxt_item, 0);
+    }
     }
     if (ovf) atomicExch(err_flag, 2);
     cp_async_wait<0>();

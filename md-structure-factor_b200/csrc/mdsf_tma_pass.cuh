@@ -1,0 +1,192 @@
+// K4 / K5 for 512-point axes: persistent, warp-specialised y and x passes fed by the TMA copy engine.
+//
+// Layout: z-chunked volumes [pair][z/8][x][y][8] (lw = 8).  A tile is [512][8] complex = 64 KB:
+//   y pass: tile (pair, chunk, x) is ONE contiguous 64 KB run -> 32 bulk copies of 2 KB in, 32 bulk stores of 2 KB out;
+//   x pass: tile (pair, chunk, y) is 512 rows of 128 bytes, 64 KB apart.  128-byte bulk copies are far too slow for that
+//           (measured: 27 ms per 16 c3 frames, the copy engine retires one small copy per ~60 cycles); every compute thread
+//           issues eight 16-byte cp.async copies instead (8 threads = one row), two tiles ahead, completion counted on the
+//           buffer's mbarrier (cp.async.mbarrier.arrive.noinc).
+// One CTA per SM walks its tiles (unit u = blockIdx.x + k * gridDim.x) through a ring of three 64 KB buffers:
+//   producer warp:  [y: wait until the compute warps released the buffer, store it (cp.async.bulk shared -> global), wait
+//                   until the store has read it]  ->  arm the buffer's mbarrier with the tile's byte count  ->  issue the
+//                   bulk loads (cp.async.bulk global -> shared, completion on the mbarrier)
+//   16 compute warps: wait on the mbarrier, run the three radix-8 stages in place (one butterfly per thread and stage,
+//                   rows are 128 bytes = all 32 banks: every 16-byte access of a quarter-warp is conflict-free without
+//                   padding, so the TMA image is the compute layout), release the buffer.
+// While one buffer is transformed, one is being loaded and one stored: the loads of a tile never wait for the arithmetic
+// of another, which is what kept the register-staged passes (fft3_pass_kernel: load phase / compute phase / store phase
+// of two CTAs per SM) at 55-68 % of the HBM peak.  The x pass keeps sum_q |C_q|^2 of its 8 outputs per thread in
+// registers over the pairs of the batch and makes one read-modify-write of P per tile (P values requested one pair
+// early).  Stage order, twiddles and output positions are those of fft3_pass_kernel<8,8,8> (in place, digit-reversed).
+#pragma once
+#include "mdsf_yx.cuh"
+
+#define MDSF_TP_THREADS 512                        // compute threads: one radix-8 butterfly each per stage of a [512][8] tile
+#define MDSF_TP_CTA (MDSF_TP_THREADS + 32)         // + the producer warp
+#define MDSF_TP_NBUF 3
+#define MDSF_TP_N 512
+#define MDSF_TP_TILE (MDSF_TP_N * 8)               // cells of one tile
+#define MDSF_TP_SMEM (MDSF_TP_NBUF * MDSF_TP_TILE * 16)
+
+struct TPParams {
+    double2* vol;              // [npairs][nch][Nx][Ny][8]
+    double* P;                 // [nch][Nx][Ny][8]
+    const double2* tws;        // per-stage twiddle tables of the axis (stage_tables: w_N^(n2 N/L))
+    int nx, ny, nch, npairs;
+};
+
+__device__ __forceinline__ void tp_bar() { asm volatile("bar.sync 1, %0;" ::"n"(MDSF_TP_THREADS) : "memory"); }
+
+// this thread's butterfly of the stage with block length L: rows b*L + n2 + j*M (M = L/8) of column f
+template <int L>
+__device__ __forceinline__ void tp_load_butterfly(const double2* __restrict__ tile, int (&a)[8], double (&xr)[8], double (&xi)[8]) {
+    constexpr int M = L / 8;
+    const int f = threadIdx.x & 7, bf = threadIdx.x >> 3;
+    const int base = (bf / M) * L + (bf % M);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = (base + j * M) * 8 + f;
+        const double2 v = tile[a[j]];
+        xr[j] = v.x; xi[j] = v.y;
+    }
+}
+__device__ __forceinline__ void tp_twiddle(double2 w1, double (&xr)[8], double (&xi)[8]) {
+    double wr[8], wi[8];
+    wr[1] = w1.x; wi[1] = w1.y;
+#pragma unroll
+    for (int k = 2; k < 8; ++k) {                  // w^k = w^(k/2) * w^(k - k/2)
+        const int ka = k >> 1, kb = k - ka;
+        wr[k] = wr[ka] * wr[kb] - wi[ka] * wi[kb];
+        wi[k] = wr[ka] * wi[kb] + wi[ka] * wr[kb];
+    }
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        const double yr = xr[k] * wr[k] - xi[k] * wi[k];
+        xi[k] = xr[k] * wi[k] + xi[k] * wr[k];
+        xr[k] = yr;
+    }
+}
+
+template <bool XPASS>
+__global__ void __launch_bounds__(MDSF_TP_CTA, 1)
+tma_pass_kernel(TPParams p)
+{
+    constexpr int N = MDSF_TP_N, TILE = MDSF_TP_TILE, NBUF = MDSF_TP_NBUF;
+    extern __shared__ __align__(128) double2 tp_smem[];          // [NBUF][N][8]
+    __shared__ unsigned long long full[NBUF], rel[NBUF];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // y pass: unit = tile (pair, chunk, x) = 64 KB run number u; x pass: unit = (chunk, y), its npairs tiles in turn
+    const long long nunits = XPASS ? (long long)p.nch * p.ny : (long long)p.npairs * p.nch * p.nx;
+    const long long mine = nunits > blockIdx.x ? (nunits - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long ntile = XPASS ? mine * p.npairs : mine;      // tiles this CTA moves
+    const long long row_stride = (long long)p.ny * 8;            // cells between x rows
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], XPASS ? MDSF_TP_THREADS : 1); mbar_init(&rel[b], MDSF_TP_THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == MDSF_TP_THREADS / 32) {
+        // ------------------------------------------------------------------ producer warp (y pass only)
+        if (XPASS) return;
+        const unsigned long long pol = policy_evict_first();
+        for (long long i = 0; i < ntile + NBUF; ++i) {
+            const int b = (int)(i % NBUF);
+            const unsigned use = (unsigned)(i / NBUF);
+            double2* tile = tp_smem + (size_t)b * TILE;
+            if (i >= NBUF) {
+                mbar_wait(&rel[b], (use - 1) & 1);                   // tile i - NBUF is transformed
+                const long long uo = blockIdx.x + (i - NBUF) * (long long)gridDim.x;
+                bulk_s2g(p.vol + uo * TILE + lane * (TILE / 32), tile + lane * (TILE / 32), (TILE / 32) * 16, pol);
+                bulk_commit();
+                bulk_wait_read0();                                     // the store has read the buffer
+                __syncwarp();
+            }
+            if (i >= ntile) continue;
+            if (lane == 0) mbar_expect_tx(&full[b], TILE * 16);
+            __syncwarp();                                              // expect_tx precedes every complete_tx
+            const long long u = blockIdx.x + i * (long long)gridDim.x;
+            bulk_g2s(tile + lane * (TILE / 32), p.vol + u * TILE + lane * (TILE / 32), (TILE / 32) * 16, &full[b], pol);
+        }
+        bulk_wait0();
+        return;
+    }
+
+    // ---------------------------------------------------------------------- compute warps
+    const int f = threadIdx.x & 7, bf = threadIdx.x >> 3;
+    const double2 w1 = __ldg(p.tws + bf);                    // stage 1: L = 512, M = 64, n2 = bf
+    const double2 w2 = __ldg(p.tws + 64 + (bf & 7));         // stage 2: L = 64, M = 8, n2 = bf % 8
+    double acc[8];
+    double pv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc[k] = 0.0; pv[k] = 0.0; }
+    const unsigned long long polx = policy_evict_first();
+    auto issue_x = [&](long long i) {                            // my 8 x 16 bytes of x-pass tile i -> its ring buffer
+        if (i >= ntile) return;
+        const long long k = i / p.npairs;
+        const int q = (int)(i - k * p.npairs);
+        const long long g = blockIdx.x + k * (long long)gridDim.x;
+        const int ch = (int)(g / p.ny), y = (int)(g - (long long)ch * p.ny);
+        const double2* src = p.vol + (((long long)q * p.nch + ch) * p.nx + bf) * row_stride + (long long)y * 8 + f;
+        const int b = (int)(i % NBUF);
+        const unsigned dst = smem_u32(tp_smem + (size_t)b * TILE + bf * 8 + f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + (unsigned)(j * 64 * 8 * 16)),
+                         "l"(src + (long long)(j * 64) * row_stride), "l"(polx) : "memory");
+        cp_async_arrive_noinc(&full[b]);
+    };
+    if (XPASS) { issue_x(0); issue_x(1); }
+    for (long long i = 0; i < ntile; ++i) {
+        const int b = (int)(i % NBUF);
+        const unsigned use = (unsigned)(i / NBUF);
+        double2* tile = tp_smem + (size_t)b * TILE;
+        int q = 0;
+        double* Pt = nullptr;
+        if (XPASS) {
+            const long long k = i / p.npairs;
+            q = (int)(i - k * p.npairs);
+            const long long g = blockIdx.x + k * (long long)gridDim.x;
+            const int ch = (int)(g / p.ny), y = (int)(g - (long long)ch * p.ny);
+            Pt = p.P + ((long long)ch * p.nx) * row_stride + (long long)y * 8 + f;
+            if (q == p.npairs - 1) {                             // my 8 cells of P, needed after this tile's last stage
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) pv[k2] = __ldcs(Pt + (long long)(bf * 8 + k2) * row_stride);
+            }
+        }
+        mbar_wait(&full[b], use & 1);
+        int a[8];
+        double xr[8], xi[8];
+        tp_load_butterfly<512>(tile, a, xr, xi);
+        dft8(xr, xi);
+        tp_twiddle(w1, xr, xi);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tile[a[k]] = make_double2(xr[k], xi[k]);
+        tp_bar();
+        if (XPASS) issue_x(i + 2);                               // (everybody is past the last stage of tile i - 1: its buffer is free)
+        tp_load_butterfly<64>(tile, a, xr, xi);
+        dft8(xr, xi);
+        tp_twiddle(w2, xr, xi);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tile[a[k]] = make_double2(xr[k], xi[k]);
+        tp_bar();
+        tp_load_butterfly<8>(tile, a, xr, xi);
+        dft8(xr, xi);
+        if (!XPASS) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tile[a[k]] = make_double2(xr[k], xi[k]);
+            fence_async_smem();                                  // my writes, before the producer's bulk store reads them
+            mbar_arrive(&rel[b]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += xr[k] * xr[k] + xi[k] * xi[k];
+            if (q == p.npairs - 1) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    __stcs(Pt + (long long)(bf * 8 + k) * row_stride, pv[k] + acc[k]);
+                    acc[k] = 0.0;
+                }
+            }
+        }
+    }
+}
