@@ -11,8 +11,8 @@ fi
 for wl in ${WLS:-c3 c2}; do
   F=$( [ $wl = c2 ] && echo 64 || echo 16 )
   B="python bench.py --workload $wl --steps 1 --warmup 1 --no-cpu --no-extra --frames-per-step $F --pool $F"
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_$wl.csv $B > gpurun_out/ncu_l.log 2>&1
-  timeout 1200 ncu --set full --clock-control none -k regex:'splat|bin_place|prep_atoms|fft|yx_pass' -s 6 -c 6 -o /tmp/prof_r02_$wl -f $B > gpurun_out/ncu_$wl.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$wl.csv $B > gpurun_out/ncu_l.log 2>&1
+  timeout 1200 ncu --set full --clock-control none -k regex:'splat|bin_place|bin_count|order_atoms|prep_atoms|fft|yx_pass|tma_pass' -s ${NK:-7} -c ${NK:-7} -o /tmp/prof_r02_$wl -f $B > gpurun_out/ncu_$wl.log 2>&1
   ncu -i /tmp/prof_r02_$wl.ncu-rep --page raw --csv > gpurun_out/prof_r02_${wl}_raw.csv 2>/dev/null
 done
 ls -la gpurun_out/

@@ -18,7 +18,7 @@ want = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'lts__t_sector_hit_rate.pct']
 stalls = [n for n in h if 'issue_stalled' in n and n.endswith('.ratio')]
-short = {'prep_atoms': 'prep_bin', 'bin_place': 'prep_bin', 'DeviceScan': 'prep_bin', 'splat_zfft': 'splat_zfft', 'fft3_pass_kernel<8, 8, 8, 3, 256, 2, 0>': 'fft_y',
+short = {'prep_atoms': 'prep_bin', 'bin_place': 'prep_bin', 'bin_count': 'prep_bin', 'order_atoms': 'prep_bin', 'tma_pass_kernel<0>': 'fft_y', 'tma_pass_kernel<1>': 'fft_x_accum', 'DeviceScan': 'prep_bin', 'splat_zfft': 'splat_zfft', 'fft3_pass_kernel<8, 8, 8, 3, 256, 2, 0>': 'fft_y',
          'fft3_pass_kernel<8, 8, 8, 3, 256, 2, 1>': 'fft_x_accum', 'fft_y': 'fft_y', 'fft_x': 'fft_x_accum', 'yx_pass': 'fft_yx'}
 out, traffic = ['# ncu --set full, %s, one launch per kernel (%d frames per launch); peak = %.2f TB/s measured' % (wl, F, PEAK), ''], collections.OrderedDict()
 seen = set()
