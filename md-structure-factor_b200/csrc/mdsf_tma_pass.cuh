@@ -5,7 +5,10 @@
 //   x pass: tile (pair, chunk, y) is 512 rows of 128 bytes, 64 KB apart.  128-byte bulk copies are far too slow for that
 //           (measured: 27 ms per 16 c3 frames, the copy engine retires one small copy per ~60 cycles); every compute thread
 //           issues eight 16-byte cp.async copies instead (8 threads = one row), two tiles ahead, completion counted on the
-//           buffer's mbarrier (cp.async.mbarrier.arrive.noinc).
+//           buffer's mbarrier (cp.async.mbarrier.arrive.noinc).  The x pass stays at 53 % of the HBM peak with either kernel:
+//           one DRAM page activation per 128-byte piece.  Tried and dropped: a warp that requests the contiguous runs the
+//           G CTAs' pieces form per x row into L2 ahead of the copies (cp.async.bulk.prefetch.L2) -- DRAM reads doubled
+//           (35.4 GB instead of 18.3 GB per 16 frames, 11.2 ms): the CTAs drift apart and the lines are gone before use.
 // One CTA per SM walks its tiles (unit u = blockIdx.x + k * gridDim.x) through a ring of three 64 KB buffers:
 //   producer warp:  [y: wait until the compute warps released the buffer, store it (cp.async.bulk shared -> global), wait
 //                   until the store has read it]  ->  arm the buffer's mbarrier with the tile's byte count  ->  issue the

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 run() {  # name workload frames env...
   name=$1; wl=$2; fr=$3; shift 3
-  env "$@" timeout 300 python bench.py --workload $wl --steps 4 --warmup 2 --no-cpu --no-extra --frames-per-step $fr > gpurun_out/ab_${name}_$wl.json 2> gpurun_out/ab_${name}_$wl.err
+  env "$@" timeout 120 python bench.py --workload $wl --steps 4 --warmup 2 --no-cpu --no-extra --frames-per-step $fr > gpurun_out/ab_${name}_$wl.json 2> gpurun_out/ab_${name}_$wl.err
   python - <<PY
 import json
 try:
