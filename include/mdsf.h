@@ -111,6 +111,14 @@ int mdsf_sync(mdsf_handle* h);
  * array dens.py:318 accumulates.  Host or device destination. */
 int mdsf_read_sf(mdsf_handle* h, double* sf_host);
 int mdsf_export_sf_device(mdsf_handle* h, void* sf_device);
+/* Plot grids of dens.py:323-344 assembled on the GPU from the resident S(q): sfplt = get_dplot(sf) (dens.py:142-163)
+ * [Nx-2][Ny-2][2M-3], kgrid [Nx][Ny][M][4] (dens.py:325-334) and kgridplt [Nx-2][Ny-2][2M-3][4] (dens.py:336-344), M = Nz/2+1,
+ * written to caller-owned host arrays (any of the three may be NULL).  kx[Nx], ky[Ny], kz[M] and px[Nx-2], py[Ny-2],
+ * pz[2M-3] are the per-index axis values of the reference's expressions, evaluated by the caller; the GPU broadcasts,
+ * gathers and interleaves only, so all values are bit-identical to the numpy route. */
+int mdsf_export_plot_grids(mdsf_handle* h, const double* kx, const double* ky, const double* kz,
+                           const double* px, const double* py, const double* pz,
+                           double* sfplt_host, double* kgrid_host, double* kgridplt_host);
 /* Zero the accumulator (start a new trajectory on the same handle). */
 int mdsf_reset(mdsf_handle* h);
 

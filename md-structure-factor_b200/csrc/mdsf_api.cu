@@ -928,6 +928,96 @@ extern "C" int mdsf_read_sf(mdsf_handle* h, double* sf_host) {
     return MDSF_OK;
 }
 
+// ------------------------------------------------------------------------------------------ plot grids
+// sfplt = get_dplot(sf) (dens.py:142-163) as ONE gather: element (i, j, k) of the cropped view is cell (X, Y, Z) =
+// (i+1, j+1, k+1) of the (Nx, Ny, 2M-1) array the reference assembles from four quadrant copies (Z >= M-1:
+// sf[(X - Nx/2) mod Nx][(Y - Ny/2) mod Ny][Z - (M-1)]), the point inversion of that half (Z < M-1:
+// sf[(Nx/2 - X) mod Nx][(Ny/2 - Y) mod Ny][(M-1) - Z]) and the DC cell replaced by 1/3 (+x + +y + +z neighbours), :161.
+__device__ __forceinline__ double dplot_cell(const double* __restrict__ sf, int nx, int ny, int m, int X, int Y, int Z) {
+    const int hz = m - 1;
+    int sx, sy, sz;
+    if (Z >= hz) { sx = X - nx / 2; sy = Y - ny / 2; sz = Z - hz; }
+    else { sx = nx / 2 - X; sy = ny / 2 - Y; sz = hz - Z; }
+    sx = (sx % nx + nx) % nx; sy = (sy % ny + ny) % ny;
+    return sf[((long long)sx * ny + sy) * m + sz];
+}
+__device__ __forceinline__ double sfplt_value(const double* __restrict__ sf, int nx, int ny, int m, int i, int j, int k) {
+    const int X = i + 1, Y = j + 1, Z = k + 1;
+    const int cx = nx / 2, cy = ny / 2, cz = (2 * m - 1) / 2;
+    if (X == cx && Y == cy && Z == cz)
+        return 1.0 / 3.0 * ((dplot_cell(sf, nx, ny, m, cx + 1, cy, cz) + dplot_cell(sf, nx, ny, m, cx, cy + 1, cz)) + dplot_cell(sf, nx, ny, m, cx, cy, cz + 1));
+    return dplot_cell(sf, nx, ny, m, X, Y, Z);
+}
+// out[(i*n1 + j)*n2 + k][0..2] = axis values, [3] = sfplt(i,j,k) (kgridplt, dens.py:336-344) or 0 (kgrid, :325-334);
+// channels == 1: plain sfplt
+static __global__ void plot_grid_kernel(const double* __restrict__ sf, int nx, int ny, int m, const double* __restrict__ a0,
+                                        const double* __restrict__ a1, const double* __restrict__ a2, int n0, int n1, int n2,
+                                        int channels, int with_sf, double* __restrict__ out)
+{
+    const long long total = (long long)n0 * n1 * n2;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % n2);
+        const long long t = e / n2;
+        const int j = (int)(t % n1), i = (int)(t / n1);
+        const double v = with_sf ? sfplt_value(sf, nx, ny, m, i, j, k) : 0.0;
+        if (channels == 1) out[e] = v;
+        else {
+            double2* o = reinterpret_cast<double2*>(out + 4 * e);
+            o[0] = make_double2(a0[i], a1[j]);
+            o[1] = make_double2(a2[k], v);
+        }
+    }
+}
+
+// sfplt (Nx-2, Ny-2, 2M-3), kgrid (Nx, Ny, M, 4), kgridplt (Nx-2, Ny-2, 2M-3, 4) of dens.py:323-344 assembled on the GPU from
+// the resident S(q) and copied to the caller's host arrays (any of the three may be NULL).  The six axis-value vectors are
+// the reference's per-index scalar expressions, evaluated by the caller (host, once): kx[Nx], ky[Ny], kz[M] for kgrid and
+// px[Nx-2], py[Ny-2], pz[2M-3] for kgridplt -- the GPU only broadcasts, gathers and interleaves, so every value is bit-exact.
+extern "C" int mdsf_export_plot_grids(mdsf_handle* h, const double* kx, const double* ky, const double* kz,
+                                      const double* px, const double* py, const double* pz,
+                                      double* sfplt_host, double* kgrid_host, double* kgridplt_host) {
+    if (!h) return fail(MDSF_EINVAL, "null handle");
+    if ((kgrid_host && (!kx || !ky || !kz)) || (kgridplt_host && (!px || !py || !pz))) return fail(MDSF_EINVAL, "axis values missing");
+    int rc = mdsf_sync(h);
+    if (rc) return rc;
+    rc = mdsf_export_sf_device(h, h->d_sf);
+    if (rc) return rc;
+    const GridParams& gp = h->gp;
+    const int nx = gp.n[0], ny = gp.n[1], m = gp.n[2] / 2 + 1;
+    if (nx < 4 || ny < 4 || m < 3) return fail(MDSF_EINVAL, "grid too small for the plot view");
+    const int q0 = nx - 2, q1 = ny - 2, q2 = 2 * m - 3;
+    const long long nplt = (long long)q0 * q1 * q2, ngrid = (long long)nx * ny * m;
+    double *d_ax = nullptr, *d_out = nullptr;
+    const size_t nax = (size_t)nx + ny + m + q0 + q1 + q2;
+    CU(cudaMalloc(&d_ax, sizeof(double) * nax));
+    size_t need = 0;
+    if (sfplt_host) need = std::max(need, sizeof(double) * (size_t)nplt);
+    if (kgrid_host) need = std::max(need, sizeof(double) * 4 * (size_t)ngrid);
+    if (kgridplt_host) need = std::max(need, sizeof(double) * 4 * (size_t)nplt);
+    cudaError_t ce = need ? cudaMalloc(&d_out, need) : cudaSuccess;
+    if (ce != cudaSuccess) { cudaFree(d_ax); return fail(MDSF_ECUDA, "plot grids: %s", cudaGetErrorString(ce)); }
+    double *dkx = d_ax, *dky = dkx + nx, *dkz = dky + ny, *dpx = dkz + m, *dpy = dpx + q0, *dpz = dpy + q1;
+    auto up = [&](double* d, const double* s, int n) { return s ? cudaMemcpy(d, s, sizeof(double) * n, cudaMemcpyHostToDevice) : cudaSuccess; };
+    ce = up(dkx, kx, nx); if (ce == cudaSuccess) ce = up(dky, ky, ny); if (ce == cudaSuccess) ce = up(dkz, kz, m);
+    if (ce == cudaSuccess) ce = up(dpx, px, q0); if (ce == cudaSuccess) ce = up(dpy, py, q1); if (ce == cudaSuccess) ce = up(dpz, pz, q2);
+    auto run = [&](int n0, int n1, int n2, const double* a0, const double* a1, const double* a2, int channels, int with_sf, double* host) {
+        if (ce != cudaSuccess || !host) return;
+        const long long total = (long long)n0 * n1 * n2;
+        plot_grid_kernel<<<grid_for(total, 256, h->nsm), 256, 0, h->s_comp>>>(h->d_sf, nx, ny, m, a0, a1, a2, n0, n1, n2, channels, with_sf, d_out);
+        ++h->launches;
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->s_comp);
+        if (ce == cudaSuccess) ce = cudaMemcpy(host, d_out, sizeof(double) * channels * total, cudaMemcpyDeviceToHost);
+    };
+    run(q0, q1, q2, dpx, dpy, dpz, 1, 1, sfplt_host);
+    run(nx, ny, m, dkx, dky, dkz, 4, 0, kgrid_host);
+    run(q0, q1, q2, dpx, dpy, dpz, 4, 1, kgridplt_host);
+    cudaFree(d_ax);
+    if (d_out) cudaFree(d_out);
+    if (ce != cudaSuccess) return fail(MDSF_ECUDA, "plot grids: %s", cudaGetErrorString(ce));
+    return MDSF_OK;
+}
+
 extern "C" int mdsf_reset(mdsf_handle* h) {
     if (!h) return fail(MDSF_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));

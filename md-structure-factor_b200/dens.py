@@ -38,6 +38,7 @@ FFT_MODE = "auto"         # "auto" | "native" | "cufft"
 BATCH_FRAMES = 0          # frames per device batch (0 = automatic)
 SAVE_COMPRESSED = True    # np.savez_compressed like the reference; False writes an uncompressed npz
 GPU_MONOCLINIC = True     # compute_sf_stream: the monoclinic transform of main_gromacs.py:204-207 runs inside the first kernel, not in numpy
+GPU_PLOT_GRIDS = True     # sfplt / kgrid / kgridplt (dens.py:323-344) assembled on the GPU from the resident S(q); False = numpy
 PARALLEL_NPZ = True       # deflate the npz members on all host cores (same container, np.load reads it); False = numpy's writer
 LAST_RUN = {}             # filled by compute_sf: grid, batch size, FFT path, kernel launches
 
@@ -132,12 +133,10 @@ def _grid(L, Sres):
     return n, np.divide(L, n)
 
 
-def _k_lattices(shape, L):
-    """kgrid / kgridplt coordinate lattices (reference dens.py:325-342)."""
+def _k_axes(shape, L):
+    """Per-index axis values of kgrid (reference dens.py:327-334) and kgridplt (dens.py:337-342): the reference's scalar
+    expressions, one evaluation per index.  Indices kgrid never writes (the middle one of an odd axis) stay 0."""
     nx, ny, m = shape
-    # the reference fills kgrid slice by slice (dens.py:327-334); the per-index scalars below are its expressions, the
-    # assignment is one broadcast per channel (indices it never writes, e.g. the middle one of an odd axis, stay 0)
-    kgrid = np.zeros((nx, ny, m, 4))
     vx, vy, vz = np.zeros(nx), np.zeros(ny), np.zeros(m)
     for ix in range(int(nx / 2)):
         vx[ix] = ix * 2.0 * math.pi / L[0]
@@ -147,16 +146,25 @@ def _k_lattices(shape, L):
         vy[ny - 1 - iy] = -(iy + 0.5) * 2.0 * math.pi / L[1]
     for iz in range(m):
         vz[iz] = iz * 2.0 * math.pi / L[2]
+    paxes = []
+    for d, nd in enumerate((nx - 2, ny - 2, m * 2 - 3)):
+        paxes.append(np.asarray([(i - nd / 2) * 2.0 * math.pi / L[d] for i in range(nd)], dtype=np.float64))
+    return (vx, vy, vz), tuple(paxes)
+
+
+def _k_lattices(shape, L):
+    """kgrid / kgridplt coordinate lattices (reference dens.py:325-342), host route: one broadcast per channel."""
+    nx, ny, m = shape
+    (vx, vy, vz), paxes = _k_axes(shape, L)
+    kgrid = np.zeros((nx, ny, m, 4))
     kgrid[..., 0] = vx[:, None, None]
     kgrid[..., 1] = vy[None, :, None]
     kgrid[..., 2] = vz[None, None, :]
     kplt = np.zeros((nx - 2, ny - 2, m * 2 - 3, 4))
     for d in range(3):
-        nd = kplt.shape[d]
-        vals = [(i - nd / 2) * 2.0 * math.pi / L[d] for i in range(nd)]
         view = [None, None, None]
         view[d] = slice(None)
-        kplt[..., d] = np.asarray(vals, dtype=np.float64)[tuple(view)]
+        kplt[..., d] = paxes[d][tuple(view)]
     return kgrid, kplt
 
 
@@ -182,11 +190,18 @@ def make_engine(L_mean, typ, rad, ucell, Sres, coord_dtype, arith_dtype, keep_de
     return eng, n, dr, nborder
 
 
-def finish_sf(sf, L, n, out_filename):
-    """Plot grids and the sf npz (reference dens.py:323-346)."""
-    sfplt = get_dplot(sf)
-    kgrid, kgridplt = _k_lattices(sf.shape, L)
-    kgridplt[:, :, :, 3] = sfplt
+def finish_sf(sf, L, n, out_filename, eng=None):
+    """Plot grids and the sf npz (reference dens.py:323-346).  With a live engine (and GPU_PLOT_GRIDS) sfplt, kgrid and
+    kgridplt are assembled on the GPU from the resident S(q) (mdsf_export_plot_grids: gather + broadcast, bit-identical);
+    otherwise -- e.g. after the NCCL reduce of sf_distributed -- by the numpy expressions."""
+    if eng is not None and GPU_PLOT_GRIDS and min(sf.shape[0], sf.shape[1]) >= 4 and sf.shape[2] >= 3:
+        kaxes, paxes = _k_axes(sf.shape, L)
+        g = eng.export_plot_grids(kaxes, paxes)
+        sfplt, kgrid, kgridplt = g["sfplt"], g["kgrid"], g["kgridplt"]
+    else:
+        sfplt = get_dplot(sf)
+        kgrid, kgridplt = _k_lattices(sf.shape, L)
+        kgridplt[:, :, :, 3] = sfplt
     if PARALLEL_NPZ:      # same zip-of-npy container as np.savez_compressed, deflated on all cores (npz_writer.py)
         npz_writer.savez_parallel(out_filename, compressed=SAVE_COMPRESSED, sf=sf, sfplt=sfplt, L=L, N=n, kgrid=kgrid, kgridplt=kgridplt)
     else:
@@ -250,9 +265,9 @@ def compute_sf_stream(frames, L, typ, out_filename, rad, ucell, Sres, first_fram
         LAST_RUN.clear()
         LAST_RUN.update(N=n.copy(), dr=dr.copy(), Nborder=nborder, batch_frames=eng.batch_frames, fft=eng.fft_path, splat=eng.splat_path,
                         kernel_launches=eng.kernel_launches, frames=eng.frames_done, streamed_chunks=i, chunk_frames=chunk)
+        finish_sf(sf, Lm, n, out_filename, eng)
     finally:
         eng.close()
-    finish_sf(sf, Lm, n, out_filename)
 
 
 def compute_sf(r, L, typ, out_filename, rad, ucell, Sres):
@@ -315,8 +330,8 @@ def compute_sf(r, L, typ, out_filename, rad, ucell, Sres):
         LAST_RUN.clear()
         LAST_RUN.update(N=n.copy(), dr=dr.copy(), Nborder=nborder, batch_frames=eng.batch_frames, fft=eng.fft_path, splat=eng.splat_path,
                         kernel_launches=eng.kernel_launches, frames=eng.frames_done)
+        if WRITE_BACK_COORDS and r is not r_in and RANDOM_NOISE <= 0:
+            r_in[...] = r
+        finish_sf(sf, L, n, out_filename, eng)
     finally:
         eng.close()
-    if WRITE_BACK_COORDS and r is not r_in and RANDOM_NOISE <= 0:
-        r_in[...] = r
-    finish_sf(sf, L, n, out_filename)

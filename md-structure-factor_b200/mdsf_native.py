@@ -20,7 +20,7 @@ FFT_AUTO, FFT_NATIVE, FFT_CUFFT = 0, 1, 2
 EXPORTS = [
     "mdsf_create", "mdsf_destroy", "mdsf_set_atoms", "mdsf_host_alloc", "mdsf_host_free",
     "mdsf_host_register", "mdsf_host_unregister", "mdsf_push_frames", "mdsf_push_density", "mdsf_sync",
-    "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
+    "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_export_plot_grids", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
     "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_splat_path",
     "mdsf_batch_frames", "mdsf_geometry", "mdsf_set_pretransform",
     "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_timer_start", "mdsf_timer_stop", "mdsf_last_error",
@@ -72,6 +72,7 @@ def load():
         "mdsf_sync": (C.c_int, [vp]),
         "mdsf_read_sf": (C.c_int, [vp, dp]),
         "mdsf_export_sf_device": (C.c_int, [vp, vp]),
+        "mdsf_export_plot_grids": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp, dp, dp]),
         "mdsf_reset": (C.c_int, [vp]),
         "mdsf_debug_cell_indices": (C.c_int, [vp, i64, C.POINTER(i32)]),
         "mdsf_debug_coords": (C.c_int, [vp, i64, dp]),
@@ -230,6 +231,20 @@ class Engine:
         elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
         _check(self._lib.mdsf_read_sf(self._h, _dptr(out)))
+        return out
+
+    def export_plot_grids(self, kaxes, paxes, want=("sfplt", "kgrid", "kgridplt")):
+        """sfplt / kgrid / kgridplt of reference dens.py:323-344, assembled on the GPU from the resident S(q).
+        ``kaxes`` = (kx[Nx], ky[Ny], kz[M]), ``paxes`` = (px[Nx-2], py[Ny-2], pz[2M-3]): per-index axis values."""
+        nx, ny, m = self.n[0], self.n[1], self.n[2] // 2 + 1
+        ax = [np.ascontiguousarray(a, dtype=np.float64) for a in tuple(kaxes) + tuple(paxes)]
+        if [a.size for a in ax] != [nx, ny, m, nx - 2, ny - 2, 2 * m - 3]:
+            raise ValueError("axis vectors do not match the grid")
+        out = {"sfplt": np.empty((nx - 2, ny - 2, 2 * m - 3)) if "sfplt" in want else None,
+               "kgrid": np.empty((nx, ny, m, 4)) if "kgrid" in want else None,
+               "kgridplt": np.empty((nx - 2, ny - 2, 2 * m - 3, 4)) if "kgridplt" in want else None}
+        ptr = lambda a: _dptr(a) if a is not None else None
+        _check(self._lib.mdsf_export_plot_grids(self._h, *[_dptr(a) for a in ax], ptr(out["sfplt"]), ptr(out["kgrid"]), ptr(out["kgridplt"])))
         return out
 
     def export_sf_device(self, device_ptr):

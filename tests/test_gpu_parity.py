@@ -96,6 +96,36 @@ def test_compute_sf_dropin_writes_reference_npz(mdsf, name, tmp_path):
     assert rel <= 1e-5 and norm <= 1e-12
 
 
+@pytest.mark.parametrize("name", ["mono_f32", "gas_f64_ortho", "corner_na_f64"])
+def test_gpu_plot_grids_are_bitwise_the_numpy_route(mdsf, name):
+    """sfplt = get_dplot(sf), kgrid and kgridplt (reference dens.py:142-163, 323-344) assembled on the GPU from the
+    resident S(q) (mdsf_export_plot_grids) against the numpy expressions on the same sf: every value bit-identical;
+    and against the reference's own kgrid / kgridplt lattices of the golden run."""
+    dens = mdsf.dens
+    c = load_case(name)
+    r = c["coords"].copy()
+    dims = c["dims"]
+    arith = np.float32 if (r.dtype == np.float32 and dims.dtype == np.float32) else np.float64
+    L = np.average(dims, axis=0)
+    eng, n, dr, nb = dens.make_engine(L, c["typ"], c["rad"], c["ucell"], c["sres"], r.dtype, arith)
+    try:
+        eng.push_frames(r, (L / dims).astype(np.float64), dens._wrapped_atoms(r.shape[0], r.shape[1]), write_back=False)
+        sf = eng.read_sf()
+        kaxes, paxes = dens._k_axes(sf.shape, L)
+        g = eng.export_plot_grids(kaxes, paxes)
+        only = eng.export_plot_grids(kaxes, paxes, want=("sfplt",))
+    finally:
+        eng.close()
+    sfplt = dens.get_dplot(sf)
+    kgrid, kgridplt = dens._k_lattices(sf.shape, L)
+    kgridplt[..., 3] = sfplt
+    assert np.array_equal(g["sfplt"], sfplt) and np.array_equal(only["sfplt"], sfplt)
+    assert only["kgrid"] is None and only["kgridplt"] is None
+    assert np.array_equal(g["kgrid"], kgrid) and np.array_equal(g["kgridplt"], kgridplt)
+    assert np.array_equal(g["kgrid"], c["ref_kgrid"])
+    assert np.array_equal(g["kgridplt"][..., :3], c["ref_kgridplt"][..., :3])
+
+
 def test_unknown_label_raises_keyerror_like_reference(mdsf, tmp_path):
     c = load_case("gas_f64_ortho")
     typ = c["typ"].copy()
