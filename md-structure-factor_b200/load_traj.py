@@ -44,6 +44,20 @@ def load_gro(gro):
     return [row[10:15].strip() for row in rows[2:-1]]
 
 
+def _gro_width(row):
+    """Width of the coordinate fields of a .gro atom line: GROMACS writes %(n+5).(n)f (8 columns at the default 3
+    decimals, 10 with -ndec 5, ...); like GROMACS and mdtraj, take it from the spacing of the decimal points."""
+    p1 = row.find(".", 20)
+    p2 = row.find(".", p1 + 1) if p1 >= 0 else -1
+    return p2 - p1 if p1 >= 0 and p2 > p1 else 8
+
+
+def _gro_xyz(rows):
+    w = _gro_width(rows[0]) if rows else 8
+    return np.array([[float(row[20:20 + w]), float(row[20 + w:20 + 2 * w]), float(row[20 + 2 * w:20 + 3 * w])] for row in rows],
+                    dtype=np.float32)
+
+
 def read_gro(gro):
     """One-frame .gro reader: (names, coords in Angstrom float32 (Na,3), box lengths in Angstrom float32 (3,)).
 
@@ -52,8 +66,7 @@ def read_gro(gro):
         rows = handle.readlines()
     natoms = int(rows[1])
     names = [row[10:15].strip() for row in rows[2:2 + natoms]]
-    xyz = np.array([[float(row[20:28]), float(row[28:36]), float(row[36:44])] for row in rows[2:2 + natoms]],
-                   dtype=np.float32)
+    xyz = _gro_xyz(rows[2:2 + natoms])
     b = [float(v) for v in rows[2 + natoms].split()]
     if len(b) == 3:
         lengths = np.array(b, dtype=np.float64)
@@ -77,7 +90,7 @@ def read_gro_frames(gro):
             names = [row[10:15].strip() for row in body]
         elif len(body) != len(names):
             raise ValueError("%s: frame %d has %d atoms, frame 0 has %d" % (gro, len(frames), len(body), len(names)))
-        frames.append(np.array([[float(row[20:28]), float(row[28:36]), float(row[36:44])] for row in body], dtype=np.float32))
+        frames.append(_gro_xyz(body))
         b = [float(v) for v in rows[pos + 2 + natoms].split()]
         if len(b) == 3:
             boxes.append(np.array(b, dtype=np.float64))

@@ -126,6 +126,15 @@ def test_load_gro_and_traj_npz_layout(tmp_path):
     assert sorted(z.files) == ["coords", "dims", "mass", "name", "typ"]
     assert z["coords"].shape == (1, 6, 3) and z["coords"].dtype == np.float32 and z["dims"].shape == (1, 3)
     assert list(z["typ"]) == names                                                  # typ = atom NAMES (load_traj.py:110)
+    # higher-precision files (gmx ... -ndec 5 writes %10.5f fields): the width follows the decimal points, as in GROMACS / mdtraj
+    hp = tmp_path / "hp.gro"
+    hp.write_text("hp\n    2\n"
+                  "    1WATER  OW1    1   0.12600   1.62400   1.67900\n    1WATER  HW2    2  -0.19012  11.66123   1.74700\n"
+                  "   1.82060   1.82060   1.82060\n")
+    _, xyz5, _ = lt.read_gro(str(hp))
+    assert np.allclose(xyz5, [[1.26, 16.24, 16.79], [-1.9012, 116.6123, 17.47]])
+    _, xyz5f, _ = lt.read_gro_frames(str(hp))
+    assert np.array_equal(xyz5f[0], xyz5)
 
 
 def test_workloads_are_deterministic_and_inside_the_box():
