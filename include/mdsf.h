@@ -120,6 +120,14 @@ int mdsf_export_plot_grids(mdsf_handle* h, const double* kx, const double* ky, c
                            const double* px, const double* py, const double* pz,
                            double* sfplt_host, double* kgrid_host, double* kgridplt_host);
 /* Zero the accumulator (start a new trajectory on the same handle). */
+/* Cylindrical average of plot2d.PLOT_RAD_NEW (reference plot2d.py:575-632), stand-alone (no handle): sf_host[n0][n1][n2]
+ * and its axis vectors X, Y, Z are channel 3 and the coordinate channels of kgridplt (plot2d.py:571-574); binv9 = inverse
+ * of the reciprocal-vector matrix (plot2d.py:594-598, row-major); rarr[rbins], ntheta[rbins] (theta samples per ring,
+ * plot2d.py:616), zar[zbins].  oa_host[rbins][zbins] = mean over theta of the trilinear interpolant (scipy
+ * RegularGridInterpolator semantics, NaN outside the grid). */
+int mdsf_cylindrical_average(int device, const double* sf_host, int n0, int n1, int n2, const double* X, const double* Y,
+                             const double* Z, const double* binv9, int rbins, const double* rarr, const int* ntheta,
+                             int zbins, const double* zar, double* oa_host);
 int mdsf_reset(mdsf_handle* h);
 
 /* Parity taps (tests only; each synchronises). `frame` indexes the frames of the LAST push. */

@@ -19,5 +19,6 @@ import dens  # noqa: E402
 import npz_writer  # noqa: E402
 import load_traj  # noqa: E402
 import sf_distributed as distributed  # noqa: E402
+import plot2d_gpu  # noqa: E402
 
-__all__ = ["native", "dens", "load_traj", "distributed"]
+__all__ = ["native", "dens", "load_traj", "distributed", "plot2d_gpu"]

@@ -20,6 +20,7 @@
 #include "mdsf_fft.cuh"
 #include "mdsf_launch.h"
 #include "mdsf_prep.cuh"
+#include "mdsf_post.cuh"
 #include "mdsf_yx.cuh"
 #include "mdsf_tma_pass.cuh"
 
@@ -1015,6 +1016,43 @@ extern "C" int mdsf_export_plot_grids(mdsf_handle* h, const double* kx, const do
     cudaFree(d_ax);
     if (d_out) cudaFree(d_out);
     if (ce != cudaSuccess) return fail(MDSF_ECUDA, "plot grids: %s", cudaGetErrorString(ce));
+    return MDSF_OK;
+}
+
+// Cylindrical average of plot2d.PLOT_RAD_NEW (reference plot2d.py:575-632) over a host structure-factor volume (the
+// channel-3 values of kgridplt and its three axis vectors, as plot2d.py:571-574 slices them).  Stand-alone: needs no
+// engine handle, like the reference's plot2d which works from the sf npz.  oa_host[rbins][zbins] = mean over theta
+// (NaN where a ring leaves the grid; the caller applies the reference's nanmin fill and normalisation, plot2d.py:634-638).
+extern "C" int mdsf_cylindrical_average(int device, const double* sf_host, int n0, int n1, int n2, const double* X, const double* Y,
+                                        const double* Z, const double* binv9, int rbins, const double* rarr, const int* ntheta,
+                                        int zbins, const double* zar, double* oa_host) {
+    if (!sf_host || !X || !Y || !Z || !binv9 || !rarr || !ntheta || !zar || !oa_host) return fail(MDSF_EINVAL, "null argument");
+    if (n0 < 2 || n1 < 2 || n2 < 2 || rbins < 1 || zbins < 1) return fail(MDSF_EINVAL, "cylindrical average: bad sizes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(MDSF_ECUDA, "no CUDA device available; libmdsf has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(MDSF_EINVAL, "device %d out of range", device);
+    CU(cudaSetDevice(device));
+    const size_t nsf = (size_t)n0 * n1 * n2;
+    double *d_sf = nullptr, *d_ax = nullptr, *d_oa = nullptr;
+    int* d_nt = nullptr;
+    cudaError_t ce = cudaMalloc(&d_sf, sizeof(double) * nsf);
+    const size_t nax = (size_t)n0 + n1 + n2 + 9 + rbins + zbins;
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_ax, sizeof(double) * nax);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_oa, sizeof(double) * (size_t)rbins * zbins);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_nt, sizeof(int) * rbins);
+    double *dX = d_ax, *dY = dX + n0, *dZ = dY + n1, *dB = dZ + n2, *dR = dB + 9, *dZa = dR + rbins;
+    auto up = [&](void* d, const void* s, size_t b) { if (ce == cudaSuccess) ce = cudaMemcpy(d, s, b, cudaMemcpyHostToDevice); };
+    up(d_sf, sf_host, sizeof(double) * nsf);
+    if (ce == cudaSuccess) { up(dX, X, 8 * (size_t)n0); up(dY, Y, 8 * (size_t)n1); up(dZ, Z, 8 * (size_t)n2); up(dB, binv9, 72); up(dR, rarr, 8 * (size_t)rbins); up(dZa, zar, 8 * (size_t)zbins); up(d_nt, ntheta, 4 * (size_t)rbins); }
+    if (ce == cudaSuccess) {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+        cyl_average_kernel<<<grid_for((long long)rbins * zbins, 128, nsm), 128>>>(d_sf, n0, n1, n2, dX, dY, dZ, dB, rbins, dR, d_nt, zbins, dZa, d_oa);
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpy(oa_host, d_oa, sizeof(double) * (size_t)rbins * zbins, cudaMemcpyDeviceToHost);
+    cudaFree(d_sf); cudaFree(d_ax); cudaFree(d_oa); cudaFree(d_nt);
+    if (ce != cudaSuccess) return fail(MDSF_ECUDA, "cylindrical average: %s", cudaGetErrorString(ce));
     return MDSF_OK;
 }
 

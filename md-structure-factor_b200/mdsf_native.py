@@ -20,7 +20,7 @@ FFT_AUTO, FFT_NATIVE, FFT_CUFFT = 0, 1, 2
 EXPORTS = [
     "mdsf_create", "mdsf_destroy", "mdsf_set_atoms", "mdsf_host_alloc", "mdsf_host_free",
     "mdsf_host_register", "mdsf_host_unregister", "mdsf_push_frames", "mdsf_push_density", "mdsf_sync",
-    "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_export_plot_grids", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
+    "mdsf_read_sf", "mdsf_export_sf_device", "mdsf_export_plot_grids", "mdsf_cylindrical_average", "mdsf_reset", "mdsf_debug_cell_indices", "mdsf_debug_coords",
     "mdsf_debug_density", "mdsf_kernel_launches", "mdsf_frames_done", "mdsf_fft_path", "mdsf_splat_path",
     "mdsf_batch_frames", "mdsf_geometry", "mdsf_set_pretransform",
     "mdsf_enable_timing", "mdsf_stage_ms", "mdsf_timer_start", "mdsf_timer_stop", "mdsf_last_error",
@@ -73,6 +73,7 @@ def load():
         "mdsf_read_sf": (C.c_int, [vp, dp]),
         "mdsf_export_sf_device": (C.c_int, [vp, vp]),
         "mdsf_export_plot_grids": (C.c_int, [vp, dp, dp, dp, dp, dp, dp, dp, dp, dp]),
+        "mdsf_cylindrical_average": (C.c_int, [C.c_int, dp, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_int, dp, C.POINTER(i32), C.c_int, dp, dp]),
         "mdsf_reset": (C.c_int, [vp]),
         "mdsf_debug_cell_indices": (C.c_int, [vp, i64, C.POINTER(i32)]),
         "mdsf_debug_coords": (C.c_int, [vp, i64, dp]),

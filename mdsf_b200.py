@@ -8,3 +8,4 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 _pkg = importlib.import_module("md-structure-factor_b200")
 native, dens, load_traj, distributed = _pkg.native, _pkg.dens, _pkg.load_traj, _pkg.distributed
+plot2d_gpu = _pkg.plot2d_gpu

@@ -126,6 +126,28 @@ def test_gpu_plot_grids_are_bitwise_the_numpy_route(mdsf, name):
     assert np.array_equal(g["kgridplt"][..., :3], c["ref_kgridplt"][..., :3])
 
 
+@pytest.mark.parametrize("name,theta", [("mono_f32", 120.0), ("gas_f64_ortho", 90.0)])
+def test_gpu_cylindrical_average_matches_scipy_restatement(mdsf, name, theta):
+    """The (r, z) ring averages of plot2d.PLOT_RAD_NEW (reference plot2d.py:571-638) on the GPU against the CPU restatement
+    that calls scipy's RegularGridInterpolator like the reference: same NaN rings, values within 1e-10 relative
+    (cos / sin and the matmul's summation order differ in the last place; everything else follows scipy step by step)."""
+    from oracle import plot2d_oracle as po
+    c = load_case(name)
+    D = c["ref_kgridplt"]
+    th = theta * np.pi / 180.0
+    ucell = np.array([[1, 0, 0], [np.cos(th), np.sin(th), 0], [0, 0, 1]])
+    want, rr, zz = po.cylindrical_average(D, ucell, rbins=60, fill=False)
+    got, rr2, zz2 = mdsf.plot2d_gpu.cylindrical_average(D, ucell, rbins=60, fill=False)
+    assert np.array_equal(rr, rr2) and np.array_equal(zz, zz2)
+    assert np.array_equal(np.isnan(want), np.isnan(got)) and np.isfinite(want).sum() > want.size // 4
+    ok = np.isfinite(want)
+    assert np.max(np.abs(got[ok] - want[ok]) / np.abs(want[ok]).max()) <= 1e-10
+    assert np.max(np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-300)) <= 1e-8
+    filled, _, _ = mdsf.plot2d_gpu.cylindrical_average(D, ucell, rbins=60, fill=True, normalize=True)
+    ref_filled, _, _ = po.cylindrical_average(D, ucell, rbins=60, fill=True)
+    assert np.allclose(filled, ref_filled / np.average(ref_filled), rtol=1e-9, atol=0)
+
+
 def test_unknown_label_raises_keyerror_like_reference(mdsf, tmp_path):
     c = load_case("gas_f64_ortho")
     typ = c["typ"].copy()
