@@ -355,10 +355,12 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         while (gp.lcol > 2 && mdsf_splat_smem(gp.lcol, 1, gp.nzp, gp.n[2]) > tile_budget) --gp.lcol;
     }
     gp.zswz = 0;
-    if (h->native_fft && mdsf_zswizzle_wanted(gp.lcol, gp.n[2])) {      // swizzled columns need no padding
-        gp.zswz = 1;
+    gp.zilv = 0;
+    if (h->native_fft && mdsf_zspec_length(gp.n[2]) && env_int("MDSF_ZILV", 1) != 0) {
+        // compile-time z stages on the interleaved tile: [col][nz + 1] cells of 16 bytes (odd column stride, no padding inside a column)
+        gp.zilv = 1;
         gp.pad_shift = 31;
-        gp.nzp = gp.n[2] + 8;
+        gp.nzp = gp.n[2] + 1;
     }
     if (mdsf_splat_smem(gp.lcol, 1, gp.nzp, gp.n[2]) > (size_t)kMaxSmem)
         return fail(MDSF_EINVAL, "grid too long in z (%d) for the column-tile splat", gp.n[2]);
@@ -368,7 +370,7 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         gp.nty = (gp.n[1] + TY - 1) / TY;
     }
     // ---- compile-time z stages: per-stage twiddle tables [n2] = w^(n2 N/L)
-    if (h->native_fft && mdsf_zspec_applies(gp.lcol, gp.n[2], gp.pad_shift, gp.zswz)) {
+    if (gp.zilv) {
         int rc = stage_tables(h->ax[2].plan, &h->d_tws, &h->tws_n);
         if (rc) return rc;
     }

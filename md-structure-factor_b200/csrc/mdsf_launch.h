@@ -15,8 +15,7 @@ struct SplatArgs {
 cudaError_t mdsf_launch_splat(int lcol, int mode, bool fuse, dim3 grid, size_t smem, cudaStream_t st, const SplatArgs& a);
 cudaError_t mdsf_splat_configure(void);                   // opt in to the large dynamic shared memory sizes
 size_t mdsf_splat_smem(int lcol, int sub, int nzp, int nz, int zlane = 0);        // dynamic shared memory of one splat CTA (without a twiddle region)
-bool mdsf_zspec_applies(int lcol, int nz, int pad_shift, int swz); // compile-time z stages available for this geometry
-bool mdsf_zswizzle_wanted(int lcol, int nz);              // ... with XOR-swizzled columns (no padding)
+bool mdsf_zspec_length(int nz);                           // compile-time z stages (interleaved tile) exist for this z length
 
 struct PassArgs {
     double2* vol; double* P; const FftPlan* plan; const double2* tw; PassGeom pg; int npairs; int nouter;   // nouter: Nx (y pass) / Ny (x pass)

@@ -89,27 +89,31 @@ __device__ __forceinline__ int zpos(int z, int swz, int pad) {
     return swz ? (z ^ (((z >> 4) & 7) | (((z >> 6) & 1) << 3))) : z + (z >> pad);
 }
 
-// In-place decimation-in-frequency stages over [NCOL][nzp] re / im planes: same scheme and output order as
-// fft_stage, with every stride and index split a constant.  Only w = w_N^(n2 N/L) is read per butterfly (per-stage table
-// tws[TOFF + n2], host-built, conflict-free for consecutive n2); its powers w^2 .. w^(R-1) come from complex
-// multiplications: the fp64 pipe idles at 15% here while the load/store pipe is the bottleneck, and seven strided
-// twiddle loads per radix-8 butterfly were a third of a stage's shared-memory wavefronts.
-template <int NCOL, int N, int R, int L, int SWZ, int PAD, int TOFF>
-__device__ __forceinline__ void zstage(double* __restrict__ sre, double* __restrict__ sim, const double2* __restrict__ tws, int nzp)
+// In-place decimation-in-frequency stages with every stride and index split a constant (same scheme and output order as
+// fft_stage).  Only w = w_N^(n2 N/L) is read per butterfly (per-stage table tws[TOFF + n2], host-built); its powers
+// w^2 .. w^(R-1) come from complex multiplications: the fp64 pipe idles at 15% here while the load/store pipe is the
+// bottleneck, and seven strided twiddle loads per radix-8 butterfly were a third of a stage's shared-memory wavefronts.
+// ---- interleaved tile (gp.zilv): [NCOL][nz + 1] complex cells of 16 bytes, frame 2q in .x, frame 2q+1 in .y.  The odd
+// column stride puts the same cell of 8 consecutive columns into 8 different 16-byte bank groups, so with the column
+// index fastest across the lanes every 16-byte access of a quarter-warp is conflict-free in every stage, whatever the
+// row stride -- no swizzle arithmetic, half the shared-memory instructions of the split re / im planes.
+__device__ __forceinline__ int tile_index(const GridParams& gp, int ncol, int c, int z, int part) {
+    return gp.zilv ? (((c * gp.nzp + z) << 1) + part)
+                   : (part * ncol * gp.nzp + c * gp.nzp + (gp.zswz ? (z ^ (((z >> 4) & 7) | (((z >> 6) & 1) << 3))) : z + (z >> gp.pad_shift)));
+}
+
+template <int NCOL, int N, int R, int L, int TOFF>
+__device__ __forceinline__ void zstage2(double2* __restrict__ tile, const double2* __restrict__ tws, int nzp)
 {
     constexpr int M = L / R, NBF = N / R;
     constexpr int ITEMS = NCOL * NBF;
     for (int it = threadIdx.x; it < ITEMS; it += MDSF_SPLAT_THREADS) {
-        const int f = it / NBF, bf = it % NBF;              // constants: shifts / masks for powers of two
+        const int f = it % NCOL, bf = it / NCOL;            // constants: shifts / masks
         const int b = bf / M, n2 = bf % M;
-        const int base = b * L + n2;
+        double2* col = tile + f * nzp + b * L + n2;
         double xr[R], xi[R];
-        int a[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            a[j] = f * nzp + zpos(base + j * M, SWZ, PAD);
-            xr[j] = sre[a[j]]; xi[j] = sim[a[j]];
-        }
+        for (int j = 0; j < R; ++j) { const double2 v = col[j * M]; xr[j] = v.x; xi[j] = v.y; }
         Dft<R>::run(xr, xi, nullptr, nullptr, N);
         if (M > 1) {
             const double2 w1 = tws[TOFF + n2];
@@ -129,48 +133,28 @@ __device__ __forceinline__ void zstage(double* __restrict__ sre, double* __restr
             }
         }
 #pragma unroll
-        for (int k = 0; k < R; ++k) { sre[a[k]] = xr[k]; sim[a[k]] = xi[k]; }
+        for (int k = 0; k < R; ++k) col[k * M] = make_double2(xr[k], xi[k]);
     }
     __syncthreads();
 }
+template <int NCOL> __device__ __forceinline__ void zfft2(double2* t, const double2* tws, int nzp, int nz) {
+    if (nz == 64) {
+        zstage2<NCOL, 64, 8, 64, 0>(t, tws, nzp); zstage2<NCOL, 64, 8, 8, 8>(t, tws, nzp);
+    } else if (nz == 256) {
+        zstage2<NCOL, 256, 4, 256, 0>(t, tws, nzp); zstage2<NCOL, 256, 8, 64, 64>(t, tws, nzp); zstage2<NCOL, 256, 8, 8, 72>(t, tws, nzp);
+    } else if (nz == 512) {
+        zstage2<NCOL, 512, 8, 512, 0>(t, tws, nzp); zstage2<NCOL, 512, 8, 64, 64>(t, tws, nzp); zstage2<NCOL, 512, 8, 8, 72>(t, tws, nzp);
+    } else if (nz == 1024) {
+        zstage2<NCOL, 1024, 4, 1024, 0>(t, tws, nzp); zstage2<NCOL, 1024, 4, 256, 256>(t, tws, nzp);
+        zstage2<NCOL, 1024, 8, 64, 320>(t, tws, nzp); zstage2<NCOL, 1024, 8, 8, 328>(t, tws, nzp);
+    } else {      // 768
+        zstage2<NCOL, 768, 4, 768, 0>(t, tws, nzp); zstage2<NCOL, 768, 8, 192, 192>(t, tws, nzp);
+        zstage2<NCOL, 768, 8, 24, 216>(t, tws, nzp); zstage2<NCOL, 768, 3, 3, 219>(t, tws, nzp);
+    }
+}
 
-// radix lists as produced by factorize() for the z axis (radices <= 8); table offsets = running sum of M over the stages
-template <int NCOL> __device__ __forceinline__ void zfft_64(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 64, 8, 64, 0, 3, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 64, 8, 8, 0, 3, 8>(sre, sim, tws, nzp);
-}
-template <int NCOL> __device__ __forceinline__ void zfft_256(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 256, 4, 256, 1, 31, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 256, 8, 64, 1, 31, 64>(sre, sim, tws, nzp);
-    zstage<NCOL, 256, 8, 8, 1, 31, 72>(sre, sim, tws, nzp);
-}
-template <int NCOL> __device__ __forceinline__ void zfft_512(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 512, 8, 512, 1, 31, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 512, 8, 64, 1, 31, 64>(sre, sim, tws, nzp);
-    zstage<NCOL, 512, 8, 8, 1, 31, 72>(sre, sim, tws, nzp);
-}
-template <int NCOL> __device__ __forceinline__ void zfft_1024(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 1024, 4, 1024, 1, 31, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 1024, 4, 256, 1, 31, 256>(sre, sim, tws, nzp);
-    zstage<NCOL, 1024, 8, 64, 1, 31, 320>(sre, sim, tws, nzp);
-    zstage<NCOL, 1024, 8, 8, 1, 31, 328>(sre, sim, tws, nzp);
-}
-template <int NCOL> __device__ __forceinline__ void zfft_768(double* sre, double* sim, const double2* tws, int nzp) {
-    zstage<NCOL, 768, 4, 768, 0, 31, 0>(sre, sim, tws, nzp);
-    zstage<NCOL, 768, 8, 192, 0, 31, 192>(sre, sim, tws, nzp);
-    zstage<NCOL, 768, 8, 24, 0, 31, 216>(sre, sim, tws, nzp);
-    zstage<NCOL, 768, 3, 3, 0, 31, 219>(sre, sim, tws, nzp);
-}
-// does the compile-time path cover this (tile, z length, column layout)?  (host and device agree through this function)
-__host__ __device__ inline bool zspec_applies(int lcol, int nz, int pad_shift, int swz) {
-    (void)lcol;
-    return (nz == 64 && pad_shift == 3 && !swz) || ((nz == 256 || nz == 512 || nz == 1024) && swz) || (nz == 768 && pad_shift == 31 && !swz);
-}
-// z lengths whose columns use the XOR swizzle (chosen by the host before the tile is sized)
-__host__ __device__ inline bool zswizzle_wanted(int lcol, int nz) {
-    (void)lcol;
-    return nz == 256 || nz == 512 || nz == 1024;
-}
+// z lengths with compile-time stages (and the interleaved tile); host and device agree through this function
+__host__ __device__ inline bool zspec_length(int nz) { return nz == 64 || nz == 256 || nz == 512 || nz == 768 || nz == 1024; }
 
 #ifndef MDSF_SPLAT_MINB
 #define MDSF_SPLAT_MINB 2
@@ -207,7 +191,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
     double* slots = reinterpret_cast<double*>(reinterpret_cast<char*>(rbuf) + NREC * 24);      // [NS][SUB][SLOTG] / [2][NCOL]
     const unsigned slots_s = (unsigned)__cvta_generic_to_shared(slots);
     bool ovf = false;
-    const bool zspec = FUSE && tws_g != nullptr;
+    const bool zspec = FUSE && tws_g != nullptr && gp.zilv;
     double2* tws_s = reinterpret_cast<double2*>(reinterpret_cast<char*>(smem) + tws_off);
     if (threadIdx.x == 0) s_next = MDSF_SPLAT_WARPS;
     if (zspec && tws_off > 0) {                               // the twiddles arrive behind the splat
@@ -352,11 +336,12 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
 #pragma unroll
             for (int kk = 0; kk < KZZ; ++kk) {
                 const int z = s * ZW + zlz + ZLNZ * kk;
-                double* cell = (part ? tile_im : tile_re) + (size_t)(cg * NCL) * nzp + zpos(z, gp.zswz, gp.pad_shift);
+                double* cell = smem + tile_index(gp, NCOL, cg * NCL, z, part);
+                const int cstride = gp.zilv ? 2 * nzp : nzp;            // doubles between consecutive columns
 #pragma unroll
                 for (int c = 0; c < NCL; ++c) {
                     any |= acc[c][kk];
-                    if (z < nz) cell[(size_t)c * nzp] = fx_to_double(acc[c][kk]) * gp.fx_inv;
+                    if (z < nz) cell[(size_t)c * cstride] = fx_to_double(acc[c][kk]) * gp.fx_inv;
                 }
             }
             ovf |= (any >> 62) != 0;
@@ -373,7 +358,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
         const int zbase = s * ZW + zl;                        // my cells: x = X0 + i, y = Y0 + cy, z = zbase + ZLN * k (lanes walk z: conflict-free stores)
         {
             const int f = 2 * q + part;
-            double* row = (part ? tile_im : tile_re) + (size_t)cy * nzp;        // column (i, cy) at row + i*TY*nzp
+            const int cstride = gp.zilv ? 2 * nzp : nzp;                        // doubles between consecutive columns
             if (MODE == SPLAT_DENSITY) {
 #pragma unroll
                 for (int i = 0; i < TX; ++i) {
@@ -382,7 +367,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
 #pragma unroll
                     for (int k = 0; k < KZ; ++k) {
                         const int z = zbase + ZLN * k;
-                        if (slab_ok && z < nz) row[(size_t)i * TY * nzp + zpos(z, gp.zswz, gp.pad_shift)] = live ? src[z] : 0.0;
+                        if (slab_ok && z < nz) smem[tile_index(gp, NCOL, i * TY + cy, z, part)] = live ? src[z] : 0.0;
                     }
                 }
             } else {
@@ -508,11 +493,11 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
             for (int k = 0; k < KZ; ++k) {
                 const int z = zbase + ZLN * k;
                 const bool live = slab_ok && z < nz;
-                double* cell = row + zpos(z, gp.zswz, gp.pad_shift);
+                double* cell = smem + tile_index(gp, NCOL, cy, z, part);             // column (i, cy) = i * TY + cy
 #pragma unroll
                 for (int i = 0; i < TX; ++i) {
                     any |= acc[i][k];
-                    if (live) cell[i * TY * nzp] = fx_to_double(acc[i][k]) * gp.fx_inv;
+                    if (live) cell[i * TY * cstride] = fx_to_double(acc[i][k]) * gp.fx_inv;
                 }
             }
             ovf |= (any >> 62) != 0;                           // terms are >= 0: bit 62 or 63 set in any sum
@@ -540,8 +525,8 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
             const int cc = i / nz, z = i - cc * nz;
             const int x = X0 + (cc >> LTY), y = Y0 + (cc & (TY - 1));
             if (x < gp.n[0] && y < gp.n[1]) {
-                const int a = cc * nzp + zpos(z, gp.zswz, gp.pad_shift);
-                dens_dump[(((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + z] = make_double2(tile_re[a], tile_im[a]);
+                dens_dump[(((long long)q * gp.n[0] + x) * gp.n[1] + y) * nz + z] =
+                    make_double2(smem[tile_index(gp, NCOL, cc, z, 0)], smem[tile_index(gp, NCOL, cc, z, 1)]);
             }
         }
     }
@@ -554,11 +539,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
         // the tile size a grid selects fixes its z length class: compile-time stages for the power-of-two lengths
         // (and 768) the BASELINE configs use, the generic run-time stages for everything else
         if (!zspec) fft_tile_z(tile_re, tile_im, twr, twi, zplan, NCOL, nzp, gp.pad_shift);      // ends with a barrier
-        else if (nz == 64) zfft_64<NCOL>(tile_re, tile_im, tws_s, nzp);
-        else if (nz == 256) zfft_256<NCOL>(tile_re, tile_im, tws_s, nzp);
-        else if (nz == 512) zfft_512<NCOL>(tile_re, tile_im, tws_s, nzp);
-        else if (nz == 1024) zfft_1024<NCOL>(tile_re, tile_im, tws_s, nzp);
-        else zfft_768<NCOL>(tile_re, tile_im, tws_s, nzp);
+        else zfft2<NCOL>(reinterpret_cast<double2*>(smem), tws_s, nzp, nz);
     }
     // store: every tile row x is one run of TY * Nz contiguous cells (plain layout), or Nz / lw runs of TY * lw cells
     // (chunked layout): 16-byte stores, consecutive threads -> consecutive addresses.  One flat index over the tile,
@@ -584,7 +565,11 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
             o = (long long)ch * cs_ + (long long)(xx * rowlen + yy * gp.lw + zw);
         }
         if (yy >= yvalid) continue;
-        const int a = ((xx << LTY) + yy) * nzp + zpos(z, gp.zswz, gp.pad_shift);
-        dst0[o] = make_double2(tile_re[a], tile_im[a]);
+        if (gp.zilv) {
+            dst0[o] = reinterpret_cast<const double2*>(smem)[((xx << LTY) + yy) * nzp + z];
+        } else {
+            const int a = ((xx << LTY) + yy) * nzp + zpos(z, gp.zswz, gp.pad_shift);
+            dst0[o] = make_double2(tile_re[a], tile_im[a]);
+        }
     }
 }

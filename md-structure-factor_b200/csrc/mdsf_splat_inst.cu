@@ -18,8 +18,7 @@ size_t mdsf_splat_smem(int lcol, int sub, int nzp, int nz, int zlane) {
     return (size_t)2 * ((size_t)1 << lcol) * nzp * sizeof(double) + area;
 }
 
-bool mdsf_zspec_applies(int lcol, int nz, int pad_shift, int swz) { return zspec_applies(lcol, nz, pad_shift, swz); }
-bool mdsf_zswizzle_wanted(int lcol, int nz) { return zswizzle_wanted(lcol, nz); }
+bool mdsf_zspec_length(int nz) { return zspec_length(nz); }
 
 template <int LCOL, int MODE>
 static cudaError_t launch1(bool fuse, dim3 grid, size_t smem, cudaStream_t st, const SplatArgs& a) {
