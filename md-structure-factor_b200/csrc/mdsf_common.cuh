@@ -9,7 +9,9 @@
 #define MDSF_MAX_RADIX_STAGES 12
 #define MDSF_MAX_STAMP 1023        // 2*A: stamp indices travel in 10-bit fields / int offsets
 #ifndef MDSF_SPLAT_WARPS
-#define MDSF_SPLAT_WARPS 12        // warps per splat CTA: 2 CTAs x 384 threads leave 80 registers per thread (16 warps: 64 registers, the inner loop re-materialised its lane constants; measured c3 splat 10.97 -> 9.92 ms)
+#define MDSF_SPLAT_WARPS 16        // warps per splat CTA: 2 CTAs x 512 threads at 64 registers.  With the interleaved tile the z stages no longer
+                                   // spill at 64 registers, 32 work items are exactly two per warp and 512 butterflies per stage one per thread
+                                   // (c3 splat 19.1 -> 17.2 ms against 12 warps at 80 registers; c1 / c4 lose 3-4 %)
 #endif
 
 // Frame-invariant geometry, passed to kernels by value.
