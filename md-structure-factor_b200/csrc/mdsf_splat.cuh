@@ -256,9 +256,9 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
         bounds(item, lbeg, n);
         fetch(lbeg, n, 0);
         while (item < nitems) {
-            int item2 = 0;
-            if (lane == 0) item2 = atomicAdd(&s_next, 1);
-            item2 = __shfl_sync(0xffffffffu, item2, 0);
+            // (static round robin: with one item claimed ahead a dynamic counter hands the items out in start order anyway,
+            // and its shared-memory atomic + shuffle sat on every item's critical path)
+            const int item2 = item + MDSF_SPLAT_WARPS;
             unsigned lbeg2;
             int n2;
             bounds(item2, lbeg2, n2);
