@@ -251,14 +251,41 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
                 if (MODE != SPLAT_ORTHO) { const uint4 t = prec[2 * (size_t)(lb + b + lane) + 1]; nxa = make_uint2(t.x, t.y); }
             }
         };
-        int item = warp, n = 0;
+        // Item order.  The list lengths of all items of the CTA are known up front (s_bnd), and the warps meet at a CTA barrier
+        // before the z stages: the longest pair of lists decides when (ncu: 10 % of all warp time waited there).  With at most
+        // two items per warp, warp 0 ranks the items by length (bitonic sort of 32 keys in registers) and warp w takes
+        // the w-th longest and the w-th shortest.  Otherwise: static round robin (with one item claimed ahead a dynamic
+        // counter hands the items out in start order anyway, and its atomic sat on every item's critical path).
+        __shared__ unsigned char s_order[32];
+        const bool ranked = bnd_s && nitems <= 32 && nitems > MDSF_SPLAT_WARPS && 2 * MDSF_SPLAT_WARPS >= nitems;
+        if (ranked) {
+            if (warp == 0) {
+                unsigned lb0; int c0;
+                bounds(lane, lb0, c0);
+                unsigned key = lane < nitems ? ((unsigned)(0xffffff - min(c0, 0xffffff)) << 8) | (unsigned)lane : 0xffffffffu;
+#pragma unroll
+                for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        const unsigned o = __shfl_xor_sync(0xffffffffu, key, j);
+                        const bool asc = (lane & k) == 0, low = (lane & j) == 0;
+                        key = (asc == low) ? min(key, o) : max(key, o);
+                    }
+                s_order[lane] = (unsigned char)(key & 255u);         // position p: p-th longest list
+            }
+            __syncthreads();
+        }
+        auto item_at = [&](int k) -> int {                               // k-th item of this warp (>= nitems: none)
+            if (!ranked) return warp + k * MDSF_SPLAT_WARPS;
+            const int p = k == 0 ? warp : (k == 1 ? 2 * MDSF_SPLAT_WARPS - 1 - warp : nitems);
+            return p < nitems ? (int)s_order[p] : nitems;
+        };
+        int turn = 0, item = item_at(0), n = 0;
         unsigned lbeg = 0u;
         bounds(item, lbeg, n);
         fetch(lbeg, n, 0);
         while (item < nitems) {
-            // (static round robin: with one item claimed ahead a dynamic counter hands the items out in start order anyway,
-            // and its shared-memory atomic + shuffle sat on every item's critical path)
-            const int item2 = item + MDSF_SPLAT_WARPS;
+            const int item2 = item_at(++turn);
             unsigned lbeg2;
             int n2;
             bounds(item2, lbeg2, n2);
