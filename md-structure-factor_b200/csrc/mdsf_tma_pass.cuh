@@ -124,38 +124,41 @@ tma_pass_kernel(TPParams p)
 #pragma unroll
     for (int k = 0; k < 8; ++k) { acc[k] = 0.0; pv[k] = 0.0; }
     const unsigned long long polx = policy_evict_first();
-    auto issue_x = [&](long long i) {                            // my 8 x 16 bytes of x-pass tile i -> its ring buffer
-        if (i >= ntile) return;
-        const long long k = i / p.npairs;
-        const int q = (int)(i - k * p.npairs);
+    // x pass bookkeeping without divisions in the tile loop (64-bit divides were half of this kernel's instructions): the
+    // load stream (two tiles ahead) and the compute stream each carry (pair q, ring buffer b, source / P pointer) and step them.
+    const long long pair_cells = (long long)p.nch * p.nx * row_stride;       // cells of one pair volume
+    auto group_offset = [&](long long k) {                       // cell offset of (chunk, y) group blockIdx.x + k * gridDim.x, x = 0
         const long long g = blockIdx.x + k * (long long)gridDim.x;
         const int ch = (int)(g / p.ny), y = (int)(g - (long long)ch * p.ny);
-        const double2* src = p.vol + (((long long)q * p.nch + ch) * p.nx + bf) * row_stride + (long long)y * 8 + f;
-        const int b = (int)(i % NBUF);
-        const unsigned dst = smem_u32(tp_smem + (size_t)b * TILE + bf * 8 + f);
+        return ((long long)ch * p.nx) * row_stride + (long long)y * 8;
+    };
+    long long li = 0, lk = 0;                                    // load stream: tile index, group round
+    int lq = 0, lb = 0;
+    const double2* lsrc = p.vol + group_offset(0) + (long long)bf * row_stride + f;
+    auto issue_x = [&]() {                                       // my 8 x 16 bytes of the next x-pass tile -> its ring buffer
+        if (li >= ntile) return;
+        const unsigned dst = smem_u32(tp_smem + (size_t)lb * TILE + bf * 8 + f);
+        const double2* src = lsrc + (long long)lq * pair_cells;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + (unsigned)(j * 64 * 8 * 16)),
                          "l"(src + (long long)(j * 64) * row_stride), "l"(polx) : "memory");
-        cp_async_arrive_noinc(&full[b]);
+        cp_async_arrive_noinc(&full[lb]);
+        ++li;
+        lb = (lb + 1 == NBUF) ? 0 : lb + 1;
+        if (++lq == p.npairs) { lq = 0; ++lk; lsrc = p.vol + group_offset(lk) + (long long)bf * row_stride + f; }
     };
-    if (XPASS) { issue_x(0); issue_x(1); }
+    if (XPASS) { issue_x(); issue_x(); }
+    int b = 0, cq = 0;                                           // compute stream: ring buffer, pair
+    unsigned use = 0;
+    long long ck = 0;
+    double* Pt = XPASS ? p.P + group_offset(0) + f : nullptr;
     for (long long i = 0; i < ntile; ++i) {
-        const int b = (int)(i % NBUF);
-        const unsigned use = (unsigned)(i / NBUF);
         double2* tile = tp_smem + (size_t)b * TILE;
-        int q = 0;
-        double* Pt = nullptr;
-        if (XPASS) {
-            const long long k = i / p.npairs;
-            q = (int)(i - k * p.npairs);
-            const long long g = blockIdx.x + k * (long long)gridDim.x;
-            const int ch = (int)(g / p.ny), y = (int)(g - (long long)ch * p.ny);
-            Pt = p.P + ((long long)ch * p.nx) * row_stride + (long long)y * 8 + f;
-            if (q == p.npairs - 1) {                             // my 8 cells of P, needed after this tile's last stage
+        const int q = cq;
+        if (XPASS && q == p.npairs - 1) {                        // my 8 cells of P, needed after this tile's last stage
 #pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) pv[k2] = __ldcs(Pt + (long long)(bf * 8 + k2) * row_stride);
-            }
+            for (int k2 = 0; k2 < 8; ++k2) pv[k2] = __ldcs(Pt + (long long)(bf * 8 + k2) * row_stride);
         }
         mbar_wait(&full[b], use & 1);
         int a[8];
@@ -166,7 +169,7 @@ tma_pass_kernel(TPParams p)
 #pragma unroll
         for (int k = 0; k < 8; ++k) tile[a[k]] = make_double2(xr[k], xi[k]);
         tp_bar();
-        if (XPASS) issue_x(i + 2);                               // (everybody is past the last stage of tile i - 1: its buffer is free)
+        if (XPASS) issue_x();                                    // tile i + 2 (everybody is past the last stage of tile i - 1: its buffer is free)
         tp_load_butterfly<64>(tile, a, xr, xi);
         dft8(xr, xi);
         tp_twiddle(w2, xr, xi);
@@ -191,5 +194,8 @@ tma_pass_kernel(TPParams p)
                 }
             }
         }
+        b = (b + 1 == NBUF) ? 0 : b + 1;
+        if (b == 0) ++use;
+        if (XPASS && ++cq == p.npairs) { cq = 0; ++ck; Pt = p.P + group_offset(ck) + f; }
     }
 }
