@@ -5,10 +5,12 @@
 //   x pass: tile (pair, chunk, y) is 512 rows of 128 bytes, 64 KB apart.  128-byte bulk copies are far too slow for that
 //           (measured: 27 ms per 16 c3 frames, the copy engine retires one small copy per ~60 cycles); every compute thread
 //           issues eight 16-byte cp.async copies instead (8 threads = one row), two tiles ahead, completion counted on the
-//           buffer's mbarrier (cp.async.mbarrier.arrive.noinc).  The x pass stays at 53 % of the HBM peak with either kernel:
-//           one DRAM page activation per 128-byte piece.  Tried and dropped: a warp that requests the contiguous runs the
+//           buffer's mbarrier (cp.async.mbarrier.arrive.noinc).  Tried and dropped: a warp that requests the contiguous runs the
 //           G CTAs' pieces form per x row into L2 ahead of the copies (cp.async.bulk.prefetch.L2) -- DRAM reads doubled
-//           (35.4 GB instead of 18.3 GB per 16 frames, 11.2 ms): the CTAs drift apart and the lines are gone before use.
+//           (35.4 GB instead of 18.3 GB per 16 frames, 11.2 ms): the CTAs drift apart and the lines are gone before use;
+//           clusters of 2 / 4 CTAs kept in step by a cluster barrier per tile (8.2 / 16.8 ms); the .L2::256B hint (no change).
+//           The pass is bound by its arithmetic (three barrier-separated radix-8 stages, ~3 us per tile and SM), not by DRAM:
+//           4.22 ms per 16 c3 frames = 70 % of the HBM peak once the tile loop carried pointers instead of 64-bit divisions.
 // One CTA per SM walks its tiles (unit u = blockIdx.x + k * gridDim.x) through a ring of three 64 KB buffers:
 //   producer warp:  [y: wait until the compute warps released the buffer, store it (cp.async.bulk shared -> global), wait
 //                   until the store has read it]  ->  arm the buffer's mbarrier with the tile's byte count  ->  issue the
