@@ -54,7 +54,7 @@ template <int LCOL, int SUB> struct SplatGeom {
 // and a warp claims its next item and requests that item's first records before it works on the current one, so the
 // only global round trip left on an item's critical path is the one of the factor tables.
 #ifndef MDSF_ZL_RB
-#define MDSF_ZL_RB 8
+#define MDSF_ZL_RB 16
 #endif
 template <int LCOL> struct ZLaneGeom {
     static constexpr int NCOL = 1 << LCOL, NCL = NCOL < 8 ? NCOL : 8, CG = NCOL / NCL, ZLN = 32 / CG, KZ = 8 / NCL;
