@@ -58,6 +58,36 @@ def uniform_box(natoms, L, composition, seed):
     return typ, base, box
 
 
+def _test_system():
+    """c1 as specified: frame 0 = the reference's test/test_system.gro (a gzip copy travels as
+    tests/golden/test_system.gro.gz: 55 680 atoms, hexagonal box, atom NAMES as labels, sodium stamps of 34^3 cells), transformed
+    like main_gromacs.py:204-207 (theta = 120), Sres = 1 -> 88 x 88 x 84; frames = frame 0 + N(0, 0.3 A).  None when the fixture
+    is not there (the xtc of the reference is a missing blob anyway)."""
+    import gzip
+    import os
+    import shutil
+    import tempfile
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, os.pardir, "tests", "golden", "test_system.gro.gz")
+    if not os.path.exists(path):
+        return None
+    import dens
+    import load_traj
+    with tempfile.TemporaryDirectory() as tmp:
+        gro = os.path.join(tmp, "test_system.gro")
+        with gzip.open(path, "rb") as src, open(gro, "wb") as dst:
+            shutil.copyfileobj(src, dst)
+        names, coords, dims = load_traj.read_gro_frames(gro)
+    theta = 120.0 * math.pi / 180.0
+    base = coords[0].copy()
+    base[:, 1] = base[:, 1] / np.sin(theta)
+    base[:, 0] = base[:, 0] - base[:, 1] * np.cos(theta)
+    box = dims[0].astype(np.float32)
+    rad = dens.load_radii(os.path.join(here, "radii.txt"))
+    return dict(typ=np.array(names), base=_inside(base, box), box=box, ucell=ucell_for(120.0), sres=1.0, grid=(88, 88, 84), jitter=0.3,
+                seed0=1000, rad=rad, desc="test/test_system.gro of the reference (55680 atoms, hexagonal box), monoclinic transform, 88x88x84, theta=120")
+
+
 LLC_COMPOSITION = [("C", 0.35), ("H", 0.58), ("O", 0.06), ("N", 0.003), ("NA", 0.007)]
 BOX_COMPOSITION = [("C", 0.40), ("H", 0.50), ("O", 0.08), ("N", 0.01), ("NA", 0.01)]
 
@@ -69,7 +99,12 @@ def get(name):
         n = 256
         return dict(typ=typ, base=base, box=box, ucell=np.eye(3), sres=float(box[0]) / n * (1 + 1e-6), grid=(n, n, n),
                     jitter=0.5, seed0=2000, rad=RAD, desc="SPC water 26^3 replicas, 105456 atoms, 256^3 grid, ucell=I")
-    if name == "c1":   # size/composition of test_system.gro (55 680 atoms, hexagonal 86.59 x 86.59 x 83.43 A), theta=120
+    if name == "c1":   # BASELINE configs[0]: the reference's own fixture test/test_system.gro through the CLI's monoclinic transform
+        real = _test_system()
+        if real is not None:
+            return real
+        name = "c1u"
+    if name == "c1u":  # size/composition of test_system.gro (55 680 atoms, hexagonal 86.59 x 86.59 x 83.43 A), theta=120, uniform random
         rng = np.random.default_rng(1000)
         box = np.array([86.5915, 86.591576, 83.431305], dtype=np.float32)
         natoms = 55680
