@@ -137,6 +137,21 @@ def test_load_gro_and_traj_npz_layout(tmp_path):
     assert np.array_equal(xyz5f[0], xyz5)
 
 
+def test_c1_workload_is_the_reference_fixture():
+    """BASELINE configs[0]: workloads.get('c1') is the reference's test/test_system.gro frame (gzip copy under tests/golden),
+    monoclinic-transformed like main_gromacs.py:204-207, labelled with the atom NAMES (load_traj.py:110), 88 x 88 x 84 at Sres = 1."""
+    w = __import__("workloads")
+    c = w.get("c1")
+    assert c["base"].shape == (55680, 3) and c["base"].dtype == np.float32 and c["grid"] == (88, 88, 84)
+    assert "test_system.gro" in c["desc"] and len(set(c["typ"])) > 100 and "NA" in set(c["typ"])
+    assert all(label in c["rad"] for label in set(c["typ"]))            # every name has a form factor (radii.txt superset)
+    n, dr = mdsf_b200.dens._grid(np.asarray(c["box"]), c["sres"])
+    assert tuple(int(v) for v in n) == c["grid"]
+    assert np.all(c["base"] > 0) and np.all(c["base"] < c["box"])
+    u = w.get("c1u")
+    assert u["base"].shape == (55680, 3) and "LLC-composition" in u["desc"]
+
+
 def test_workloads_are_deterministic_and_inside_the_box():
     w = __import__("workloads")
     c = w.get("tiny")
