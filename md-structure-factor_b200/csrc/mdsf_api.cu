@@ -354,7 +354,6 @@ extern "C" int mdsf_create(const mdsf_config* cfg, mdsf_handle** out) {
         const size_t tile_budget = (size_t)env_int("MDSF_TILE_KB", 112) * 1024;      // 112 KB: two CTAs per SM
         while (gp.lcol > 2 && mdsf_splat_smem(gp.lcol, 1, gp.nzp, gp.n[2]) > tile_budget) --gp.lcol;
     }
-    gp.zswz = 0;
     gp.zilv = 0;
     if (h->native_fft && mdsf_zspec_length(gp.n[2]) && env_int("MDSF_ZILV", 1) != 0) {
         // compile-time z stages on the interleaved tile: [col][nz + 1] cells of 16 bytes (odd column stride, no padding inside a column)

@@ -28,7 +28,6 @@ struct GridParams {
     int natoms;
     int nzp;            // padded z length of one column in shared memory
     int pad_shift;      // column position p is stored at p + (p >> pad_shift) ...
-    int zswz;           // ... or at p ^ swizzle(p) (mdsf_splat.cuh zpos; unused since the interleaved tile)
     int zilv;           // 1: interleaved tile [col][nz + 1] of 16-byte complex cells (compile-time z path; mdsf_splat.cuh tile_index)
     // volume layout: element (x, y, z) of a pair volume sits at ((z / lw * Nx + x) * Ny + y) * lw + z % lw.
     // lw = Nz is the plain C order [x][y][z]; a smaller lw makes every (x, z-chunk) row block of the y pass one

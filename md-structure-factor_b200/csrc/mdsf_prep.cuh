@@ -112,7 +112,7 @@ __device__ __forceinline__ int axis_count(int ir, int A, int N, int lt) {
 template <typename F>
 __device__ __forceinline__ void walk_pairs_warp(const AtomRec* __restrict__ recs, const unsigned* __restrict__ perm,
                                                 long long slot0, long long total, const GridParams& gp, const TypeTable& tt,
-                                                AtomRec* __restrict__ s_rec /* [32] */, unsigned* __restrict__ s_idx /* [32] */, F&& fn) {
+                                                AtomRec* __restrict__ s_rec /* [32] */, unsigned* __restrict__ s_idx /* [2][32]: atom index, frame */, F&& fn) {
     const int lane = threadIdx.x & 31;
     const int ltx = (gp.lcol + 1) >> 1, lty = gp.lcol >> 1;
     int nys = 1, nu = 0;
@@ -122,7 +122,9 @@ __device__ __forceinline__ void walk_pairs_warp(const AtomRec* __restrict__ recs
         const uint4* src = reinterpret_cast<const uint4*>(recs + idx);
         uint4* dst = reinterpret_cast<uint4*>(s_rec + lane);
         dst[0] = __ldcs(src); dst[1] = __ldcs(src + 1); dst[2] = __ldcs(src + 2);
-        s_idx[lane] = (unsigned)idx;
+        const int f0 = (int)(idx / gp.natoms);                  // (once per atom, not once per work unit)
+        s_idx[lane] = (unsigned)(idx - (long long)f0 * gp.natoms);
+        s_idx[32 + lane] = (unsigned)f0;
         const AtomRec& rec = s_rec[lane];
         const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
         if (!rec.pad_ && Ax > 0 && Ay > 0 && Az > 0) {       // atoms K1 rejected have no pairs
@@ -150,8 +152,7 @@ __device__ __forceinline__ void walk_pairs_warp(const AtomRec* __restrict__ recs
         const int nys_o = __shfl_sync(0xffffffffu, nys, o & 31);
         if (u >= tot) continue;
         const AtomRec rec = s_rec[o];
-        const long long idx = (long long)s_idx[o];
-        const int f = (int)(idx / gp.natoms), a = (int)(idx - (long long)f * gp.natoms);
+        const int a = (int)s_idx[o], f = (int)s_idx[32 + o];
         const int Ax = tt.halfw[rec.type * 3 + 0], Ay = tt.halfw[rec.type * 3 + 1], Az = tt.halfw[rec.type * 3 + 2];
         const int local = u - excl_o, kx = local / nys_o, ky = local - kx * nys_o;
         int sx, tX, dx0, dx1, ix0, sy, tY, dy0, dy1, jy0;
@@ -332,7 +333,7 @@ bin_count_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ 
                  GridParams gp, TypeTable tt, int nframes)
 {
     __shared__ __align__(16) AtomRec s_rec[8][32];
-    __shared__ unsigned s_idx[8][32];
+    __shared__ unsigned s_idx[8][64];
     const int warp = threadIdx.x >> 5;
     const long long total = (long long)nframes * gp.natoms;
     for (long long slot0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) & ~31LL; slot0 < total;
@@ -348,7 +349,7 @@ bin_place_kernel(const AtomRec* __restrict__ recs, const unsigned* __restrict__ 
                  unsigned nkeys, unsigned long long cap, int* __restrict__ err_flag)
 {
     __shared__ __align__(16) AtomRec s_rec[8][32];
-    __shared__ unsigned s_idx[8][32];
+    __shared__ unsigned s_idx[8][64];
     if ((unsigned long long)cur[nkeys] > cap) {         // total pairs (no list has index nkeys, so nobody moves this entry); cannot
                                                         // exceed the capacity unless the host bound is wrong: refuse to overrun
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(err_flag, 4);

@@ -2,21 +2,21 @@
 //
 // Replaces the per-atom Python loop dens.py:283-308 and the 26-region fold dens.py:86-108.
 // A CTA owns 2^LCOL (x,y) columns over all z for ONE pair of frames (frame 2q -> real part, frame 2q+1 ->
-// imaginary part).  A warp owns one z slab of the tile at a time: lane = (tile row y, z lane) holds the TX columns of
-// its row x KZ = 8/TX consecutive cells in REGISTERS as 64-bit fixed-point sums (LSB = 2^-52 of the largest
-// Nel/sigma^3); per record it needs EX[0..TX) (the same for every lane: broadcast loads), one EY, its row of the
-// cross-term table and KZ entries of EZ -- a third of the shared-memory wavefronts of a (column, 8 cells) lane.  The warp walks its
-// own (tile, slab) list of pair records (K2): per record the slab's window of the atom's EZ table and the tile's
-// slices of its EX / EY (/ cross-term) tables arrive in a small per-warp staging ring by cp.async, NS-1 records
-// ahead.  EZ entries outside the record's z window are zero-filled by the copy, EX / EY entries of columns outside
-// the stamp come from the zero pads of the table block, so the accumulation is branch-free:
-//     acc[i][k] += int(EX[i] * EY[cy] * C[cy][i] * EZ[zl*KZ + k])   one DFMA (magic-number rounding) + one 64-bit add
-// Integer addition commutes, so the density is bitwise reproducible whatever order K2's atomics filled the lists
-// in -- no float atomics, no shared-memory atomics, no CTA barriers inside the splat.  The fold (incl. the corner
-// rule of dens.py:107) was resolved by K2: every record is one box in destination space.
+// imaginary part).  A warp owns one z slab of the tile at a time and holds its cells in REGISTERS as 64-bit fixed-point
+// sums (LSB = 2^-52 of the largest Nel/sigma^3).  It walks its own (tile, slab) list of pair records (K2); per record:
+//     acc[col][k] += int(EX[i] * EY[j] * C[j][i] * EZ[z])   one DFMA (magic-number rounding) + one 64-bit add
+// EZ entries outside the record's z window are zero, EX / EY entries of columns outside the stamp come from the zero
+// pads of the atom's table block, so the accumulation is branch-free.  Integer addition commutes, so the density is
+// bitwise reproducible whatever order K2's atomics filled the lists in -- no float atomics, no shared-memory atomics,
+// no CTA barriers inside the splat.  The fold (incl. the corner rule of dens.py:107) was resolved by K2: every record
+// is one box in destination space.  Two lane mappings:
+//   * z-lane (ZL, see ZLaneGeom): lanes walk z, a lane holds up to 8 columns; products of a batch of records formed
+//     up front, EZ straight from global memory two records ahead;
+//   * half-warp lists (SUB = 2, 4x4-column tiles): lane = (tile row, z lane) x TX columns x KZ = 8/TX cells, two lists
+//     side by side per warp, table slices staged by cp.async in a per-warp ring NS-1 records ahead.
 // Afterwards the slab sums are converted to fp64 into the shared-memory tile, which is transformed along z in
-// place (native FFT path; compile-time radix stages for Nz = 64 / 256 / 512 / 768 / 1024) and stored: the density
-// never touches HBM.
+// place (native FFT path; compile-time radix stages on an interleaved 16-byte tile for Nz = 64 / 256 / 512 / 768 /
+// 1024, run-time stages on split re / im planes otherwise) and stored: the density never touches HBM.
 #pragma once
 #include "mdsf_common.cuh"
 #include "mdsf_fft.cuh"
@@ -80,14 +80,8 @@ __device__ __forceinline__ double fx_to_double(long long v) {
 }
 
 // ------------------------------------------------------------------ z FFT of the tile, compile-time radices
-// Position of cell z inside a shared-memory column.  Power-of-two z lengths use an XOR swizzle of the bank bits
-// (bits 0-2 ^= bits 4-6, bit 3 ^= bit 6): the 16 lanes of a half-warp then hit 16 different 8-byte banks in every
-// stage -- 16 consecutive cells (first stages), two runs of 8 cells 64 apart (the stride-8 stage) and 16 cells 8 apart
-// (last stage).  The padded form p + (p >> pad) of the generic path costs the first stages a third of their
-// wavefronts (a run of 16 cells straddles a pad and folds onto 15 banks).
-__device__ __forceinline__ int zpos(int z, int swz, int pad) {
-    return swz ? (z ^ (((z >> 4) & 7) | (((z >> 6) & 1) << 3))) : z + (z >> pad);
-}
+// Position of cell z inside a column of the split re / im planes (run-time z stages): padded form p + (p >> pad).
+__device__ __forceinline__ int zpos(int z, int pad) { return z + (z >> pad); }
 
 // In-place decimation-in-frequency stages with every stride and index split a constant (same scheme and output order as
 // fft_stage).  Only w = w_N^(n2 N/L) is read per butterfly (per-stage table tws[TOFF + n2], host-built); its powers
@@ -99,7 +93,7 @@ __device__ __forceinline__ int zpos(int z, int swz, int pad) {
 // row stride -- no swizzle arithmetic, half the shared-memory instructions of the split re / im planes.
 __device__ __forceinline__ int tile_index(const GridParams& gp, int ncol, int c, int z, int part) {
     return gp.zilv ? (((c * gp.nzp + z) << 1) + part)
-                   : (part * ncol * gp.nzp + c * gp.nzp + (gp.zswz ? (z ^ (((z >> 4) & 7) | (((z >> 6) & 1) << 3))) : z + (z >> gp.pad_shift)));
+                   : (part * ncol * gp.nzp + c * gp.nzp + z + (z >> gp.pad_shift));
 }
 
 template <int NCOL, int N, int R, int L, int TOFF>
@@ -595,7 +589,7 @@ splat_zfft_kernel(const uint4* __restrict__ prec /* 32-byte pair records */, con
         if (gp.zilv) {
             dst0[o] = reinterpret_cast<const double2*>(smem)[((xx << LTY) + yy) * nzp + z];
         } else {
-            const int a = ((xx << LTY) + yy) * nzp + zpos(z, gp.zswz, gp.pad_shift);
+            const int a = ((xx << LTY) + yy) * nzp + zpos(z, gp.pad_shift);
             dst0[o] = make_double2(tile_re[a], tile_im[a]);
         }
     }

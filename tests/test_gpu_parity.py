@@ -270,6 +270,23 @@ def test_cli_lattice_mode_gives_bragg_peaks_only(mdsf, tmp_path, monkeypatch):
     assert sf[~on].max() < 1e-20 * sf[on].max()
 
 
+def test_cli_random_gas_mode_matches_oracle(mdsf, tmp_path, monkeypatch):
+    """The CLI's random-gas mode (reference main_gromacs.py:160-186, -RC / -RT / -RL): float64 coordinates drawn by numpy, cached
+    as RAND.npz, S(q) written as RND.npz.  The coordinates the CLI cached go through the oracle: same S(q) within 1e-5 per bin."""
+    import importlib
+    from oracle import dens_oracle as orc
+    monkeypatch.chdir(tmp_path)
+    cli = importlib.import_module("main_gromacs")
+    assert cli.main(["-RC", "150", "-RT", "2", "-RL", "C", "-SR", "5.0", "-ct", "90", "-RS", "7"]) == 0
+    cache, out = np.load("RAND.npz", allow_pickle=True), np.load("RND.npz")
+    assert cache["coords"].shape == (2, 150, 3) and cache["coords"].dtype == np.float64 and np.all(cache["dims"] == 100.0)
+    assert sorted(out.files) == sorted(["sf", "sfplt", "L", "N", "kgrid", "kgridplt"]) and tuple(out["N"]) == (20, 20, 20)
+    rad = mdsf.dens.load_radii(os.path.join(os.path.dirname(mdsf.dens.__file__), "radii.txt"))
+    ref = orc.structure_factor(cache["coords"].copy(), cache["dims"].copy(), np.array(["C"] * 150), rad, np.eye(3), 5.0)
+    rel, norm = sf_errors(out["sf"], ref["sf"])
+    assert rel <= 1e-5 and norm <= 1e-12
+
+
 def test_full_size_c2_frame_against_oracle(mdsf):
     """One full-size frame of the benchmark workload (105 456 atoms, 256^3): bit-exact cell indices,
     density and S(q) against the CPU oracle (takes ~5 s of numpy)."""
