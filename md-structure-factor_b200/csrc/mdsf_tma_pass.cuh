@@ -31,7 +31,8 @@
 #define MDSF_TP_NBUF 3
 #define MDSF_TP_N 512
 #define MDSF_TP_TILE (MDSF_TP_N * 8)               // cells of one tile
-#define MDSF_TP_SMEM (MDSF_TP_NBUF * MDSF_TP_TILE * 16)
+#define MDSF_TP_NTW 72                             // twiddle rows: 64 (stage 1) + 8 (stage 2), 7 powers each
+#define MDSF_TP_SMEM (MDSF_TP_NBUF * MDSF_TP_TILE * 16 + MDSF_TP_NTW * 7 * 16)
 
 struct TPParams {
     double2* vol;              // [npairs][nch][Nx][Ny][8]
@@ -55,11 +56,27 @@ __device__ __forceinline__ void tp_load_butterfly(const double2* __restrict__ ti
         xr[j] = v.x; xi[j] = v.y;
     }
 }
-__device__ __forceinline__ void tp_twiddle(double2 w1, double (&xr)[8], double (&xi)[8]) {
+// w^1 .. w^7 of one table entry, by the multiplication tree w^k = w^(k/2) * w^(k - k/2) (what every butterfly used to do
+// for itself: 24 of its ~108 fp64 instructions; the passes are bound by exactly those)
+__device__ __forceinline__ void tp_powers(double2 w1, double2* __restrict__ out7) {
     double wr[8], wi[8];
     wr[1] = w1.x; wi[1] = w1.y;
 #pragma unroll
-    for (int k = 2; k < 8; ++k) {                  // w^k = w^(k/2) * w^(k - k/2)
+    for (int k = 2; k < 8; ++k) {
+        const int ka = k >> 1, kb = k - ka;
+        wr[k] = wr[ka] * wr[kb] - wi[ka] * wi[kb];
+        wi[k] = wr[ka] * wi[kb] + wi[ka] * wr[kb];
+    }
+#pragma unroll
+    for (int k = 1; k < 8; ++k) out7[k - 1] = make_double2(wr[k], wi[k]);
+}
+// x pass: powers in registers per butterfly (its stage loads already wait on shared memory: the table made it slower,
+// 4.24 -> 5.26 ms); y pass: table (5.85 -> 5.63 ms = 93 % of the HBM peak)
+__device__ __forceinline__ void tp_twiddle_w1(double2 w1, double (&xr)[8], double (&xi)[8]) {
+    double wr[8], wi[8];
+    wr[1] = w1.x; wi[1] = w1.y;
+#pragma unroll
+    for (int k = 2; k < 8; ++k) {
         const int ka = k >> 1, kb = k - ka;
         wr[k] = wr[ka] * wr[kb] - wi[ka] * wi[kb];
         wi[k] = wr[ka] * wi[kb] + wi[ka] * wr[kb];
@@ -68,6 +85,15 @@ __device__ __forceinline__ void tp_twiddle(double2 w1, double (&xr)[8], double (
     for (int k = 1; k < 8; ++k) {
         const double yr = xr[k] * wr[k] - xi[k] * wi[k];
         xi[k] = xr[k] * wi[k] + xi[k] * wr[k];
+        xr[k] = yr;
+    }
+}
+__device__ __forceinline__ void tp_twiddle(const double2* __restrict__ w7, double (&xr)[8], double (&xi)[8]) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        const double2 w = w7[k - 1];
+        const double yr = xr[k] * w.x - xi[k] * w.y;
+        xi[k] = xr[k] * w.y + xi[k] * w.x;
         xr[k] = yr;
     }
 }
@@ -85,6 +111,8 @@ tma_pass_kernel(TPParams p)
     const long long mine = nunits > blockIdx.x ? (nunits - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long ntile = XPASS ? mine * p.npairs : mine;      // tiles this CTA moves
     const long long row_stride = (long long)p.ny * 8;            // cells between x rows
+    double2* twp = tp_smem + (size_t)NBUF * TILE;                 // [MDSF_TP_NTW][7] twiddle powers, built once per CTA
+    if (!XPASS && threadIdx.x < MDSF_TP_NTW) tp_powers(__ldg(p.tws + threadIdx.x), twp + threadIdx.x * 7);
     if (threadIdx.x == 0) {
         for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], XPASS ? MDSF_TP_THREADS : 1); mbar_init(&rel[b], MDSF_TP_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,8 +147,9 @@ tma_pass_kernel(TPParams p)
 
     // ---------------------------------------------------------------------- compute warps
     const int f = threadIdx.x & 7, bf = threadIdx.x >> 3;
-    const double2 w1 = __ldg(p.tws + bf);                    // stage 1: L = 512, M = 64, n2 = bf
-    const double2 w2 = __ldg(p.tws + 64 + (bf & 7));         // stage 2: L = 64, M = 8, n2 = bf % 8
+    const double2* w1 = twp + bf * 7;                        // stage 1: L = 512, M = 64, n2 = bf
+    const double2* w2 = twp + (64 + (bf & 7)) * 7;           // stage 2: L = 64, M = 8, n2 = bf % 8
+    const double2 w1r = __ldg(p.tws + bf), w2r = __ldg(p.tws + 64 + (bf & 7));      // (x pass: the same entries in registers)
     double acc[8];
     double pv[8];
 #pragma unroll
@@ -167,14 +196,14 @@ tma_pass_kernel(TPParams p)
         double xr[8], xi[8];
         tp_load_butterfly<512>(tile, a, xr, xi);
         dft8(xr, xi);
-        tp_twiddle(w1, xr, xi);
+        if (XPASS) tp_twiddle_w1(w1r, xr, xi); else tp_twiddle(w1, xr, xi);
 #pragma unroll
         for (int k = 0; k < 8; ++k) tile[a[k]] = make_double2(xr[k], xi[k]);
         tp_bar();
         if (XPASS) issue_x();                                    // tile i + 2 (everybody is past the last stage of tile i - 1: its buffer is free)
         tp_load_butterfly<64>(tile, a, xr, xi);
         dft8(xr, xi);
-        tp_twiddle(w2, xr, xi);
+        if (XPASS) tp_twiddle_w1(w2r, xr, xi); else tp_twiddle(w2, xr, xi);
 #pragma unroll
         for (int k = 0; k < 8; ++k) tile[a[k]] = make_double2(xr[k], xi[k]);
         tp_bar();
