@@ -1,14 +1,15 @@
 #!/usr/bin/env python
-"""Per-region instruction / stall-sample shares of the splat kernel from an ncu source-page CSV
-(`ncu -i rep --page source --csv --print-source cuda,sass`).  usage: ncu_regions.py csv [n_top_lines]"""
+"""Per-region instruction / stall-sample shares of the splat kernel (z-lane variant) from an ncu source-page CSV
+(`ncu -i rep --page source --csv --print-source cuda,sass`, see tools/gpu_src.sh), plus the top stall reasons by source
+line.  usage: ncu_regions.py source.csv [raw.csv] > profiles/r02_splat_regions_c3.md"""
 import collections, csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
-ntop = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-cur = hdr = mode = None
-agg, samp, wf, txt = collections.Counter(), collections.Counter(), collections.Counter(), {}
 def f(x):
     try: return float(x)
     except ValueError: return 0.0
+cur = hdr = mode = None
+agg, samp, txt = collections.Counter(), collections.Counter(), {}
+stall, tot = collections.defaultdict(collections.Counter), collections.Counter()
 for r in rows:
     if not r: continue
     if r[0] == 'File Path': cur = r[1].split('/')[-1]; hdr = None; continue
@@ -17,30 +18,40 @@ for r in rows:
     if hdr and mode == 'cuda' and cur:
         try: ln = int(r[0])
         except ValueError: continue
-        k = (cur, ln)
+        k = (cur, ln); txt[k] = r[1][:90]
         agg[k] += f(r[hdr.index('Instructions Executed')]); samp[k] += f(r[hdr.index('# Samples')])
-        if 'L1 Wavefronts Shared' in hdr: wf[k] += f(r[hdr.index('L1 Wavefronts Shared')])
-        txt[k] = r[1][:80]
-tot, ts, tw = sum(agg.values()), sum(samp.values()), max(sum(wf.values()), 1)
-print('total warp inst %.3g  samples %d  smem wavefronts %.3g' % (tot, ts, tw))
-S = 'mdsf_splat.cuh'
+        for i, hn in enumerate(hdr):
+            if hn.startswith('stall_') and 'Not Issued' not in hn:
+                stall[hn][k] += f(r[i]); tot[hn] += f(r[i])
+T, S = sum(agg.values()), sum(samp.values())
 src = open('md-structure-factor_b200/csrc/mdsf_splat.cuh').read().split('\n')
-def ln(marker, start=0):
+def ln(m, start=0):
     for i, l in enumerate(src):
-        if i >= start and marker in l: return i + 1
+        if i >= start and m in l: return i + 1
     return -1
-marks = [('zstage + helpers', 1), ('setup', ln('splat_zfft_kernel(const uint4')), ('item / list head', ln('for (int item = warp; item < nitems;)')),
-         ('batch head, produce()', ln('for (int b = 0; b < nmax; b += RB)')), ('record loop', ln('for (int r_i = 0; r_i < mmax; ++r_i)')),
-         ('convert', ln('// fixed point -> fp64 (overflow')), ('twiddle load / dump', ln('if (ovf) atomicExch(err_flag, 2);')),
-         ('fft dispatch', ln('if (FUSE) {', ln('if (ovf) atomicExch(err_flag, 2);'))), ('store', ln('// store: every tile row x')), ('end', 10 ** 9)]
+end = ln('if (ovf) atomicExch(err_flag, 2);')
+marks = [('helpers, z stages (zstage2)', 1), ('kernel set-up', ln('splat_zfft_kernel(const uint4')), ('z-lane: list bounds, item order', ln('if constexpr (ZL &&')),
+         ('z-lane: batch head + products', ln('const int m = min(RBZ, n - b);')), ('z-lane: record loop', ln('auto accumulate = [&]')),
+         ('z-lane: convert', ln('// fixed point -> fp64 (overflow: a cell held > 2048 peak amplitudes)')), ('half-warp / general / density loop', ln('// work items: (group of SUB consecutive slabs')),
+         ('twiddle late load, density tap', end), ('z FFT dispatch', ln('if (FUSE) {', end)), ('tile store', ln('// store: every tile row x')), ('end', 10 ** 9)]
+print('# splat_zfft_kernel (c3, 8 frames), ncu source view: %.3g warp instructions, %d stall samples\n' % (T, S))
+print('| region of mdsf_splat.cuh | lines | instructions | stall samples |\n|---|---|---|---|')
 for (name, a), (_, b) in zip(marks, marks[1:]):
-    p = lambda k: k[0] == S and a <= k[1] < b
-    print('%-24s lines %4d-%-4d inst %5.1f%%  samples %5.1f%%  smem wf %5.1f%%' % (name, a, min(b, len(src)), 100 * sum(v for k, v in agg.items() if p(k)) / tot,
-          100 * sum(v for k, v in samp.items() if p(k)) / ts, 100 * sum(v for k, v in wf.items() if p(k)) / tw))
-for fn in sorted(set(k[0] for k in agg) - {S}):
-    p = lambda k: k[0] == fn
-    print('%-24s %16s inst %5.1f%%  samples %5.1f%%  smem wf %5.1f%%' % (fn[:24], '', 100 * sum(v for k, v in agg.items() if p(k)) / tot,
-          100 * sum(v for k, v in samp.items() if p(k)) / ts, 100 * sum(v for k, v in wf.items() if p(k)) / tw))
-print()
-for k, v in agg.most_common(ntop):
-    print('%5.2f%% inst %5.2f%% samp %5.2f%% wf  %s:%d %s' % (100 * v / tot, 100 * samp[k] / ts, 100 * wf[k] / tw, k[0], k[1], txt[k]))
+    sel = [k for k in agg if k[0] == 'mdsf_splat.cuh' and a <= k[1] < b]
+    print('| %s | %d-%d | %.1f %% | %.1f %% |' % (name, a, min(b, len(src)), 100 * sum(agg[k] for k in sel) / T, 100 * sum(samp[k] for k in sel) / S))
+for fn in sorted(set(k[0] for k in agg) - {'mdsf_splat.cuh'}):
+    sel = [k for k in agg if k[0] == fn]
+    print('| %s | | %.1f %% | %.1f %% |' % (fn, 100 * sum(agg[k] for k in sel) / T, 100 * sum(samp[k] for k in sel) / S))
+TT = sum(tot.values())
+print('\n## stall reasons (share of all samples) and their top source lines\n')
+for hn, v in tot.most_common(6):
+    print('* **%s %.1f %%**' % (hn.replace('stall_', ''), 100 * v / TT))
+    for k, x in stall[hn].most_common(3): print('  * %.0f %% at `%s:%d` `%s`' % (100 * x / v, k[0], k[1], txt[k].strip()[:70]))
+if len(sys.argv) > 2:
+    raw = list(csv.reader(open(sys.argv[2])))
+    h, v = raw[0], raw[2]
+    print('\n## kernel metrics\n')
+    for w in ('gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.per_cycle_active', 'launch__registers_per_thread',
+              'launch__shared_mem_per_block_dynamic', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+              'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'):
+        if w in h: print('- %s = %s %s' % (w, v[h.index(w)], raw[1][h.index(w)]))
