@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Development aid (no GPU needed): a line-by-line Python mirror of K2's pair enumeration (csrc/mdsf_prep.cuh
-for_each_pair) and of the way the splat kernel consumes a pair record (csrc/mdsf_splat.cuh), run on the golden cases
+axis_slot / pairs_of_tile, walked by walk_pairs_warp) and of the way the splat kernel consumes a pair record (csrc/mdsf_splat.cuh), run on the golden cases
 and compared with the reference density d1 stored in tests/golden/*.npz.  Validates the index logic (fold images,
 corner rule, tile / slab clipping, table offsets) before a GPU run.  Not part of the product or of the test suite.
 
